@@ -1,0 +1,220 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy restatements of OpenCV's published 8-bit algorithms.
+
+OpenCV itself is not under /root/reference (third-party dependency, `pkg-config opencv4`,
+configure.py:27-33; behaviour pinned to the installed cv2 4.13.0).  These functions restate the
+algorithms of modules/imgproc/src/color_hsv.simd.hpp, color_lab.cpp, color_yuv.simd.hpp,
+color_rgb.simd.hpp and resize.cpp as arithmetic on integers / float32, which is exactly what the
+CUDA kernels implement.  tests/test_oracle_spec.py checks every one against cv2 (all 2^24 colours
+for the conversions), so they are pinned by the reference's own call sites:
+utils/color.py:26-32, modules/bins.py:13, modules/preprocessor.py:56-86,136-143.
+"""
+import numpy as np
+
+# ---------------------------------------------------------------------------------------------
+# BGR -> HSV (8-bit, H in [0,180))
+# ---------------------------------------------------------------------------------------------
+HSV_SHIFT = 12
+
+
+def hsv_div_tables():
+    sdiv = np.zeros(256, np.int32)
+    hdiv = np.zeros(256, np.int32)
+    i = np.arange(1, 256, dtype=np.float64)
+    sdiv[1:] = np.rint((255 << HSV_SHIFT) / i).astype(np.int32)
+    hdiv[1:] = np.rint((180 << HSV_SHIFT) / (6.0 * i)).astype(np.int32)
+    return sdiv, hdiv
+
+
+def bgr2hsv(img):
+    sdiv, hdiv = hsv_div_tables()
+    b = img[..., 0].astype(np.int32)
+    g = img[..., 1].astype(np.int32)
+    r = img[..., 2].astype(np.int32)
+    v = np.maximum(np.maximum(b, g), r)
+    vmin = np.minimum(np.minimum(b, g), r)
+    diff = v - vmin
+    h = np.where(v == r, g - b, np.where(v == g, b - r + 2 * diff, r - g + 4 * diff))
+    s = (diff * sdiv[v] + (1 << (HSV_SHIFT - 1))) >> HSV_SHIFT
+    h = (h * hdiv[diff] + (1 << (HSV_SHIFT - 1))) >> HSV_SHIFT      # arithmetic shift
+    h = np.where(h < 0, h + 180, h)
+    return np.stack([h, s, v], axis=-1).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# HSV -> BGR (8-bit), float32, truncating
+# ---------------------------------------------------------------------------------------------
+_SECTOR = np.array([[1, 3, 0], [1, 0, 2], [3, 0, 1], [0, 2, 1], [0, 1, 3], [2, 1, 0]], np.int64)
+
+
+def _fmaf(a, b, c):
+    """float32 fused multiply-add emulated through float64 (a*b is exact in float64; the sum may
+    round twice, which differs from a true fmaf only on vanishingly rare ties)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def hsv2bgr(img, vector_path=True):
+    """cv2 4.13.0 as measured: the bracket is a single-rounding multiply-add on both paths; the
+    vector path (whole 32-px groups of each row) truncates x*255, the scalar row tail rounds to
+    nearest-even.  Use hsv2bgr_rows for the per-row mix."""
+    f32 = np.float32
+    h = img[..., 0].astype(f32) * f32(6.0 / 180.0)
+    s = img[..., 1].astype(f32) * f32(1.0 / 255.0)
+    v = img[..., 2].astype(f32) * f32(1.0 / 255.0)
+    fl = np.floor(h)
+    sector = fl.astype(np.int64) % 6
+    f = (h - fl).astype(f32)
+    one = np.ones_like(s)
+    t0 = v
+    t1 = (v * (one - s)).astype(f32)
+    t2 = (v * _fmaf(-s, f, one)).astype(f32)
+    t3 = (v * _fmaf(-s, (one - f).astype(f32), one)).astype(f32)
+    tab = np.stack([t0, t1, t2, t3], axis=-1)
+    out = np.empty(img.shape, f32)
+    for c in range(3):
+        out[..., c] = np.take_along_axis(tab, _SECTOR[sector][..., c][..., None], axis=-1)[..., 0]
+    grey = s == 0
+    for c in range(3):
+        out[..., c] = np.where(grey, v, out[..., c])
+    x = out * f32(255.0)
+    return np.clip(np.trunc(x) if vector_path else np.rint(x), 0, 255).astype(np.uint8)
+
+
+def hsv2bgr_rows(img):
+    """Per-row vector/scalar mix of cv2: columns [0, 32*floor(W/32)) truncate, the rest round."""
+    w = img.shape[1]
+    ve = w - (w % 32)
+    out = np.empty_like(img)
+    if ve:
+        out[:, :ve] = hsv2bgr(img[:, :ve], True)
+    if ve < w:
+        out[:, ve:] = hsv2bgr(img[:, ve:], False)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# BGR -> Lab (8-bit), fixed point
+# ---------------------------------------------------------------------------------------------
+LAB_C = np.array([[1777, 1541, 778], [871, 2929, 296], [73, 448, 3575]], np.int64)  # rows XYZ x cols RGB
+
+
+def lab_tables():
+    f32 = np.float32
+    x = np.arange(256, dtype=f32) / f32(255.0)
+    lin = np.where(x <= f32(0.04045), x / f32(12.92),
+                   np.power((x + f32(0.055)) / f32(1.055), f32(2.4)).astype(f32)).astype(f32)
+    gtab = np.clip(np.rint(f32(2040.0) * lin), 0, 65535).astype(np.uint16)
+    y = np.arange(3072, dtype=f32) / f32(2040.0)
+    fy = np.where(y < f32(0.008856), y * f32(7.787) + f32(0.13793103448275862), np.cbrt(y).astype(f32)).astype(f32)
+    ctab = np.clip(np.rint(f32(32768.0) * fy), 0, 65535).astype(np.uint16)
+    return gtab, ctab
+
+
+def _descale(x, n):
+    return (x + (1 << (n - 1))) >> n
+
+
+def bgr2lab(img):
+    gtab, ctab = lab_tables()
+    gt = gtab.astype(np.int64)
+    ct = ctab.astype(np.int64)
+    B = gt[img[..., 0]]
+    G = gt[img[..., 1]]
+    R = gt[img[..., 2]]
+    fX = ct[_descale(R * LAB_C[0, 0] + G * LAB_C[0, 1] + B * LAB_C[0, 2], 12)]
+    fY = ct[_descale(R * LAB_C[1, 0] + G * LAB_C[1, 1] + B * LAB_C[1, 2], 12)]
+    fZ = ct[_descale(R * LAB_C[2, 0] + G * LAB_C[2, 1] + B * LAB_C[2, 2], 12)]
+    L = _descale(296 * fY - 1336934, 15)
+    a = _descale(500 * (fX - fY) + (128 << 15), 15)
+    b = _descale(200 * (fY - fZ) + (128 << 15), 15)
+    return np.clip(np.stack([L, a, b], axis=-1), 0, 255).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# BGR -> GRAY / YCrCb (8-bit)
+# ---------------------------------------------------------------------------------------------
+def bgr2gray(img):
+    b = img[..., 0].astype(np.int32)
+    g = img[..., 1].astype(np.int32)
+    r = img[..., 2].astype(np.int32)
+    return ((b * 3735 + g * 19235 + r * 9798 + 16384) >> 15).astype(np.uint8)
+
+
+def bgr2ycrcb(img):
+    b = img[..., 0].astype(np.int32)
+    g = img[..., 1].astype(np.int32)
+    r = img[..., 2].astype(np.int32)
+    y = (b * 1868 + g * 9617 + r * 4899 + 8192) >> 14
+    cr = ((r - y) * 11682 + (128 << 14) + 8192) >> 14
+    cb = ((b - y) * 9241 + (128 << 14) + 8192) >> 14
+    return np.clip(np.stack([y, cr, cb], axis=-1), 0, 255).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# BGR -> HLS (8-bit), float32, rint.  fused=True is the vector path.
+# ---------------------------------------------------------------------------------------------
+def bgr2hls(img, fused=True):
+    f32 = np.float32
+    b = img[..., 0].astype(f32) * f32(1.0 / 255.0)
+    g = img[..., 1].astype(f32) * f32(1.0 / 255.0)
+    r = img[..., 2].astype(f32) * f32(1.0 / 255.0)
+    vmax = np.maximum(np.maximum(b, g), r)
+    vmin = np.minimum(np.minimum(b, g), r)
+    diff = (vmax - vmin).astype(f32)
+    sm = (vmax + vmin).astype(f32)
+    l = (sm * f32(0.5)).astype(f32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = np.where(l < f32(0.5), diff / sm, diff / (f32(2.0) - sm)).astype(f32)
+        k = (f32(60.0) / diff).astype(f32)
+        if fused:
+            hg = _fmaf((b - r).astype(f32), k, np.full_like(k, 120.0))
+            hb = _fmaf((r - g).astype(f32), k, np.full_like(k, 240.0))
+        else:
+            hg = (((b - r).astype(f32) * k).astype(f32) + f32(120.0)).astype(f32)
+            hb = (((r - g).astype(f32) * k).astype(f32) + f32(240.0)).astype(f32)
+        h = np.where(vmax == r, ((g - b).astype(f32) * k).astype(f32), np.where(vmax == g, hg, hb)).astype(f32)
+    h = np.where(h < 0, (h + f32(360.0)).astype(f32), h)
+    chroma = diff > np.finfo(np.float32).eps
+    h = np.where(chroma, h, f32(0))
+    s = np.where(chroma, s, f32(0))
+    out = np.stack([np.rint(h * f32(0.5)), np.rint(l * f32(255.0)), np.rint(s * f32(255.0))], axis=-1)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# cv2.resize(..., INTER_LINEAR) on 8-bit: 11-bit fixed-point coefficients
+# ---------------------------------------------------------------------------------------------
+def linear_coeffs(src, dst, horizontal):
+    """Returns (idx0, idx1, w0, w1) as int arrays of length dst (weights are int16, sum 2048)."""
+    scale = np.float64(src) / np.float64(dst)
+    d = np.arange(dst, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    if horizontal:
+        neg = s < 0
+        f = np.where(neg, np.float32(0), f)
+        s = np.where(neg, 0, s)
+        big = s >= src - 1
+        f = np.where(big, np.float32(0), f)
+        s = np.where(big, src - 1, s)
+    w1 = np.clip(np.rint(f * np.float32(2048.0)), -32768, 32767).astype(np.int64)
+    w0 = np.clip(np.rint((np.float32(1.0) - f) * np.float32(2048.0)), -32768, 32767).astype(np.int64)
+    i0 = np.clip(s, 0, src - 1)
+    i1 = np.clip(s + 1, 0, src - 1)
+    return i0, i1, w0, w1
+
+
+def resize_linear(img, dst_w, dst_h):
+    squeeze = img.ndim == 2
+    if squeeze:
+        img = img[..., None]
+    sh, sw = img.shape[:2]
+    x0, x1, a0, a1 = linear_coeffs(sw, dst_w, True)
+    y0, y1, b0, b1 = linear_coeffs(sh, dst_h, False)
+    src = img.astype(np.int64)
+    hor = src[:, x0, :] * a0[None, :, None] + src[:, x1, :] * a1[None, :, None]     # [sh, dst_w, c]
+    r0 = hor[y0] >> 4
+    r1 = hor[y1] >> 4
+    out = (((b0[:, None, None] * r0) >> 16) + ((b1[:, None, None] * r1) >> 16) + 2) >> 2
+    out = np.clip(out, 0, 255).astype(np.uint8)
+    return out[..., 0] if squeeze else out
