@@ -1,0 +1,166 @@
+// api.cu -- context management and error plumbing of libb200vision.so.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "lab_tables.inc"
+
+namespace bv {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int ensure_scratch(bv_ctx *ctx, int slot, size_t bytes) {
+    if (ctx->scratch_bytes[slot] >= bytes) return BV_OK;
+    // grow-only; steady state performs no allocation.  cudaFree synchronises the device, so any
+    // kernel still using the old block has finished before it is released.
+    if (ctx->scratch[slot]) {
+        BV_CUDA(cudaFree(ctx->scratch[slot]));
+        ctx->scratch[slot] = nullptr;
+        ctx->scratch_bytes[slot] = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&ctx->scratch[slot], want);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) for scratch slot %d: %s", want, slot, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return BV_ERR_NOMEM;
+    }
+    ctx->scratch_bytes[slot] = want;
+    return BV_OK;
+}
+
+}  // namespace bv
+
+using namespace bv;
+
+extern "C" int bv_version(void) { return BV_VERSION; }
+
+extern "C" const char *bv_last_error(void) { return g_error; }
+
+extern "C" int bv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" void bv_balance_default(bv_balance_params *p) {
+    if (!p) return;
+    // defaults of balance(), modules/color_balance.py:93-96
+    p->equalize_rgb = 1;
+    p->rgb_contrast_correct = 0;
+    p->hsv_contrast_correct = 1;
+    p->hsi_contrast_correct = 0;
+    p->rgb_extrema_clipping = 1;
+    p->adaptive_cast_correction = 0;
+    p->horizontal_blocks = 1;
+    p->vertical_blocks = 1;
+}
+
+extern "C" int bv_create(int device, bv_ctx **out) {
+    BV_REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("bv_create: no usable CUDA device (%s); this library has no CPU path",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return BV_ERR_CUDA;
+    }
+    BV_REQUIRE(device >= 0 && device < n, "device index out of range");
+    BV_CUDA(cudaSetDevice(device));
+    bv_ctx *ctx = (bv_ctx *)calloc(1, sizeof(bv_ctx));
+    if (!ctx) {
+        set_error("bv_create: out of host memory");
+        return BV_ERR_NOMEM;
+    }
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+        free(ctx);
+        return BV_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+        free(ctx);
+        return BV_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    bool ok_aux = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok_aux && i < BV_MAX_CHUNKS; ++i)
+        ok_aux = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok_aux) {
+        set_error("bv_create: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        bv_destroy(ctx);
+        return BV_ERR_CUDA;
+    }
+    double pow_tab[256];
+    for (int x = 0; x < 256; ++x) pow_tab[x] = pow((255. - x) / 255., 0.25);  // color_balance.cpp:490
+    bool ok = cudaMalloc(&ctx->d_lab_gamma, sizeof(kLabGammaTab)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_lab_cbrt, sizeof(kLabCbrtTab)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_pow_quarter, sizeof(pow_tab)) == cudaSuccess &&
+              cudaMemcpy(ctx->d_lab_gamma, kLabGammaTab, sizeof(kLabGammaTab), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(ctx->d_lab_cbrt, kLabCbrtTab, sizeof(kLabCbrtTab), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(ctx->d_pow_quarter, pow_tab, sizeof(pow_tab), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        set_error("bv_create: table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        bv_destroy(ctx);
+        return BV_ERR_CUDA;
+    }
+    *out = ctx;
+    return BV_OK;
+}
+
+extern "C" void bv_destroy(bv_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    for (int i = 0; i < SCR_COUNT; ++i)
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->d_lab_gamma) cudaFree(ctx->d_lab_gamma);
+    if (ctx->d_lab_cbrt) cudaFree(ctx->d_lab_cbrt);
+    if (ctx->d_pow_quarter) cudaFree(ctx->d_pow_quarter);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    for (int i = 0; i < BV_MAX_CHUNKS; ++i) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    }
+    (void)cudaGetLastError();
+    free(ctx);
+}
+
+extern "C" int bv_sync(bv_ctx *ctx) {
+    BV_REQUIRE(ctx, "null context");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    BV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BV_OK;
+}
+
+extern "C" void *bv_stream(bv_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int bv_set_stream(bv_ctx *ctx, void *cuda_stream) {
+    BV_REQUIRE(ctx, "null context");
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return BV_OK;
+}
+
+extern "C" uint64_t bv_launch_count(const bv_ctx *ctx) { return ctx ? ctx->launches : 0; }

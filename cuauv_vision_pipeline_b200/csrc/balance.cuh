@@ -1,0 +1,33 @@
+// balance.cuh -- device-side state of the colour balance, shared by balance.cu and stage.cu.
+#pragma once
+#include "common.cuh"
+
+namespace bv {
+
+// Per-frame working state in HBM (3.9 KB + 1.75 KB of tables per tile).
+struct BalFrame {
+    uint32_t hist_bgr[3][256];  // pass 1: histograms of B, G, R
+    uint32_t hist_sv[2][256];   // pass 2: histograms of S, V after the BGR tables
+    uint8_t lut_bgr[3][256];    // clip -> equalise -> rgb-contrast, composed per channel
+    uint8_t lut_sv[2][256];     // clip -> stretch for S and V
+    bv_balance_stats stats;
+};
+
+// What the final pass does with each balanced pixel.
+struct BalOutputs {
+    uint8_t *balanced;   // BGR after balance (may be null)
+    uint8_t *converted;  // after the conversion CODE (may be null)
+    uint8_t *mask;       // uint8 0/255 in-range mask (may be null)
+    uint16_t *mask_bits; // bit-packed mask, one uint16 per 16-px group (needs width % 16 == 0)
+    uint8_t lo[3], hi[3];
+};
+
+// Enqueues the complete colour balance of `batch` frames.  `out.balanced == src` is allowed.
+int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int width, const bv_balance_params &prm,
+                int cvt_code, const BalOutputs &out, bv_balance_stats *stats_host);
+
+// Convert (+inRange) without balance, writing any of converted / mask / mask_bits.
+int convert_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int width, int cvt_code,
+                const BalOutputs &out);
+
+}  // namespace bv

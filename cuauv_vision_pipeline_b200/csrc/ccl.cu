@@ -1,0 +1,461 @@
+// ccl.cu -- 8-connected component labelling with per-blob raster moments, on bit-packed masks.
+//
+// Role in the reference: blob extraction after threshold + morphology, i.e. outer_contours +
+// contour_centroid + contour_area (utils/feature.py:5-21,240-265; modules/bins.py:27,
+// modules/red_buoy.py:38-44).  The reference uses cv2.findContours + polygon moments; the
+// labelling form computed here has the declared oracle cv2.connectedComponentsWithStats(8) +
+// cv2.moments(binaryImage=True) with labels in first-pixel raster order.
+//
+// Algorithm (union-find over word runs):
+//   nodes   = maximal runs of set bits inside one 32-px word; a node's id is the pixel index of its
+//             first pixel, and `parent[]` is only ever touched at those sparse positions
+//   init    parent[node] = node
+//   merge   each word unions its runs with (a) the run ending at bit 31 of the word to the left,
+//           (b) every run of the row above that touches the run's 3-neighbourhood, found with
+//           bit tricks on a 34-bit window; unions link the larger root under the smaller with
+//           atomicMin, so a component's root is its first pixel in raster order
+//   count   compress every node to its root, count roots per row
+//   scan    exclusive scan of the row counts per frame -> number of blobs
+//   rank    roots receive 1, 2, 3... in raster order; stored negated in parent[root]
+//   final   each word looks its runs' labels up, writes 32 int32 labels, and accumulates closed-form
+//           run moments (sum of x^k over a run is a polynomial in its end points) with a warp
+//           segmented reduction over equal labels, then one set of 64-bit atomics per segment
+//
+// HBM traffic: mask bits (1/8 B/px) are re-read from L2; the label image is written once (4 B/px);
+// parent[] traffic is proportional to the number of runs, not pixels.
+#include "morph.cuh"
+
+namespace bv {
+
+__device__ __forceinline__ int find_root(int *parent, int a) {
+    int p = parent[a];
+    while (p != a) {
+        a = p;
+        p = parent[a];
+    }
+    return a;
+}
+
+__device__ __forceinline__ int find_compress(int *parent, int a) {
+    const int a0 = a;
+    int p = parent[a];
+    while (p != a) {
+        a = p;
+        p = parent[a];
+    }
+    if (a != a0) atomicMin(&parent[a0], a);
+    return a;
+}
+
+__device__ void union_nodes(int *parent, int a, int b) {
+    bool done;
+    do {
+        a = find_compress(parent, a);
+        b = find_compress(parent, b);
+        if (a < b) {
+            const int old = atomicMin(&parent[b], a);
+            done = (old == b);
+            b = old;
+        } else if (b < a) {
+            const int old = atomicMin(&parent[a], b);
+            done = (old == a);
+            a = old;
+        } else {
+            done = true;
+        }
+    } while (!done);
+}
+
+// first bit of the run of ones containing bit `pos` of w (w has bit pos set)
+__device__ __forceinline__ int run_start(uint32_t w, int pos) {
+    const uint32_t zeros_below = ~w & ((pos == 0) ? 0u : (0xFFFFFFFFu >> (32 - pos)));
+    return zeros_below ? 32 - __clz(zeros_below) : 0;
+}
+
+struct WordPos {
+    int wx, y;
+    size_t row;  // frame * height + y
+};
+
+__device__ __forceinline__ WordPos word_pos(size_t i, int wpr, int height) {
+    WordPos p;
+    p.wx = (int)(i % wpr);
+    p.row = i / wpr;
+    p.y = (int)(p.row % height);
+    return p;
+}
+
+__global__ void __launch_bounds__(256) ccl_init_kernel(const uint32_t *__restrict__ bits, int *__restrict__ parent,
+                                                       int height, int width, int wpr, size_t total_words) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+        const uint32_t w = bits[i];
+        if (!w) continue;
+        const WordPos wp = word_pos(i, wpr, height);
+        int *fp = parent + (wp.row - wp.y) * (size_t)width;  // this frame's parent array
+        uint32_t starts = w & ~(w << 1);
+        while (starts) {
+            const int s = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const int node = wp.y * width + wp.wx * 32 + s;
+            fp[node] = node;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ccl_merge_kernel(const uint32_t *__restrict__ bits, int *__restrict__ parent,
+                                                        int height, int width, int wpr, size_t total_words) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+        const uint32_t w = bits[i];
+        if (!w) continue;
+        const WordPos wp = word_pos(i, wpr, height);
+        int *fp = parent + (wp.row - wp.y) * (size_t)width;
+        const int xbase = wp.wx * 32;
+        // (a) continuation of the previous word's last run
+        if ((w & 1u) && wp.wx > 0) {
+            const uint32_t pw = bits[i - 1];
+            if (pw >> 31) union_nodes(fp, wp.y * width + xbase, wp.y * width + xbase - 32 + run_start(pw, 31));
+        }
+        if (wp.y == 0) continue;
+        // (b) row above, 34-bit window: bit k <-> x = xbase + k - 1
+        const uint32_t up = bits[i - wpr];
+        const uint32_t upl = wp.wx > 0 ? bits[i - wpr - 1] : 0u;
+        const uint32_t upr = wp.wx < wpr - 1 ? bits[i - wpr + 1] : 0u;
+        const unsigned long long U = ((unsigned long long)up << 1) | (unsigned long long)(upl >> 31) |
+                                     ((unsigned long long)(upr & 1u) << 33);
+        if (!U) continue;
+        const int up_row = (wp.y - 1) * width;
+        uint32_t starts = w & ~(w << 1);
+        while (starts) {
+            const int s = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const uint32_t above_s = w >> s;                       // run from bit s
+            const int len = __ffs(~above_s) - 1;                   // ~above_s != 0 unless run spans to bit 31
+            const int e = (len < 0) ? 31 : s + len - 1;            // __ffs(0) = 0 -> len = -1
+            // run occupies window bits s+1..e+1; its 8-neighbourhood above is s..e+2
+            const int nb = e - s + 3;
+            const unsigned long long dil = ((nb >= 64) ? ~0ull : ((1ull << nb) - 1ull)) << s;
+            unsigned long long T = U & dil;
+            const int node = wp.y * width + xbase + s;
+            while (T) {
+                const int k = __ffsll((long long)T) - 1;           // first bit of a touching run
+                // clear this touching run from T
+                const unsigned long long from_k = T >> k;
+                const int rl = __ffsll((long long)~from_k) - 1;    // length of ones starting at k (<= 34)
+                T &= ~(((1ull << rl) - 1ull) << k);
+                int other;
+                if (k == 0)
+                    other = up_row + xbase - 32 + run_start(upl, 31);
+                else if (k == 33)
+                    other = up_row + xbase + 32;                   // bit 0 of the next word starts a run
+                else
+                    other = up_row + xbase + run_start(up, k - 1);
+                // a run of `up` reaching bit 0 may continue from the previous word; the horizontal
+                // union (a) of the row above already ties those nodes together
+                union_nodes(fp, node, other);
+            }
+        }
+    }
+}
+
+// one warp per row: compress every node of the row to its root, count the roots
+__global__ void __launch_bounds__(256) ccl_count_kernel(const uint32_t *__restrict__ bits, int *__restrict__ parent,
+                                                        int *__restrict__ row_count, int height, int width, int wpr,
+                                                        size_t total_rows) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t row = warp0; row < total_rows; row += nwarps) {
+        const int y = (int)(row % height);
+        int *fp = parent + (row - y) * (size_t)width;
+        int cnt = 0;
+        for (int wx = lane; wx < wpr; wx += 32) {
+            const uint32_t w = bits[row * wpr + wx];
+            uint32_t starts = w & ~(w << 1);
+            while (starts) {
+                const int s = __ffs(starts) - 1;
+                starts &= starts - 1;
+                const int node = y * width + wx * 32 + s;
+                const int r = find_root(fp, node);
+                if (r == node)
+                    ++cnt;
+                else
+                    fp[node] = r;
+            }
+        }
+        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+        if (lane == 0) row_count[row] = cnt;
+    }
+}
+
+// one block per frame: exclusive scan of the row counts
+__global__ void __launch_bounds__(1024) ccl_scan_kernel(const int *__restrict__ row_count, int *__restrict__ row_off,
+                                                        int *__restrict__ n_blobs, int height) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int f = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < height; base += blockDim.x) {
+        const int y = base + threadIdx.x;
+        const int v = y < height ? row_count[(size_t)f * height + y] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int ws = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xFFFFFFFFu, ws, d);
+                if (lane >= d) ws += o;
+            }
+            warp_sums[lane] = ws;  // inclusive over warps
+        }
+        __syncthreads();
+        const int before = carry + (wid ? warp_sums[wid - 1] : 0) + incl - v;
+        if (y < height) row_off[(size_t)f * height + y] = before;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_blobs[f] = carry;
+}
+
+// one warp per row: number the roots of the row in raster order, store -(label) in parent[root]
+__global__ void __launch_bounds__(256) ccl_rank_kernel(const uint32_t *__restrict__ bits, int *__restrict__ parent,
+                                                       const int *__restrict__ row_off, int height, int width, int wpr,
+                                                       size_t total_rows) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t row = warp0; row < total_rows; row += nwarps) {
+        const int y = (int)(row % height);
+        int *fp = parent + (row - y) * (size_t)width;
+        int next = row_off[row];  // labels handed out so far (0-based rank of the next root)
+        for (int wbase = 0; wbase < wpr; wbase += 32) {
+            const int wx = wbase + lane;
+            const uint32_t w = wx < wpr ? bits[row * wpr + wx] : 0u;
+            uint32_t starts = w & ~(w << 1);
+            uint32_t roots = 0;
+            for (uint32_t s_it = starts; s_it;) {
+                const int s = __ffs(s_it) - 1;
+                s_it &= s_it - 1;
+                const int node = y * width + wx * 32 + s;
+                if (fp[node] == node) roots |= 1u << s;
+            }
+            const int c = __popc(roots);
+            int incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            int rank = next + incl - c;
+            while (roots) {
+                const int s = __ffs(roots) - 1;
+                roots &= roots - 1;
+                fp[y * width + wx * 32 + s] = -(rank + 1);
+                ++rank;
+            }
+            next += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ccl_blob_init_kernel(bv_blob *__restrict__ blobs, const int *__restrict__ n_blobs,
+                                                            int max_blobs, int height, int width) {
+    const int f = blockIdx.y;
+    const int n = min(n_blobs[f], max_blobs);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        bv_blob b;
+        b.m00 = b.m10 = b.m01 = b.m20 = b.m11 = b.m02 = b.m30 = b.m21 = b.m12 = b.m03 = 0;
+        b.x0 = width;
+        b.y0 = height;
+        b.x1 = -1;
+        b.y1 = -1;
+        blobs[(size_t)f * max_blobs + i] = b;
+    }
+}
+
+struct RunSums {
+    long long m00, m10, m01, m20, m11, m02, m30, m21, m12, m03;
+    int x0, y0, x1, y1;
+};
+
+// sum_{x=a}^{b} x^k in closed form (exact in 64-bit for any image size that fits 32-bit pixels indices)
+__device__ __forceinline__ void run_sums(int a, int b, int y, RunSums &r) {
+    const long long n = b - a + 1;
+    const long long A = a, B = b;
+    const long long s1 = (A + B) * n / 2;
+    // S2(k) = k(k+1)(2k+1)/6, S3(k) = (k(k+1)/2)^2
+    const long long Am = A - 1;
+    const long long s2 = B * (B + 1) * (2 * B + 1) / 6 - Am * (Am + 1) * (2 * Am + 1) / 6;
+    const long long tb = B * (B + 1) / 2, ta = Am * (Am + 1) / 2;
+    const long long s3 = tb * tb - ta * ta;
+    const long long Y = y;
+    r.m00 = n;
+    r.m10 = s1;
+    r.m01 = Y * n;
+    r.m20 = s2;
+    r.m11 = Y * s1;
+    r.m02 = Y * Y * n;
+    r.m30 = s3;
+    r.m21 = Y * s2;
+    r.m12 = Y * Y * s1;
+    r.m03 = Y * Y * Y * n;
+    r.x0 = a;
+    r.x1 = b;
+    r.y0 = r.y1 = y;
+}
+
+__device__ __forceinline__ void blob_atomic_add(bv_blob *b, const RunSums &r) {
+    atomicAdd((unsigned long long *)&b->m00, (unsigned long long)r.m00);
+    atomicAdd((unsigned long long *)&b->m10, (unsigned long long)r.m10);
+    atomicAdd((unsigned long long *)&b->m01, (unsigned long long)r.m01);
+    atomicAdd((unsigned long long *)&b->m20, (unsigned long long)r.m20);
+    atomicAdd((unsigned long long *)&b->m11, (unsigned long long)r.m11);
+    atomicAdd((unsigned long long *)&b->m02, (unsigned long long)r.m02);
+    atomicAdd((unsigned long long *)&b->m30, (unsigned long long)r.m30);
+    atomicAdd((unsigned long long *)&b->m21, (unsigned long long)r.m21);
+    atomicAdd((unsigned long long *)&b->m12, (unsigned long long)r.m12);
+    atomicAdd((unsigned long long *)&b->m03, (unsigned long long)r.m03);
+    atomicMin(&b->x0, r.x0);
+    atomicMin(&b->y0, r.y0);
+    atomicMax(&b->x1, r.x1);
+    atomicMax(&b->y1, r.y1);
+}
+
+// final: labels + moments.  All 32 lanes of a warp stay in the loop together (the segmented
+// reduction uses full-warp shuffles).
+__global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ parent,
+                                                        int *__restrict__ labels, bv_blob *__restrict__ blobs,
+                                                        int max_blobs, int height, int width, int wpr,
+                                                        size_t total_words) {
+    const int lane = threadIdx.x & 31;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t rounded = (total_words + 31) / 32 * 32;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+        const bool valid = i < total_words;
+        const uint32_t w = valid ? bits[i] : 0u;
+        const WordPos wp = word_pos(valid ? i : 0, wpr, height);
+        const size_t frame = (wp.row - wp.y) / height;
+        const int *fp = parent + (wp.row - wp.y) * (size_t)width;
+        const int xbase = wp.wx * 32;
+        const int nvalid = min(32, width - xbase);
+        int *out = labels ? labels + wp.row * (size_t)width + xbase : nullptr;
+        uint32_t rest = w;
+        int written = 0;  // pixels of this word already emitted
+        // per-word label buffer is emitted run by run to keep registers low
+        while (__any_sync(0xFFFFFFFFu, rest != 0)) {
+            int lab = 0;
+            RunSums rs;
+            rs.m00 = rs.m10 = rs.m01 = rs.m20 = rs.m11 = rs.m02 = rs.m30 = rs.m21 = rs.m12 = rs.m03 = 0;
+            rs.x0 = rs.y0 = 0x7FFFFFFF;
+            rs.x1 = rs.y1 = -1;
+            if (rest) {
+                const int s = __ffs(rest) - 1;
+                const uint32_t from_s = rest >> s;
+                const int len_raw = __ffs(~from_s) - 1;
+                const int e = (len_raw < 0) ? 31 : s + len_raw - 1;
+                rest &= (e == 31) ? 0u : ~((2u << e) - 1u);
+                const int node = wp.y * width + xbase + s;
+                const int v = fp[node];
+                lab = v < 0 ? -v : -fp[v];
+                if (out) {
+                    for (int x = written; x < s; ++x) out[x] = 0;
+                    for (int x = s; x <= e; ++x) out[x] = lab;
+                    written = e + 1;
+                }
+                if (blobs) run_sums(xbase + s, xbase + e, wp.y, rs);
+            }
+            if (blobs) {
+                // segmented reduction over consecutive lanes with the same (frame, label)
+                const long long key = lab ? ((long long)frame << 32) | (unsigned)lab : -(long long)lane - 1;
+                const long long prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
+                const bool head = lane == 0 || prev != key;
+                const unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
+                const unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+                const int seg_end = above ? __ffs(above) - 2 : 31;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const bool take = lane + d <= seg_end;
+#define BV_SEG_ADD(field)                                                         \
+    {                                                                             \
+        const long long o = __shfl_down_sync(0xFFFFFFFFu, rs.field, d);           \
+        if (take) rs.field += o;                                                  \
+    }
+                    BV_SEG_ADD(m00) BV_SEG_ADD(m10) BV_SEG_ADD(m01) BV_SEG_ADD(m20) BV_SEG_ADD(m11)
+                    BV_SEG_ADD(m02) BV_SEG_ADD(m30) BV_SEG_ADD(m21) BV_SEG_ADD(m12) BV_SEG_ADD(m03)
+#undef BV_SEG_ADD
+                    const int ox0 = __shfl_down_sync(0xFFFFFFFFu, rs.x0, d), oy0 = __shfl_down_sync(0xFFFFFFFFu, rs.y0, d);
+                    const int ox1 = __shfl_down_sync(0xFFFFFFFFu, rs.x1, d), oy1 = __shfl_down_sync(0xFFFFFFFFu, rs.y1, d);
+                    if (take) {
+                        rs.x0 = min(rs.x0, ox0);
+                        rs.y0 = min(rs.y0, oy0);
+                        rs.x1 = max(rs.x1, ox1);
+                        rs.y1 = max(rs.y1, oy1);
+                    }
+                }
+                if (head && lab && lab <= max_blobs) blob_atomic_add(&blobs[frame * (size_t)max_blobs + (lab - 1)], rs);
+            }
+        }
+        if (out && valid)
+            for (int x = written; x < nvalid; ++x) out[x] = 0;
+    }
+}
+
+int label_bits(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, int height, int width, bv_blob *blobs,
+               int max_blobs, int32_t *n_blobs) {
+    const int wpr = words_per_row(width);
+    const size_t total_words = (size_t)batch * height * wpr;
+    const size_t total_rows = (size_t)batch * height;
+    if ((size_t)height * width >= (1ull << 31)) {
+        set_error("bv_label: frame too large for 32-bit pixel indices");
+        return BV_ERR_INVALID;
+    }
+    BV_TRY(ensure_scratch(ctx, SCR_CCL_PARENT, total_rows * width * sizeof(int)));
+    BV_TRY(ensure_scratch(ctx, SCR_CCL_AUX, (total_rows * 2 + batch) * sizeof(int)));
+    int *parent = (int *)ctx->scratch[SCR_CCL_PARENT];
+    int *row_count = (int *)ctx->scratch[SCR_CCL_AUX];
+    int *row_off = row_count + total_rows;
+    int *nb = n_blobs ? n_blobs : row_off + total_rows;
+    const int gw = grid_for(ctx, total_words, 256, 8);
+    const int gr = grid_for(ctx, total_rows * 32, 256, 8);
+    BV_LAUNCH(ctx, ccl_init_kernel, gw, 256, 0, bits, parent, height, width, wpr, total_words);
+    BV_LAUNCH(ctx, ccl_merge_kernel, gw, 256, 0, bits, parent, height, width, wpr, total_words);
+    BV_LAUNCH(ctx, ccl_count_kernel, gr, 256, 0, bits, parent, row_count, height, width, wpr, total_rows);
+    BV_LAUNCH(ctx, ccl_scan_kernel, batch, 1024, 0, row_count, row_off, nb, height);
+    BV_LAUNCH(ctx, ccl_rank_kernel, gr, 256, 0, bits, parent, row_off, height, width, wpr, total_rows);
+    if (blobs && max_blobs > 0) {
+        dim3 g((unsigned)min(64, (max_blobs + 255) / 256), batch);
+        BV_LAUNCH(ctx, ccl_blob_init_kernel, g, 256, 0, blobs, nb, max_blobs, height, width);
+    }
+    if (labels || (blobs && max_blobs > 0))
+        BV_LAUNCH(ctx, ccl_final_kernel, gw, 256, 0, bits, parent, labels, (max_blobs > 0 ? blobs : nullptr), max_blobs,
+                  height, width, wpr, total_words);
+    return BV_OK;
+}
+
+}  // namespace bv
+
+using namespace bv;
+
+extern "C" int bv_label(bv_ctx *ctx, const uint8_t *mask_dev, int32_t *labels_dev, int batch, int height, int width,
+                        bv_blob *blobs_dev, int max_blobs, int32_t *n_blobs_dev) {
+    BV_REQUIRE(ctx && mask_dev, "null argument");
+    BV_REQUIRE(batch > 0 && height > 0 && width > 0, "batch, height and width must be positive");
+    BV_REQUIRE(max_blobs >= 0, "max_blobs must be >= 0");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)batch * bits_frame_words(height, width);
+    BV_TRY(ensure_scratch(ctx, SCR_BITS_A, words * 4));
+    uint32_t *bits = (uint32_t *)ctx->scratch[SCR_BITS_A];
+    BV_TRY(mask_to_bits(ctx, mask_dev, bits, batch, height, width));
+    return label_bits(ctx, bits, labels_dev, batch, height, width, blobs_dev, max_blobs, n_blobs_dev);
+}

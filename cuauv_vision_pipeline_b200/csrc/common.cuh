@@ -1,0 +1,162 @@
+// common.cuh -- context, error plumbing and small device helpers shared by all translation units
+// of libb200vision.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200vision.h"
+#include "pixel_math.cuh"
+
+namespace bv {
+
+// ---- error plumbing ------------------------------------------------------------------------
+void set_error(const char *fmt, ...);  // thread-local message, api.cu
+
+#define BV_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            bv::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));   \
+            return BV_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define BV_REQUIRE(cond, msg)                                                                      \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            bv::set_error("%s: %s", __func__, msg);                                                \
+            return BV_ERR_INVALID;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+#define BV_TRY(expr)                                                                               \
+    do {                                                                                           \
+        int _s = (expr);                                                                           \
+        if (_s != BV_OK) return _s;                                                                \
+    } while (0)
+
+// Launch + count + check.  Every kernel of the library goes through this macro so that
+// bv_launch_count() is the true number of launches.
+#define BV_LAUNCH(ctx, kernel, grid, block, smem, ...)                                             \
+    do {                                                                                           \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                           \
+        (ctx)->launches++;                                                                         \
+        BV_CUDA(cudaGetLastError());                                                               \
+    } while (0)
+
+// ---- scratch slots ---------------------------------------------------------------------------
+enum ScratchSlot {
+    SCR_BAL_STATE = 0,  // per-frame histograms, LUTs, stats of the colour balance
+    SCR_BITS_A,         // bit-packed masks (ping)
+    SCR_BITS_B,         // bit-packed masks (pong)
+    SCR_CCL_PARENT,     // union-find parents, int32 per pixel
+    SCR_CCL_AUX,        // per-block root counts / offsets
+    SCR_MORPH_TMP,      // intermediate image of multi-step grey morphology
+    SCR_MORPH_TMP2,
+    SCR_MORPH_SE,       // structuring-element offsets
+    SCR_STAGE_IMG,      // balanced frame when the caller does not want it
+    SCR_LETTERBOX,      // per-image descriptors
+    SCR_HOST_IN,        // device staging of bv_stage_host
+    SCR_HOST_BAL,
+    SCR_HOST_CVT,
+    SCR_HOST_MASK,
+    SCR_HOST_LABELS,
+    SCR_HOST_BLOBS,
+    SCR_HOST_NBLOBS,
+    SCR_COUNT
+};
+
+}  // namespace bv
+
+#define BV_MAX_CHUNKS 64
+
+struct bv_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+    uint64_t launches;
+    void *scratch[bv::SCR_COUNT];
+    size_t scratch_bytes[bv::SCR_COUNT];
+    uint16_t *d_lab_gamma;  // 256
+    uint16_t *d_lab_cbrt;   // 3072
+    double *d_pow_quarter;  // 256: pow((255-x)/255, 0.25) from the host libm (adaptive cast correction)
+    // host-memory pipeline (bv_stage_host): copy streams and per-chunk events
+    cudaStream_t copy_in, copy_out;
+    cudaEvent_t ev_in[BV_MAX_CHUNKS], ev_done[BV_MAX_CHUNKS];
+};
+
+namespace bv {
+
+int ensure_scratch(bv_ctx *ctx, int slot, size_t bytes);  // api.cu
+
+// ---- device helpers --------------------------------------------------------------------------
+#if defined(__CUDACC__)
+
+// streaming 128-bit load that does not pollute L1
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+// plain 128-bit load (keeps the line in L1/L2: used when a later pass re-reads the frame)
+__device__ __forceinline__ uint4 ld_keep(const uint4 *p) { return __ldg(p); }
+
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w));
+}
+
+// 16 interleaved 3-channel pixels = 48 bytes = 12 words
+struct Px16 {
+    uint32_t w[12];
+};
+
+template <bool KEEP>
+__device__ __forceinline__ void load_px16(const uint8_t *base, size_t group, Px16 &p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(base) + group * 3;
+    uint4 a, b, c;
+    if (KEEP) {
+        a = ld_keep(q);
+        b = ld_keep(q + 1);
+        c = ld_keep(q + 2);
+    } else {
+        a = ld_stream(q);
+        b = ld_stream(q + 1);
+        c = ld_stream(q + 2);
+    }
+    p.w[0] = a.x; p.w[1] = a.y; p.w[2] = a.z; p.w[3] = a.w;
+    p.w[4] = b.x; p.w[5] = b.y; p.w[6] = b.z; p.w[7] = b.w;
+    p.w[8] = c.x; p.w[9] = c.y; p.w[10] = c.z; p.w[11] = c.w;
+}
+
+__device__ __forceinline__ void store_px16(uint8_t *base, size_t group, const Px16 &p) {
+    uint4 *q = reinterpret_cast<uint4 *>(base) + group * 3;
+    st_stream(q, make_uint4(p.w[0], p.w[1], p.w[2], p.w[3]));
+    st_stream(q + 1, make_uint4(p.w[4], p.w[5], p.w[6], p.w[7]));
+    st_stream(q + 2, make_uint4(p.w[8], p.w[9], p.w[10], p.w[11]));
+}
+
+// byte k (compile-time constant after unrolling) of a packed word array
+#define BV_GETB(W, k) (((W)[(k) >> 2] >> (8 * ((k)&3))) & 0xFFu)
+#define BV_PUTB(W, k, v) ((W)[(k) >> 2] |= ((uint32_t)(v)) << (8 * ((k)&3)))
+
+__device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+#endif  // __CUDACC__
+
+inline bool host_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Grid sizing for grid-stride kernels: a whole number of waves of 148-SM multiples.
+inline int grid_for(const bv_ctx *ctx, size_t work_items, int block, int max_blocks_per_sm) {
+    size_t need = (work_items + block - 1) / block;
+    size_t cap = (size_t)ctx->sm_count * max_blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+}  // namespace bv

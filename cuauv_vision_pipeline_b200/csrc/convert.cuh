@@ -1,0 +1,76 @@
+// convert.cuh -- shared-memory tables and the per-pixel conversion switch used by every kernel
+// that converts colour spaces (cvt.cu, balance.cu).
+#pragma once
+#include "common.cuh"
+
+namespace bv {
+
+struct SmemTabs {
+    int sdiv[256];
+    int hdiv[256];
+    uint16_t gtab[kLabGammaSize];
+    uint16_t ctab[kLabCbrtSize];
+};
+
+template <int CODE>
+__device__ __forceinline__ void init_tabs(SmemTabs &t, const uint16_t *__restrict__ g_gamma,
+                                          const uint16_t *__restrict__ g_cbrt) {
+    if (CODE == BV_BGR2HSV) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            t.sdiv[i] = hsv_sdiv(i);
+            t.hdiv[i] = hsv_hdiv(i);
+        }
+    }
+    if (CODE == BV_BGR2LAB) {
+        for (int i = threadIdx.x; i < kLabGammaSize; i += blockDim.x) t.gtab[i] = g_gamma[i];
+        for (int i = threadIdx.x; i < kLabCbrtSize; i += blockDim.x) t.ctab[i] = g_cbrt[i];
+    }
+    __syncthreads();
+}
+
+// One pixel through conversion CODE.  `vec` is the cv2 vector-path flag (HSV2BGR / HLS only).
+template <int CODE>
+__device__ __forceinline__ void convert_px(int c0, int c1, int c2, bool vec, const SmemTabs &t, int &o0, int &o1,
+                                           int &o2) {
+    if (CODE == BV_BGR2HSV) {
+        bgr2hsv(c0, c1, c2, t.sdiv, t.hdiv, o0, o1, o2);
+    } else if (CODE == BV_BGR2LAB) {
+        bgr2lab(c0, c1, c2, t.gtab, t.ctab, o0, o1, o2);
+    } else if (CODE == BV_BGR2GRAY) {
+        o0 = bgr2gray(c0, c1, c2);
+        o1 = o2 = 0;
+    } else if (CODE == BV_BGR2YCRCB) {
+        bgr2ycrcb(c0, c1, c2, o0, o1, o2);
+    } else if (CODE == BV_HSV2BGR) {
+        hsv2bgr(c0, c1, c2, vec, o0, o1, o2);
+    } else if (CODE == BV_BGR2HLS) {
+        bgr2hls(c0, c1, c2, vec, o0, o1, o2);
+    } else if (CODE == BV_BGR2RGB) {
+        o0 = c2;
+        o1 = c1;
+        o2 = c0;
+    } else {  // identity (-1)
+        o0 = c0;
+        o1 = c1;
+        o2 = c2;
+    }
+}
+
+template <int CODE>
+struct CvtTraits {
+    static constexpr bool kOneChannel = (CODE == BV_BGR2GRAY);
+    static constexpr bool kNeedsX = (CODE == BV_HSV2BGR || CODE == BV_BGR2HLS);
+};
+
+struct Bounds3 {
+    uint8_t lo[3], hi[3];
+};
+
+template <int CODE>
+__device__ __forceinline__ bool in_range_px(int o0, int o1, int o2, const Bounds3 &bd) {
+    bool in_r = o0 >= bd.lo[0] && o0 <= bd.hi[0];
+    if (!CvtTraits<CODE>::kOneChannel) in_r = in_r && o1 >= bd.lo[1] && o1 <= bd.hi[1] && o2 >= bd.lo[2] && o2 <= bd.hi[2];
+    return in_r;
+}
+
+}  // namespace bv

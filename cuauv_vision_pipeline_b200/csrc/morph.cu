@@ -1,0 +1,391 @@
+// morph.cu -- flat-structuring-element morphology.  Replaces cv2.erode / cv2.dilate /
+// cv2.morphologyEx at utils/transform.py:80-164, modules/bins.py:24, modules/red_buoy.py:33-34
+// and modules/preprocessor.py:120-129.
+//
+// Semantics (cv2, verified in SURVEY.md A.5): erode = min over the SE support with out-of-image
+// taps ignored (+inf border), dilate = max with the SE reflected about the anchor and out-of-image
+// taps ignored (0 border); anchor = centre; OPEN/CLOSE/GRADIENT with `iterations=n` apply n
+// erosions then n dilations (resp. the reverse, resp. the difference).
+//
+// Two implementations:
+//   * binary masks, bit-packed 32 px per word: a 5x5 erosion is 4 funnel-shift/AND pairs per row
+//     and an AND across 5 rows per 32 pixels; the whole mask of a 2208x1242 frame is 343 KB and
+//     lives in L2.  Used by the fused stage (stage.cu).
+//   * grey / multi-channel uint8 with an arbitrary SE given as horizontal runs (bv_morph).
+#include "morph.cuh"
+
+namespace bv {
+
+// ----------------------------------------------------------------------------------------------
+// uint8 mask <-> bits
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_to_bits_kernel(const uint8_t *__restrict__ mask, uint32_t *__restrict__ bits,
+                                                           int height, int width, int wpr, size_t total_words) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+        const int wx = (int)(i % wpr);
+        const size_t row = i / wpr;  // frame * height + y
+        const uint8_t *p = mask + row * (size_t)width + (size_t)wx * 32;
+        const int n = min(32, width - wx * 32);
+        uint32_t w = 0;
+        if (n == 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p));
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+                if (BV_GETB(v, k)) w |= 1u << k;
+        } else {
+            for (int k = 0; k < n; ++k)
+                if (p[k]) w |= 1u << k;
+        }
+        bits[i] = w;
+    }
+}
+
+__global__ void __launch_bounds__(256) bits_to_mask_kernel(const uint32_t *__restrict__ bits, uint8_t *__restrict__ mask,
+                                                           int height, int width, int wpr, size_t total_words) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+        const int wx = (int)(i % wpr);
+        const size_t row = i / wpr;
+        uint8_t *p = mask + row * (size_t)width + (size_t)wx * 32;
+        const int n = min(32, width - wx * 32);
+        const uint32_t w = bits[i];
+        if (n == 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+            uint32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t nib = (w >> (4 * k)) & 0xF;
+                v[k] = ((nib & 1) * 0xFFu) | (((nib >> 1) & 1) * 0xFF00u) | (((nib >> 2) & 1) * 0xFF0000u) |
+                       (((nib >> 3) & 1) * 0xFF000000u);
+            }
+            st_stream(reinterpret_cast<uint4 *>(p), make_uint4(v[0], v[1], v[2], v[3]));
+            st_stream(reinterpret_cast<uint4 *>(p) + 1, make_uint4(v[4], v[5], v[6], v[7]));
+        } else {
+            for (int k = 0; k < n; ++k) p[k] = ((w >> k) & 1) ? 255 : 0;
+        }
+    }
+}
+
+int mask_to_bits(bv_ctx *ctx, const uint8_t *mask, uint32_t *bits, int batch, int height, int width) {
+    const int wpr = words_per_row(width);
+    const size_t total = (size_t)batch * height * wpr;
+    BV_LAUNCH(ctx, mask_to_bits_kernel, grid_for(ctx, total, 256, 8), 256, 0, mask, bits, height, width, wpr, total);
+    return BV_OK;
+}
+
+int bits_to_mask(bv_ctx *ctx, const uint32_t *bits, uint8_t *mask, int batch, int height, int width) {
+    const int wpr = words_per_row(width);
+    const size_t total = (size_t)batch * height * wpr;
+    BV_LAUNCH(ctx, bits_to_mask_kernel, grid_for(ctx, total, 256, 8), 256, 0, bits, mask, height, width, wpr, total);
+    return BV_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// binary erode / dilate with a rectangle: taps x-L..x+R, y-U..y+D (each <= 31)
+// ----------------------------------------------------------------------------------------------
+template <bool ERODE>
+__global__ void __launch_bounds__(256) morph_bits_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
+                                                         int height, int width, int wpr, size_t total_words, int L, int R,
+                                                         int U, int D) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint32_t neutral = ERODE ? 0xFFFFFFFFu : 0u;
+    const int last = wpr - 1;
+    const int tail = width - last * 32;  // valid bits in the last word of a row
+    const uint32_t tail_mask = tail == 32 ? 0xFFFFFFFFu : ((1u << tail) - 1u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+        const int wx = (int)(i % wpr);
+        const size_t row = i / wpr;
+        const int y = (int)(row % height);
+        const uint32_t *frame_row0 = src + (row - y) * (size_t)wpr;
+        uint32_t acc = neutral;
+        for (int yy = max(0, y - U); yy <= min(height - 1, y + D); ++yy) {
+            const uint32_t *r = frame_row0 + (size_t)yy * wpr;
+            uint32_t c = r[wx];
+            uint32_t l = wx > 0 ? r[wx - 1] : neutral;
+            uint32_t n = wx < last ? r[wx + 1] : neutral;
+            if (ERODE) {  // pixels beyond the right image edge count as set
+                if (wx == last) c |= ~tail_mask;
+                if (wx + 1 == last) n |= ~tail_mask;
+            }
+            uint32_t h = c;
+            for (int d = 1; d <= L; ++d) {  // tap x-d
+                const uint32_t s = __funnelshift_l(l, c, d);
+                h = ERODE ? (h & s) : (h | s);
+            }
+            for (int d = 1; d <= R; ++d) {  // tap x+d
+                const uint32_t s = __funnelshift_r(c, n, d);
+                h = ERODE ? (h & s) : (h | s);
+            }
+            acc = ERODE ? (acc & h) : (acc | h);
+        }
+        if (wx == last) acc &= tail_mask;
+        dst[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) bits_andnot_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                                                          uint32_t *__restrict__ dst, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = a[i] & ~b[i];
+}
+
+// one erosion or dilation src -> dst (src != dst), extents already multiplied by the iteration count
+static int morph_bits_basic(bv_ctx *ctx, const uint32_t *src, uint32_t *dst, uint32_t *tmp, int batch, int height,
+                            int width, bool erode, int L, int R, int U, int D) {
+    const int wpr = words_per_row(width);
+    const size_t total = (size_t)batch * height * wpr;
+    const int grid = grid_for(ctx, total, 256, 8);
+    // extents above 31 are applied in several passes (erosions / dilations by rectangles compose);
+    // pass k of P writes dst when (P - k) is even, tmp otherwise, so the last pass lands in dst.
+    const int mx = max(max(L, R), max(U, D));
+    const int passes = mx <= 31 ? 1 : (mx + 30) / 31;
+    if (passes > 1 && !tmp) {
+        set_error("binary morphology: structuring element too large for a single pass");
+        return BV_ERR_UNSUPPORTED;
+    }
+    const uint32_t *cur = src;
+    for (int k = 1; k <= passes; ++k) {
+        const int l = L > 31 ? 31 : L, r = R > 31 ? 31 : R, u = U > 31 ? 31 : U, d = D > 31 ? 31 : D;
+        L -= l; R -= r; U -= u; D -= d;
+        uint32_t *out = ((passes - k) % 2 == 0) ? dst : tmp;
+        if (erode)
+            BV_LAUNCH(ctx, morph_bits_kernel<true>, grid, 256, 0, cur, out, height, width, wpr, total, l, r, u, d);
+        else
+            BV_LAUNCH(ctx, morph_bits_kernel<false>, grid, 256, 0, cur, out, height, width, wpr, total, l, r, u, d);
+        cur = out;
+    }
+    return BV_OK;
+}
+
+int morph_bits_rect(bv_ctx *ctx, uint32_t *bits, uint32_t *tmp, uint32_t *tmp2, int batch, int height, int width, int op,
+                    int kw, int kh, int iterations) {
+    if (iterations < 1 || (kw == 1 && kh == 1)) return BV_OK;
+    const int ax = kw / 2, ay = kh / 2;
+    // erode taps: x-ax .. x+(kw-1-ax); dilate uses the reflected SE
+    const int eL = ax * iterations, eR = (kw - 1 - ax) * iterations, eU = ay * iterations, eD = (kh - 1 - ay) * iterations;
+    const int dL = eR, dR = eL, dU = eD, dD = eU;
+    const size_t total = (size_t)batch * height * words_per_row(width);
+    switch (op) {
+        case BV_MORPH_ERODE:
+            BV_TRY(morph_bits_basic(ctx, bits, tmp, tmp2, batch, height, width, true, eL, eR, eU, eD));
+            BV_CUDA(cudaMemcpyAsync(bits, tmp, total * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            return BV_OK;
+        case BV_MORPH_DILATE:
+            BV_TRY(morph_bits_basic(ctx, bits, tmp, tmp2, batch, height, width, false, dL, dR, dU, dD));
+            BV_CUDA(cudaMemcpyAsync(bits, tmp, total * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            return BV_OK;
+        case BV_MORPH_OPEN:
+            BV_TRY(morph_bits_basic(ctx, bits, tmp, tmp2, batch, height, width, true, eL, eR, eU, eD));
+            return morph_bits_basic(ctx, tmp, bits, tmp2, batch, height, width, false, dL, dR, dU, dD);
+        case BV_MORPH_CLOSE:
+            BV_TRY(morph_bits_basic(ctx, bits, tmp, tmp2, batch, height, width, false, dL, dR, dU, dD));
+            return morph_bits_basic(ctx, tmp, bits, tmp2, batch, height, width, true, eL, eR, eU, eD);
+        case BV_MORPH_GRADIENT: {
+            // needs three images: bits (input), tmp (dilated), tmp2 (eroded); both basics must be single-pass
+            if (eL > 31 || eR > 31 || eU > 31 || eD > 31) {
+                set_error("binary gradient: structuring element too large");
+                return BV_ERR_UNSUPPORTED;
+            }
+            BV_TRY(morph_bits_basic(ctx, bits, tmp, nullptr, batch, height, width, false, dL, dR, dU, dD));
+            BV_TRY(morph_bits_basic(ctx, bits, tmp2, nullptr, batch, height, width, true, eL, eR, eU, eD));
+            BV_LAUNCH(ctx, bits_andnot_kernel, grid_for(ctx, total, 256, 8), 256, 0, tmp, tmp2, bits, total);
+            return BV_OK;
+        }
+        default: set_error("unknown morphology op %d", op); return BV_ERR_INVALID;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// grey morphology, arbitrary SE as horizontal runs
+// ----------------------------------------------------------------------------------------------
+constexpr int kMaxRuns = 256;
+struct RunList {
+    int n;
+    short dy[kMaxRuns], x0[kMaxRuns], x1[kMaxRuns];  // taps (x + x0 .. x + x1, y + dy)
+};
+
+template <bool ERODE>
+__global__ void __launch_bounds__(256) morph_grey_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                         int height, int width, int cn, size_t total, RunList runs) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t row_bytes = (size_t)width * cn;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t row = i / row_bytes;  // frame * height + y
+        const int xb = (int)(i - row * row_bytes);
+        const int x = xb / cn, c = xb - x * cn;
+        const int y = (int)(row % height);
+        const uint8_t *frame = src + (row - y) * row_bytes;
+        int v = ERODE ? 255 : 0;
+        for (int r = 0; r < runs.n; ++r) {
+            const int yy = y + runs.dy[r];
+            if (yy < 0 || yy >= height) continue;
+            const int xa = max(0, x + runs.x0[r]), xe = min(width - 1, x + runs.x1[r]);
+            const uint8_t *p = frame + (size_t)yy * row_bytes + c;
+            for (int xx = xa; xx <= xe; ++xx) {
+                const int s = p[(size_t)xx * cn];
+                v = ERODE ? min(v, s) : max(v, s);
+            }
+        }
+        dst[i] = (uint8_t)v;
+    }
+}
+
+__global__ void __launch_bounds__(256) sub_u8_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
+                                                     uint8_t *__restrict__ dst, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int d = (int)a[i] - (int)b[i];
+        dst[i] = (uint8_t)(d < 0 ? 0 : d);
+    }
+}
+
+static int launch_grey(bv_ctx *ctx, const uint8_t *src, uint8_t *dst, int height, int width, int cn, size_t total,
+                       bool erode, const RunList &runs) {
+    const int grid = grid_for(ctx, total, 256, 8);
+    if (erode)
+        BV_LAUNCH(ctx, morph_grey_kernel<true>, grid, 256, 0, src, dst, height, width, cn, total, runs);
+    else
+        BV_LAUNCH(ctx, morph_grey_kernel<false>, grid, 256, 0, src, dst, height, width, cn, total, runs);
+    return BV_OK;
+}
+
+struct SeInfo {
+    bool rect;            // full rectangle: separable, iterations fold into the extents
+    RunList erode_runs;   // taps for erosion
+    RunList dilate_runs;  // taps for dilation (SE reflected about the anchor)
+    int kw, kh;
+};
+
+static int build_se(const uint8_t *se, int kw, int kh, SeInfo &info) {
+    info.kw = kw;
+    info.kh = kh;
+    info.rect = true;
+    for (int i = 0; i < kw * kh; ++i)
+        if (!se[i]) info.rect = false;
+    const int ax = kw / 2, ay = kh / 2;
+    info.erode_runs.n = info.dilate_runs.n = 0;
+    for (int j = 0; j < kh; ++j) {
+        int i = 0;
+        while (i < kw) {
+            if (!se[j * kw + i]) {
+                ++i;
+                continue;
+            }
+            int e = i;
+            while (e + 1 < kw && se[j * kw + e + 1]) ++e;
+            if (info.erode_runs.n >= kMaxRuns) {
+                set_error("bv_morph: structuring element has more than %d horizontal runs", kMaxRuns);
+                return BV_ERR_UNSUPPORTED;
+            }
+            RunList &er = info.erode_runs;
+            er.dy[er.n] = (short)(j - ay);
+            er.x0[er.n] = (short)(i - ax);
+            er.x1[er.n] = (short)(e - ax);
+            er.n++;
+            RunList &dr = info.dilate_runs;
+            dr.dy[dr.n] = (short)(ay - j);
+            dr.x0[dr.n] = (short)(ax - e);
+            dr.x1[dr.n] = (short)(ax - i);
+            dr.n++;
+            i = e + 1;
+        }
+    }
+    return BV_OK;
+}
+
+// n erosions (or dilations) src -> dst; src != dst; t1, t2 scratch images
+static int grey_basic(bv_ctx *ctx, const uint8_t *src, uint8_t *dst, uint8_t *t1, uint8_t *t2, int batch, int height,
+                      int width, int cn, bool erode, const SeInfo &se, int iterations) {
+    const size_t total = (size_t)batch * height * width * cn;
+    if (se.kw == 1 && se.kh == 1 && se.rect) {
+        BV_CUDA(cudaMemcpyAsync(dst, src, total, cudaMemcpyDeviceToDevice, ctx->stream));
+        return BV_OK;
+    }
+    if (se.rect) {
+        // separable, and n iterations of a rectangle == one rectangle with n-fold extents
+        const int ax = se.kw / 2, ay = se.kh / 2;
+        int L = ax * iterations, R = (se.kw - 1 - ax) * iterations, U = ay * iterations, D = (se.kh - 1 - ay) * iterations;
+        if (!erode) {
+            int t = L; L = R; R = t;
+            t = U; U = D; D = t;
+        }
+        RunList h, v;
+        h.n = 1;
+        h.dy[0] = 0;
+        h.x0[0] = (short)-L;
+        h.x1[0] = (short)R;
+        if (U + D + 1 > kMaxRuns) {
+            set_error("bv_morph: rectangle too tall after iterations");
+            return BV_ERR_UNSUPPORTED;
+        }
+        v.n = U + D + 1;
+        for (int k = 0; k < v.n; ++k) {
+            v.dy[k] = (short)(k - U);
+            v.x0[k] = v.x1[k] = 0;
+        }
+        BV_TRY(launch_grey(ctx, src, t1, height, width, cn, total, erode, h));
+        return launch_grey(ctx, t1, dst, height, width, cn, total, erode, v);
+    }
+    const RunList &runs = erode ? se.erode_runs : se.dilate_runs;
+    const uint8_t *cur = src;
+    for (int it = 0; it < iterations; ++it) {
+        uint8_t *out = (it == iterations - 1) ? dst : (cur == t1 ? t2 : t1);
+        BV_TRY(launch_grey(ctx, cur, out, height, width, cn, total, erode, runs));
+        cur = out;
+    }
+    return BV_OK;
+}
+
+}  // namespace bv
+
+using namespace bv;
+
+extern "C" int bv_morph(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, int height, int width,
+                        int channels, int op, const uint8_t *se_host, int kw, int kh, int iterations) {
+    BV_REQUIRE(ctx && src_dev && dst_dev && se_host, "null argument");
+    BV_REQUIRE(batch > 0 && height > 0 && width > 0, "batch, height and width must be positive");
+    BV_REQUIRE(channels >= 1 && channels <= 4, "channels must be 1..4");
+    BV_REQUIRE(kw >= 1 && kh >= 1 && kw <= 255 && kh <= 255, "structuring element size must be 1..255");
+    BV_REQUIRE(op >= BV_MORPH_ERODE && op <= BV_MORPH_GRADIENT, "unknown morphology op");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    const size_t total = (size_t)batch * height * width * channels;
+    if (iterations < 1) {  // cv2 treats iterations == 0 as "no-op copy"
+        if (src_dev != dst_dev) BV_CUDA(cudaMemcpyAsync(dst_dev, src_dev, total, cudaMemcpyDeviceToDevice, ctx->stream));
+        return BV_OK;
+    }
+    static thread_local SeInfo se;
+    BV_TRY(build_se(se_host, kw, kh, se));
+    BV_REQUIRE(se.erode_runs.n > 0, "structuring element is empty");
+    BV_TRY(ensure_scratch(ctx, SCR_MORPH_TMP, total * 3));
+    uint8_t *t0 = (uint8_t *)ctx->scratch[SCR_MORPH_TMP];
+    uint8_t *t1 = t0 + total, *t2 = t1 + total;
+    BV_TRY(ensure_scratch(ctx, SCR_MORPH_TMP2, total * 2));
+    uint8_t *u0 = (uint8_t *)ctx->scratch[SCR_MORPH_TMP2];
+    uint8_t *u1 = u0 + total;
+    switch (op) {
+        case BV_MORPH_ERODE:
+        case BV_MORPH_DILATE: {
+            const bool er = op == BV_MORPH_ERODE;
+            if (src_dev == dst_dev) {
+                BV_TRY(grey_basic(ctx, src_dev, t0, t1, t2, batch, height, width, channels, er, se, iterations));
+                BV_CUDA(cudaMemcpyAsync(dst_dev, t0, total, cudaMemcpyDeviceToDevice, ctx->stream));
+                return BV_OK;
+            }
+            return grey_basic(ctx, src_dev, dst_dev, t1, t2, batch, height, width, channels, er, se, iterations);
+        }
+        case BV_MORPH_OPEN:
+        case BV_MORPH_CLOSE: {
+            const bool first_erode = op == BV_MORPH_OPEN;
+            BV_TRY(grey_basic(ctx, src_dev, t0, t1, t2, batch, height, width, channels, first_erode, se, iterations));
+            return grey_basic(ctx, t0, dst_dev, t1, t2, batch, height, width, channels, !first_erode, se, iterations);
+        }
+        default: {  // gradient
+            BV_TRY(grey_basic(ctx, src_dev, u0, t1, t2, batch, height, width, channels, false, se, iterations));
+            BV_TRY(grey_basic(ctx, src_dev, u1, t1, t2, batch, height, width, channels, true, se, iterations));
+            BV_LAUNCH(ctx, sub_u8_kernel, grid_for(ctx, total, 256, 8), 256, 0, u0, u1, dst_dev, total);
+            return BV_OK;
+        }
+    }
+}

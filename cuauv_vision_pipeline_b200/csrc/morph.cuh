@@ -1,0 +1,21 @@
+// morph.cuh -- internal interface of the morphology / bit-mask kernels (morph.cu).
+#pragma once
+#include "common.cuh"
+
+namespace bv {
+
+// Bit-packed binary image: per frame `height` rows of `words_per_row(width)` uint32; bit i of
+// word w is pixel x = 32*w + i; bits at x >= width are always 0.
+inline int words_per_row(int width) { return (width + 31) / 32; }
+inline size_t bits_frame_words(int height, int width) { return (size_t)height * words_per_row(width); }
+
+// uint8 mask (non-zero = set) -> bits, and bits -> uint8 0/255
+int mask_to_bits(bv_ctx *ctx, const uint8_t *mask, uint32_t *bits, int batch, int height, int width);
+int bits_to_mask(bv_ctx *ctx, const uint32_t *bits, uint8_t *mask, int batch, int height, int width);
+
+// One bv_morph_op with a kw x kh rectangle (anchor = centre) on bit-packed images.  `bits` holds
+// the input and receives the result; `tmp` is a same-sized scratch image.
+int morph_bits_rect(bv_ctx *ctx, uint32_t *bits, uint32_t *tmp, uint32_t *tmp2, int batch, int height, int width, int op,
+                    int kw, int kh, int iterations);
+
+}  // namespace bv

@@ -1,0 +1,245 @@
+// stage.cu -- the fused per-frame stage and the host-memory entry points.
+//
+// bv_stage strings the kernels of balance.cu / morph.cu / ccl.cu together without ever
+// materialising intermediates the caller did not ask for:
+//
+//   frame (BGR, 3 B/px) --[balance passes 1-2: statistics only]--> pass 3 (balance -> convert ->
+//   inRange) --> bit-packed mask (1/8 B/px, L2 resident) --> binary morphology on bits -->
+//   {uint8 mask (1 B/px), labels (4 B/px), blob table}
+//
+// which is modules/bins.py:13-27 / modules/red_buoy.py:21-44 behind an optional balance()
+// (modules/preprocessor.py:87-88) in one call.
+//
+// bv_stage_host and the legacy process_frame symbol take HOST buffers (the reference's calling
+// convention, modules/color_balance.py:93-110): upload, run, download, return when done.
+#include <mutex>
+
+#include "balance.cuh"
+#include "morph.cuh"
+
+namespace bv {
+int label_bits(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, int height, int width, bv_blob *blobs,
+               int max_blobs, int32_t *n_blobs);  // ccl.cu
+
+static int validate_desc(const bv_stage_desc *d) {
+    BV_REQUIRE(d, "null stage description");
+    BV_REQUIRE(d->n_morph >= 0 && d->n_morph <= 4, "n_morph must be 0..4");
+    for (int i = 0; i < d->n_morph; ++i) {
+        BV_REQUIRE(d->morph_op[i] >= BV_MORPH_ERODE && d->morph_op[i] <= BV_MORPH_GRADIENT, "unknown morphology op");
+        BV_REQUIRE(d->morph_kw[i] >= 1 && d->morph_kh[i] >= 1 && d->morph_kw[i] <= 255 && d->morph_kh[i] <= 255,
+                   "structuring element size must be 1..255");
+        BV_REQUIRE(d->morph_iters[i] >= 0, "iterations must be >= 0");
+    }
+    BV_REQUIRE(d->cvt_code == -1 || d->cvt_code == BV_BGR2HSV || d->cvt_code == BV_BGR2LAB ||
+                   d->cvt_code == BV_BGR2GRAY || d->cvt_code == BV_BGR2YCRCB || d->cvt_code == BV_BGR2HLS,
+               "cvt_code must be -1, BGR2HSV, BGR2LAB, BGR2GRAY, BGR2YCRCB or BGR2HLS");
+    return BV_OK;
+}
+
+int stage_run(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src, int batch, int height, int width,
+              uint8_t *balanced, uint8_t *converted, uint8_t *mask, int32_t *labels, bv_blob *blobs, int max_blobs,
+              int32_t *n_blobs) {
+    const size_t npx = (size_t)height * width;
+    const bool want_label = desc->do_label && (labels || blobs || n_blobs);
+    const bool need_bits = desc->n_morph > 0 || want_label;
+    BalOutputs out;
+    memset(&out, 0, sizeof(out));
+    out.balanced = balanced;
+    out.converted = converted;
+    for (int k = 0; k < 3; ++k) {
+        out.lo[k] = desc->lo[k];
+        out.hi[k] = desc->hi[k];
+    }
+    uint32_t *bits = nullptr, *tmp = nullptr, *tmp2 = nullptr;
+    const size_t words = (size_t)batch * bits_frame_words(height, width);
+    bool bits_direct = false;
+    if (need_bits) {
+        BV_TRY(ensure_scratch(ctx, SCR_BITS_A, words * 4));
+        BV_TRY(ensure_scratch(ctx, SCR_BITS_B, words * 8));
+        bits = (uint32_t *)ctx->scratch[SCR_BITS_A];
+        tmp = (uint32_t *)ctx->scratch[SCR_BITS_B];
+        tmp2 = tmp + words;
+        const bool aligned = host_aligned16(src) && (!balanced || host_aligned16(balanced)) &&
+                             (!converted || host_aligned16(converted)) && (!mask || host_aligned16(mask));
+        bits_direct = aligned && (width % 16 == 0);
+        if (bits_direct) {
+            if (width % 32 != 0) BV_CUDA(cudaMemsetAsync(bits, 0, words * 4, ctx->stream));
+            out.mask_bits = (uint16_t *)bits;
+            if (desc->n_morph == 0) out.mask = mask;  // the thresholded mask is already final
+        } else {
+            // odd widths: go through a uint8 mask (the caller's buffer doubles as the intermediate)
+            if (mask) {
+                out.mask = mask;
+            } else {
+                BV_TRY(ensure_scratch(ctx, SCR_STAGE_IMG, (size_t)batch * npx));
+                out.mask = (uint8_t *)ctx->scratch[SCR_STAGE_IMG];
+            }
+        }
+    } else {
+        out.mask = mask;
+    }
+    if (out.balanced || out.converted || out.mask || out.mask_bits) {
+        if (desc->do_balance)
+            BV_TRY(balance_run(ctx, src, batch, height, width, desc->balance, desc->cvt_code, out, nullptr));
+        else
+            BV_TRY(convert_run(ctx, src, batch, height, width, desc->cvt_code, out));
+    }
+    if (!need_bits) return BV_OK;
+    if (!bits_direct) BV_TRY(mask_to_bits(ctx, out.mask, bits, batch, height, width));
+    for (int i = 0; i < desc->n_morph; ++i)
+        BV_TRY(morph_bits_rect(ctx, bits, tmp, tmp2, batch, height, width, desc->morph_op[i], desc->morph_kw[i],
+                               desc->morph_kh[i], desc->morph_iters[i]));
+    if (mask && (desc->n_morph > 0)) BV_TRY(bits_to_mask(ctx, bits, mask, batch, height, width));
+    if (want_label) BV_TRY(label_bits(ctx, bits, labels, batch, height, width, blobs, max_blobs, n_blobs));
+    return BV_OK;
+}
+
+// process-wide context behind the legacy symbol
+static std::mutex g_legacy_mutex;
+static bv_ctx *g_legacy_ctx = nullptr;
+
+}  // namespace bv
+
+using namespace bv;
+
+extern "C" int bv_stage(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src_dev, int batch, int height, int width,
+                        uint8_t *balanced_dev, uint8_t *converted_dev, uint8_t *mask_dev, int32_t *labels_dev,
+                        bv_blob *blobs_dev, int max_blobs, int32_t *n_blobs_dev) {
+    BV_REQUIRE(ctx && src_dev, "null context or source");
+    BV_REQUIRE(batch > 0 && height > 0 && width > 0, "batch, height and width must be positive");
+    BV_REQUIRE(max_blobs >= 0, "max_blobs must be >= 0");
+    BV_TRY(validate_desc(desc));
+    BV_CUDA(cudaSetDevice(ctx->device));
+    return stage_run(ctx, desc, src_dev, batch, height, width, balanced_dev, converted_dev, mask_dev, labels_dev,
+                     blobs_dev, blobs_dev ? max_blobs : 0, n_blobs_dev);
+}
+
+extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src_host, int batch, int height,
+                             int width, uint8_t *balanced_host, uint8_t *converted_host, uint8_t *mask_host,
+                             int32_t *labels_host, bv_blob *blobs_host, int max_blobs, int32_t *n_blobs_host) {
+    BV_REQUIRE(ctx && src_host, "null context or source");
+    BV_REQUIRE(batch > 0 && height > 0 && width > 0, "batch, height and width must be positive");
+    BV_REQUIRE(max_blobs >= 0, "max_blobs must be >= 0");
+    BV_TRY(validate_desc(desc));
+    BV_CUDA(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)height * width;
+    const size_t cvt_bpp = desc->cvt_code == BV_BGR2GRAY ? 1 : 3;
+    if (!blobs_host) max_blobs = 0;
+    // device staging for the whole batch: no buffer is reused inside one call, so the three
+    // streams below need no back-pressure
+    BV_TRY(ensure_scratch(ctx, SCR_HOST_IN, (size_t)batch * npx * 3));
+    if (balanced_host) BV_TRY(ensure_scratch(ctx, SCR_HOST_BAL, (size_t)batch * npx * 3));
+    if (converted_host) BV_TRY(ensure_scratch(ctx, SCR_HOST_CVT, (size_t)batch * npx * cvt_bpp));
+    if (mask_host) BV_TRY(ensure_scratch(ctx, SCR_HOST_MASK, (size_t)batch * npx));
+    if (labels_host) BV_TRY(ensure_scratch(ctx, SCR_HOST_LABELS, (size_t)batch * npx * 4));
+    if (max_blobs) BV_TRY(ensure_scratch(ctx, SCR_HOST_BLOBS, (size_t)batch * max_blobs * sizeof(bv_blob)));
+    BV_TRY(ensure_scratch(ctx, SCR_HOST_NBLOBS, (size_t)batch * sizeof(int32_t)));
+    uint8_t *d_in = (uint8_t *)ctx->scratch[SCR_HOST_IN];
+    uint8_t *d_bal = balanced_host ? (uint8_t *)ctx->scratch[SCR_HOST_BAL] : nullptr;
+    uint8_t *d_cvt = converted_host ? (uint8_t *)ctx->scratch[SCR_HOST_CVT] : nullptr;
+    uint8_t *d_mask = mask_host ? (uint8_t *)ctx->scratch[SCR_HOST_MASK] : nullptr;
+    int32_t *d_lab = labels_host ? (int32_t *)ctx->scratch[SCR_HOST_LABELS] : nullptr;
+    bv_blob *d_blobs = max_blobs ? (bv_blob *)ctx->scratch[SCR_HOST_BLOBS] : nullptr;
+    int32_t *d_nb = (int32_t *)ctx->scratch[SCR_HOST_NBLOBS];
+
+    // chunked three-stage pipeline: H2D (copy-in stream) -> kernels (context stream) -> D2H
+    // (copy-out stream); PCIe is full duplex, so uploads of chunk k+1 overlap downloads of k-1.
+    int chunk = (int)(((size_t)32 << 20) / (npx * 3));
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    int nchunks = (batch + chunk - 1) / chunk;
+    if (nchunks > BV_MAX_CHUNKS) {
+        chunk = (batch + BV_MAX_CHUNKS - 1) / BV_MAX_CHUNKS;
+        nchunks = (batch + chunk - 1) / chunk;
+    }
+    for (int k = 0; k < nchunks; ++k) {
+        const int f0 = k * chunk, nf = (batch - f0 < chunk) ? batch - f0 : chunk;
+        const size_t po = (size_t)f0 * npx;
+        BV_CUDA(cudaMemcpyAsync(d_in + po * 3, src_host + po * 3, (size_t)nf * npx * 3, cudaMemcpyHostToDevice,
+                                ctx->copy_in));
+        BV_CUDA(cudaEventRecord(ctx->ev_in[k], ctx->copy_in));
+        BV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[k], 0));
+        BV_TRY(stage_run(ctx, desc, d_in + po * 3, nf, height, width, d_bal ? d_bal + po * 3 : nullptr,
+                         d_cvt ? d_cvt + po * cvt_bpp : nullptr, d_mask ? d_mask + po : nullptr,
+                         d_lab ? d_lab + po : nullptr, d_blobs ? d_blobs + (size_t)f0 * max_blobs : nullptr, max_blobs,
+                         d_nb + f0));
+        BV_CUDA(cudaEventRecord(ctx->ev_done[k], ctx->stream));
+        BV_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[k], 0));
+        if (balanced_host)
+            BV_CUDA(cudaMemcpyAsync(balanced_host + po * 3, d_bal + po * 3, (size_t)nf * npx * 3, cudaMemcpyDeviceToHost,
+                                    ctx->copy_out));
+        if (converted_host)
+            BV_CUDA(cudaMemcpyAsync(converted_host + po * cvt_bpp, d_cvt + po * cvt_bpp, (size_t)nf * npx * cvt_bpp,
+                                    cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (mask_host)
+            BV_CUDA(cudaMemcpyAsync(mask_host + po, d_mask + po, (size_t)nf * npx, cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (labels_host)
+            BV_CUDA(cudaMemcpyAsync(labels_host + po, d_lab + po, (size_t)nf * npx * 4, cudaMemcpyDeviceToHost,
+                                    ctx->copy_out));
+        if (max_blobs)
+            BV_CUDA(cudaMemcpyAsync(blobs_host + (size_t)f0 * max_blobs, d_blobs + (size_t)f0 * max_blobs,
+                                    (size_t)nf * max_blobs * sizeof(bv_blob), cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (n_blobs_host && desc->do_label)
+            BV_CUDA(cudaMemcpyAsync(n_blobs_host + f0, d_nb + f0, (size_t)nf * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                    ctx->copy_out));
+    }
+    BV_CUDA(cudaStreamSynchronize(ctx->copy_out));
+    BV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BV_OK;
+}
+
+extern "C" int process_frame(unsigned char *arr, size_t height, size_t width, size_t depth, bool equalize_rgb,
+                             bool rgb_contrast_correct, bool hsv_contrast_correct, bool hsi_contrast_correct,
+                             bool rgb_extrema_clipping, bool adaptive_cast_correction, int horizontal_blocks,
+                             int vertical_blocks) {
+    if (!arr || height == 0 || width == 0 || depth != 3 || height > 65535 || width > 65535) {
+        set_error("process_frame: need a non-empty height x width x 3 uint8 buffer");
+        return BV_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lock(g_legacy_mutex);
+    if (!g_legacy_ctx) {
+        const char *e = getenv("BV_DEVICE");
+        BV_TRY(bv_create(e ? atoi(e) : 0, &g_legacy_ctx));
+    }
+    bv_stage_desc d;
+    memset(&d, 0, sizeof(d));
+    d.do_balance = 1;
+    d.balance.equalize_rgb = equalize_rgb;
+    d.balance.rgb_contrast_correct = rgb_contrast_correct;
+    d.balance.hsv_contrast_correct = hsv_contrast_correct;
+    d.balance.hsi_contrast_correct = hsi_contrast_correct;
+    d.balance.rgb_extrema_clipping = rgb_extrema_clipping;
+    d.balance.adaptive_cast_correction = adaptive_cast_correction;
+    d.balance.horizontal_blocks = horizontal_blocks;
+    d.balance.vertical_blocks = vertical_blocks;
+    d.cvt_code = -1;
+    for (int k = 0; k < 3; ++k) d.hi[k] = 255;
+    return bv_stage_host(g_legacy_ctx, &d, arr, 1, (int)height, (int)width, arr, nullptr, nullptr, nullptr, nullptr, 0,
+                         nullptr);
+}
+
+// ---- pinned host memory helpers (full PCIe speed for the *_host entry points) -----------------
+extern "C" void *bv_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void bv_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int bv_host_register(void *p, size_t bytes) {
+    BV_REQUIRE(p && bytes, "null buffer");
+    BV_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return BV_OK;
+}
+
+extern "C" int bv_host_unregister(void *p) {
+    BV_REQUIRE(p, "null buffer");
+    BV_CUDA(cudaHostUnregister(p));
+    return BV_OK;
+}

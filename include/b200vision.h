@@ -1,0 +1,227 @@
+/*
+ * b200vision.h -- C ABI of libb200vision.so: the per-frame pixel hot path of
+ * ayf7/cuauv-vision-pipeline as hand-written CUDA for NVIDIA B200 (sm_100a).
+ *
+ * Style follows the reference's own FFI (lib/camera_message_framework_c.cpp:20-102, bound from
+ * core/bindings/camera_message_framework.py:13-70 with cffi in ABI mode): extern "C", opaque
+ * handles, plain pointers and sizes, int status codes.  No torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - Images are uint8, interleaved HWC, tightly packed (row stride = width * channels), a batch is
+ *     `batch` such images back to back.  This is the layout ModuleBase hands to process()
+ *     (core/base.py:762-768: C-contiguous np.uint8[H,W,3], BGR).
+ *   - Pointers named *_dev are CUDA device pointers (e.g. torch.Tensor.data_ptr()); pointers named
+ *     *_host are host pointers.  Small parameter arrays (bounds, structuring elements) are host.
+ *   - Every bv_* call on a context enqueues on that context's CUDA stream and returns without
+ *     waiting, unless stated otherwise; call bv_sync() (or synchronise the stream) before reading
+ *     results on the host.  A context is bound to one device and must be used by one thread at a
+ *     time (the reference runs process() calls strictly serially on one worker thread per module,
+ *     core/base.py:701-703).
+ *   - Return value: BV_OK (0) or a negative bv_status.  bv_last_error() gives the message for
+ *     the calling thread.  The library never aborts or exits the process.
+ *   - There is no CPU fallback: when no CUDA device is usable, bv_create fails.
+ */
+#ifndef B200VISION_H
+#define B200VISION_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BV_VERSION 100 /* 0.1.0 */
+
+typedef struct bv_ctx bv_ctx;
+
+typedef enum bv_status {
+    BV_OK = 0,
+    BV_ERR_INVALID = -1,     /* bad argument                                            */
+    BV_ERR_CUDA = -2,        /* a CUDA runtime call failed; see bv_last_error()          */
+    BV_ERR_UNSUPPORTED = -3, /* valid in the reference but not implemented here          */
+    BV_ERR_NOMEM = -4,       /* device or host allocation failed                         */
+    BV_ERR_CAPACITY = -5     /* caller-provided table too small                          */
+} bv_status;
+
+/* Colour conversions.  Replaces cv2.cvtColor as called from utils/color.py:11-32
+ * (_convert_colorspace and the bgr_to_* / *_to_bgr family), modules/bins.py:13,
+ * modules/preprocessor.py:56-86.  Values are private to this ABI (not cv2's enum). */
+typedef enum bv_cvt_code {
+    BV_BGR2HSV = 0,   /* 8-bit, H in [0,180)                                               */
+    BV_BGR2LAB = 1,
+    BV_BGR2GRAY = 2,  /* 3 -> 1 channel                                                  */
+    BV_BGR2YCRCB = 3,
+    BV_HSV2BGR = 4,   /* float32 path of OpenCV incl. its 32-px vector/tail rounding rule  */
+    BV_BGR2HLS = 5,
+    BV_GRAY2BGR = 6,  /* 1 -> 3 channels                                                 */
+    BV_BGR2RGB = 7
+} bv_cvt_code;
+
+/* cv2.threshold types used by utils/color.py:124-201. */
+typedef enum bv_thresh_type {
+    BV_THRESH_BINARY = 0,     /* x >  t ? maxval : 0   */
+    BV_THRESH_BINARY_INV = 1, /* x >  t ? 0 : maxval   */
+    BV_THRESH_TRUNC = 2,      /* x >  t ? t : x        */
+    BV_THRESH_TOZERO = 3,     /* x >  t ? x : 0        */
+    BV_THRESH_TOZERO_INV = 4  /* x >  t ? 0 : x        */
+} bv_thresh_type;
+
+/* Morphology.  Replaces cv2.erode / cv2.dilate / cv2.morphologyEx as called from
+ * utils/transform.py:80-164 and modules/preprocessor.py:120-129. */
+typedef enum bv_morph_op {
+    BV_MORPH_ERODE = 0,
+    BV_MORPH_DILATE = 1,
+    BV_MORPH_OPEN = 2,    /* erode^n then dilate^n */
+    BV_MORPH_CLOSE = 3,   /* dilate^n then erode^n */
+    BV_MORPH_GRADIENT = 4 /* dilate^n - erode^n    */
+} bv_morph_op;
+
+/* Flags of the reference's process_frame (utils/color_correction/color_balance.hpp:9-14), in the
+ * same order.  bv_balance_default() fills the defaults of balance()
+ * (modules/color_balance.py:93-96). */
+typedef struct bv_balance_params {
+    int32_t equalize_rgb;
+    int32_t rgb_contrast_correct;
+    int32_t hsv_contrast_correct;
+    int32_t hsi_contrast_correct; /* must be 0: HSI branch is BV_ERR_UNSUPPORTED */
+    int32_t rgb_extrema_clipping;
+    int32_t adaptive_cast_correction;
+    int32_t horizontal_blocks;
+    int32_t vertical_blocks;
+} bv_balance_params;
+
+/* Per-frame statistics the colour balance derived on the device (optional output, host side). */
+typedef struct bv_balance_stats {
+    int32_t bgr_min[3], bgr_max[3]; /* percentile (or extrema) clip bounds, order B,G,R */
+    double bgr_avg[3];              /* exact means of the clipped channels              */
+    int32_t dominant;               /* 0=B 1=G 2=R (whole-frame tile)                   */
+    int32_t s_min, s_max, v_min, v_max;
+    int32_t degenerate;             /* 1 if s_max==s_min or v_max==v_min (reference: SIGFPE) */
+} bv_balance_stats;
+
+/* One labelled blob: exact integer raster moments up to third order and the bounding box
+ * (inclusive).  Labels are 1..n in raster order of each blob's first pixel.  Plays the role of
+ * outer_contours + contour_centroid + contour_area (utils/feature.py:5-21,240-265). */
+typedef struct bv_blob {
+    int64_t m00, m10, m01, m20, m11, m02, m30, m21, m12, m03;
+    int32_t x0, y0, x1, y1;
+} bv_blob;
+
+/* Description of the fused per-frame stage: [colour balance] -> colour conversion -> inRange ->
+ * up to 4 morphology steps -> [labelling + moments].  This is modules/bins.py:13-27 and
+ * modules/red_buoy.py:21-44 with an optional balance() in front (modules/preprocessor.py:87-88). */
+typedef struct bv_stage_desc {
+    int32_t do_balance;           /* run colour balance first                             */
+    bv_balance_params balance;
+    int32_t cvt_code;             /* bv_cvt_code applied to the (balanced) BGR frame;       */
+                                  /* -1 = threshold the BGR frame itself                  */
+    uint8_t lo[3], hi[3];         /* inclusive bounds per converted channel; a channel is  */
+                                  /* ignored by giving lo=0, hi=255                       */
+    int32_t n_morph;              /* 0..4 steps on the mask                               */
+    int32_t morph_op[4];          /* bv_morph_op                                          */
+    int32_t morph_kw[4], morph_kh[4]; /* rectangular structuring element, anchor = centre  */
+    int32_t morph_iters[4];
+    int32_t do_label;             /* label the final mask and accumulate blob moments      */
+} bv_stage_desc;
+
+/* ---- library / context ------------------------------------------------------------------- */
+int bv_version(void);
+const char *bv_last_error(void);
+int bv_device_count(void);
+int bv_create(int device, bv_ctx **out);
+void bv_destroy(bv_ctx *ctx);
+int bv_sync(bv_ctx *ctx);
+/* The context's cudaStream_t as an opaque pointer (to wrap it, e.g. torch.cuda.ExternalStream). */
+void *bv_stream(bv_ctx *ctx);
+/* Use a caller-owned cudaStream_t (NULL restores the context's own stream). */
+int bv_set_stream(bv_ctx *ctx, void *cuda_stream);
+/* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
+uint64_t bv_launch_count(const bv_ctx *ctx);
+void bv_balance_default(bv_balance_params *p);
+
+/* ---- colour balance: replaces process_frame (color_balance.cpp:343-780) ------------------- */
+/* src_dev -> dst_dev (may alias), batch frames of height x width BGR.  stats_host (optional, may
+ * be NULL) receives `batch` records; asking for it forces a stream synchronisation. */
+int bv_color_balance(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, int height, int width,
+                     const bv_balance_params *params, bv_balance_stats *stats_host);
+
+/* ---- colour conversion / thresholds -------------------------------------------------------- */
+/* planes_dev: optional 3 device pointers receiving the split channels (cv2.split of the result,
+ * utils/color.py:22), each batch*height*width bytes; pass NULL to skip.  dst_dev may be NULL when
+ * only the planes are wanted. */
+int bv_cvt_color(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, uint8_t *const *planes_dev, int batch,
+                 int height, int width, int code);
+/* cv2.inRange (utils/color.py:121, modules/bins.py:16): channels = 1 or 3. */
+int bv_in_range(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *mask_dev, int batch, int height, int width,
+                int channels, const uint8_t *lo_host, const uint8_t *hi_host);
+/* cv2.threshold on uint8 (utils/color.py:124-201); n = number of bytes. */
+int bv_threshold(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, size_t n, int thresh, int maxval,
+                 int type);
+/* cvtColor + inRange in one pass, nothing but the mask is written. */
+int bv_cvt_in_range(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *mask_dev, int batch, int height, int width,
+                    int code, const uint8_t *lo_host, const uint8_t *hi_host);
+/* Per-channel 256-entry look-up tables (lut_host: channels*256 bytes).  Carries the bias /
+ * contrast / brightness steps of modules/preprocessor.py:89-109, composed on the host. */
+int bv_apply_lut(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, size_t n_pixels, int channels,
+                 const uint8_t *lut_host);
+
+/* ---- morphology ------------------------------------------------------------------------------ */
+/* se_host: kh*kw bytes (non-zero = member), anchor = centre; channels 1 or 3 (per channel).
+ * Border handling is cv2's default (BORDER_CONSTANT with morphologyDefaultBorderValue). */
+int bv_morph(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, int height, int width,
+             int channels, int op, const uint8_t *se_host, int kw, int kh, int iterations);
+
+/* ---- connected components + moments ------------------------------------------------------- */
+/* 8-connected labelling of mask != 0.  labels_dev: int32[batch,H,W] (0 = background).
+ * blobs_dev: bv_blob[batch * max_blobs] (may be NULL), n_blobs_dev: int32[batch] total blob
+ * count per frame (blobs beyond max_blobs are labelled but have no table entry). */
+int bv_label(bv_ctx *ctx, const uint8_t *mask_dev, int32_t *labels_dev, int batch, int height, int width,
+             bv_blob *blobs_dev, int max_blobs, int32_t *n_blobs_dev);
+
+/* ---- resize / YOLO input ------------------------------------------------------------------ */
+/* cv2.resize(..., INTER_LINEAR) on uint8 (utils/transform.py:179, modules/preprocessor.py:136-143). */
+int bv_resize_linear(bv_ctx *ctx, const uint8_t *src_dev, int src_h, int src_w, uint8_t *dst_dev, int dst_h,
+                     int dst_w, int channels, int batch);
+/* Letterbox + BGR->RGB + HWC->CHW + /255 for n frames of possibly different sizes
+ * (the Ultralytics pre-transform behind modules/yolo.py:112).  srcs_host: n device pointers;
+ * out_dev: [n,3,out_h,out_w] of fp16 (out_fp16 != 0) or fp32. */
+int bv_letterbox(bv_ctx *ctx, const uint8_t *const *srcs_host, const int32_t *heights_host,
+                 const int32_t *widths_host, int n, void *out_dev, int out_h, int out_w, int pad_value,
+                 int out_fp16);
+
+/* ---- fused stage --------------------------------------------------------------------------- */
+/* Any output pointer may be NULL to skip it.  balanced_dev: BGR after colour balance;
+ * converted_dev: image after desc->cvt_code; mask_dev: uint8 0/255 after the morphology steps;
+ * labels_dev / blobs_dev / n_blobs_dev as in bv_label. */
+int bv_stage(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src_dev, int batch, int height, int width,
+             uint8_t *balanced_dev, uint8_t *converted_dev, uint8_t *mask_dev, int32_t *labels_dev,
+             bv_blob *blobs_dev, int max_blobs, int32_t *n_blobs_dev);
+/* Same stage fed from and returning to HOST memory (pinned memory gives full PCIe speed):
+ * uploads, runs, downloads, and returns after the results are in the host buffers. */
+int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src_host, int batch, int height,
+                  int width, uint8_t *balanced_host, uint8_t *converted_host, uint8_t *mask_host,
+                  int32_t *labels_host, bv_blob *blobs_host, int max_blobs, int32_t *n_blobs_host);
+
+/* ---- pinned host memory (so the *_host entry points run at full PCIe speed) ---------------- */
+void *bv_host_alloc(size_t bytes);               /* cudaHostAlloc; NULL on failure            */
+void bv_host_free(void *p);
+int bv_host_register(void *p, size_t bytes);      /* pin an existing buffer (e.g. a CMF frame) */
+int bv_host_unregister(void *p);
+
+/* ---- legacy symbol ------------------------------------------------------------------------- */
+/* Exact signature of the reference's libauv-color-balance.so entry point
+ * (utils/color_correction/color_balance.hpp:9-14), so modules/color_balance.py:93-110 works
+ * unchanged: host buffer, in place, blocking.  Returns 0 on success (the reference always
+ * returns 0, color_balance.cpp:779), non-zero bv_status on failure.  Uses a process-wide context
+ * on device $BV_DEVICE (default 0), serialised by a mutex. */
+int process_frame(unsigned char *arr, size_t height, size_t width, size_t depth, bool equalize_rgb,
+                  bool rgb_contrast_correct, bool hsv_contrast_correct, bool hsi_contrast_correct,
+                  bool rgb_extrema_clipping, bool adaptive_cast_correction, int horizontal_blocks,
+                  int vertical_blocks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VISION_H */
