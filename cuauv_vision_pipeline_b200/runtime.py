@@ -1,0 +1,390 @@
+"""Context object and tensor-level operations over the C ABI.
+
+PyTorch is used only to own device memory and to copy between host and device
+(`torch.Tensor.data_ptr()` is what crosses the boundary); every pixel operation is a hand-written
+CUDA kernel inside libb200vision.so.  There is no CPU path: creating a Context without a usable
+CUDA device raises BVError.
+"""
+import threading
+
+import numpy as np
+import torch
+
+from ._ffi import ffi, lib, check, BVError  # noqa: F401
+
+CVT = {
+    "bgr2hsv": lib.BV_BGR2HSV, "bgr2lab": lib.BV_BGR2LAB, "bgr2gray": lib.BV_BGR2GRAY,
+    "bgr2ycrcb": lib.BV_BGR2YCRCB, "hsv2bgr": lib.BV_HSV2BGR, "bgr2hls": lib.BV_BGR2HLS,
+    "gray2bgr": lib.BV_GRAY2BGR, "bgr2rgb": lib.BV_BGR2RGB,
+}
+MORPH = {"erode": lib.BV_MORPH_ERODE, "dilate": lib.BV_MORPH_DILATE, "open": lib.BV_MORPH_OPEN,
+         "close": lib.BV_MORPH_CLOSE, "gradient": lib.BV_MORPH_GRADIENT}
+THRESH = {"binary": lib.BV_THRESH_BINARY, "binary_inv": lib.BV_THRESH_BINARY_INV, "trunc": lib.BV_THRESH_TRUNC,
+          "tozero": lib.BV_THRESH_TOZERO, "tozero_inv": lib.BV_THRESH_TOZERO_INV}
+
+BLOB_DTYPE = np.dtype([(k, "<i8") for k in ("m00", "m10", "m01", "m20", "m11", "m02", "m30", "m21", "m12", "m03")] +
+                      [(k, "<i4") for k in ("x0", "y0", "x1", "y1")])
+assert BLOB_DTYPE.itemsize == ffi.sizeof("bv_blob")
+
+
+def _u8ptr(t):
+    return ffi.cast("uint8_t *", t.data_ptr()) if t is not None else ffi.NULL
+
+
+class Context:
+    """Owns one bv_ctx (one device, one CUDA stream).  Use as a context manager or keep it for the
+    life of the module, like the reference's BlockAccessor (core/bindings/...py:388-441)."""
+
+    def __init__(self, device=0):
+        out = ffi.new("bv_ctx **")
+        check(lib.bv_create(int(device), out))
+        self._ctx = out[0]
+        self.device = torch.device("cuda", int(device))
+        # torch allocations / copies are issued on the context's own stream so that they are
+        # ordered with the kernels without any extra synchronisation
+        self.torch_stream = torch.cuda.ExternalStream(int(ffi.cast("uintptr_t", lib.bv_stream(self._ctx))),
+                                                      device=self.device)
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if self._ctx is not None:
+            lib.bv_destroy(self._ctx)
+            self._ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        if self._ctx is None:
+            raise BVError(-1, "context is closed")
+        return self._ctx
+
+    def sync(self):
+        check(lib.bv_sync(self.handle))
+
+    @property
+    def launches(self):
+        return int(lib.bv_launch_count(self.handle))
+
+    # -- memory -----------------------------------------------------------------------------
+    def empty(self, shape, dtype=torch.uint8):
+        with torch.cuda.stream(self.torch_stream):
+            return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def upload(self, arr):
+        """numpy (or CPU tensor) -> device tensor on this context's stream."""
+        if isinstance(arr, torch.Tensor):
+            if arr.is_cuda:
+                return arr.contiguous()
+            src = arr.contiguous()
+        else:
+            src = torch.from_numpy(np.ascontiguousarray(arr))
+        with torch.cuda.stream(self.torch_stream):
+            return src.to(self.device, non_blocking=True)
+
+    def download(self, t):
+        with torch.cuda.stream(self.torch_stream):
+            out = t.cpu()
+        return out.numpy()
+
+    # -- operations (device tensors in, device tensors out) ----------------------------------
+    @staticmethod
+    def _bhw(t, channels=None):
+        """Returns (batch, height, width, channels) of a [H,W], [H,W,C], [B,H,W,C] tensor."""
+        if t.dtype != torch.uint8 or not t.is_cuda or not t.is_contiguous():
+            raise BVError(-1, "expected a contiguous CUDA uint8 tensor")
+        if t.dim() == 2:
+            return 1, t.shape[0], t.shape[1], 1
+        if t.dim() == 3:
+            if channels == 1:          # [B,H,W] single-channel batch
+                return t.shape[0], t.shape[1], t.shape[2], 1
+            return 1, t.shape[0], t.shape[1], t.shape[2]
+        if t.dim() == 4:
+            return t.shape[0], t.shape[1], t.shape[2], t.shape[3]
+        raise BVError(-1, "unsupported tensor rank")
+
+    def cvt_color(self, src, code, split=False):
+        code_i = CVT[code] if isinstance(code, str) else int(code)
+        if code_i != lib.BV_GRAY2BGR:
+            b, h, w, c = self._bhw(src)
+        if code_i == lib.BV_GRAY2BGR:
+            if src.dim() not in (2, 3):
+                raise BVError(-1, "GRAY2BGR needs [H,W] or [B,H,W]")
+            gb = 1 if src.dim() == 2 else src.shape[0]
+            dst = self.empty(tuple(src.shape) + (3,))
+            check(lib.bv_cvt_color(self.handle, _u8ptr(src), _u8ptr(dst), ffi.NULL, gb, src.shape[-2], src.shape[-1],
+                                   code_i))
+            return dst
+        if c != 3:
+            raise BVError(-1, "colour conversion needs a 3-channel image")
+        one = code_i == lib.BV_BGR2GRAY
+        lead = tuple(src.shape[:-1])
+        dst = self.empty(lead if one else lead + (3,))
+        planes = None
+        if split and not one:
+            planes = [self.empty(lead) for _ in range(3)]
+            pp = ffi.new("uint8_t *[3]", [_u8ptr(p) for p in planes])
+        else:
+            pp = ffi.NULL
+        check(lib.bv_cvt_color(self.handle, _u8ptr(src), _u8ptr(dst), pp, b, h, w, code_i))
+        return (dst, planes) if split else dst
+
+    def in_range(self, src, lo, hi):
+        lo = np.atleast_1d(np.asarray(lo)).astype(np.int64)
+        hi = np.atleast_1d(np.asarray(hi)).astype(np.int64)
+        if src.dim() == 2 or (src.dim() == 3 and lo.size == 1 and src.shape[-1] != 3):
+            b, h, w, c = self._bhw(src, channels=1)
+        else:
+            b, h, w, c = self._bhw(src)
+        if c not in (1, 3):
+            raise BVError(-1, "inRange needs 1 or 3 channels")
+        if lo.size == 1 and c == 3:
+            lo, hi = np.repeat(lo, 3), np.repeat(hi, 3)
+        # cv2.inRange compares in the scalar's domain: bounds outside [0,255] saturate harmlessly
+        empty = bool(np.any(lo > 255) or np.any(hi < 0))
+        lo8 = np.clip(lo, 0, 255).astype(np.uint8)
+        hi8 = np.clip(hi, 0, 255).astype(np.uint8)
+        if empty:
+            lo8[:] = 255
+            hi8[:] = 0
+        mask = self.empty((b, h, w) if (src.dim() == 4 or (src.dim() == 3 and c == 1)) else (h, w))
+        check(lib.bv_in_range(self.handle, _u8ptr(src), _u8ptr(mask), b, h, w, c,
+                              ffi.from_buffer("uint8_t[]", lo8), ffi.from_buffer("uint8_t[]", hi8)))
+        return mask
+
+    def threshold(self, src, thresh, maxval, kind):
+        dst = self.empty(tuple(src.shape))
+        check(lib.bv_threshold(self.handle, _u8ptr(src), _u8ptr(dst), src.numel(), int(np.floor(thresh)), int(maxval),
+                               THRESH[kind]))
+        return dst
+
+    def apply_lut(self, src, lut):
+        lut = np.ascontiguousarray(lut, dtype=np.uint8)
+        channels = 1 if lut.ndim == 1 else lut.shape[0]
+        dst = self.empty(tuple(src.shape))
+        check(lib.bv_apply_lut(self.handle, _u8ptr(src), _u8ptr(dst), src.numel() // channels, channels,
+                               ffi.from_buffer("uint8_t[]", lut)))
+        return dst
+
+    def morph(self, src, op, kernel, iterations=1):
+        kernel = np.ascontiguousarray(np.asarray(kernel) != 0, dtype=np.uint8)
+        kh, kw = kernel.shape
+        if src.dim() == 2:
+            b, h, w, c = 1, src.shape[0], src.shape[1], 1
+        elif src.dim() == 3:
+            b, h, w, c = 1, src.shape[0], src.shape[1], src.shape[2]
+        else:
+            b, h, w, c = src.shape
+        dst = self.empty(tuple(src.shape))
+        check(lib.bv_morph(self.handle, _u8ptr(src), _u8ptr(dst), b, h, w, c, MORPH[op] if isinstance(op, str) else op,
+                           ffi.from_buffer("uint8_t[]", kernel), kw, kh, int(iterations)))
+        return dst
+
+    def color_balance(self, src, want_stats=False, **flags):
+        b, h, w, c = self._bhw(src)
+        if c != 3:
+            raise BVError(-1, "colour balance needs BGR input")
+        prm = ffi.new("bv_balance_params *")
+        lib.bv_balance_default(prm)
+        for k, v in flags.items():
+            setattr(prm, k, int(v))
+        dst = self.empty(tuple(src.shape))
+        stats = ffi.new("bv_balance_stats[]", b) if want_stats else ffi.NULL
+        check(lib.bv_color_balance(self.handle, _u8ptr(src), _u8ptr(dst), b, h, w, prm, stats))
+        if want_stats:
+            out = []
+            for i in range(b):
+                s = stats[i]
+                out.append(dict(bgr_min=tuple(s.bgr_min), bgr_max=tuple(s.bgr_max), bgr_avg=tuple(s.bgr_avg),
+                                dominant=s.dominant, s_min=s.s_min, s_max=s.s_max, v_min=s.v_min, v_max=s.v_max,
+                                degenerate=s.degenerate))
+            return dst, out
+        return dst
+
+    def label(self, mask, max_blobs=4096, want_labels=True):
+        if mask.dim() == 2:
+            b, h, w = 1, mask.shape[0], mask.shape[1]
+        else:
+            b, h, w = mask.shape[0], mask.shape[1], mask.shape[2]
+        labels = self.empty(tuple(mask.shape), torch.int32) if want_labels else None
+        blobs = self.empty((b, max_blobs, BLOB_DTYPE.itemsize), torch.uint8) if max_blobs else None
+        nb = self.empty((b,), torch.int32)
+        check(lib.bv_label(self.handle, _u8ptr(mask), ffi.cast("int32_t *", labels.data_ptr()) if want_labels else ffi.NULL,
+                           b, h, w, ffi.cast("bv_blob *", blobs.data_ptr()) if max_blobs else ffi.NULL, max_blobs,
+                           ffi.cast("int32_t *", nb.data_ptr())))
+        return labels, blobs, nb
+
+    def blobs_to_numpy(self, blobs, nb):
+        """Device blob table -> list (per frame) of structured numpy arrays."""
+        n = self.download(nb)
+        raw = self.download(blobs)
+        out = []
+        for f in range(raw.shape[0]):
+            k = int(min(n[f], raw.shape[1]))
+            out.append(raw[f, :k].copy().view(BLOB_DTYPE).reshape(k))
+        return n, out
+
+    def resize(self, src, width, height):
+        if src.dim() == 2:
+            b, sh, sw, c = 1, src.shape[0], src.shape[1], 1
+            shape = (height, width)
+        elif src.dim() == 3:
+            b, sh, sw, c = 1, src.shape[0], src.shape[1], src.shape[2]
+            shape = (height, width, c)
+        else:
+            b, sh, sw, c = src.shape
+            shape = (b, height, width, c)
+        dst = self.empty(shape)
+        check(lib.bv_resize_linear(self.handle, _u8ptr(src), sh, sw, _u8ptr(dst), height, width, c, b))
+        return dst
+
+    def letterbox(self, images, out_h=640, out_w=640, pad=114, half=True):
+        n = len(images)
+        for im in images:
+            if im.dim() != 3 or im.shape[2] != 3 or im.dtype != torch.uint8 or not im.is_cuda:
+                raise BVError(-1, "letterbox needs CUDA uint8 [H,W,3] tensors")
+        srcs = ffi.new("uint8_t *[]", [_u8ptr(im) for im in images])
+        hs = ffi.new("int32_t[]", [int(im.shape[0]) for im in images])
+        ws = ffi.new("int32_t[]", [int(im.shape[1]) for im in images])
+        out = self.empty((n, 3, out_h, out_w), torch.float16 if half else torch.float32)
+        check(lib.bv_letterbox(self.handle, ffi.cast("const uint8_t *const *", srcs), hs, ws, n,
+                               ffi.cast("void *", out.data_ptr()), out_h, out_w, pad, 1 if half else 0))
+        return out
+
+    # -- fused stage ---------------------------------------------------------------------------
+    @staticmethod
+    def make_stage(balance=None, cvt=None, lo=(0, 0, 0), hi=(255, 255, 255), morph=(), label=False):
+        """Builds a bv_stage_desc.  balance: None or dict of process_frame flags ({} = defaults);
+        cvt: None or conversion name; morph: sequence of (op, kw, kh, iterations)."""
+        d = ffi.new("bv_stage_desc *")
+        d.do_balance = 0 if balance is None else 1
+        lib.bv_balance_default(ffi.addressof(d, "balance"))
+        if balance:
+            for k, v in balance.items():
+                setattr(d.balance, k, int(v))
+        d.cvt_code = -1 if cvt is None else (CVT[cvt] if isinstance(cvt, str) else int(cvt))
+        lo = np.broadcast_to(np.asarray(lo), (3,)) if np.ndim(lo) else (int(lo), 0, 0)
+        hi = np.broadcast_to(np.asarray(hi), (3,)) if np.ndim(hi) else (int(hi), 255, 255)
+        for k in range(3):
+            d.lo[k] = int(lo[k])
+            d.hi[k] = int(hi[k])
+        if len(morph) > 4:
+            raise BVError(-1, "at most 4 morphology steps")
+        d.n_morph = len(morph)
+        for i, (op, kw, kh, it) in enumerate(morph):
+            d.morph_op[i] = MORPH[op] if isinstance(op, str) else int(op)
+            d.morph_kw[i], d.morph_kh[i], d.morph_iters[i] = int(kw), int(kh), int(it)
+        d.do_label = 1 if label else 0
+        return d
+
+    def stage(self, desc, src, want=("mask",), max_blobs=1024, out=None):
+        """Runs the fused stage on a device tensor [B,H,W,3] (or [H,W,3]).  `want` selects the
+        outputs among balanced, converted, mask, labels, blobs; returns a dict of device tensors.
+        `out` may carry preallocated tensors to reuse."""
+        b, h, w, c = self._bhw(src)
+        lead = tuple(src.shape[:-1])
+        out = dict(out or {})
+        one = desc.cvt_code == lib.BV_BGR2GRAY
+
+        def get(name, shape, dtype=torch.uint8):
+            if name not in want:
+                return None
+            if name not in out:
+                out[name] = self.empty(shape, dtype)
+            return out[name]
+        balanced = get("balanced", lead + (3,))
+        converted = get("converted", lead if one else lead + (3,))
+        mask = get("mask", lead)
+        labels = get("labels", lead, torch.int32)
+        blobs = get("blobs", (b, max_blobs, BLOB_DTYPE.itemsize))
+        if desc.do_label and "n_blobs" not in out:
+            out["n_blobs"] = self.empty((b,), torch.int32)
+        nb = out.get("n_blobs")
+        check(lib.bv_stage(self.handle, desc, _u8ptr(src), b, h, w, _u8ptr(balanced), _u8ptr(converted), _u8ptr(mask),
+                           ffi.cast("int32_t *", labels.data_ptr()) if labels is not None else ffi.NULL,
+                           ffi.cast("bv_blob *", blobs.data_ptr()) if blobs is not None else ffi.NULL,
+                           max_blobs if blobs is not None else 0,
+                           ffi.cast("int32_t *", nb.data_ptr()) if nb is not None else ffi.NULL))
+        return out
+
+    def stage_host(self, desc, src, want=("mask",), max_blobs=1024, out=None):
+        """Same stage on HOST arrays (numpy, ideally pinned): upload, run, download, blocking.
+        Returns a dict of numpy arrays; `out` may carry preallocated (pinned) arrays."""
+        src = np.ascontiguousarray(src, dtype=np.uint8)
+        if src.ndim == 3:
+            b, (h, w, c) = 1, src.shape
+        else:
+            b, h, w, c = src.shape
+        lead = tuple(src.shape[:-1])
+        out = dict(out or {})
+        one = desc.cvt_code == lib.BV_BGR2GRAY
+
+        def get(name, shape, dtype=np.uint8):
+            if name not in want:
+                return None
+            if name not in out:
+                out[name] = np.empty(shape, dtype)
+            return out[name]
+        balanced = get("balanced", lead + (3,))
+        converted = get("converted", lead if one else lead + (3,))
+        mask = get("mask", lead)
+        labels = get("labels", lead, np.int32)
+        blobs = get("blobs", (b, max_blobs), BLOB_DTYPE)
+        if desc.do_label and "n_blobs" not in out:
+            out["n_blobs"] = np.zeros((b,), np.int32)
+        nb = out.get("n_blobs")
+
+        def p(a, ctype):
+            return ffi.cast(ctype, a.ctypes.data) if a is not None else ffi.NULL
+        check(lib.bv_stage_host(self.handle, desc, p(src, "uint8_t *"), b, h, w, p(balanced, "uint8_t *"),
+                                p(converted, "uint8_t *"), p(mask, "uint8_t *"), p(labels, "int32_t *"),
+                                p(blobs, "bv_blob *"), max_blobs if blobs is not None else 0, p(nb, "int32_t *")))
+        return out
+
+
+# ---- pinned numpy buffers --------------------------------------------------------------------
+class PinnedArray:
+    """numpy array over cudaHostAlloc'ed memory (full-speed PCIe for the *_host entry points)."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        self._ptr = lib.bv_host_alloc(max(nbytes, 1))
+        if self._ptr == ffi.NULL:
+            raise BVError(-4, ffi.string(lib.bv_last_error()).decode())
+        self.array = np.frombuffer(ffi.buffer(self._ptr, nbytes), dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self._ptr is not None and self._ptr != ffi.NULL:
+            self.array = None
+            lib.bv_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---- default contexts (one per device, created on first use) ----------------------------------
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_context(device=0):
+    with _default_lock:
+        ctx = _default.get(device)
+        if ctx is None:
+            ctx = _default[device] = Context(device)
+        return ctx

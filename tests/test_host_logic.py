@@ -1,0 +1,101 @@
+"""Host-side logic that needs no GPU: table composition of the preprocessor point ops, structuring
+elements, stream sharding and the world_size-2 detection gather on gloo."""
+import os
+import socket
+
+import cv2
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import cv_ops, synth
+from cuauv_vision_pipeline_b200 import sharding, transform
+from cuauv_vision_pipeline_b200.preprocessor import point_lut
+
+
+@pytest.mark.parametrize("rb,gb,bb,con,bri", [(25, 0, 0, 1, 0), (0, -30, 255, 1, 0), (0, 0, 0, 1.7, 0),
+                                              (0, 0, 0, 0.35, 0), (0, 0, 0, 1, -40), (10, -20, 30, 2.5, 17),
+                                              (-255, 255, 0, 5, -255)])
+def test_point_lut_equals_reference_chain(rb, gb, bb, con, bri):
+    img = synth.gen_random_bgr(32, 48, 5)
+    ref = img
+    if rb != 0:
+        ref = cv_ops.channel_bias(ref, 2, rb)
+    if gb != 0:
+        ref = cv_ops.channel_bias(ref, 1, gb)
+    if bb != 0:
+        ref = cv_ops.channel_bias(ref, 0, bb)
+    if con != 1:
+        ref = cv_ops.contrast(ref, con)
+    if bri != 0:
+        ref = cv_ops.brightness(ref, bri)
+    lut = point_lut(rb, gb, bb, con, bri)
+    got = np.stack([lut[c][img[..., c]] for c in range(3)], axis=-1)
+    assert np.array_equal(got, ref)
+
+
+def test_structuring_elements_match_cv2():
+    for x in range(1, 103, 2):
+        for y in (x, 1, 3, 21):
+            assert np.array_equal(transform.elliptic_kernel(x, y), cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (x, y)))
+    assert np.array_equal(transform.rect_kernel(5, 3), cv2.getStructuringElement(cv2.MORPH_RECT, (5, 3)))
+    with pytest.raises(ValueError):
+        transform.elliptic_kernel(4)
+    with pytest.raises(ValueError):
+        transform.rect_kernel(0)
+
+
+def test_stream_partition():
+    for world in (1, 2, 4, 8):
+        owned = [sharding.streams_for_rank(8, r, world) for r in range(world)]
+        assert sorted(s for o in owned for s in o) == list(range(8))
+        assert all(len(o) == 8 // world for o in owned)
+    assert sharding.streams_for_rank(3, 1, 2) == [1]
+    with pytest.raises(ValueError):
+        sharding.streams_for_rank(8, 2, 2)
+
+
+def test_merge_in_order():
+    assert sharding.merge_in_order([{0: "a", 2: "c"}, {1: "b"}]) == ["a", "b", "c"]
+    with pytest.raises(ValueError):
+        sharding.merge_in_order([{0: 1}, {0: 2}])
+    with pytest.raises(ValueError):
+        sharding.merge_in_order([{0: 1}, {2: 2}])
+    assert sharding.gather_detections({0: "x"}) == ["x"]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    frames = sharding.frames_for_rank(7, rank, world)
+    local = {f: {"frame": f, "rank": rank, "blobs": [(f, f * 2)]} for f in frames}
+    merged = sharding.gather_detections(local, dst=0)
+    if rank == 0:
+        q.put(merged)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_on_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert [m["frame"] for m in merged] == list(range(7))
+    assert [m["rank"] for m in merged] == [0, 1, 0, 1, 0, 1, 0]

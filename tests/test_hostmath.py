@@ -1,0 +1,83 @@
+"""The per-pixel arithmetic of the CUDA kernels (csrc/pixel_math.cuh, __host__ __device__) compiled
+for the host and swept against cv2: all 2^24 colours per conversion, every (H<180,S,V) for
+HSV2BGR incl. the 32-px vector / tail rounding rule, and the fixed-point bilinear resize.  This
+checks the exact source the device runs, in a container without a GPU; the GPU tests repeat the
+sweeps through the real kernels."""
+import ctypes
+import os
+import subprocess
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostmath", "hostmath.cpp")
+OUT = os.path.join(HERE, "hostmath", "_build", "libhostmath.so")
+
+
+@pytest.fixture(scope="module")
+def hm():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    deps = [SRC, os.path.join(HERE, "..", "cuauv_vision_pipeline_b200", "csrc", "pixel_math.cuh")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", SRC, "-o", OUT])
+    return ctypes.CDLL(OUT)
+
+
+def convert(hm, img, code, one=False):
+    h, w = img.shape[:2]
+    out = np.empty((h, w) if one else (h, w, 3), np.uint8)
+    rc = hm.hm_convert(img.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p),
+                       ctypes.c_size_t(h * w), w, code)
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("name,code,cvc", [("hsv", 0, cv2.COLOR_BGR2HSV), ("lab", 1, cv2.COLOR_BGR2LAB),
+                                           ("gray", 2, cv2.COLOR_BGR2GRAY), ("ycrcb", 3, cv2.COLOR_BGR2YCrCb)])
+def test_device_math_all_colors(hm, name, code, cvc):
+    img = synth.all_colors_image()
+    assert np.array_equal(convert(hm, img, code, one=(code == 2)), cv2.cvtColor(img, cvc))
+
+
+@pytest.mark.parametrize("width", [4096, 100, 63, 33])
+def test_device_math_hsv2bgr(hm, width):
+    hh, ss, vv = np.meshgrid(np.arange(180), np.arange(256), np.arange(256), indexing="ij")
+    flat = np.stack([hh, ss, vv], -1).astype(np.uint8).reshape(-1, 3)
+    n = (flat.shape[0] // width) * width
+    im = np.ascontiguousarray(flat[:n].reshape(-1, width, 3))
+    assert np.array_equal(convert(hm, im, 4), cv2.cvtColor(im, cv2.COLOR_HSV2BGR))
+
+
+def test_device_math_hls_within_one_hue_step(hm):
+    """BGR2HLS is P1: the float32 model matches cv2 on all but 3 of 2^24 colours in the vector path
+    (hue off by one at exact ties); stated tolerance: |dH| <= 1, L and S exact."""
+    img = synth.all_colors_image()
+    mine = convert(hm, img, 5).astype(np.int16)
+    ref = cv2.cvtColor(img, cv2.COLOR_BGR2HLS).astype(np.int16)
+    d = np.abs(mine - ref)
+    assert d[..., 1].max() == 0 and d[..., 2].max() == 0
+    assert d[..., 0].max() <= 1 and int((d[..., 0] > 0).sum()) <= 8
+
+
+def test_hsv_division_tables(hm):
+    sdiv = (ctypes.c_int * 256)()
+    hdiv = (ctypes.c_int * 256)()
+    hm.hm_hsv_tables(sdiv, hdiv)
+    i = np.arange(1, 256, dtype=np.float64)
+    assert list(sdiv)[1:] == np.rint((255 << 12) / i).astype(int).tolist() and sdiv[0] == 0
+    assert list(hdiv)[1:] == np.rint((180 << 12) / (6 * i)).astype(int).tolist() and hdiv[0] == 0
+
+
+@pytest.mark.parametrize("shape", [(1242, 2208, 360, 640, 3), (479, 641, 777, 333, 3), (480, 640, 960, 1280, 1),
+                                   (100, 100, 37, 53, 3), (2160, 3840, 360, 640, 3)])
+def test_device_math_resize(hm, shape):
+    sh, sw, dh, dw, c = shape
+    im = np.random.default_rng(7).integers(0, 256, (sh, sw, c), dtype=np.uint8)
+    ref = cv2.resize(im, (dw, dh), interpolation=cv2.INTER_LINEAR).reshape(dh, dw, c)
+    out = np.empty((dh, dw, c), np.uint8)
+    hm.hm_resize(im.ctypes.data_as(ctypes.c_void_p), sh, sw, out.ctypes.data_as(ctypes.c_void_p), dh, dw, c)
+    assert np.array_equal(out, ref)

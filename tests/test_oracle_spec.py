@@ -1,0 +1,98 @@
+"""Pins the arithmetic specification (oracle/spec_np.py) against the installed cv2: every 8-bit
+conversion over all 2^24 colours, resize over mixed shapes, morphology / inRange semantics."""
+import hashlib
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import spec_np as S
+from oracle import synth, ccl, letterbox, cv_ops
+
+
+@pytest.fixture(scope="module")
+def all_colors():
+    return synth.all_colors_image()
+
+
+@pytest.mark.parametrize("name,fn,code", [("hsv", S.bgr2hsv, cv2.COLOR_BGR2HSV), ("lab", S.bgr2lab, cv2.COLOR_BGR2LAB),
+                                          ("gray", S.bgr2gray, cv2.COLOR_BGR2GRAY),
+                                          ("ycrcb", S.bgr2ycrcb, cv2.COLOR_BGR2YCrCb)])
+def test_conversion_all_colors(all_colors, name, fn, code):
+    ref = cv2.cvtColor(all_colors, code)
+    for y0 in range(0, 4096, 512):
+        assert np.array_equal(fn(all_colors[y0:y0 + 512]), ref[y0:y0 + 512]), name
+
+
+def test_lab_tables_checksums():
+    g, c = S.lab_tables()
+    assert hashlib.sha256(g.astype("<u2").tobytes()).hexdigest()[:16] == "8bfeace00785402e"
+    assert hashlib.sha256(c.astype("<u2").tobytes()).hexdigest()[:16] == "8d9ac99d93fa1ed9"
+
+
+def _all_hsv():
+    hh, ss, vv = np.meshgrid(np.arange(180), np.arange(256), np.arange(256), indexing="ij")
+    return np.stack([hh, ss, vv], -1).astype(np.uint8).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("width", [4096, 63, 33])
+def test_hsv2bgr_vector_and_tail_rule(width):
+    flat = _all_hsv()
+    n = (flat.shape[0] // width) * width
+    im = np.ascontiguousarray(flat[:n].reshape(-1, width, 3))
+    step = max(1, im.shape[0] // 400)       # a stride of rows keeps the run short; every (S,V) pair still appears
+    im = np.ascontiguousarray(im[::step])
+    assert np.array_equal(S.hsv2bgr_rows(im), cv2.cvtColor(im, cv2.COLOR_HSV2BGR))
+
+
+@pytest.mark.parametrize("shape", [(1242, 2208, 360, 640, 3), (479, 641, 777, 333, 3), (480, 640, 960, 1280, 1),
+                                   (100, 100, 37, 53, 3), (720, 1280, 360, 640, 3), (1080, 1920, 459, 816, 3)])
+def test_resize_linear(shape):
+    sh, sw, dh, dw, c = shape
+    im = np.random.default_rng(sh + dw).integers(0, 256, (sh, sw, c), dtype=np.uint8)
+    if c == 1:
+        im = im[..., 0]
+    assert np.array_equal(S.resize_linear(im, dw, dh), cv2.resize(im, (dw, dh), interpolation=cv2.INTER_LINEAR))
+
+
+def test_morphology_border_semantics():
+    m = synth.mask_random(40, 50, 3, 0.6)
+    k = np.ones((5, 5), np.uint8)
+    pad = cv2.copyMakeBorder(m, 2, 2, 2, 2, cv2.BORDER_CONSTANT, value=255)
+    er = np.min(np.stack([pad[dy:dy + 40, dx:dx + 50] for dy in range(5) for dx in range(5)]), 0)
+    assert np.array_equal(cv2.erode(m, k), er)
+    pad0 = cv2.copyMakeBorder(m, 2, 2, 2, 2, cv2.BORDER_CONSTANT, value=0)
+    di = np.max(np.stack([pad0[dy:dy + 40, dx:dx + 50] for dy in range(5) for dx in range(5)]), 0)
+    assert np.array_equal(cv2.dilate(m, k), di)
+    assert np.array_equal(cv2.morphologyEx(m, cv2.MORPH_OPEN, k, iterations=2),
+                          cv2.dilate(cv2.erode(m, k, iterations=2), k, iterations=2))
+
+
+def test_canonical_labels_and_moments():
+    m = synth.mask_blobs(120, 200, 2, sigma=4.0)
+    n, lab, tab = ccl.label_and_moments(m)
+    assert n > 3
+    firsts = [int(np.flatnonzero(lab.reshape(-1) == i)[0]) for i in range(1, n + 1)]
+    assert firsts == sorted(firsts)
+    for i in (1, n // 2, n):
+        mm = ccl.cv2_moments_of_label(lab, i)
+        for k in ccl.MOMENT_KEYS:
+            assert int(mm[k]) == int(tab[k][i - 1])
+    n2, _, stats, _ = cv2.connectedComponentsWithStats((m != 0).astype(np.uint8), connectivity=8)
+    assert n2 - 1 == n and sorted(stats[1:, cv2.CC_STAT_AREA].tolist()) == sorted(tab["m00"].tolist())
+
+
+def test_letterbox_geometry():
+    assert letterbox.letterbox_geometry(1242, 2208) == (640, 360, 140, 140, 0, 0)
+    assert letterbox.letterbox_geometry(720, 1280) == (640, 360, 140, 140, 0, 0)
+    assert letterbox.letterbox_geometry(480, 640) == (640, 480, 80, 80, 0, 0)
+    out = letterbox.yolo_input([synth.gen_underwater(90, 160, 1)], 64, 64)
+    assert out.shape == (1, 3, 64, 64) and out.dtype == np.float16
+    assert float(out[0, 0, 0, 0]) == pytest.approx(114 / 255, abs=1e-3)
+
+
+def test_preprocessor_point_ops_semantics():
+    img = synth.gen_random_bgr(16, 16, 0)
+    assert np.array_equal(cv_ops.contrast(img, 1.7), np.minimum(np.floor(img * 1.7), 255).astype(np.uint8))
+    assert np.array_equal(cv_ops.brightness(img, -40), np.clip(img.astype(int) - 40, 0, 255).astype(np.uint8))
+    assert np.array_equal(cv_ops.channel_bias(img, 2, 25)[..., 2], np.clip(img[..., 2].astype(int) + 25, 0, 255))
