@@ -3,7 +3,10 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "lab_tables.inc"
@@ -39,9 +42,97 @@ int ensure_scratch(bv_ctx *ctx, int slot, size_t bytes) {
     return BV_OK;
 }
 
+// ---- per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg) ----
+struct ProfRecord {
+    const char *name;
+    cudaEvent_t start, stop;
+};
+struct Profiler {
+    std::vector<ProfRecord> records;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
+void prof_begin(bv_ctx *ctx, const char *kernel) {
+    Profiler *p = (Profiler *)ctx->prof;
+    ProfRecord r{kernel, p->get(), p->get()};
+    cudaEventRecord(r.start, ctx->stream);
+    p->records.push_back(r);
+}
+
+void prof_end(bv_ctx *ctx) {
+    Profiler *p = (Profiler *)ctx->prof;
+    cudaEventRecord(p->records.back().stop, ctx->stream);
+}
+
 }  // namespace bv
 
 using namespace bv;
+
+extern "C" int bv_profile_enable(bv_ctx *ctx, int on) {
+    BV_REQUIRE(ctx, "null context");
+    if (on && !ctx->prof) ctx->prof = new Profiler();
+    if (!on && ctx->prof) {
+        Profiler *p = (Profiler *)ctx->prof;
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &r : p->records) {
+            cudaEventDestroy(r.start);
+            cudaEventDestroy(r.stop);
+        }
+        for (auto e : p->pool) cudaEventDestroy(e);
+        delete p;
+        ctx->prof = nullptr;
+    }
+    return BV_OK;
+}
+
+extern "C" int bv_profile_dump(bv_ctx *ctx, char *buf, size_t cap) {
+    BV_REQUIRE(ctx && buf && cap > 2, "null argument");
+    BV_REQUIRE(ctx->prof, "profiling is not enabled");
+    Profiler *p = (Profiler *)ctx->prof;
+    BV_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::map<std::string, std::pair<long, double>> agg;
+    for (auto &r : p->records) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.start, r.stop) != cudaSuccess) (void)cudaGetLastError();
+        std::string name(r.name);
+        // "(final_kernel<MODE, CODE, true>)" -> "final_kernel"
+        size_t b = name.find_first_not_of("( ");
+        size_t e = name.find_first_of("<) ", b);
+        name = name.substr(b, e == std::string::npos ? std::string::npos : e - b);
+        auto &a = agg[name];
+        a.first += 1;
+        a.second += ms;
+        p->pool.push_back(r.start);
+        p->pool.push_back(r.stop);
+    }
+    p->records.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto &kv : agg) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(),
+                 kv.second.first, kv.second.second);
+        out += tmp;
+        first = false;
+    }
+    out += "}";
+    if (out.size() + 1 > cap) {
+        set_error("bv_profile_dump: buffer too small (%zu needed)", out.size() + 1);
+        return BV_ERR_CAPACITY;
+    }
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return BV_OK;
+}
 
 extern "C" int bv_version(void) { return BV_VERSION; }
 
@@ -143,6 +234,10 @@ extern "C" void bv_destroy(bv_ctx *ctx) {
     for (int i = 0; i < BV_MAX_CHUNKS; ++i) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    }
+    if (ctx->prof) {
+        ctx->stream = ctx->own_stream;
+        bv_profile_enable(ctx, 0);
     }
     (void)cudaGetLastError();
     free(ctx);

@@ -41,8 +41,10 @@ void set_error(const char *fmt, ...);  // thread-local message, api.cu
 // bv_launch_count() is the true number of launches.
 #define BV_LAUNCH(ctx, kernel, grid, block, smem, ...)                                             \
     do {                                                                                           \
+        if ((ctx)->prof) bv::prof_begin((ctx), #kernel);                                           \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                           \
         (ctx)->launches++;                                                                         \
+        if ((ctx)->prof) bv::prof_end((ctx));                                                      \
         BV_CUDA(cudaGetLastError());                                                               \
     } while (0)
 
@@ -86,11 +88,14 @@ struct bv_ctx {
     // host-memory pipeline (bv_stage_host): copy streams and per-chunk events
     cudaStream_t copy_in, copy_out;
     cudaEvent_t ev_in[BV_MAX_CHUNKS], ev_done[BV_MAX_CHUNKS];
+    void *prof;  // per-kernel CUDA-event timing, only while bv_profile_enable(ctx, 1)
 };
 
 namespace bv {
 
 int ensure_scratch(bv_ctx *ctx, int slot, size_t bytes);  // api.cu
+void prof_begin(bv_ctx *ctx, const char *kernel);          // api.cu
+void prof_end(bv_ctx *ctx);
 
 // ---- device helpers --------------------------------------------------------------------------
 #if defined(__CUDACC__)

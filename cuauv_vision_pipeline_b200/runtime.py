@@ -76,6 +76,17 @@ class Context:
     def launches(self):
         return int(lib.bv_launch_count(self.handle))
 
+    def profile(self, on=True):
+        """Bracket every kernel launch with CUDA events on the context's stream."""
+        check(lib.bv_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_dump(self):
+        """{kernel: {"launches": n, "ms": total}} since the last dump (synchronises)."""
+        import json
+        buf = ffi.new("char[]", 1 << 16)
+        check(lib.bv_profile_dump(self.handle, buf, 1 << 16))
+        return json.loads(ffi.string(buf).decode())
+
     # -- memory -----------------------------------------------------------------------------
     def empty(self, shape, dtype=torch.uint8):
         with torch.cuda.stream(self.torch_stream):

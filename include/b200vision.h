@@ -140,6 +140,11 @@ int bv_set_stream(bv_ctx *ctx, void *cuda_stream);
 /* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
 uint64_t bv_launch_count(const bv_ctx *ctx);
 void bv_balance_default(bv_balance_params *p);
+/* Per-kernel timing: while enabled, every kernel launch is bracketed by CUDA events on the
+ * context's stream.  bv_profile_dump synchronises, writes a JSON object
+ * {"kernel": {"launches": n, "ms": total}, ...} into buf and clears the records. */
+int bv_profile_enable(bv_ctx *ctx, int on);
+int bv_profile_dump(bv_ctx *ctx, char *buf, size_t cap);
 
 /* ---- colour balance: replaces process_frame (color_balance.cpp:343-780) ------------------- */
 /* src_dev -> dst_dev (may alias), batch frames of height x width BGR.  stats_host (optional, may

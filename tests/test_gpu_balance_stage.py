@@ -1,0 +1,318 @@
+"""GPU parity: colour balance against the compiled, unmodified reference (oracle/_ref) and its
+golden vectors; the fused stage against the reference's module pipelines (modules/bins.py,
+modules/red_buoy.py) expressed as cv2 calls; resize / YOLO input; drop-in modules.
+
+Colour balance tolerance (stated): the device computes the channel means as exact integer sums / N
+where the reference uses a sequential running mean (color_balance.cpp:459-470, equal to <= 1.2e-12);
+a differing gain could move a table entry by 1 LSB, so the stated bound is max |diff| <= 1 LSB --
+and 0 differing bytes is what is asserted on every case here."""
+import glob
+import os
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import ccl, color_balance_np as cb, cv_ops, letterbox, ref_balance, synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_cases():
+    return sorted(glob.glob(os.path.join(GOLDEN, "balance_*.npz")))
+
+
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: os.path.basename(p)[8:-4])
+def test_balance_golden_vectors_from_the_reference(ctx, path):
+    z = np.load(path, allow_pickle=True)
+    flags = {k: v for k, v in z["flags"]} if z["flags"].size else {}
+    got = ctx.download(ctx.color_balance(ctx.upload(z["src"]), **flags))
+    assert np.array_equal(got, z["out"])
+
+
+def oracle_balance(img, **flags):
+    """compiled reference when it travelled to this box, else its pinned restatement"""
+    if ref_balance.available():
+        return ref_balance.balance(img, **flags)
+    return cb.process_frame_np(img, **flags)
+
+
+@pytest.mark.parametrize("shape,seed", [((480, 640), 1), ((479, 641), 2), ((1080, 1920), 3), ((1242, 2208), 7),
+                                        ((1243, 2209), 8), ((2160, 3840), 9)])
+def test_balance_default_flags_vs_reference(ctx, shape, seed):
+    img = synth.gen_underwater(shape[0], shape[1], seed)
+    want = oracle_balance(img)
+    got, stats = ctx.color_balance(ctx.upload(img), want_stats=True)
+    got = ctx.download(got)
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert int(diff.max()) <= 1, "stated tolerance: 1 LSB"
+    assert int((diff != 0).sum()) == 0, "expected: identical bytes"
+    _, st = cb.process_frame_np(img, return_stats=True)
+    s = stats[0]
+    assert s["bgr_min"] == tuple(st["bgr_min"]) and s["bgr_max"] == tuple(st["bgr_max"])
+    assert s["bgr_avg"] == pytest.approx(st["bgr_avg"], rel=0, abs=0)
+    assert (s["s_min"], s["s_max"], s["v_min"], s["v_max"]) == (st["s_min"], st["s_max"], st["v_min"], st["v_max"])
+    assert "bgr"[s["dominant"]] == st["tiles"][0]["dom"]
+
+
+@pytest.mark.parametrize("flags", [dict(hsv_contrast_correct=False), dict(rgb_extrema_clipping=False),
+                                   dict(rgb_contrast_correct=True), dict(adaptive_cast_correction=True),
+                                   dict(equalize_rgb=False), dict(equalize_rgb=False, hsv_contrast_correct=False),
+                                   dict(rgb_contrast_correct=True, hsv_contrast_correct=False,
+                                        adaptive_cast_correction=True)],
+                         ids=lambda f: ",".join(sorted(f)))
+def test_balance_flag_combinations(ctx, flags):
+    img = synth.gen_underwater(360, 640, 21)
+    got = ctx.download(ctx.color_balance(ctx.upload(img), **flags))
+    assert np.array_equal(got, oracle_balance(img, **flags))
+
+
+def test_balance_batch_of_distinct_frames_and_in_place(ctx):
+    frames = np.stack([synth.gen_underwater(242, 368, 40 + s) for s in range(11)])
+    d = ctx.upload(frames)
+    got = ctx.download(ctx.color_balance(d))
+    for i in range(frames.shape[0]):
+        assert np.array_equal(got[i], oracle_balance(frames[i])), i
+    from cuauv_vision_pipeline_b200.runtime import ffi, lib, check, _u8ptr
+    prm = ffi.new("bv_balance_params *")
+    lib.bv_balance_default(prm)
+    check(lib.bv_color_balance(ctx.handle, _u8ptr(d), _u8ptr(d), frames.shape[0], 242, 368, prm, ffi.NULL))
+    assert np.array_equal(ctx.download(d), got)
+
+
+def test_balance_red_and_green_dominant(ctx):
+    for perm in ((2, 1, 0), (1, 0, 2)):
+        img = np.ascontiguousarray(synth.gen_underwater(240, 320, 5)[..., list(perm)])
+        assert np.array_equal(ctx.download(ctx.color_balance(ctx.upload(img))), oracle_balance(img))
+
+
+def test_balance_unsupported_flags_fail_loudly(ctx):
+    import cuauv_vision_pipeline_b200 as bv
+    d = ctx.upload(synth.gen_underwater(64, 64, 1))
+    with pytest.raises(bv.BVError):
+        ctx.color_balance(d, hsi_contrast_correct=True)
+    with pytest.raises(bv.BVError):
+        ctx.color_balance(d, horizontal_blocks=2)
+
+
+def test_balance_degenerate_frame_is_defined(ctx):
+    """Constant frame: the reference dies with an integer division by zero (color_balance.cpp:684).
+    Here the stretch of a zero-width range is defined as 0 and flagged; nothing crashes."""
+    img = np.full((48, 64, 3), 90, np.uint8)
+    out, stats = ctx.color_balance(ctx.upload(img), want_stats=True)
+    assert stats[0]["degenerate"] == 1
+    assert ctx.download(out).shape == img.shape
+
+
+def test_legacy_process_frame_symbol_is_a_drop_in(ctx):
+    """modules/color_balance.py:93-110 verbatim against the CUDA-backed libauv-color-balance.so."""
+    from cuauv_vision_pipeline_b200.color_balance import balance, balance_legacy
+    img = synth.gen_underwater(479, 641, 17)
+    want = oracle_balance(img)
+    assert np.array_equal(balance_legacy(img), want)
+    assert np.array_equal(balance(img), want)
+    assert np.array_equal(balance_legacy(img, hsv_contrast_correct=False), oracle_balance(img, hsv_contrast_correct=False))
+
+
+# ----------------------------------------------------------------------------------------------
+# fused stage
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1080, 1920), (480, 640), (479, 641), (270, 496)])
+def test_stage_bins_pipeline(ctx, shape):
+    """modules/bins.py:13-27: BGR2HSV -> inRange -> OPEN 5x5 -> blobs."""
+    img = synth.gen_underwater(shape[0], shape[1], 30)
+    mask_ref, cleaned_ref = cv_ops.bins_mask(img)
+    desc = ctx.make_stage(cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255), morph=[("open", 5, 5, 1)], label=True)
+    out = ctx.stage(desc, ctx.upload(img), want=("converted", "mask", "labels", "blobs"), max_blobs=4096)
+    assert np.array_equal(ctx.download(out["converted"]), cv2.cvtColor(img, cv2.COLOR_BGR2HSV))
+    assert np.array_equal(ctx.download(out["mask"]), cleaned_ref)
+    n_ref, lab_ref, tab = ccl.label_and_moments(cleaned_ref)
+    n, tables = ctx.blobs_to_numpy(out["blobs"], out["n_blobs"])
+    assert int(n[0]) == n_ref and np.array_equal(ctx.download(out["labels"]), lab_ref)
+    for key in ccl.MOMENT_KEYS:
+        assert np.array_equal(tables[0][key].astype(np.int64), tab[key]), key
+    # threshold only (no morphology): the raw mask
+    desc0 = ctx.make_stage(cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255))
+    assert np.array_equal(ctx.download(ctx.stage(desc0, ctx.upload(img), want=("mask",))["mask"]), mask_ref)
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (1242, 2208), (479, 641)])
+def test_stage_buoy_pipeline(ctx, shape):
+    """modules/red_buoy.py:21-34: LAB a-channel inRange -> OPEN -> CLOSE."""
+    img = synth.gen_underwater(shape[0], shape[1], 31)
+    th_ref, cl_ref = cv_ops.buoy_mask(img, 150, 255)
+    desc = ctx.make_stage(cvt="bgr2lab", lo=(0, 150, 0), hi=(255, 255, 255), morph=[("open", 5, 5, 1), ("close", 5, 5, 1)])
+    assert np.array_equal(ctx.download(ctx.stage(desc, ctx.upload(img), want=("mask",))["mask"]), cl_ref)
+    desc0 = ctx.make_stage(cvt="bgr2lab", lo=(0, 150, 0), hi=(255, 255, 255))
+    assert np.array_equal(ctx.download(ctx.stage(desc0, ctx.upload(img), want=("mask",))["mask"]), th_ref)
+
+
+@pytest.mark.parametrize("shape", [(1242, 2208), (479, 641)])
+def test_stage_balance_convert_threshold_morph(ctx, shape):
+    """The north-star stage: balance -> LAB / HSV -> inRange -> OPEN, every output checked."""
+    frames = np.stack([synth.gen_underwater(shape[0], shape[1], 50 + s) for s in range(3)])
+    desc = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=(0, 40, 60), hi=(179, 255, 255), morph=[("open", 5, 5, 1)], label=True)
+    out = ctx.stage(desc, ctx.upload(frames), want=("balanced", "converted", "mask", "labels", "blobs"), max_blobs=8192)
+    bal = ctx.download(out["balanced"])
+    cvt = ctx.download(out["converted"])
+    mask = ctx.download(out["mask"])
+    lab = ctx.download(out["labels"])
+    n, tables = ctx.blobs_to_numpy(out["blobs"], out["n_blobs"])
+    for i in range(frames.shape[0]):
+        b_ref = oracle_balance(frames[i])
+        assert np.array_equal(bal[i], b_ref)
+        hsv_ref = cv2.cvtColor(b_ref, cv2.COLOR_BGR2HSV)
+        assert np.array_equal(cvt[i], hsv_ref)
+        m_ref = cv2.morphologyEx(cv2.inRange(hsv_ref, np.array([0, 40, 60]), np.array([179, 255, 255])), cv2.MORPH_OPEN,
+                                 cv_ops.rect_kernel(5))
+        assert np.array_equal(mask[i], m_ref)
+        n_ref, lab_ref, tab = ccl.label_and_moments(m_ref)
+        assert int(n[i]) == n_ref and np.array_equal(lab[i], lab_ref)
+        k = min(n_ref, 8192)
+        assert np.array_equal(tables[i]["m10"].astype(np.int64), tab["m10"][:k])
+    # config 2 of BASELINE.json: balance -> LAB image
+    desc2 = ctx.make_stage(balance={}, cvt="bgr2lab")
+    lab_img = ctx.download(ctx.stage(desc2, ctx.upload(frames), want=("converted",))["converted"])
+    for i in range(frames.shape[0]):
+        assert np.array_equal(lab_img[i], cv2.cvtColor(oracle_balance(frames[i]), cv2.COLOR_BGR2LAB))
+
+
+def test_stage_host_equals_device_stage(ctx):
+    frames = np.stack([synth.gen_underwater(360, 640, 70 + s) for s in range(9)])
+    desc = ctx.make_stage(balance={}, cvt="bgr2lab", lo=(0, 130, 0), hi=(255, 255, 255), morph=[("open", 5, 5, 1)], label=True)
+    want = ("balanced", "converted", "mask", "labels", "blobs")
+    dev = ctx.stage(desc, ctx.upload(frames), want=want, max_blobs=512)
+    host = ctx.stage_host(desc, frames, want=want, max_blobs=512)
+    for k in ("balanced", "converted", "mask", "labels"):
+        assert np.array_equal(host[k], ctx.download(dev[k])), k
+    assert np.array_equal(host["n_blobs"], ctx.download(dev["n_blobs"]))
+    n, tables = ctx.blobs_to_numpy(dev["blobs"], dev["n_blobs"])
+    for i in range(frames.shape[0]):
+        assert np.array_equal(host["blobs"][i][:int(n[i])], tables[i])
+    # pinned buffers take the same path
+    import cuauv_vision_pipeline_b200 as bv
+    pin = bv.PinnedArray(frames.shape)
+    pin.array[...] = frames
+    out = bv.PinnedArray(frames.shape)
+    res = ctx.stage_host(desc, pin.array, want=("converted",), out={"converted": out.array})
+    assert np.array_equal(res["converted"], host["converted"])
+
+
+def test_stage_gradient_and_threshold_on_bgr(ctx):
+    img = synth.gen_underwater(200, 320, 33)
+    desc = ctx.make_stage(cvt=None, lo=(60, 40, 0), hi=(255, 200, 120), morph=[("gradient", 3, 3, 1)])
+    m_ref = cv2.morphologyEx(cv2.inRange(img, np.array([60, 40, 0]), np.array([255, 200, 120])), cv2.MORPH_GRADIENT,
+                             cv_ops.rect_kernel(3))
+    assert np.array_equal(ctx.download(ctx.stage(desc, ctx.upload(img), want=("mask",))["mask"]), m_ref)
+
+
+# ----------------------------------------------------------------------------------------------
+# resize / YOLO input / preprocessor / modules
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1242, 2208, 360, 640, 3), (479, 641, 777, 333, 3), (480, 640, 960, 1280, 1),
+                                   (2160, 3840, 459, 816, 3), (100, 100, 37, 53, 3)])
+def test_resize_linear(ctx, shape):
+    sh, sw, dh, dw, c = shape
+    im = np.random.default_rng(3).integers(0, 256, (sh, sw, c), dtype=np.uint8)
+    if c == 1:
+        im = im[..., 0]
+    assert np.array_equal(ctx.download(ctx.resize(ctx.upload(im), dw, dh)), cv2.resize(im, (dw, dh)))
+
+
+def test_yolo_input_batch_of_mixed_cameras(ctx):
+    """config 4: 16 frames of mixed sizes -> [16,3,640,640] fp16.  The uint8 letterbox is exact
+    (cv2.resize + copyMakeBorder); the normalised tensor is compared at <= 1 fp16 ulp (stated),
+    0 differing values expected.  Parity of the Ultralytics side itself is unpinned (not installed)."""
+    from cuauv_vision_pipeline_b200.yolo_input import yolo_input
+    sizes = [(1242, 2208), (1080, 1920), (720, 1280), (480, 640)] * 4
+    imgs = [synth.gen_underwater(h, w, 90 + i) for i, (h, w) in enumerate(sizes)]
+    got = yolo_input(imgs)
+    want = letterbox.yolo_input(imgs)
+    assert got.shape == (16, 3, 640, 640) and got.dtype == np.float16
+    assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
+    got32 = yolo_input(imgs[:2], half=False)
+    assert np.array_equal(got32, letterbox.yolo_input(imgs[:2], half=False))
+    # scale-up and identity geometry
+    small = [synth.gen_underwater(90, 160, 5), synth.gen_underwater(64, 64, 6)]
+    assert np.array_equal(yolo_input(small, (64, 64)).view(np.uint16), letterbox.yolo_input(small, 64, 64).view(np.uint16))
+
+
+def test_letterbox_golden(ctx):
+    from cuauv_vision_pipeline_b200.yolo_input import yolo_input
+    z = np.load(os.path.join(GOLDEN, "letterbox_90x160_to_64.npz"))
+    assert np.array_equal(yolo_input([z["src"]], (64, 64)).view(np.uint16), z["f16"].view(np.uint16))
+
+
+def test_cv_call_site_golden(ctx):
+    z = np.load(os.path.join(GOLDEN, "cv_calls_72x128.npz"))
+    d = ctx.upload(z["src"])
+    for code in ("bgr2lab", "bgr2hsv", "bgr2ycrcb", "bgr2gray"):
+        assert np.array_equal(ctx.download(ctx.cvt_color(d, code)), z[code]), code
+    assert np.array_equal(ctx.download(ctx.cvt_color(ctx.upload(z["bgr2hsv"]), "hsv2bgr")), z["hsv2bgr"])
+    desc = ctx.make_stage(cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255), morph=[("open", 5, 5, 1)])
+    assert np.array_equal(ctx.download(ctx.stage(desc, d, want=("mask",))["mask"]), z["bins_cleaned"])
+    assert np.array_equal(ctx.download(ctx.resize(d, 50, 37)), z["resize_50x37"])
+    from cuauv_vision_pipeline_b200 import transform
+    assert np.array_equal(ctx.download(ctx.morph(d, "erode", transform.elliptic_kernel(5))), z["ellipse_erode_2"])
+    assert np.array_equal(ctx.download(ctx.morph(d, "dilate", transform.elliptic_kernel(7))), z["ellipse_dilate_3"])
+
+
+def test_preprocessor_mirror(ctx):
+    from cuauv_vision_pipeline_b200.preprocessor import Preprocessor
+
+    class Mod:
+        def __init__(self):
+            self.posted = {}
+
+        def post(self, name, img):
+            self.posted[name] = np.asarray(img)
+    mod = Mod()
+    pp = Preprocessor(mod)
+    img = synth.gen_underwater(242, 368, 12)
+    for k, v in dict(PPX_lab=True, PPX_hsv_split=True, PPX_grayscale=True, PPX_color_correction=True, PPX_r_bias=20,
+                     PPX_contrast=1.3, PPX_brightness=-15, PPX_erode=True, PPX_erode_kernel=2, PPX_dilate=True,
+                     PPX_dilate_kernel=1, PPX_resize_ratio=0.37).items():
+        pp.options_dict[k].value = v
+    out = pp.process(img)[0]
+    assert np.array_equal(mod.posted["PPX_lab"], cv2.cvtColor(img, cv2.COLOR_BGR2LAB))
+    assert np.array_equal(mod.posted["PPX_hsv_s_channel"], cv2.cvtColor(img, cv2.COLOR_BGR2HSV)[..., 1])
+    assert np.array_equal(mod.posted["PPX_grayscale"], cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    ref = oracle_balance(img)
+    ref = cv_ops.channel_bias(ref, 2, 20)
+    ref = cv_ops.contrast(ref, 1.3)
+    ref = cv_ops.brightness(ref, -15)
+    ref = cv_ops.ellipse_erode(ref, 2)
+    ref = cv_ops.ellipse_dilate(ref, 1)
+    ref = cv_ops.resize_ratio(ref, 0.37)
+    assert np.array_equal(out, ref)
+    pp.options_dict["PPX_rotate"].value = 10
+    with pytest.raises(NotImplementedError):
+        pp.process(img)
+
+
+def test_drop_in_modules(ctx):
+    from cuauv_vision_pipeline_b200.modules import BinDetectorGPU, BuoyLABGPU, ColorBalanceGPU
+    img = synth.gen_underwater(480, 640, 77)
+    mod = BinDetectorGPU(video_sources=["forward"], tuners=[])
+    blobs = mod.process("forward", img)
+    _, cleaned = cv_ops.bins_mask(img)
+    assert np.array_equal(mod.posted["bins"], cleaned)
+    n_ref, _, tab = ccl.label_and_moments(cleaned)
+    w = tab["x1"] - tab["x0"] + 1
+    h = tab["y1"] - tab["y0"] + 1
+    keep = (w * h >= 500) & (np.maximum(w, h) / np.minimum(w, h) <= 3.0)
+    assert [b["label"] for b in blobs] == (np.flatnonzero(keep) + 1).tolist()
+    buoy = BuoyLABGPU(["zed"], thresh_min=150, thresh_max=255)
+    res = buoy.process("zed", img)
+    th, cl = cv_ops.buoy_mask(img, 150, 255)
+    assert np.array_equal(buoy.posted["threshed"], th) and np.array_equal(buoy.posted["threshed_cleaned"], cl)
+    n_ref, _, tab = ccl.label_and_moments(cl)
+    if n_ref:
+        i = int(np.argmax(tab["m00"]))
+        assert res["pixel"] == (int(tab["m10"][i] / tab["m00"][i]), int(tab["m01"][i] / tab["m00"][i]))
+        assert res["area"] == float(tab["m00"][i])
+    else:
+        assert res is None
+    cbm = ColorBalanceGPU(["forward"])
+    assert np.array_equal(cbm.process("forward", img), oracle_balance(img))

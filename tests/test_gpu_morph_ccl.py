@@ -1,0 +1,215 @@
+"""GPU parity: morphology against cv2 (reference call sites utils/transform.py:80-164,
+modules/preprocessor.py:120-129) and labelling + raster moments against the declared oracle
+(oracle/ccl.py).  All bit-exact."""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import ccl, cv_ops, synth
+
+pytestmark = pytest.mark.gpu
+
+CV_OP = {"erode": cv2.MORPH_ERODE, "dilate": cv2.MORPH_DILATE, "open": cv2.MORPH_OPEN, "close": cv2.MORPH_CLOSE,
+         "gradient": cv2.MORPH_GRADIENT}
+
+
+@pytest.mark.parametrize("op", list(CV_OP))
+@pytest.mark.parametrize("shape", [(270, 480), (479, 641), (33, 31)])
+def test_rect5_on_masks(ctx, op, shape):
+    m = synth.mask_random(shape[0], shape[1], 5, 0.55)
+    k = cv_ops.rect_kernel(5)
+    got = ctx.download(ctx.morph(ctx.upload(m), op, k))
+    assert np.array_equal(got, cv2.morphologyEx(m, CV_OP[op], k))
+
+
+@pytest.mark.parametrize("kw,kh", [(3, 3), (5, 5), (7, 3), (1, 9), (4, 4), (2, 5), (6, 1), (15, 15)])
+@pytest.mark.parametrize("op", ["erode", "dilate", "open", "close"])
+def test_rect_sizes_incl_even(ctx, kw, kh, op):
+    m = synth.mask_blobs(131, 173, 7, sigma=3.0, pct=55)
+    k = np.ones((kh, kw), np.uint8)
+    got = ctx.download(ctx.morph(ctx.upload(m), op, k))
+    assert np.array_equal(got, cv2.morphologyEx(m, CV_OP[op], k))
+
+
+@pytest.mark.parametrize("iters", [1, 2, 3])
+@pytest.mark.parametrize("op", list(CV_OP))
+def test_iterations(ctx, iters, op):
+    m = synth.mask_blobs(150, 210, 9, sigma=5.0, pct=60)
+    k = cv_ops.rect_kernel(3)
+    got = ctx.download(ctx.morph(ctx.upload(m), op, k, iterations=iters))
+    assert np.array_equal(got, cv2.morphologyEx(m, CV_OP[op], k, iterations=iters))
+    e = cv_ops.elliptic_kernel(5)
+    got = ctx.download(ctx.morph(ctx.upload(m), op, e, iterations=iters))
+    assert np.array_equal(got, cv2.morphologyEx(m, CV_OP[op], e, iterations=iters))
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 12])
+def test_ellipse_on_three_channel_grey(ctx, k):
+    """modules/preprocessor.py:120-129: MORPH_ELLIPSE (2k+1)^2 on the BGR frame."""
+    img = synth.gen_underwater(96, 150, 3)
+    d = ctx.upload(img)
+    se = cv_ops.elliptic_kernel(2 * k + 1)
+    assert np.array_equal(ctx.download(ctx.morph(d, "erode", se)), cv_ops.ellipse_erode(img, k))
+    assert np.array_equal(ctx.download(ctx.morph(d, "dilate", se)), cv_ops.ellipse_dilate(img, k))
+
+
+def test_ellipse_101(ctx):
+    img = synth.gen_underwater(130, 170, 4)
+    se = cv_ops.elliptic_kernel(101)
+    assert np.array_equal(ctx.download(ctx.morph(ctx.upload(img), "erode", se)), cv2.erode(img, se))
+
+
+def test_transform_mirrors(ctx):
+    from cuauv_vision_pipeline_b200 import transform
+    m = synth.mask_blobs(120, 160, 1, sigma=4.0)
+    k = transform.rect_kernel(5)
+    assert np.array_equal(transform.morph_remove_noise(m, k), cv_ops.morph_remove_noise(m, cv_ops.rect_kernel(5)))
+    assert np.array_equal(transform.morph_close_holes(m, k), cv_ops.morph_close_holes(m, cv_ops.rect_kernel(5)))
+    assert np.array_equal(transform.morph_borders(m, k), cv_ops.morph_borders(m, cv_ops.rect_kernel(5)))
+    assert np.array_equal(transform.erode(m, k, 2), cv_ops.erode(m, cv_ops.rect_kernel(5), 2))
+    assert np.array_equal(transform.dilate(m, transform.elliptic_kernel(7)), cv_ops.dilate(m, cv_ops.elliptic_kernel(7)))
+    img = synth.gen_underwater(120, 160, 2)
+    assert np.array_equal(transform.resize(img, 77, 45), cv_ops.resize(img, 77, 45))
+
+
+# ----------------------------------------------------------------------------------------------
+# labelling + moments
+# ----------------------------------------------------------------------------------------------
+def check_labels(ctx, mask, max_blobs=None):
+    n_ref, lab_ref, tab = ccl.label_and_moments(mask)
+    cap = max_blobs if max_blobs is not None else max(n_ref, 1)
+    labels, blobs, nb = ctx.label(ctx.upload(mask), max_blobs=cap)
+    n, tables = ctx.blobs_to_numpy(blobs, nb)
+    assert int(n[0]) == n_ref
+    assert np.array_equal(ctx.download(labels), lab_ref)
+    t = tables[0]
+    k = min(n_ref, cap)
+    for key in ccl.MOMENT_KEYS + ("x0", "y0", "x1", "y1"):
+        assert np.array_equal(t[key].astype(np.int64), tab[key][:k]), key
+    return n_ref
+
+
+@pytest.mark.parametrize("shape", [(270, 480), (479, 641), (64, 32), (65, 33), (100, 31)])
+def test_ccl_blobs(ctx, shape):
+    assert check_labels(ctx, synth.mask_blobs(shape[0], shape[1], 3, sigma=4.0)) > 0
+
+
+@pytest.mark.parametrize("density", [0.1, 0.4, 0.5, 0.6, 0.9])
+def test_ccl_random_noise(ctx, density):
+    check_labels(ctx, synth.mask_random(211, 307, 13, density))
+
+
+def test_ccl_lattice_of_isolated_pixels(ctx):
+    m = synth.mask_lattice(270, 480)
+    assert check_labels(ctx, m) == 135 * 240
+
+
+def test_ccl_serpentine_single_component(ctx):
+    assert check_labels(ctx, synth.mask_serpentine(241, 333)) == 1
+
+
+def test_ccl_nested_rings(ctx):
+    assert check_labels(ctx, synth.mask_rings(301, 403)) > 10
+
+
+def test_ccl_diagonals_are_8_connected(ctx):
+    m = synth.mask_diagonals(200, 260)
+    n4 = cv2.connectedComponents((m != 0).astype(np.uint8), connectivity=4)[0] - 1
+    n8 = check_labels(ctx, m)
+    assert n8 < n4
+
+
+@pytest.mark.parametrize("kind", ["empty", "full", "single", "corners"])
+def test_ccl_trivial_masks(ctx, kind):
+    m = np.zeros((67, 97), np.uint8)
+    if kind == "full":
+        m[:] = 255
+    elif kind == "single":
+        m[31, 64] = 1            # any non-zero value counts
+    elif kind == "corners":
+        m[0, 0] = m[0, -1] = m[-1, 0] = m[-1, -1] = 255
+    check_labels(ctx, m)
+
+
+def test_ccl_word_boundary_cases(ctx):
+    """Runs that end / start exactly at 32-px word boundaries, and diagonal contacts across them."""
+    m = np.zeros((12, 130), np.uint8)
+    m[0, 0:32] = 255            # full word
+    m[1, 32:64] = 255           # next word, diagonal contact at (0,31)-(1,32)
+    m[3, 31] = 255
+    m[4, 32] = 255              # single-pixel diagonal across the boundary
+    m[6, 63:65] = 255           # run straddling a boundary
+    m[7, 95] = 255
+    m[8, 96] = 255
+    m[8, 94] = 255
+    m[10, 100:130] = 255        # run reaching the (partial) last word's end
+    m[11, 129] = 255
+    check_labels(ctx, m)
+
+
+def test_ccl_batch_frames_are_independent(ctx):
+    masks = np.stack([synth.mask_blobs(90, 160, s, sigma=4.0) for s in (1, 2, 3)])
+    labels, blobs, nb = ctx.label(ctx.upload(masks), max_blobs=512)
+    n, tables = ctx.blobs_to_numpy(blobs, nb)
+    lab = ctx.download(labels)
+    for i in range(3):
+        n_ref, lab_ref, tab = ccl.label_and_moments(masks[i])
+        assert int(n[i]) == n_ref and np.array_equal(lab[i], lab_ref)
+        assert np.array_equal(tables[i]["m11"].astype(np.int64), tab["m11"])
+
+
+def test_ccl_capacity_smaller_than_blob_count(ctx):
+    m = synth.mask_lattice(40, 64)
+    check_labels(ctx, m, max_blobs=100)
+
+
+def test_golden_ccl_fixture(ctx):
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ccl_90x160.npz"))
+    labels, blobs, nb = ctx.label(ctx.upload(z["mask"]), max_blobs=int(z["n"]))
+    n, tables = ctx.blobs_to_numpy(blobs, nb)
+    assert int(n[0]) == int(z["n"]) and np.array_equal(ctx.download(labels), z["labels"])
+    for key in ccl.MOMENT_KEYS:
+        assert np.array_equal(tables[0][key].astype(np.int64), z[key])
+
+
+def test_feature_mirror_centroids(ctx):
+    from cuauv_vision_pipeline_b200 import feature
+    m = synth.mask_blobs(200, 300, 8, sigma=6.0)
+    labels, blobs, n = feature.label_blobs(m)
+    n_ref, lab_ref, tab = ccl.label_and_moments(m)
+    assert n == n_ref and np.array_equal(labels, lab_ref)
+    for b in blobs:
+        i = b["label"] - 1
+        assert feature.blob_centroid(b) == (int(tab["m10"][i] / tab["m00"][i]), int(tab["m01"][i] / tab["m00"][i]))
+        assert feature.blob_area(b) == float(tab["m00"][i])
+
+
+@pytest.mark.parametrize("shape", [(2160, 3840), (1080, 1920)])
+def test_full_size_properties(ctx, shape):
+    """At BASELINE sizes: properties that need no oracle pass over the frame.  Sum of m00 equals the
+    mask popcount; full-frame blob moments are the closed forms (m30 exceeds 2^53 at 4K); opening is
+    idempotent; lattice gives exactly W*H/4 blobs."""
+    h, w = shape
+    full = np.full((h, w), 255, np.uint8)
+    labels, blobs, nb = ctx.label(ctx.upload(full), max_blobs=4)
+    n, tables = ctx.blobs_to_numpy(blobs, nb)
+    assert int(n[0]) == 1
+    b = tables[0][0]
+    xs = np.arange(w, dtype=object)
+    ys = np.arange(h, dtype=object)
+    assert int(b["m00"]) == h * w and int(b["m30"]) == int((xs ** 3).sum()) * h and int(b["m03"]) == int((ys ** 3).sum()) * w
+    assert int(b["m21"]) == int((xs ** 2).sum()) * int(ys.sum()) and int(b["m12"]) == int(xs.sum()) * int((ys ** 2).sum())
+    m = synth.mask_blobs(h, w, 3, sigma=6.0)
+    d = ctx.upload(m)
+    k = cv_ops.rect_kernel(5)
+    opened = ctx.morph(d, "open", k)
+    assert np.array_equal(ctx.download(ctx.morph(opened, "open", k)), ctx.download(opened))
+    labels, blobs, nb = ctx.label(opened, max_blobs=8192)
+    n, tables = ctx.blobs_to_numpy(blobs, nb)
+    assert int(tables[0]["m00"].sum()) == int((ctx.download(opened) != 0).sum())
+    lab = ctx.download(labels)
+    assert int(lab.max()) == int(n[0]) and np.array_equal(lab != 0, ctx.download(opened) != 0)
+    lat = synth.mask_lattice(h, w)
+    _, _, nb = ctx.label(ctx.upload(lat), max_blobs=0, want_labels=False)
+    assert int(ctx.download(nb)[0]) == (h // 2) * (w // 2)

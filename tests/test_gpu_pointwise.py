@@ -1,0 +1,152 @@
+"""GPU parity: colour conversions, inRange, thresholds, LUT -- CUDA kernels through the C ABI
+against the reference's own cv2 calls (oracle/cv_ops.py).  Bit-exact unless a tolerance is stated."""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import cv_ops, synth
+
+pytestmark = pytest.mark.gpu
+
+CODES = [("bgr2hsv", cv2.COLOR_BGR2HSV), ("bgr2lab", cv2.COLOR_BGR2LAB), ("bgr2ycrcb", cv2.COLOR_BGR2YCrCb),
+         ("bgr2gray", cv2.COLOR_BGR2GRAY)]
+
+
+@pytest.fixture(scope="module")
+def all_colors():
+    return synth.all_colors_image()
+
+
+@pytest.mark.parametrize("name,cvc", CODES)
+def test_cvt_all_2_24_colours(ctx, all_colors, name, cvc):
+    d = ctx.upload(all_colors)
+    got = ctx.download(ctx.cvt_color(d, name))
+    assert np.array_equal(got, cv2.cvtColor(all_colors, cvc))
+
+
+@pytest.mark.parametrize("name,cvc", CODES[:3])
+def test_cvt_split_planes(ctx, name, cvc):
+    img = synth.gen_underwater(242, 368, 3)
+    conv, planes = ctx.cvt_color(ctx.upload(img), name, split=True)
+    ref = cv2.cvtColor(img, cvc)
+    assert np.array_equal(ctx.download(conv), ref)
+    for k, p in enumerate(planes):
+        assert np.array_equal(ctx.download(p), ref[..., k])
+
+
+@pytest.mark.parametrize("width", [4096, 100, 63, 33])
+def test_hsv2bgr_every_hsv_and_tail_rule(ctx, width):
+    hh, ss, vv = np.meshgrid(np.arange(180), np.arange(256), np.arange(256), indexing="ij")
+    flat = np.stack([hh, ss, vv], -1).astype(np.uint8).reshape(-1, 3)
+    n = (flat.shape[0] // width) * width
+    im = np.ascontiguousarray(flat[:n].reshape(-1, width, 3))
+    got = ctx.download(ctx.cvt_color(ctx.upload(im), "hsv2bgr"))
+    assert np.array_equal(got, cv2.cvtColor(im, cv2.COLOR_HSV2BGR))
+
+
+def test_hls_within_stated_tolerance(ctx, all_colors):
+    """P1 conversion.  Tolerance: L and S exact, |dH| <= 1 on at most 8 of 2^24 colours."""
+    got = ctx.download(ctx.cvt_color(ctx.upload(all_colors), "bgr2hls")).astype(np.int16)
+    ref = cv2.cvtColor(all_colors, cv2.COLOR_BGR2HLS).astype(np.int16)
+    d = np.abs(got - ref)
+    assert d[..., 1].max() == 0 and d[..., 2].max() == 0
+    assert d[..., 0].max() <= 1 and int((d[..., 0] > 0).sum()) <= 8
+
+
+@pytest.mark.parametrize("shape", [(479, 641), (1, 1), (3, 5), (17, 16), (1243, 2209)])
+@pytest.mark.parametrize("name,cvc", CODES)
+def test_cvt_odd_shapes(ctx, shape, name, cvc):
+    img = synth.gen_random_bgr(shape[0], shape[1], 11)
+    assert np.array_equal(ctx.download(ctx.cvt_color(ctx.upload(img), name)), cv2.cvtColor(img, cvc))
+
+
+def test_cvt_batch_and_misaligned_views(ctx):
+    batch = np.stack([synth.gen_random_bgr(37, 53, s) for s in range(5)])
+    d = ctx.upload(batch)
+    got = ctx.download(ctx.cvt_color(d, "bgr2lab"))
+    for i in range(5):
+        assert np.array_equal(got[i], cv2.cvtColor(batch[i], cv2.COLOR_BGR2LAB))
+    # frame 1 of this batch starts at an odd byte offset: exercises the scalar kernels
+    one = d[1]
+    assert one.data_ptr() % 16 != 0
+    assert np.array_equal(ctx.download(ctx.cvt_color(one.contiguous(), "bgr2hsv")), cv2.cvtColor(batch[1], cv2.COLOR_BGR2HSV))
+
+
+def test_gray2bgr_and_bgr2rgb(ctx):
+    img = synth.gen_random_bgr(40, 72, 2)
+    g = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+    assert np.array_equal(ctx.download(ctx.cvt_color(ctx.upload(g), "gray2bgr")), cv2.cvtColor(g, cv2.COLOR_GRAY2BGR))
+    assert np.array_equal(ctx.download(ctx.cvt_color(ctx.upload(img), "bgr2rgb")), img[..., ::-1])
+
+
+def test_mirror_of_utils_color(ctx):
+    """Same call shapes as utils/color.py: (converted, [planes])."""
+    from cuauv_vision_pipeline_b200 import color
+    img = synth.gen_underwater(120, 160, 8)
+    for fn, name in ((color.bgr_to_lab, "bgr2lab"), (color.bgr_to_hsv, "bgr2hsv"), (color.bgr_to_ycrcb, "bgr2ycrcb")):
+        conv, planes = fn(img)
+        rconv, rplanes = cv_ops.convert(img, name)
+        assert np.array_equal(conv, rconv) and len(planes) == 3
+        assert all(np.array_equal(a, b) for a, b in zip(planes, rplanes))
+    gray, _ = color.bgr_to_gray(img)
+    assert np.array_equal(gray, cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    hsv = cv2.cvtColor(img, cv2.COLOR_BGR2HSV)
+    assert np.array_equal(color.hsv_to_bgr(hsv)[0], cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR))
+    lab_a = rplanes[1] if False else cv_ops.convert(img, "bgr2lab")[1][1]
+    assert np.array_equal(color.range_threshold(lab_a, 120, 140), cv2.inRange(lab_a, 120, 140))
+
+
+@pytest.mark.parametrize("shape", [(1080, 1920), (479, 641), (5, 7)])
+def test_in_range_three_channel(ctx, shape):
+    img = synth.gen_underwater(shape[0], shape[1], 4)
+    hsv = cv2.cvtColor(img, cv2.COLOR_BGR2HSV)
+    lo, hi = np.array([10, 20, 60]), np.array([30, 100, 255])        # modules/bins.py:14-15
+    assert np.array_equal(ctx.download(ctx.in_range(ctx.upload(hsv), lo, hi)), cv2.inRange(hsv, lo, hi))
+    # fused convert + inRange
+    from cuauv_vision_pipeline_b200.runtime import ffi, lib, check, _u8ptr
+    d = ctx.upload(img)
+    m = ctx.empty(shape)
+    lo8, hi8 = lo.astype(np.uint8), hi.astype(np.uint8)
+    check(lib.bv_cvt_in_range(ctx.handle, _u8ptr(d), _u8ptr(m), 1, shape[0], shape[1], lib.BV_BGR2HSV,
+                              ffi.from_buffer("uint8_t[]", lo8), ffi.from_buffer("uint8_t[]", hi8)))
+    assert np.array_equal(ctx.download(m), cv2.inRange(hsv, lo, hi))
+
+
+def test_in_range_single_channel_and_edge_bounds(ctx):
+    img = synth.gen_random_bgr(123, 77, 9)[..., 0].copy()
+    d = ctx.upload(img)
+    for lo, hi in ((0, 255), (100, 100), (200, 50), (0, 0), (255, 255), (-5, 300), (256, 300)):
+        assert np.array_equal(ctx.download(ctx.in_range(d, lo, hi)), cv2.inRange(img, lo, hi)), (lo, hi)
+
+
+@pytest.mark.parametrize("kind,cvt", [("binary", cv2.THRESH_BINARY), ("binary_inv", cv2.THRESH_BINARY_INV),
+                                      ("trunc", cv2.THRESH_TRUNC), ("tozero", cv2.THRESH_TOZERO),
+                                      ("tozero_inv", cv2.THRESH_TOZERO_INV)])
+def test_thresholds(ctx, kind, cvt):
+    img = synth.gen_random_bgr(97, 131, 1)[..., 1].copy()
+    d = ctx.upload(img)
+    for t in (0, 1, 127, 128, 254, 255):
+        mv = 255 if kind.startswith("binary") else 0
+        assert np.array_equal(ctx.download(ctx.threshold(d, t, mv, kind)), cv2.threshold(img, t, mv, cvt)[1]), t
+
+
+def test_threshold_mirrors(ctx):
+    from cuauv_vision_pipeline_b200 import color
+    img = synth.gen_random_bgr(64, 64, 3)[..., 2].copy()
+    assert np.array_equal(color.binary_threshold(img, 99), cv_ops.binary_threshold(img, 99))
+    assert np.array_equal(color.binary_threshold_inv(img, 99), cv_ops.binary_threshold_inv(img, 99))
+    assert np.array_equal(color.max_threshold(img, 99), cv_ops.max_threshold(img, 99))
+    assert np.array_equal(color.above_threshold(img, 99), cv_ops.above_threshold(img, 99))
+    assert np.array_equal(color.below_threshold(img, 99), cv_ops.below_threshold(img, 99))
+
+
+@pytest.mark.parametrize("shape", [(242, 368), (479, 641)])
+def test_apply_lut_carries_preprocessor_point_ops(ctx, shape):
+    from cuauv_vision_pipeline_b200.preprocessor import point_lut
+    img = synth.gen_random_bgr(shape[0], shape[1], 6)
+    ref = cv_ops.brightness(cv_ops.contrast(cv_ops.channel_bias(img, 2, 25), 1.7), -40)
+    got = ctx.download(ctx.apply_lut(ctx.upload(img), point_lut(25, 0, 0, 1.7, -40)))
+    assert np.array_equal(got, ref)
+    one = img[..., 0].copy()
+    lut1 = np.arange(255, -1, -1, dtype=np.uint8)
+    assert np.array_equal(ctx.download(ctx.apply_lut(ctx.upload(one), lut1)), lut1[one])
