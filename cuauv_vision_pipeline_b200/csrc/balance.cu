@@ -3,14 +3,15 @@
 // branch (702-774) and tiled equalisation (horizontal/vertical_blocks > 1).
 //
 // The reference makes ~14 full passes over split planes on the CPU.  Here the whole algorithm is
-// three streaming passes over the interleaved frame plus two tiny per-frame statistics kernels:
+// three streaming passes over the interleaved frame; the per-frame statistics run inside the last
+// block of passes 1 and 2 ("last block done" ticket), so a frame costs three launches:
 //
 //   pass 1  hist_bgr    256-bin histograms of B, G, R                      (reads 3 B/px)
-//   stats1  percentile bounds (112-142), exact clipped means from the histogram (426-428),
+//   stats1  (last block of pass 1) percentile bounds (112-142), exact clipped means from the histogram (426-428),
 //           dominant channel + gains in double (480-544), optional RGB contrast stretch
 //           (546-645) -> ONE composed 256-entry table per channel
 //   pass 2  hist_sv     table -> BGR2HSV -> histograms of S and V          (re-reads 3 B/px, L2)
-//   stats2  S/V percentile bounds (671-681) -> stretch tables (683-686)
+//   stats2  (last block of pass 2) S/V percentile bounds (671-681) -> stretch tables (683-686)
 //   pass 3  final       table -> BGR2HSV -> S/V tables -> HSV2BGR -> [convert -> inRange]
 //                       writes balanced BGR and/or converted image and/or mask
 //
@@ -28,14 +29,199 @@ namespace bv {
 constexpr int kBalThreads = 256;
 constexpr int kBalWarps = kBalThreads / 32;
 
+// constrain(val, 0, 255) of color_balance.cpp:13-23: clamp in double, truncate.  NaN (0 * inf when
+// a channel mean is 0) is undefined behaviour in the reference; defined here as 0.
+__device__ __forceinline__ int constrain255(double v) {
+    if (v < 0.0) return 0;
+    if (v > 255.0) return 255;
+    if (v != v) return 0;
+    return (int)v;
+}
+
+// `(unsigned char)double` as the compiled reference does it on x86-64 (truncate to int, keep the
+// low byte); out-of-range input is undefined behaviour in the reference (634-640).
+__device__ __forceinline__ int uchar_cast(double v) {
+    if (v != v || v >= 2147483648.0 || v <= -2147483649.0) return 0;
+    return ((int)v) & 0xFF;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Block-wide (256 threads) statistics of one finished 256-bin histogram; thread t owns bin t.
+//   lo = first bin i with  sum_{j<=i} cnt[j] > low_bound     (percentile_min_max, 128-136)
+//   hi = last  bin i with  sum_{j>=i} cnt[j] > high_bound    (137-145)
+// which is exactly what the reference's subtract-as-you-go loops compute; with both bounds 0 they
+// are the first / last non-empty bins (cv::minMaxLoc, 421-423).  Also the exact sum of the clipped
+// channel, sum_i clamp(i, lo, hi) * cnt[i]  (the numerator of cv::mean, 426-428).
+// ----------------------------------------------------------------------------------------------
+struct StatScratch {
+    unsigned long long warp_sum[kBalWarps];
+    uint32_t warp_cnt[kBalWarps];
+};
+
+__device__ void hist_stats_block(uint32_t c, size_t npx, long long low_bound, long long high_bound, StatScratch &sc,
+                                 int &lo, int &hi, unsigned long long &clipped_sum) {
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    __syncthreads();  // protects sc from the previous call
+    if (lane == 31) sc.warp_cnt[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < kBalWarps; ++w)
+        if (w < wid) before += sc.warp_cnt[w];
+    const long long prefix = (long long)before + incl;          // inclusive prefix sum
+    const long long suffix = (long long)npx - prefix + c;       // inclusive suffix sum
+    lo = __syncthreads_count(prefix <= low_bound);
+    hi = __syncthreads_count(suffix > high_bound) - 1;
+    if (lo > 255) lo = 255;
+    if (hi < 0) hi = 0;
+    const int cl = t < lo ? lo : (t > hi ? hi : t);
+    unsigned long long v = (unsigned long long)cl * c;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+    if (lane == 0) sc.warp_sum[wid] = v;
+    __syncthreads();
+    unsigned long long tot = 0;
+#pragma unroll
+    for (int w = 0; w < kBalWarps; ++w) tot += sc.warp_sum[w];
+    clipped_sum = tot;
+}
+
+// float32 products truncated to int, exactly as color_balance.cpp:113-114
+__device__ __forceinline__ void percentile_limits(size_t n, long long &low_bound, long long &high_bound) {
+    low_bound = (int)__fmul_rn(0.002f, (float)n);
+    high_bound = (int)(n - (size_t)(int)__fmul_rn(0.998f, (float)n));
+}
+
+// Run by the LAST block of a frame's pass 1: bounds, exact means, gains, composed tables.
+__device__ void stats_bgr_block(BalFrame &F, size_t npx, const bv_balance_params &prm,
+                                const double *__restrict__ pow_quarter, StatScratch &sc) {
+    __shared__ int s_lo[3], s_hi[3], s_dom;
+    __shared__ double s_avg[3], s_gain[3], s_ratio[3];
+    const int t = threadIdx.x;
+    long long lb = 0, hb = 0;
+    if (prm.rgb_extrema_clipping) percentile_limits(npx, lb, hb);
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t cnt = __ldcg(&F.hist_bgr[c][t]);  // written by other blocks' atomics: read at L2
+        int lo, hi;
+        unsigned long long sum;
+        hist_stats_block(cnt, npx, lb, hb, sc, lo, hi, sum);
+        if (t == 0) {
+            s_lo[c] = lo;
+            s_hi[c] = hi;
+            s_avg[c] = (double)sum / (double)npx;
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        const double b = s_avg[0], g = s_avg[1], r = s_avg[2];
+        int dom;
+        // 480 / 501 / 522: red if strictly largest, else green if strictly largest, else blue
+        if (r > g && r > b) dom = 2;
+        else if (g > r && g > b) dom = 1;
+        else dom = 0;
+        for (int c = 0; c < 3; ++c) s_gain[c] = (c == dom) ? 1.0 : s_avg[dom] / s_avg[c];
+        s_dom = dom;
+        F.stats.dominant = dom;
+        for (int c = 0; c < 3; ++c) {
+            F.stats.bgr_min[c] = s_lo[c];
+            F.stats.bgr_max[c] = s_hi[c];
+            F.stats.bgr_avg[c] = s_avg[c];
+        }
+        F.stats.s_min = F.stats.v_min = 0;
+        F.stats.s_max = F.stats.v_max = 255;
+        F.stats.degenerate = 0;
+        if (prm.rgb_contrast_correct) {
+            // 560-627: order channels by the (pre-equalisation) means
+            int mx, md, mn;
+            if (r > g) {
+                if (r > b) { mx = 2; if (g > b) { md = 1; mn = 0; } else { md = 0; mn = 1; } }
+                else { mx = 0; md = 2; mn = 1; }
+            } else {
+                if (g > b) { mx = 1; if (r > b) { md = 2; mn = 0; } else { md = 0; mn = 2; } }
+                else { mx = 0; md = 1; mn = 2; }
+            }
+            const double desired_max = (double)((s_hi[mn] + s_hi[md] + s_hi[mx]) / 3);   // 629: int division
+            s_ratio[mn] = (desired_max - s_lo[mn]) / (double)(s_hi[mn] - s_lo[mn]);
+            s_ratio[md] = (desired_max - 0.0) / (double)(s_hi[md] - s_lo[md]);
+            s_ratio[mx] = ((double)s_hi[mx] - 0.0) / (double)(s_hi[mx] - s_lo[mx]);
+        }
+    }
+    __syncthreads();
+    // every thread builds entry t of the three composed tables
+    for (int c = 0; c < 3; ++c) {
+        int x = t < s_lo[c] ? s_lo[c] : (t > s_hi[c] ? s_hi[c] : t);                 // clip_channel, 25-45
+        if (prm.equalize_rgb && c != s_dom) {
+            const double xd = (double)x;
+            if (prm.adaptive_cast_correction)                                        // 489-491
+                x = constrain255(xd * (pow_quarter[x] * (s_gain[c] - 1.) + 1.));
+            else                                                                     // 494-495
+                x = constrain255(xd * s_gain[c]);
+        }
+        if (prm.rgb_contrast_correct) x = uchar_cast((double)(x - s_lo[c]) * s_ratio[c]);  // 634-640
+        F.lut_bgr[c][t] = (uint8_t)x;
+    }
+}
+
+// Run by the LAST block of a frame's pass 2: S/V percentile bounds and stretch tables (671-686).
+__device__ void stats_sv_block(BalFrame &F, size_t npx, StatScratch &sc) {
+    __shared__ int lo[2], hi[2];
+    const int t = threadIdx.x;
+    long long lb, hb;
+    percentile_limits(npx, lb, hb);
+    for (int c = 0; c < 2; ++c) {
+        const uint32_t cnt = __ldcg(&F.hist_sv[c][t]);
+        int l, h;
+        unsigned long long sum;
+        hist_stats_block(cnt, npx, lb, hb, sc, l, h, sum);
+        if (t == 0) {
+            lo[c] = l;
+            hi[c] = h;
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        F.stats.s_min = lo[0];
+        F.stats.s_max = hi[0];
+        F.stats.v_min = lo[1];
+        F.stats.v_max = hi[1];
+        F.stats.degenerate = (lo[0] == hi[0] || lo[1] == hi[1]) ? 1 : 0;
+    }
+    for (int c = 0; c < 2; ++c) {
+        const int x = t < lo[c] ? lo[c] : (t > hi[c] ? hi[c] : t);
+        // int32, C division.  The reference divides by zero (SIGFPE) when hi == lo; defined as 0 here.
+        const int d = hi[c] - lo[c];
+        F.lut_sv[c][t] = (uint8_t)(d ? ((x - lo[c]) * 255) / d : 0);
+    }
+}
+
+// "last block done": every block of a frame calls this after merging its histogram into HBM; the
+// block that draws the final ticket sees all merges (fence + atomic) and does the statistics.
+__device__ __forceinline__ bool last_block_of_frame(uint32_t *ticket) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    return is_last;
+}
+
 // ----------------------------------------------------------------------------------------------
 // pass 1: BGR histograms.  One private 3x256 histogram per warp in shared memory, merged into
-// the frame's global histogram with one atomic per non-empty bin per block.
+// the frame's histogram in HBM with one atomic per non-empty bin per block; the last block of a
+// frame then computes the statistics and tables (no separate launch).
 // ----------------------------------------------------------------------------------------------
 template <bool VEC>
 __global__ void __launch_bounds__(kBalThreads) hist_bgr_kernel(const uint8_t *__restrict__ src, BalFrame *__restrict__ st,
-                                                               size_t npx) {
+                                                               size_t npx, bv_balance_params prm,
+                                                               const double *__restrict__ pow_quarter) {
     __shared__ uint32_t h[kBalWarps][3][256];
+    __shared__ StatScratch sc;
     for (int i = threadIdx.x; i < kBalWarps * 768; i += blockDim.x) (&h[0][0][0])[i] = 0;
     __syncthreads();
     const int frame = blockIdx.y;
@@ -61,141 +247,11 @@ __global__ void __launch_bounds__(kBalThreads) hist_bgr_kernel(const uint8_t *__
         for (int w = 0; w < kBalWarps; ++w) s += (&h[w][0][0])[i];
         if (s) atomicAdd(&st[frame].hist_bgr[0][0] + i, s);
     }
-}
-
-// percentile_min_max (color_balance.cpp:112-142) on a finished histogram
-__device__ void percentile_bounds(const uint32_t *cnt, size_t n, int &lo, int &hi) {
-    // float32 products truncated to int, exactly as lines 113-114
-    int low_bound = (int)__fmul_rn(0.002f, (float)n);
-    int high_bound = (int)(n - (size_t)(int)__fmul_rn(0.998f, (float)n));
-    lo = 0;
-    hi = 255;
-    for (int i = 0; i < 256; ++i) {
-        if (low_bound < (int)cnt[i]) {
-            lo = i;
-            break;
-        }
-        low_bound -= (int)cnt[i];
-    }
-    for (int i = 255; i >= 0; --i) {
-        if (high_bound < (int)cnt[i]) {
-            hi = i;
-            break;
-        }
-        high_bound -= (int)cnt[i];
-    }
-}
-
-__device__ void extrema_bounds(const uint32_t *cnt, int &lo, int &hi) {  // cv::minMaxLoc, 421-423
-    lo = 0;
-    hi = 255;
-    for (int i = 0; i < 256; ++i)
-        if (cnt[i]) {
-            lo = i;
-            break;
-        }
-    for (int i = 255; i >= 0; --i)
-        if (cnt[i]) {
-            hi = i;
-            break;
-        }
-}
-
-// constrain(val, 0, 255) of color_balance.cpp:13-23: clamp in double, truncate.  NaN (0 * inf when
-// a channel mean is 0) is undefined behaviour in the reference; defined here as 0.
-__device__ __forceinline__ int constrain255(double v) {
-    if (v < 0.0) return 0;
-    if (v > 255.0) return 255;
-    if (v != v) return 0;
-    return (int)v;
-}
-
-// `(unsigned char)double` as the compiled reference does it on x86-64 (truncate to int, keep the
-// low byte); out-of-range input is undefined behaviour in the reference (634-640).
-__device__ __forceinline__ int uchar_cast(double v) {
-    if (v != v || v >= 2147483648.0 || v <= -2147483649.0) return 0;
-    return ((int)v) & 0xFF;
+    if (last_block_of_frame(&st[frame].ticket[0])) stats_bgr_block(st[frame], npx, prm, pow_quarter, sc);
 }
 
 // ----------------------------------------------------------------------------------------------
-// stats1: one block per frame
-// ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stats_bgr_kernel(BalFrame *__restrict__ st, size_t npx, bv_balance_params prm,
-                                                        const double *__restrict__ pow_quarter) {
-    BalFrame &F = st[blockIdx.x];
-    __shared__ int s_lo[3], s_hi[3];
-    __shared__ double s_avg[3], s_gain[3];
-    __shared__ double s_ratio[3];      // per channel ratio for the rgb contrast stretch
-    __shared__ int s_cc_min[3];
-    const int t = threadIdx.x;
-    if (t < 3) {  // channel t (0=B 1=G 2=R); the three channels are independent
-        int lo, hi;
-        if (prm.rgb_extrema_clipping)
-            percentile_bounds(F.hist_bgr[t], npx, lo, hi);
-        else
-            extrema_bounds(F.hist_bgr[t], lo, hi);
-        unsigned long long sum = 0;  // exact sum of the clipped channel == cv::mean numerator
-        for (int i = 0; i < 256; ++i) {
-            const int c = i < lo ? lo : (i > hi ? hi : i);
-            sum += (unsigned long long)c * F.hist_bgr[t][i];
-        }
-        s_lo[t] = lo;
-        s_hi[t] = hi;
-        s_avg[t] = (double)sum / (double)npx;
-    }
-    __syncthreads();
-    if (t == 0) {
-        const double b = s_avg[0], g = s_avg[1], r = s_avg[2];
-        int dom;
-        // 480 / 501 / 522: red if strictly largest, else green if strictly largest, else blue
-        if (r > g && r > b) dom = 2;
-        else if (g > r && g > b) dom = 1;
-        else dom = 0;
-        for (int c = 0; c < 3; ++c) s_gain[c] = (c == dom) ? 1.0 : s_avg[dom] / s_avg[c];
-        F.stats.dominant = dom;
-        for (int c = 0; c < 3; ++c) {
-            F.stats.bgr_min[c] = s_lo[c];
-            F.stats.bgr_max[c] = s_hi[c];
-            F.stats.bgr_avg[c] = s_avg[c];
-        }
-        F.stats.s_min = F.stats.v_min = 0;
-        F.stats.s_max = F.stats.v_max = 255;
-        F.stats.degenerate = 0;
-        if (prm.rgb_contrast_correct) {
-            // 560-627: order channels by the (pre-equalisation) means
-            int mx, md, mn;
-            if (r > g) {
-                if (r > b) { mx = 2; if (g > b) { md = 1; mn = 0; } else { md = 0; mn = 1; } }
-                else { mx = 0; md = 2; mn = 1; }
-            } else {
-                if (g > b) { mx = 1; if (r > b) { md = 2; mn = 0; } else { md = 0; mn = 2; } }
-                else { mx = 0; md = 1; mn = 2; }
-            }
-            const double desired_max = (double)((s_hi[mn] + s_hi[md] + s_hi[mx]) / 3);   // 629: int division
-            s_ratio[mn] = (desired_max - s_lo[mn]) / (double)(s_hi[mn] - s_lo[mn]);
-            s_ratio[md] = (desired_max - 0.0) / (double)(s_hi[md] - s_lo[md]);
-            s_ratio[mx] = ((double)s_hi[mx] - 0.0) / (double)(s_hi[mx] - s_lo[mx]);
-            for (int c = 0; c < 3; ++c) s_cc_min[c] = s_lo[c];
-        }
-    }
-    __syncthreads();
-    // every thread builds entry t of the three composed tables
-    for (int c = 0; c < 3; ++c) {
-        int x = t < s_lo[c] ? s_lo[c] : (t > s_hi[c] ? s_hi[c] : t);                 // clip_channel, 25-45
-        if (prm.equalize_rgb && c != F.stats.dominant) {
-            const double xd = (double)x;
-            if (prm.adaptive_cast_correction)                                        // 489-491
-                x = constrain255(xd * (pow_quarter[x] * (s_gain[c] - 1.) + 1.));
-            else                                                                     // 494-495
-                x = constrain255(xd * s_gain[c]);
-        }
-        if (prm.rgb_contrast_correct) x = uchar_cast((double)(x - s_cc_min[c]) * s_ratio[c]);  // 634-640
-        F.lut_bgr[c][t] = (uint8_t)x;
-    }
-}
-
-// ----------------------------------------------------------------------------------------------
-// pass 2: S and V histograms of the table-corrected frame
+// pass 2: S and V histograms of the table-corrected frame (+ statistics in the last block)
 // ----------------------------------------------------------------------------------------------
 template <bool VEC>
 __global__ void __launch_bounds__(kBalThreads) hist_sv_kernel(const uint8_t *__restrict__ src, BalFrame *__restrict__ st,
@@ -203,6 +259,7 @@ __global__ void __launch_bounds__(kBalThreads) hist_sv_kernel(const uint8_t *__r
     __shared__ uint32_t h[kBalWarps][2][256];
     __shared__ uint8_t lut[3][256];
     __shared__ int sdiv[256], hdiv[256];
+    __shared__ StatScratch sc;
     const int frame = blockIdx.y;
     for (int i = threadIdx.x; i < kBalWarps * 512; i += blockDim.x) (&h[0][0][0])[i] = 0;
     for (int i = threadIdx.x; i < 768; i += blockDim.x) (&lut[0][0])[i] = (&st[frame].lut_bgr[0][0])[i];
@@ -240,28 +297,7 @@ __global__ void __launch_bounds__(kBalThreads) hist_sv_kernel(const uint8_t *__r
         for (int w = 0; w < kBalWarps; ++w) s += (&h[w][0][0])[i];
         if (s) atomicAdd(&st[frame].hist_sv[0][0] + i, s);
     }
-}
-
-// stats2: S/V percentile bounds and stretch tables (671-686)
-__global__ void __launch_bounds__(256) stats_sv_kernel(BalFrame *__restrict__ st, size_t npx) {
-    BalFrame &F = st[blockIdx.x];
-    __shared__ int lo[2], hi[2];
-    const int t = threadIdx.x;
-    if (t < 2) percentile_bounds(F.hist_sv[t], npx, lo[t], hi[t]);
-    __syncthreads();
-    if (t == 0) {
-        F.stats.s_min = lo[0];
-        F.stats.s_max = hi[0];
-        F.stats.v_min = lo[1];
-        F.stats.v_max = hi[1];
-        F.stats.degenerate = (lo[0] == hi[0] || lo[1] == hi[1]) ? 1 : 0;
-    }
-    for (int c = 0; c < 2; ++c) {
-        const int x = t < lo[c] ? lo[c] : (t > hi[c] ? hi[c] : t);
-        // int32, C division.  The reference divides by zero (SIGFPE) when hi == lo; defined as 0 here.
-        const int d = hi[c] - lo[c];
-        F.lut_sv[c][t] = (uint8_t)(d ? ((x - lo[c]) * 255) / d : 0);
-    }
+    if (last_block_of_frame(&st[frame].ticket[1])) stats_sv_block(st[frame], npx, sc);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -275,8 +311,9 @@ struct FinalSmem {
     int sdiv[256], hdiv[256];
 };
 
+// returns the balanced pixel packed as b | g<<8 | r<<16
 template <int MODE>
-__device__ __forceinline__ void balance_px(int &b, int &g, int &r, bool vec, const FinalSmem &fs) {
+__device__ __forceinline__ uint32_t balance_px(uint32_t b, uint32_t g, uint32_t r, bool vec, const FinalSmem &fs) {
     if (MODE >= 1) {
         b = fs.lut[0][b];
         g = fs.lut[1][g];
@@ -284,10 +321,51 @@ __device__ __forceinline__ void balance_px(int &b, int &g, int &r, bool vec, con
     }
     if (MODE == 2) {
         int h, s, v;
-        bgr2hsv(b, g, r, fs.sdiv, fs.hdiv, h, s, v);
-        hsv2bgr(h, fs.lut_sv[0][s], fs.lut_sv[1][v], vec, b, g, r);
+        bgr2hsv((int)b, (int)g, (int)r, fs.sdiv, fs.hdiv, h, s, v);
+        return hsv2bgr_packed(h, fs.lut_sv[0][s], fs.lut_sv[1][v], vec);
     }
+    return b | (g << 8) | (r << 16);
 }
+
+// insert the 24-bit packed pixel J (0..15) into the 12-word output buffer
+template <int J>
+__device__ __forceinline__ void put_px(uint32_t (&w)[12], uint32_t p) {
+    constexpr int o = 3 * J, wi = o >> 2, sh = 8 * (o & 3);
+    w[wi] |= p << sh;
+    if constexpr (sh > 8) w[wi + 1] |= p >> (32 - sh);
+}
+
+// one group of 16 pixels.  TRACK_X: the group touches the row tail (width % 32 columns), where
+// cv2's scalar HSV2BGR / HLS rounding applies, or wraps to the next row.
+template <int MODE, int CODE, bool TRACK_X, int J>
+struct GroupBody {
+    static __device__ __forceinline__ void run(const Px16 &in, int x, int width, int vec_end, const FinalSmem &fs,
+                                               const SmemTabs &tabs, const Bounds3 &bd, Px16 &ob, Px16 &oc, uint32_t (&q)[4],
+                                               uint32_t &bits) {
+        constexpr bool kOne = CvtTraits<CODE>::kOneChannel;
+        const bool vec = TRACK_X ? (x < vec_end) : true;
+        const uint32_t p = balance_px<MODE>(BV_GETB(in.w, 3 * J), BV_GETB(in.w, 3 * J + 1), BV_GETB(in.w, 3 * J + 2), vec, fs);
+        put_px<J>(ob.w, p);
+        int o0, o1, o2;
+        convert_px<CODE>((int)(p & 0xFF), (int)((p >> 8) & 0xFF), (int)(p >> 16), vec, tabs, o0, o1, o2);
+        if (kOne) {
+            BV_PUTB(q, J, o0);
+        } else {
+            const uint32_t pc = (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16);
+            put_px<J>(oc.w, pc);
+        }
+        if (in_range_px<CODE>(o0, o1, o2, bd)) bits |= 1u << J;
+        if (TRACK_X) {
+            if (++x == width) x = 0;
+        }
+        GroupBody<MODE, CODE, TRACK_X, J + 1>::run(in, x, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
+    }
+};
+template <int MODE, int CODE, bool TRACK_X>
+struct GroupBody<MODE, CODE, TRACK_X, 16> {
+    static __device__ __forceinline__ void run(const Px16 &, int, int, int, const FinalSmem &, const SmemTabs &,
+                                               const Bounds3 &, Px16 &, Px16 &, uint32_t (&)[4], uint32_t &) {}
+};
 
 template <int MODE, int CODE, bool VEC>
 __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__restrict__ src, const BalFrame *__restrict__ st,
@@ -318,45 +396,28 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
         bd.lo[k] = out.lo[k];
         bd.hi[k] = out.hi[k];
     }
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t ngroups = VEC ? npx / 16 : 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t ngroups = VEC ? (uint32_t)(npx / 16) : 0u;  // npx < 2^31 (checked on the host)
+    const uint32_t height = (uint32_t)(npx / (size_t)width);
     const int wp2 = ((width + 31) / 32) * 2;  // uint16 units per bit-packed row
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
         Px16 in;
         load_px16<false>(f, g, in);
-        const size_t p0 = g * 16;
-        const int y = (int)(p0 / (size_t)width);
-        const int x0 = (int)(p0 - (size_t)y * width);
-        int x = x0;
+        uint32_t y = 0, x0 = 0;
+        if (kNeedX || out.mask_bits) {
+            const uint32_t p0 = g * 16u;
+            y = p0 / (uint32_t)width;
+            x0 = p0 - y * (uint32_t)width;
+        }
         Px16 ob, oc;
         uint32_t q[4] = {0, 0, 0, 0};
         uint32_t bits = 0;
 #pragma unroll
         for (int k = 0; k < 12; ++k) ob.w[k] = oc.w[k] = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            int b = BV_GETB(in.w, 3 * j), gg = BV_GETB(in.w, 3 * j + 1), r = BV_GETB(in.w, 3 * j + 2);
-            const bool vec = x < vec_end;
-            balance_px<MODE>(b, gg, r, vec, fs);
-            if (kNeedX) {
-                if (++x == width) x = 0;
-            }
-            BV_PUTB(ob.w, 3 * j, b);
-            BV_PUTB(ob.w, 3 * j + 1, gg);
-            BV_PUTB(ob.w, 3 * j + 2, r);
-            {
-                int o0, o1, o2;
-                convert_px<CODE>(b, gg, r, vec, tabs, o0, o1, o2);
-                if (kOne) {
-                    BV_PUTB(q, j, o0);
-                } else {
-                    BV_PUTB(oc.w, 3 * j, o0);
-                    BV_PUTB(oc.w, 3 * j + 1, o1);
-                    BV_PUTB(oc.w, 3 * j + 2, o2);
-                }
-                if (in_range_px<CODE>(o0, o1, o2, bd)) bits |= 1u << j;
-            }
-        }
+        if (kNeedX && (int)x0 + 16 > vec_end)
+            GroupBody<MODE, CODE, true, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
+        else
+            GroupBody<MODE, CODE, false, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
         if (out.balanced) store_px16(out.balanced + foff * 3, g, ob);
         if (out.converted) {
             if (kOne)
@@ -376,35 +437,33 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
             st_stream(reinterpret_cast<uint4 *>(out.mask + foff) + g, make_uint4(m[0], m[1], m[2], m[3]));
         }
         if (out.mask_bits)  // requires width % 16 == 0: a group never straddles rows
-            out.mask_bits[(size_t)frame * wp2 * (npx / (size_t)width) + (size_t)y * wp2 + (x0 >> 4)] = (uint16_t)bits;
+            out.mask_bits[((size_t)frame * height + y) * wp2 + (x0 >> 4)] = (uint16_t)bits;
     }
     // scalar path: trailing pixels of each frame, or everything for unaligned / odd-sized frames
-    for (size_t p = ngroups * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += stride) {
+    for (size_t p = (size_t)ngroups * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += stride) {
         const int x = (int)(p % (size_t)width);
-        int b = f[3 * p], gg = f[3 * p + 1], r = f[3 * p + 2];
         const bool vec = x < vec_end;
-        balance_px<MODE>(b, gg, r, vec, fs);
+        const uint32_t px = balance_px<MODE>(f[3 * p], f[3 * p + 1], f[3 * p + 2], vec, fs);
+        const int b = (int)(px & 0xFF), gg = (int)((px >> 8) & 0xFF), r = (int)(px >> 16);
         if (out.balanced) {
             uint8_t *o = out.balanced + (foff + p) * 3;
             o[0] = (uint8_t)b;
             o[1] = (uint8_t)gg;
             o[2] = (uint8_t)r;
         }
-        {
-            int o0, o1, o2;
-            convert_px<CODE>(b, gg, r, vec, tabs, o0, o1, o2);
-            if (out.converted) {
-                if (kOne) {
-                    out.converted[foff + p] = (uint8_t)o0;
-                } else {
-                    uint8_t *o = out.converted + (foff + p) * 3;
-                    o[0] = (uint8_t)o0;
-                    o[1] = (uint8_t)o1;
-                    o[2] = (uint8_t)o2;
-                }
+        int o0, o1, o2;
+        convert_px<CODE>(b, gg, r, vec, tabs, o0, o1, o2);
+        if (out.converted) {
+            if (kOne) {
+                out.converted[foff + p] = (uint8_t)o0;
+            } else {
+                uint8_t *o = out.converted + (foff + p) * 3;
+                o[0] = (uint8_t)o0;
+                o[1] = (uint8_t)o1;
+                o[2] = (uint8_t)o2;
             }
-            if (out.mask) out.mask[foff + p] = in_range_px<CODE>(o0, o1, o2, bd) ? 255 : 0;
         }
+        if (out.mask) out.mask[foff + p] = in_range_px<CODE>(o0, o1, o2, bd) ? 255 : 0;
     }
 }
 
@@ -508,16 +567,14 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
         dim3 grid(bpf, nf);
         if (vec)
-            BV_LAUNCH(ctx, hist_bgr_kernel<true>, grid, kBalThreads, 0, csrc, cst, npx);
+            BV_LAUNCH(ctx, hist_bgr_kernel<true>, grid, kBalThreads, 0, csrc, cst, npx, prm, ctx->d_pow_quarter);
         else
-            BV_LAUNCH(ctx, hist_bgr_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx);
-        BV_LAUNCH(ctx, stats_bgr_kernel, nf, 256, 0, cst, npx, prm, ctx->d_pow_quarter);
+            BV_LAUNCH(ctx, hist_bgr_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx, prm, ctx->d_pow_quarter);
         if (prm.hsv_contrast_correct) {
             if (vec)
                 BV_LAUNCH(ctx, hist_sv_kernel<true>, grid, kBalThreads, 0, csrc, cst, npx);
             else
                 BV_LAUNCH(ctx, hist_sv_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx);
-            BV_LAUNCH(ctx, stats_sv_kernel, nf, 256, 0, cst, npx);
         }
         BalOutputs co = out;
         if (co.balanced) co.balanced += (size_t)f0 * npx * 3;

@@ -10,6 +10,7 @@ struct BalFrame {
     uint32_t hist_sv[2][256];   // pass 2: histograms of S, V after the BGR tables
     uint8_t lut_bgr[3][256];    // clip -> equalise -> rgb-contrast, composed per channel
     uint8_t lut_sv[2][256];     // clip -> stretch for S and V
+    uint32_t ticket[2];         // blocks of pass 1 / pass 2 that have merged their histograms
     bv_balance_stats stats;
 };
 

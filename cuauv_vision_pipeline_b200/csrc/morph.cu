@@ -3,8 +3,9 @@
 // and modules/preprocessor.py:120-129.
 //
 // Semantics (cv2, verified in SURVEY.md A.5): erode = min over the SE support with out-of-image
-// taps ignored (+inf border), dilate = max with the SE reflected about the anchor and out-of-image
-// taps ignored (0 border); anchor = centre; OPEN/CLOSE/GRADIENT with `iterations=n` apply n
+// taps ignored (+inf border), dilate = max over the same taps dst(x,y) = max src(x+i-ax, y+j-ay)
+// (cv2 4.13.0 does not mirror the SE: probed with even and asymmetric kernels) with out-of-image
+// taps ignored (0 border); anchor = centre (kw/2, kh/2); OPEN/CLOSE/GRADIENT with `iterations=n` apply n
 // erosions then n dilations (resp. the reverse, resp. the difference).
 //
 // Two implementations:
@@ -161,11 +162,16 @@ static int morph_bits_basic(bv_ctx *ctx, const uint32_t *src, uint32_t *dst, uin
 
 int morph_bits_rect(bv_ctx *ctx, uint32_t *bits, uint32_t *tmp, uint32_t *tmp2, int batch, int height, int width, int op,
                     int kw, int kh, int iterations) {
-    if (iterations < 1 || (kw == 1 && kh == 1)) return BV_OK;
+    if (iterations < 1) return BV_OK;
+    if (kw == 1 && kh == 1) {  // identity element: dilate == erode == input, so the gradient is empty
+        if (op == BV_MORPH_GRADIENT)
+            BV_CUDA(cudaMemsetAsync(bits, 0, (size_t)batch * height * words_per_row(width) * 4, ctx->stream));
+        return BV_OK;
+    }
     const int ax = kw / 2, ay = kh / 2;
-    // erode taps: x-ax .. x+(kw-1-ax); dilate uses the reflected SE
+    // taps: x-ax .. x+(kw-1-ax) for erosion and dilation alike
     const int eL = ax * iterations, eR = (kw - 1 - ax) * iterations, eU = ay * iterations, eD = (kh - 1 - ay) * iterations;
-    const int dL = eR, dR = eL, dU = eD, dD = eU;
+    const int dL = eL, dR = eR, dU = eU, dD = eD;  // cv2 applies the same taps for dilation (probed, 4.13.0)
     const size_t total = (size_t)batch * height * words_per_row(width);
     switch (op) {
         case BV_MORPH_ERODE:
@@ -254,7 +260,7 @@ static int launch_grey(bv_ctx *ctx, const uint8_t *src, uint8_t *dst, int height
 struct SeInfo {
     bool rect;            // full rectangle: separable, iterations fold into the extents
     RunList erode_runs;   // taps for erosion
-    RunList dilate_runs;  // taps for dilation (SE reflected about the anchor)
+    RunList dilate_runs;  // taps for dilation (identical: cv2 does not mirror the SE)
     int kw, kh;
 };
 
@@ -285,9 +291,9 @@ static int build_se(const uint8_t *se, int kw, int kh, SeInfo &info) {
             er.x1[er.n] = (short)(e - ax);
             er.n++;
             RunList &dr = info.dilate_runs;
-            dr.dy[dr.n] = (short)(ay - j);
-            dr.x0[dr.n] = (short)(ax - e);
-            dr.x1[dr.n] = (short)(ax - i);
+            dr.dy[dr.n] = (short)(j - ay);
+            dr.x0[dr.n] = (short)(i - ax);
+            dr.x1[dr.n] = (short)(e - ax);
             dr.n++;
             i = e + 1;
         }
@@ -307,10 +313,6 @@ static int grey_basic(bv_ctx *ctx, const uint8_t *src, uint8_t *dst, uint8_t *t1
         // separable, and n iterations of a rectangle == one rectangle with n-fold extents
         const int ax = se.kw / 2, ay = se.kh / 2;
         int L = ax * iterations, R = (se.kw - 1 - ax) * iterations, U = ay * iterations, D = (se.kh - 1 - ay) * iterations;
-        if (!erode) {
-            int t = L; L = R; R = t;
-            t = U; U = D; D = t;
-        }
         RunList h, v;
         h.n = 1;
         h.dy[0] = 0;

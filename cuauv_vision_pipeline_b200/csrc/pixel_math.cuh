@@ -75,45 +75,63 @@ BV_HD void bgr2hsv(int b, int g, int r, const int *sdiv, const int *hdiv, int &h
 // bracket is a single-rounding multiply-add; whole 32-pixel groups of a row ("vector path")
 // truncate x*255, the remaining width%32 pixels of each row round to nearest even.
 // ------------------------------------------------------------------------------------------
-BV_HD void hsv2bgr(int H, int S, int V, bool vector_path, int &b, int &g, int &r) {
+// Branch-free form.  Of the four OpenCV table values {v, v(1-s), v*fma(-s,f,1), v*fma(-s,1-f,1)}
+// a pixel only ever uses three: max = v, min = v(1-s) and ONE mid value (f in odd sectors, 1-f in
+// even ones).  The sector then merely permutes (max, mid, min) over (b, g, r), which is a single
+// byte-permute of the packed result.  For s == 0 all three collapse to v exactly (1-0 = 1,
+// fma(-0,f,1) = 1), so OpenCV's special case needs no branch.  Returns b | g<<8 | r<<16.
+BV_HD uint32_t byte_perm3(uint32_t w, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0u, sel);
+#else
+    uint32_t out = 0;
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t n = (sel >> (4 * k)) & 0xF;
+        const uint32_t byte = n < 4 ? (w >> (8 * n)) & 0xFF : 0u;
+        out |= byte << (8 * k);
+    }
+    return out;
+#endif
+}
+
+BV_HD uint32_t hsv2bgr_packed(int H, int S, int V, bool vector_path) {
     const float hscale = 6.f / 180.f;
     const float inv255 = 1.f / 255.f;
-    float h = BV_FMUL((float)H, hscale);
+    const float h = BV_FMUL((float)H, hscale);
     const float s = BV_FMUL((float)S, inv255);
     const float v = BV_FMUL((float)V, inv255);
-    float fb, fg, fr;
-    if (s == 0.f) {
-        fb = fg = fr = v;
+    int sector = (int)h;  // h >= 0: truncation == floor
+    const float f = BV_FSUB(h, (float)sector);
+    if (sector >= 6) sector -= 6;  // H >= 180 is out of contract; stay inside the table
+    const float fm = (sector & 1) ? f : BV_FSUB(1.f, f);
+    const float ymax = BV_FMUL(v, 255.f);
+    const float ymin = BV_FMUL(BV_FMUL(v, BV_FSUB(1.f, s)), 255.f);
+    const float ymid = BV_FMUL(BV_FMUL(v, BV_FMA(-s, fm, 1.f)), 255.f);
+    uint32_t imax, imid, imin;
+    if (vector_path) {  // values lie in [0, 255]: no saturation needed
+        imax = (uint32_t)BV_F2I_RZ(ymax);
+        imid = (uint32_t)BV_F2I_RZ(ymid);
+        imin = (uint32_t)BV_F2I_RZ(ymin);
     } else {
-        const float fl = BV_FLOOR(h);
-        int sector = (int)fl;
-        const float f = BV_FSUB(h, fl);
-        sector %= 6;
-        if (sector < 0) sector += 6;
-        const float t0 = v;
-        const float t1 = BV_FMUL(v, BV_FSUB(1.f, s));
-        const float t2 = BV_FMUL(v, BV_FMA(-s, f, 1.f));
-        const float t3 = BV_FMUL(v, BV_FMA(-s, BV_FSUB(1.f, f), 1.f));
-        // sector table {{1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}} as selects
-        switch (sector) {
-            case 0: fb = t1; fg = t3; fr = t0; break;
-            case 1: fb = t1; fg = t0; fr = t2; break;
-            case 2: fb = t3; fg = t0; fr = t1; break;
-            case 3: fb = t0; fg = t2; fr = t1; break;
-            case 4: fb = t0; fg = t1; fr = t3; break;
-            default: fb = t2; fg = t1; fr = t0; break;
-        }
+        imax = (uint32_t)sat_u8(BV_F2I_RN(ymax));
+        imid = (uint32_t)sat_u8(BV_F2I_RN(ymid));
+        imin = (uint32_t)sat_u8(BV_F2I_RN(ymin));
     }
-    const float yb = BV_FMUL(fb, 255.f), yg = BV_FMUL(fg, 255.f), yr = BV_FMUL(fr, 255.f);
-    if (vector_path) {
-        b = sat_u8(BV_F2I_RZ(yb));
-        g = sat_u8(BV_F2I_RZ(yg));
-        r = sat_u8(BV_F2I_RZ(yr));
-    } else {
-        b = sat_u8(BV_F2I_RN(yb));
-        g = sat_u8(BV_F2I_RN(yg));
-        r = sat_u8(BV_F2I_RN(yr));
-    }
+    const uint32_t w = imax | (imid << 8) | (imin << 16);
+    // selector nibbles (r,g,b) -> index into (max=0, mid=1, min=2), one 10-bit field per sector:
+    // s0 r=max g=mid b=min | s1 g=max r=mid b=min | s2 g=max b=mid r=min
+    // s3 b=max g=mid r=min | s4 b=max r=mid g=min | s5 r=max b=mid g=min
+    const unsigned long long kSel = 0x012ull | (0x102ull << 10) | (0x201ull << 20) | (0x210ull << 30) |
+                                    (0x120ull << 40) | (0x021ull << 50);
+    const uint32_t sel = (uint32_t)(kSel >> (10 * sector)) & 0x3FFu;
+    return byte_perm3(w, sel | 0x4000u);  // byte 3 <- zero
+}
+
+BV_HD void hsv2bgr(int H, int S, int V, bool vector_path, int &b, int &g, int &r) {
+    const uint32_t p = hsv2bgr_packed(H, S, V, vector_path);
+    b = (int)(p & 0xFF);
+    g = (int)((p >> 8) & 0xFF);
+    r = (int)(p >> 16);
 }
 
 // ------------------------------------------------------------------------------------------

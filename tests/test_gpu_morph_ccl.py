@@ -59,6 +59,33 @@ def test_ellipse_101(ctx):
     assert np.array_equal(ctx.download(ctx.morph(ctx.upload(img), "erode", se)), cv2.erode(img, se))
 
 
+def test_asymmetric_structuring_elements(ctx):
+    """cv2 applies the SE taps unmirrored for erosion and dilation alike."""
+    m = synth.mask_blobs(90, 130, 4, sigma=3.0, pct=55)
+    img = synth.gen_underwater(60, 90, 2)
+    for se in (np.array([[1, 1, 0]], np.uint8), np.array([[1, 0, 0], [1, 0, 0], [1, 1, 1]], np.uint8),
+               np.array([[0, 1], [1, 1], [0, 0], [1, 0]], np.uint8)):
+        for op in ("erode", "dilate", "open", "close", "gradient"):
+            assert np.array_equal(ctx.download(ctx.morph(ctx.upload(m), op, se)), cv2.morphologyEx(m, CV_OP[op], se)), (se, op)
+        assert np.array_equal(ctx.download(ctx.morph(ctx.upload(img), "dilate", se, iterations=2)), cv2.dilate(img, se, iterations=2))
+
+
+@pytest.mark.parametrize("kw,kh", [(4, 4), (2, 5), (6, 1), (5, 5), (3, 7), (40, 3), (1, 1)])
+@pytest.mark.parametrize("op", list(CV_OP))
+@pytest.mark.parametrize("width", [160, 173])
+def test_bit_packed_morphology_through_the_stage(ctx, kw, kh, op, width):
+    """The fused stage runs morphology on bit-packed masks (32 px per word); same semantics."""
+    img = synth.gen_underwater(131, width, 7)
+    desc = ctx.make_stage(cvt="bgr2hsv", lo=(0, 40, 60), hi=(179, 255, 255), morph=[(op, kw, kh, 1)])
+    hsv = cv2.cvtColor(img, cv2.COLOR_BGR2HSV)
+    raw = cv2.inRange(hsv, np.array([0, 40, 60]), np.array([179, 255, 255]))
+    want = cv2.morphologyEx(raw, CV_OP[op], np.ones((kh, kw), np.uint8))
+    assert np.array_equal(ctx.download(ctx.stage(desc, ctx.upload(img), want=("mask",))["mask"]), want)
+    desc2 = ctx.make_stage(cvt="bgr2hsv", lo=(0, 40, 60), hi=(179, 255, 255), morph=[(op, 3, 3, 2), ("dilate", kw, kh, 1)])
+    want2 = cv2.dilate(cv2.morphologyEx(raw, CV_OP[op], np.ones((3, 3), np.uint8), iterations=2), np.ones((kh, kw), np.uint8))
+    assert np.array_equal(ctx.download(ctx.stage(desc2, ctx.upload(img), want=("mask",))["mask"]), want2)
+
+
 def test_transform_mirrors(ctx):
     from cuauv_vision_pipeline_b200 import transform
     m = synth.mask_blobs(120, 160, 1, sigma=4.0)
