@@ -57,21 +57,30 @@ class ClockSampler:
         self.lines = []
         self.proc = None
 
-    def start(self):
+    def start(self, wait_s=5.0):
+        """Starts nvidia-smi and waits for its first sample, so that even a short timed region is
+        covered (nvidia-smi needs ~0.5 s to come up)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < wait_s:
+                time.sleep(0.02)
         except Exception:  # noqa: BLE001
             self.proc = None
+
+    def mark(self):
+        """Index of the next sample: samples[mark_a:mark_b] belong to a timed region."""
+        return len(self.lines)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, first=0, last=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -81,7 +90,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # the device-resident region can be shorter than one sampling period: widen by one sample
+        # on each side, the rest of the window (profile + end-to-end legs) is under load as well
+        lines = self.lines[max(0, first - 1):(None if last is None else last + 1)] or self.lines
+        for ln in lines:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -270,6 +282,11 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        for s in range(args.warmup):   # keep the GPU busy while the sampler came up
+            step(s)
+        ctx.sync()
+    barrier()
+    mark_a = sampler.mark()
     launches0 = ctx.launches
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -282,7 +299,6 @@ def run_ours(args):
     barrier()
     elapsed = e0.elapsed_time(e1) / 1e3
     launches = ctx.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -298,7 +314,7 @@ def run_ours(args):
     total_ms = sum(v["ms"] for v in prof.values()) or 1.0
     dom = max(prof, key=lambda k: prof[k]["ms"])
     # one launch of any pass covers one L2-sized chunk of frames
-    chunk_frames = max(1, int(os.environ.get("BV_L2_CHUNK_MB", "40")) * (1 << 20) // (H * W * 3))
+    chunk_frames = max(1, int(os.environ.get("BV_L2_CHUNK_MB", "66")) * (1 << 20) // (H * W * 3))
     chunk_frames = min(chunk_frames, BATCH)
     dom_ms = prof[dom]["ms"] / prof[dom]["launches"]
     achieved = BPP_C2 * H * W * chunk_frames / (dom_ms / 1e3) / 1e9
@@ -330,13 +346,16 @@ def run_ours(args):
         t = torch.tensor([e2e_dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
+    clocks = sampler.stop(mark_a, None) if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "device-resident timed region + per-kernel profile + end-to-end leg"
     e2e = {"value": world * BATCH * e2e_steps / e2e_dt, "unit": "frames/s",
            "h2d_bytes_per_step": BATCH * H * W * 3, "d2h_bytes_per_step": BATCH * H * W * 3,
            "api": "bv_stage_host (C ABI, pinned host buffers, blocking)", "steps": e2e_steps}
 
     if rank == 0:
         cores = os.cpu_count() or 1
-        cpu = cpu_baseline(list(ring_np[:min(32, max(8, cores))]), cores) if world == 1 else None
+        cpu = cpu_baseline(list(ring_np[:min(32, max(8, cores))]), cores) if (world == 1 and not args.no_cpu) else None
         others = side_workloads(ctx, peak_gbs) if (world == 1 and not args.no_side) else None
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -361,10 +380,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-side", action="store_true", help="skip the short measurements of the other configs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (tuning sweeps only)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

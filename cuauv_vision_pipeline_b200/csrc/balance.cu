@@ -470,6 +470,15 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    const int v = e ? atoi(e) : dflt;
+    return v > 0 ? v : dflt;
+}
+// blocks per SM of the histogram passes and of the final pass (tuning knobs)
+static int hist_blocks_per_sm() { static int v = env_int("BV_HIST_BPS", 4); return v; }
+static int final_blocks_per_sm() { static int v = env_int("BV_FINAL_BPS", 8); return v; }
+
 static bool vec_ok(const void *p, size_t npx, int batch, int bytes_per_px) {
     (void)bytes_per_px;
     return p == nullptr || (host_aligned16(p) && (npx % 16 == 0 || batch == 1));
@@ -478,7 +487,7 @@ static bool vec_ok(const void *p, size_t npx, int batch, int bytes_per_px) {
 template <int MODE, int CODE>
 static int launch_final(bv_ctx *ctx, const uint8_t *src, const BalFrame *st, int batch, size_t npx, int width,
                         const BalOutputs &out, bool vec) {
-    int bpf = (ctx->sm_count * 4 + batch - 1) / batch;
+    int bpf = (ctx->sm_count * final_blocks_per_sm() + batch - 1) / batch;
     const size_t need = (npx / 16 + kBalThreads - 1) / kBalThreads;
     if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
     dim3 grid(bpf, batch);
@@ -509,7 +518,7 @@ static size_t l2_chunk_bytes() {
     static size_t v = 0;
     if (!v) {
         const char *e = getenv("BV_L2_CHUNK_MB");
-        long mb = e ? atol(e) : 40;
+        long mb = e ? atol(e) : 66;
         if (mb < 1) mb = 1;
         v = (size_t)mb << 20;
     }
@@ -562,7 +571,7 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         const int nf = batch - f0 < chunk ? batch - f0 : chunk;
         const uint8_t *csrc = src + (size_t)f0 * npx * 3;
         BalFrame *cst = st + f0;
-        int bpf = (ctx->sm_count * 4 + nf - 1) / nf;
+        int bpf = (ctx->sm_count * hist_blocks_per_sm() + nf - 1) / nf;
         const size_t need = (npx / 16 + kBalThreads - 1) / kBalThreads;
         if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
         dim3 grid(bpf, nf);

@@ -12,6 +12,8 @@
 //
 // bv_stage_host and the legacy process_frame symbol take HOST buffers (the reference's calling
 // convention, modules/color_balance.py:93-110): upload, run, download, return when done.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "balance.cuh"
@@ -144,7 +146,12 @@ extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8
 
     // chunked three-stage pipeline: H2D (copy-in stream) -> kernels (context stream) -> D2H
     // (copy-out stream); PCIe is full duplex, so uploads of chunk k+1 overlap downloads of k-1.
-    int chunk = (int)(((size_t)32 << 20) / (npx * 3));
+    static const size_t chunk_bytes = []() {
+        const char *e = getenv("BV_HOST_CHUNK_MB");
+        long mb = e ? atol(e) : 16;
+        return (size_t)(mb < 1 ? 1 : mb) << 20;
+    }();
+    int chunk = (int)(chunk_bytes / (npx * 3));
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;
     int nchunks = (batch + chunk - 1) / chunk;
