@@ -314,7 +314,7 @@ def run_ours(args):
     total_ms = sum(v["ms"] for v in prof.values()) or 1.0
     dom = max(prof, key=lambda k: prof[k]["ms"])
     # one launch of any pass covers one L2-sized chunk of frames
-    chunk_frames = max(1, int(os.environ.get("BV_L2_CHUNK_MB", "66")) * (1 << 20) // (H * W * 3))
+    chunk_frames = max(1, int(os.environ.get("BV_L2_CHUNK_MB", "33")) * (1 << 20) // (H * W * 3))
     chunk_frames = min(chunk_frames, BATCH)
     dom_ms = prof[dom]["ms"] / prof[dom]["launches"]
     achieved = BPP_C2 * H * W * chunk_frames / (dom_ms / 1e3) / 1e9

@@ -197,6 +197,10 @@ extern "C" int bv_create(int device, bv_ctx **out) {
     for (int i = 0; ok_aux && i < BV_MAX_CHUNKS; ++i)
         ok_aux = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok_aux && i < BV_MAX_SIDE; ++i)
+        ok_aux = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    ok_aux = ok_aux && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     if (!ok_aux) {
         set_error("bv_create: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         bv_destroy(ctx);
@@ -231,6 +235,11 @@ extern "C" void bv_destroy(bv_ctx *ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    for (int i = 0; i < BV_MAX_SIDE; ++i) {
+        if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (int i = 0; i < BV_MAX_CHUNKS; ++i) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);

@@ -337,10 +337,10 @@ __device__ __forceinline__ void put_px(uint32_t (&w)[12], uint32_t p) {
 
 // one group of 16 pixels.  TRACK_X: the group touches the row tail (width % 32 columns), where
 // cv2's scalar HSV2BGR / HLS rounding applies, or wraps to the next row.
-template <int MODE, int CODE, bool TRACK_X, int J>
+template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, int J>
 struct GroupBody {
     static __device__ __forceinline__ void run(const Px16 &in, int x, int width, int vec_end, const FinalSmem &fs,
-                                               const SmemTabs &tabs, const Bounds3 &bd, Px16 &ob, Px16 &oc, uint32_t (&q)[4],
+                                               const SmemTabs &tabs, const RangeTest &bd, Px16 &ob, Px16 &oc, uint32_t (&q)[4],
                                                uint32_t &bits) {
         constexpr bool kOne = CvtTraits<CODE>::kOneChannel;
         const bool vec = TRACK_X ? (x < vec_end) : true;
@@ -354,20 +354,21 @@ struct GroupBody {
             const uint32_t pc = (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16);
             put_px<J>(oc.w, pc);
         }
-        if (in_range_px<CODE>(o0, o1, o2, bd)) bits |= 1u << J;
+        if (NEED_MASK)
+            if (in_range_px<CODE>(o0, o1, o2, bd)) bits |= 1u << J;
         if (TRACK_X) {
             if (++x == width) x = 0;
         }
-        GroupBody<MODE, CODE, TRACK_X, J + 1>::run(in, x, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
+        GroupBody<MODE, CODE, TRACK_X, NEED_MASK, J + 1>::run(in, x, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
     }
 };
-template <int MODE, int CODE, bool TRACK_X>
-struct GroupBody<MODE, CODE, TRACK_X, 16> {
+template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK>
+struct GroupBody<MODE, CODE, TRACK_X, NEED_MASK, 16> {
     static __device__ __forceinline__ void run(const Px16 &, int, int, int, const FinalSmem &, const SmemTabs &,
-                                               const Bounds3 &, Px16 &, Px16 &, uint32_t (&)[4], uint32_t &) {}
+                                               const RangeTest &, Px16 &, Px16 &, uint32_t (&)[4], uint32_t &) {}
 };
 
-template <int MODE, int CODE, bool VEC>
+template <int MODE, int CODE, bool VEC, bool NEED_MASK>
 __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__restrict__ src, const BalFrame *__restrict__ st,
                                                             size_t npx, int width, BalOutputs out,
                                                             const uint16_t *__restrict__ g_gamma,
@@ -390,12 +391,7 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
     const int vec_end = width - (width % 32);
     constexpr bool kOne = CvtTraits<CODE>::kOneChannel;
     constexpr bool kNeedX = (MODE == 2) || CvtTraits<CODE>::kNeedsX;
-    Bounds3 bd;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        bd.lo[k] = out.lo[k];
-        bd.hi[k] = out.hi[k];
-    }
+    const RangeTest bd = make_range_test(out.lo, out.hi);
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t ngroups = VEC ? (uint32_t)(npx / 16) : 0u;  // npx < 2^31 (checked on the host)
     const uint32_t height = (uint32_t)(npx / (size_t)width);
@@ -404,7 +400,7 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
         Px16 in;
         load_px16<false>(f, g, in);
         uint32_t y = 0, x0 = 0;
-        if (kNeedX || out.mask_bits) {
+        if (kNeedX || (NEED_MASK && out.mask_bits)) {
             const uint32_t p0 = g * 16u;
             y = p0 / (uint32_t)width;
             x0 = p0 - y * (uint32_t)width;
@@ -415,9 +411,9 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
 #pragma unroll
         for (int k = 0; k < 12; ++k) ob.w[k] = oc.w[k] = 0;
         if (kNeedX && (int)x0 + 16 > vec_end)
-            GroupBody<MODE, CODE, true, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
+            GroupBody<MODE, CODE, true, NEED_MASK, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
         else
-            GroupBody<MODE, CODE, false, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
+            GroupBody<MODE, CODE, false, NEED_MASK, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
         if (out.balanced) store_px16(out.balanced + foff * 3, g, ob);
         if (out.converted) {
             if (kOne)
@@ -425,7 +421,7 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
             else
                 store_px16(out.converted + foff * 3, g, oc);
         }
-        if (out.mask) {
+        if (NEED_MASK && out.mask) {
             uint32_t m[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -436,7 +432,7 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
             }
             st_stream(reinterpret_cast<uint4 *>(out.mask + foff) + g, make_uint4(m[0], m[1], m[2], m[3]));
         }
-        if (out.mask_bits)  // requires width % 16 == 0: a group never straddles rows
+        if (NEED_MASK && out.mask_bits)  // requires width % 16 == 0: a group never straddles rows
             out.mask_bits[((size_t)frame * height + y) * wp2 + (x0 >> 4)] = (uint16_t)bits;
     }
     // scalar path: trailing pixels of each frame, or everything for unaligned / odd-sized frames
@@ -476,8 +472,12 @@ static int env_int(const char *name, int dflt) {
     return v > 0 ? v : dflt;
 }
 // blocks per SM of the histogram passes and of the final pass (tuning knobs)
-static int hist_blocks_per_sm() { static int v = env_int("BV_HIST_BPS", 4); return v; }
-static int final_blocks_per_sm() { static int v = env_int("BV_FINAL_BPS", 8); return v; }
+static int hist_blocks_per_sm() { static int v = env_int("BV_HIST_BPS", 2); return v; }
+static int side_streams() {
+    static int v = env_int("BV_SIDE_STREAMS", 4);
+    return v > BV_MAX_SIDE ? BV_MAX_SIDE : v;
+}
+static int final_blocks_per_sm() { static int v = env_int("BV_FINAL_BPS", 2); return v; }
 
 static bool vec_ok(const void *p, size_t npx, int batch, int bytes_per_px) {
     (void)bytes_per_px;
@@ -491,12 +491,16 @@ static int launch_final(bv_ctx *ctx, const uint8_t *src, const BalFrame *st, int
     const size_t need = (npx / 16 + kBalThreads - 1) / kBalThreads;
     if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
     dim3 grid(bpf, batch);
-    if (vec)
-        BV_LAUNCH(ctx, (final_kernel<MODE, CODE, true>), grid, kBalThreads, 0, src, st, npx, width, out, ctx->d_lab_gamma,
-                  ctx->d_lab_cbrt);
-    else
-        BV_LAUNCH(ctx, (final_kernel<MODE, CODE, false>), grid, kBalThreads, 0, src, st, npx, width, out, ctx->d_lab_gamma,
-                  ctx->d_lab_cbrt);
+    const bool need_mask = out.mask || out.mask_bits;
+#define BV_FINAL(V, M)                                                                                              \
+    BV_LAUNCH(ctx, (final_kernel<MODE, CODE, V, M>), grid, kBalThreads, 0, src, st, npx, width, out, ctx->d_lab_gamma, \
+              ctx->d_lab_cbrt)
+    if (vec) {
+        if (need_mask) BV_FINAL(true, true); else BV_FINAL(true, false);
+    } else {
+        if (need_mask) BV_FINAL(false, true); else BV_FINAL(false, false);
+    }
+#undef BV_FINAL
     return BV_OK;
 }
 
@@ -518,7 +522,7 @@ static size_t l2_chunk_bytes() {
     static size_t v = 0;
     if (!v) {
         const char *e = getenv("BV_L2_CHUNK_MB");
-        long mb = e ? atol(e) : 66;
+        long mb = e ? atol(e) : 33;
         if (mb < 1) mb = 1;
         v = (size_t)mb << 20;
     }
@@ -564,10 +568,26 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
     BalFrame *st = (BalFrame *)ctx->scratch[SCR_BAL_STATE];
     BV_CUDA(cudaMemsetAsync(st, 0, sizeof(BalFrame) * (size_t)batch, ctx->stream));
 
-    // chunk the batch so that one chunk's input stays in L2 across the three passes
+    // chunk the batch so that one chunk's input stays in L2 across the three passes; chunks are
+    // independent and alternate over side streams so that their passes overlap on the SMs
     int chunk = (int)(l2_chunk_bytes() / (npx * 3));
     if (chunk < 1) chunk = 1;
-    for (int f0 = 0; f0 < batch; f0 += chunk) {
+    const int nchunks = (batch + chunk - 1) / chunk;
+    int nside = side_streams();
+    if (nside > nchunks) nside = nchunks;
+    if (ctx->prof) nside = 1;  // per-kernel timing wants serialised launches
+    cudaStream_t main_stream = ctx->stream;
+    if (nside > 1) {
+        BV_CUDA(cudaEventRecord(ctx->ev_fork, main_stream));
+        for (int i = 0; i < nside; ++i) BV_CUDA(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+    }
+    struct Restore {  // every exit path puts the context's stream back
+        bv_ctx *c;
+        cudaStream_t s;
+        ~Restore() { c->stream = s; }
+    } restore{ctx, main_stream};
+    for (int f0 = 0, ci = 0; f0 < batch; f0 += chunk, ++ci) {
+        if (nside > 1) ctx->stream = ctx->side[ci % nside];
         const int nf = batch - f0 < chunk ? batch - f0 : chunk;
         const uint8_t *csrc = src + (size_t)f0 * npx * 3;
         BalFrame *cst = st + f0;
@@ -595,6 +615,12 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         else
             BV_TRY(dispatch_final<1>(ctx, csrc, cst, nf, npx, width, cvt_code, co, vec));
     }
+    ctx->stream = main_stream;
+    if (nside > 1)
+        for (int i = 0; i < nside; ++i) {
+            BV_CUDA(cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
+            BV_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join[i], 0));
+        }
     if (stats_host) {
         BV_CUDA(cudaMemcpy2DAsync(stats_host, sizeof(bv_balance_stats), &st[0].stats, sizeof(BalFrame),
                                   sizeof(bv_balance_stats), batch, cudaMemcpyDeviceToHost, ctx->stream));

@@ -73,6 +73,7 @@ enum ScratchSlot {
 }  // namespace bv
 
 #define BV_MAX_CHUNKS 64
+#define BV_MAX_SIDE 4
 
 struct bv_ctx {
     int device;
@@ -89,6 +90,10 @@ struct bv_ctx {
     cudaStream_t copy_in, copy_out;
     cudaEvent_t ev_in[BV_MAX_CHUNKS], ev_done[BV_MAX_CHUNKS];
     void *prof;  // per-kernel CUDA-event timing, only while bv_profile_enable(ctx, 1)
+    // side streams: independent chunks of one call run concurrently so that the issue-bound final
+    // pass of one chunk overlaps the atomics-bound histogram passes of the next
+    cudaStream_t side[BV_MAX_SIDE];
+    cudaEvent_t ev_fork, ev_join[BV_MAX_SIDE];
 };
 
 namespace bv {

@@ -66,6 +66,36 @@ struct Bounds3 {
     uint8_t lo[3], hi[3];
 };
 
+// inclusive range test as one subtract + one unsigned compare per channel:
+//   lo <= x <= hi  <=>  (unsigned)(x - lo) <= (unsigned)(hi - lo);   an empty range (hi < lo) is
+// encoded as lo = 256, span = 0 so that no 8-bit value passes.
+struct RangeTest {
+    int lo[3];
+    unsigned span[3];
+};
+
+__host__ __device__ inline RangeTest make_range_test(const uint8_t *lo, const uint8_t *hi) {
+    RangeTest r;
+    for (int k = 0; k < 3; ++k) {
+        if (hi[k] < lo[k]) {
+            r.lo[k] = 256;
+            r.span[k] = 0;
+        } else {
+            r.lo[k] = lo[k];
+            r.span[k] = (unsigned)(hi[k] - lo[k]);
+        }
+    }
+    return r;
+}
+
+template <int CODE>
+__device__ __forceinline__ bool in_range_px(int o0, int o1, int o2, const RangeTest &rt) {
+    bool in_r = (unsigned)(o0 - rt.lo[0]) <= rt.span[0];
+    if (!CvtTraits<CODE>::kOneChannel)
+        in_r = in_r && (unsigned)(o1 - rt.lo[1]) <= rt.span[1] && (unsigned)(o2 - rt.lo[2]) <= rt.span[2];
+    return in_r;
+}
+
 template <int CODE>
 __device__ __forceinline__ bool in_range_px(int o0, int o1, int o2, const Bounds3 &bd) {
     bool in_r = o0 >= bd.lo[0] && o0 <= bd.hi[0];
