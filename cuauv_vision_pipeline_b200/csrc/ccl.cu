@@ -333,12 +333,16 @@ __device__ __forceinline__ void blob_atomic_add(bv_blob *b, const RunSums &r) {
 }
 
 // final: labels + moments.  All 32 lanes of a warp stay in the loop together (the segmented
-// reduction uses full-warp shuffles).
+// reduction uses full-warp shuffles).  A lane owns one 32-px word; its 32 labels are staged in a
+// padded shared-memory tile (row = lane, bank-conflict-free) and the warp then writes the 32 words
+// out row by row, so every store instruction covers 128 contiguous bytes of the label image.
 __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ parent,
                                                         int *__restrict__ labels, bv_blob *__restrict__ blobs,
                                                         int max_blobs, int height, int width, int wpr,
                                                         size_t total_words) {
+    __shared__ int tile[8][32][33];
     const int lane = threadIdx.x & 31;
+    int(*my_tile)[33] = tile[threadIdx.x >> 5];
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t rounded = (total_words + 31) / 32 * 32;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
@@ -348,11 +352,8 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restri
         const size_t frame = (wp.row - wp.y) / height;
         const int *fp = parent + (wp.row - wp.y) * (size_t)width;
         const int xbase = wp.wx * 32;
-        const int nvalid = min(32, width - xbase);
-        int *out = labels ? labels + wp.row * (size_t)width + xbase : nullptr;
         uint32_t rest = w;
-        int written = 0;  // pixels of this word already emitted
-        // per-word label buffer is emitted run by run to keep registers low
+        int written = 0;  // pixels of this word already staged
         while (__any_sync(0xFFFFFFFFu, rest != 0)) {
             int lab = 0;
             RunSums rs;
@@ -368,9 +369,9 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restri
                 const int node = wp.y * width + xbase + s;
                 const int v = fp[node];
                 lab = v < 0 ? -v : -fp[v];
-                if (out) {
-                    for (int x = written; x < s; ++x) out[x] = 0;
-                    for (int x = s; x <= e; ++x) out[x] = lab;
+                if (labels) {
+                    for (int x = written; x < s; ++x) my_tile[lane][x] = 0;
+                    for (int x = s; x <= e; ++x) my_tile[lane][x] = lab;
                     written = e + 1;
                 }
                 if (blobs) run_sums(xbase + s, xbase + e, wp.y, rs);
@@ -406,8 +407,21 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restri
                 if (head && lab && lab <= max_blobs) blob_atomic_add(&blobs[frame * (size_t)max_blobs + (lab - 1)], rs);
             }
         }
-        if (out && valid)
-            for (int x = written; x < nvalid; ++x) out[x] = 0;
+        if (labels) {
+            for (int x = written; x < 32; ++x) my_tile[lane][x] = 0;
+            __syncwarp();
+            const size_t warp_first = i - lane;  // word index owned by lane 0
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                const size_t wi = warp_first + k;
+                if (wi >= total_words) break;
+                const int kwx = (int)(wi % wpr);
+                const size_t krow = wi / wpr;
+                const int x = kwx * 32 + lane;
+                if (x < width) labels[krow * (size_t)width + x] = my_tile[k][lane];
+            }
+            __syncwarp();
+        }
     }
 }
 
