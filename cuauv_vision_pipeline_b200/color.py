@@ -40,6 +40,21 @@ def range_threshold(mat, min, max):  # noqa: A002 (reference argument names)
     return like_input(ctx, mat, ctx.in_range(to_device(ctx, mat), min, max))
 
 
+def thresh_color_distance(split, color, distance, auto_distance_percentile=None, ignore_channels=[],  # noqa: B006
+                          weights=(1, 1, 1)):
+    """utils/color.py:66-103.  Returns (mask, uint8 distance image).  The percentile option needs a
+    global float percentile and is not provided."""
+    if auto_distance_percentile:
+        raise NotImplementedError("auto_distance_percentile (utils/color.py:98-99) is not provided")
+    ctx = ctx_for(split[0])
+    w = np.array([0.0 if i in ignore_channels else float(weights[i]) for i in range(3)], np.float64)
+    w /= np.linalg.norm(weights)                      # norm of the UN-zeroed weights (utils/color.py:93)
+    use = [0 if i in ignore_channels else 1 for i in range(3)]
+    planes = [to_device(ctx, p) for p in split]
+    mask, dist = ctx.color_distance(planes, color, w, use, float(distance) ** 2)
+    return like_input(ctx, split[0], mask), like_input(ctx, split[0], dist)
+
+
 def _thresh(kind, maxval=255):
     def fn(mat, threshold):
         ctx = ctx_for(mat)

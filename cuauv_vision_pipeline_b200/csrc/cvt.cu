@@ -224,6 +224,37 @@ __global__ void __launch_bounds__(256) lut3_kernel(const uint8_t *__restrict__ s
 }
 
 // ----------------------------------------------------------------------------------------------
+// weighted colour distance (utils/color.py:66-103).  Arithmetic as numpy 2.x evaluates the
+// reference's expression: the square is float32, the weight is a float64 scalar, so each channel's
+// update is dists = float32(double(dists) + w * double(float32 square)).
+// ----------------------------------------------------------------------------------------------
+struct ColorDistParams {
+    float color[3];
+    double weight[3];
+    int use[3];
+    float max_dist;  // inclusive upper bound on dists (already squared), as float32 like cv2.inRange
+};
+
+__global__ void __launch_bounds__(256) color_distance_kernel(const uint8_t *__restrict__ p0, const uint8_t *__restrict__ p1,
+                                                             const uint8_t *__restrict__ p2, uint8_t *__restrict__ mask,
+                                                             uint8_t *__restrict__ dist, size_t n, ColorDistParams prm) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint8_t v[3] = {p0[i], p1[i], p2[i]};
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (!prm.use[c]) continue;
+            const float t = __fsub_rn((float)v[c], prm.color[c]);
+            const float sq = __fmul_rn(t, t);
+            d = (float)__dadd_rn((double)d, __dmul_rn(prm.weight[c], (double)sq));
+        }
+        if (mask) mask[i] = (d >= 0.f && d <= prm.max_dist) ? 255 : 0;
+        if (dist) dist[i] = (uint8_t)(((int)__fsqrt_rn(d)) & 0xFF);  // np.uint8(np.sqrt(.)): truncate, wrap
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // host dispatch
 // ----------------------------------------------------------------------------------------------
 template <int CODE>
@@ -351,6 +382,26 @@ extern "C" int bv_threshold(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_de
         BV_LAUNCH(ctx, (op1_kernel<OP1_THRESH, true>), grid, 256, 0, src_dev, dst_dev, n, prm, nullptr);
     else
         BV_LAUNCH(ctx, (op1_kernel<OP1_THRESH, false>), grid, 256, 0, src_dev, dst_dev, n, prm, nullptr);
+    return BV_OK;
+}
+
+extern "C" int bv_color_distance(bv_ctx *ctx, const uint8_t *const *planes_dev, size_t n, const double *color_host,
+                                 const double *weights_host, const int32_t *use_host, double max_dist_sq,
+                                 uint8_t *mask_dev, uint8_t *dist_dev) {
+    BV_REQUIRE(ctx && planes_dev && planes_dev[0] && planes_dev[1] && planes_dev[2] && color_host && weights_host && use_host,
+               "null argument");
+    BV_REQUIRE(mask_dev || dist_dev, "need mask_dev or dist_dev");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return BV_OK;
+    ColorDistParams prm;
+    for (int c = 0; c < 3; ++c) {
+        prm.color[c] = (float)color_host[c];
+        prm.weight[c] = weights_host[c];
+        prm.use[c] = use_host[c];
+    }
+    prm.max_dist = (float)max_dist_sq;
+    BV_LAUNCH(ctx, color_distance_kernel, grid_for(ctx, n, 256, 8), 256, 0, planes_dev[0], planes_dev[1], planes_dev[2],
+              mask_dev, dist_dev, n, prm);
     return BV_OK;
 }
 

@@ -187,6 +187,19 @@ class Context:
                                ffi.from_buffer("uint8_t[]", lut)))
         return dst
 
+    def color_distance(self, planes, color, weights, use, max_dist_sq):
+        """planes: 3 device uint8 tensors of equal shape.  Returns (mask, dist) device tensors."""
+        n = planes[0].numel()
+        mask = self.empty(tuple(planes[0].shape))
+        dist = self.empty(tuple(planes[0].shape))
+        pp = ffi.new("uint8_t *[3]", [_u8ptr(p) for p in planes])
+        check(lib.bv_color_distance(self.handle, ffi.cast("const uint8_t *const *", pp), n,
+                                    ffi.new("double[3]", [float(c) for c in color]),
+                                    ffi.new("double[3]", [float(w) for w in weights]),
+                                    ffi.new("int32_t[3]", [int(u) for u in use]), float(max_dist_sq),
+                                    _u8ptr(mask), _u8ptr(dist)))
+        return mask, dist
+
     def morph(self, src, op, kernel, iterations=1):
         kernel = np.ascontiguousarray(np.asarray(kernel) != 0, dtype=np.uint8)
         kh, kw = kernel.shape

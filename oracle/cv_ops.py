@@ -26,6 +26,23 @@ def range_threshold(mat, lo, hi):
     return cv2.inRange(mat, lo, hi)
 
 
+def thresh_color_distance(split, color, distance, ignore_channels=(), weights=(1, 1, 1)):
+    """utils/color.py:66-103 without the percentile branch: weighted squared distance accumulated
+    in a float32 image (numpy evaluates weight * square in float64 and rounds on the in-place add),
+    thresholded with cv2.inRange(dists, 0, distance**2); second result np.uint8(np.sqrt(dists))."""
+    w = list(weights)
+    for idx in ignore_channels:
+        w[idx] = 0
+    w = np.asarray(w, dtype=np.float64) / np.linalg.norm(weights)
+    dists = np.zeros(split[0].shape, dtype=np.float32)
+    for i in range(3):
+        if i in ignore_channels:
+            continue
+        dists += w[i] * (np.float32(split[i]) - color[i]) ** 2
+    with np.errstate(invalid="ignore"):
+        return cv2.inRange(dists, 0, distance ** 2), (np.sqrt(dists).astype(np.int64) & 0xFF).astype(np.uint8)
+
+
 def binary_threshold(mat, t):            # utils/color.py:124-137
     return cv2.threshold(mat, t, 255, cv2.THRESH_BINARY)[1]
 

@@ -24,6 +24,24 @@ from oracle import ref_balance, cv_ops, synth, ccl, letterbox  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
+def load_reference_color():
+    """Imports the reference's utils/color.py itself (stubbing the two external CUAUV modules it
+    pulls in at import time) so that golden vectors come from the reference function, not from a
+    restatement."""
+    import importlib.util
+    import types
+    sys.modules.setdefault("auv_python_helpers", types.SimpleNamespace(load_library=lambda n: None))
+    for name in ("vision", "vision.utils"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    helpers = types.ModuleType("vision.utils.helpers")
+    helpers.as_mat = lambda m: m
+    sys.modules["vision.utils.helpers"] = helpers
+    spec = importlib.util.spec_from_file_location("ref_utils_color", "/root/reference/utils/color.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def main():
     assert ref_balance.available(), "build oracle/_ref first (make -C oracle)"
     # colour balance: default flags on three shapes (one with width % 32 != 0), plus flag variants
@@ -56,6 +74,20 @@ def main():
     d["contrast_1p7"] = cv_ops.contrast(img, 1.7)
     d["brightness_m40"] = cv_ops.brightness(img, -40)
     d["bias_r25"] = cv_ops.channel_bias(img, 2, 25)
+    np.savez_compressed(os.path.join(OUT, "cv_calls_72x128.npz"), **d)
+    # thresh_color_distance: outputs of the reference function itself (utils/color.py:66-103)
+    ref_color = load_reference_color()
+    lab = cv2.cvtColor(img, cv2.COLOR_BGR2LAB)
+    split = cv2.split(lab)
+    cases = [dict(color=(120, 150, 140), distance=30), dict(color=(60, 128, 128), distance=45, weights=(0.2, 1, 1)),
+             dict(color=(200, 110, 170), distance=25.5, ignore_channels=[0]),
+             dict(color=(10, 240, 20), distance=400, weights=(3, 1, 2))]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k, kw in enumerate(cases):
+            m, dimg = ref_color.thresh_color_distance(list(split), **kw)
+            d["tcd%d_mask" % k], d["tcd%d_dist" % k] = m, dimg
     np.savez_compressed(os.path.join(OUT, "cv_calls_72x128.npz"), **d)
     # labelling oracle on a small blob mask
     m = synth.mask_blobs(90, 160, 5, sigma=4.0)

@@ -150,3 +150,32 @@ def test_apply_lut_carries_preprocessor_point_ops(ctx, shape):
     one = img[..., 0].copy()
     lut1 = np.arange(255, -1, -1, dtype=np.uint8)
     assert np.array_equal(ctx.download(ctx.apply_lut(ctx.upload(one), lut1)), lut1[one])
+
+
+TCD_CASES = [dict(color=(120, 150, 140), distance=30), dict(color=(60, 128, 128), distance=45, weights=(0.2, 1, 1)),
+             dict(color=(200, 110, 170), distance=25.5, ignore_channels=[0]),
+             dict(color=(10, 240, 20), distance=400, weights=(3, 1, 2))]
+
+
+def test_thresh_color_distance_golden_from_reference_function(ctx):
+    """utils/color.py:66-103 (P1): golden outputs of the reference function itself."""
+    import os
+    from cuauv_vision_pipeline_b200 import color
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "cv_calls_72x128.npz"))
+    split = list(cv2.split(z["bgr2lab"]))
+    for k, kw in enumerate(TCD_CASES):
+        mask, dist = color.thresh_color_distance(split, **kw)
+        assert np.array_equal(mask, z["tcd%d_mask" % k]) and np.array_equal(dist, z["tcd%d_dist" % k]), k
+
+
+@pytest.mark.parametrize("shape", [(479, 641), (1080, 1920)])
+def test_thresh_color_distance_vs_oracle(ctx, shape):
+    from cuauv_vision_pipeline_b200 import color
+    img = synth.gen_underwater(shape[0], shape[1], 13)
+    split = list(cv2.split(cv2.cvtColor(img, cv2.COLOR_BGR2LAB)))
+    for kw in TCD_CASES + [dict(color=(0, 0, 0), distance=500, weights=(1, 1, 1))]:
+        mask, dist = color.thresh_color_distance(split, **kw)
+        rmask, rdist = cv_ops.thresh_color_distance(split, **kw)
+        assert np.array_equal(mask, rmask) and np.array_equal(dist, rdist), kw
+    with pytest.raises(NotImplementedError):
+        color.thresh_color_distance(split, (1, 2, 3), 10, auto_distance_percentile=50)

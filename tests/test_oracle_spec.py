@@ -96,3 +96,15 @@ def test_preprocessor_point_ops_semantics():
     assert np.array_equal(cv_ops.contrast(img, 1.7), np.minimum(np.floor(img * 1.7), 255).astype(np.uint8))
     assert np.array_equal(cv_ops.brightness(img, -40), np.clip(img.astype(int) - 40, 0, 255).astype(np.uint8))
     assert np.array_equal(cv_ops.channel_bias(img, 2, 25)[..., 2], np.clip(img[..., 2].astype(int) + 25, 0, 255))
+
+
+def test_color_distance_restatement_matches_reference_function_golden():
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "cv_calls_72x128.npz"))
+    split = list(cv2.split(z["bgr2lab"]))
+    cases = [dict(color=(120, 150, 140), distance=30), dict(color=(60, 128, 128), distance=45, weights=(0.2, 1, 1)),
+             dict(color=(200, 110, 170), distance=25.5, ignore_channels=[0]),
+             dict(color=(10, 240, 20), distance=400, weights=(3, 1, 2))]
+    for k, kw in enumerate(cases):
+        m, d = cv_ops.thresh_color_distance(split, **kw)
+        assert np.array_equal(m, z["tcd%d_mask" % k]) and np.array_equal(d, z["tcd%d_dist" % k])
