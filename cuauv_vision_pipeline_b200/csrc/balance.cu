@@ -1,6 +1,6 @@
 // balance.cu -- underwater colour balance on the device.  Replaces the reference's process_frame
 // (utils/color_correction/color_balance.cpp:343-780) for every flag combination except the HSI
-// branch (702-774) and tiled equalisation (horizontal/vertical_blocks > 1).
+// branch (702-774); tilings (horizontal/vertical_blocks > 1) must divide the frame.
 //
 // The reference makes ~14 full passes over split planes on the CPU.  Here the whole algorithm is
 // three streaming passes over the interleaved frame; the per-frame statistics run inside the last
@@ -98,11 +98,29 @@ __device__ __forceinline__ void percentile_limits(size_t n, long long &low_bound
     high_bound = (int)(n - (size_t)(int)__fmul_rn(0.998f, (float)n));
 }
 
-// Run by the LAST block of a frame's pass 1: bounds, exact means, gains, composed tables.
+// exact sum of a channel clipped to [lo, hi], from its histogram; thread t owns bin t
+__device__ unsigned long long block_clipped_sum(uint32_t c, int lo, int hi, StatScratch &sc) {
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int cl = t < lo ? lo : (t > hi ? hi : t);
+    unsigned long long v = (unsigned long long)cl * c;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+    __syncthreads();
+    if (lane == 0) sc.warp_sum[wid] = v;
+    __syncthreads();
+    unsigned long long tot = 0;
+#pragma unroll
+    for (int w = 0; w < kBalWarps; ++w) tot += sc.warp_sum[w];
+    return tot;
+}
+
+// Run by the LAST block of a frame's pass 1: bounds, exact means, gains, composed tables -- one
+// table set per tile (a single "tile" = the frame itself in the default 1x1 configuration).
 __device__ void stats_bgr_block(BalFrame &F, size_t npx, const bv_balance_params &prm,
-                                const double *__restrict__ pow_quarter, StatScratch &sc) {
+                                const double *__restrict__ pow_quarter, StatScratch &sc, BalTile *tiles, int n_tiles,
+                                size_t tile_px) {
     __shared__ int s_lo[3], s_hi[3], s_dom;
-    __shared__ double s_avg[3], s_gain[3], s_ratio[3];
+    __shared__ double s_avg[3], s_local[3], s_gain[3], s_ratio[3];
     const int t = threadIdx.x;
     long long lb = 0, hb = 0;
     if (prm.rgb_extrema_clipping) percentile_limits(npx, lb, hb);
@@ -120,14 +138,6 @@ __device__ void stats_bgr_block(BalFrame &F, size_t npx, const bv_balance_params
     __syncthreads();
     if (t == 0) {
         const double b = s_avg[0], g = s_avg[1], r = s_avg[2];
-        int dom;
-        // 480 / 501 / 522: red if strictly largest, else green if strictly largest, else blue
-        if (r > g && r > b) dom = 2;
-        else if (g > r && g > b) dom = 1;
-        else dom = 0;
-        for (int c = 0; c < 3; ++c) s_gain[c] = (c == dom) ? 1.0 : s_avg[dom] / s_avg[c];
-        s_dom = dom;
-        F.stats.dominant = dom;
         for (int c = 0; c < 3; ++c) {
             F.stats.bgr_min[c] = s_lo[c];
             F.stats.bgr_max[c] = s_hi[c];
@@ -153,18 +163,50 @@ __device__ void stats_bgr_block(BalFrame &F, size_t npx, const bv_balance_params
         }
     }
     __syncthreads();
-    // every thread builds entry t of the three composed tables
-    for (int c = 0; c < 3; ++c) {
-        int x = t < s_lo[c] ? s_lo[c] : (t > s_hi[c] ? s_hi[c] : t);                 // clip_channel, 25-45
-        if (prm.equalize_rgb && c != s_dom) {
-            const double xd = (double)x;
-            if (prm.adaptive_cast_correction)                                        // 489-491
-                x = constrain255(xd * (pow_quarter[x] * (s_gain[c] - 1.) + 1.));
-            else                                                                     // 494-495
-                x = constrain255(xd * s_gain[c]);
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        const uint32_t(*hist)[256] = tiles ? tiles[tile].hist : F.hist_bgr;
+        uint8_t(*lut)[256] = tiles ? tiles[tile].lut : F.lut_bgr;
+        for (int c = 0; c < 3; ++c) {
+            // local mean of the clipped tile (459-470; exact sum instead of the running mean)
+            const unsigned long long sum = block_clipped_sum(__ldcg(&hist[c][t]), s_lo[c], s_hi[c], sc);
+            if (t == 0) s_local[c] = (double)sum / (double)tile_px;
         }
-        if (prm.rgb_contrast_correct) x = uchar_cast((double)(x - s_lo[c]) * s_ratio[c]);  // 634-640
-        F.lut_bgr[c][t] = (uint8_t)x;
+        __syncthreads();
+        if (t == 0) {
+            double lb_ = s_local[0], lg_ = s_local[1], lr_ = s_local[2];
+            // 474: unqualified abs() == int abs(int) in the compiled reference: the difference is
+            // truncated toward zero first (see oracle/color_balance_np.py)
+            if (abs((int)(lr_ - s_avg[2])) > s_avg[2] / 6 || abs((int)(lb_ - s_avg[0])) > s_avg[0] / 6 ||
+                abs((int)(lg_ - s_avg[1])) > s_avg[1] / 6) {
+                lb_ = s_avg[0];
+                lg_ = s_avg[1];
+                lr_ = s_avg[2];
+            }
+            int dom;
+            // 480 / 501 / 522: red if strictly largest, else green if strictly largest, else blue
+            if (lr_ > lg_ && lr_ > lb_) dom = 2;
+            else if (lg_ > lr_ && lg_ > lb_) dom = 1;
+            else dom = 0;
+            const double loc[3] = {lb_, lg_, lr_};
+            for (int c = 0; c < 3; ++c) s_gain[c] = (c == dom) ? 1.0 : loc[dom] / loc[c];
+            s_dom = dom;
+            if (tile == 0) F.stats.dominant = dom;
+        }
+        __syncthreads();
+        // every thread builds entry t of the three composed tables
+        for (int c = 0; c < 3; ++c) {
+            int x = t < s_lo[c] ? s_lo[c] : (t > s_hi[c] ? s_hi[c] : t);                 // clip_channel, 25-45
+            if (prm.equalize_rgb && c != s_dom) {
+                const double xd = (double)x;
+                if (prm.adaptive_cast_correction)                                        // 489-491
+                    x = constrain255(xd * (pow_quarter[x] * (s_gain[c] - 1.) + 1.));
+                else                                                                     // 494-495
+                    x = constrain255(xd * s_gain[c]);
+            }
+            if (prm.rgb_contrast_correct) x = uchar_cast((double)(x - s_lo[c]) * s_ratio[c]);  // 634-640
+            lut[c][t] = (uint8_t)x;
+        }
+        __syncthreads();
     }
 }
 
@@ -202,11 +244,11 @@ __device__ void stats_sv_block(BalFrame &F, size_t npx, StatScratch &sc) {
 
 // "last block done": every block of a frame calls this after merging its histogram into HBM; the
 // block that draws the final ticket sees all merges (fence + atomic) and does the statistics.
-__device__ __forceinline__ bool last_block_of_frame(uint32_t *ticket) {
+__device__ __forceinline__ bool last_block_of_frame(uint32_t *ticket, unsigned blocks_per_frame) {
     __shared__ bool is_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == blocks_per_frame - 1);
     __syncthreads();
     return is_last;
 }
@@ -247,7 +289,7 @@ __global__ void __launch_bounds__(kBalThreads) hist_bgr_kernel(const uint8_t *__
         for (int w = 0; w < kBalWarps; ++w) s += (&h[w][0][0])[i];
         if (s) atomicAdd(&st[frame].hist_bgr[0][0] + i, s);
     }
-    if (last_block_of_frame(&st[frame].ticket[0])) stats_bgr_block(st[frame], npx, prm, pow_quarter, sc);
+    if (last_block_of_frame(&st[frame].ticket[0], gridDim.x)) stats_bgr_block(st[frame], npx, prm, pow_quarter, sc, nullptr, 1, npx);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -297,7 +339,7 @@ __global__ void __launch_bounds__(kBalThreads) hist_sv_kernel(const uint8_t *__r
         for (int w = 0; w < kBalWarps; ++w) s += (&h[w][0][0])[i];
         if (s) atomicAdd(&st[frame].hist_sv[0][0] + i, s);
     }
-    if (last_block_of_frame(&st[frame].ticket[1])) stats_sv_block(st[frame], npx, sc);
+    if (last_block_of_frame(&st[frame].ticket[1], gridDim.x)) stats_sv_block(st[frame], npx, sc);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -464,6 +506,176 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
 }
 
 // ----------------------------------------------------------------------------------------------
+// Tiled equalisation (P1): horizontal_blocks x vertical_blocks > 1.  One block works inside one
+// tile (grid = blocks x tiles x frames), per pixel, with that tile's tables.  Same three passes.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t tile_pixel(const TileGeom &tg, int tile, size_t idx) {
+    const int ty = tile / tg.hb, tx = tile - ty * tg.hb;
+    const int yy = (int)(idx / tg.bw), xx = (int)(idx - (size_t)yy * tg.bw);
+    return (size_t)(ty * tg.bh + yy) * tg.width + (size_t)tx * tg.bw + xx;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kBalThreads) hist_tiled_kernel(const uint8_t *__restrict__ src, BalFrame *__restrict__ st,
+                                                                 BalTile *__restrict__ tiles, size_t npx, TileGeom tg,
+                                                                 bv_balance_params prm, const double *__restrict__ pow_quarter) {
+    __shared__ uint32_t h[kBalWarps][3][256];
+    __shared__ uint8_t lut[3][256];
+    __shared__ int sdiv[256], hdiv[256];
+    __shared__ StatScratch sc;
+    const int tile = blockIdx.y, frame = blockIdx.z, n_tiles = gridDim.y;
+    BalTile &T = tiles[(size_t)frame * n_tiles + tile];
+    for (int i = threadIdx.x; i < kBalWarps * 768; i += blockDim.x) (&h[0][0][0])[i] = 0;
+    if (PASS == 2) {
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) (&lut[0][0])[i] = (&T.lut[0][0])[i];
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            sdiv[i] = hsv_sdiv(i);
+            hdiv[i] = hsv_hdiv(i);
+        }
+    }
+    __syncthreads();
+    const uint8_t *f = src + (size_t)frame * npx * 3;
+    uint32_t(*hw)[256] = h[threadIdx.x >> 5];
+    const size_t tile_px = (size_t)tg.bw * tg.bh;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tile_px; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = tile_pixel(tg, tile, idx);
+        if (PASS == 1) {
+            atomicAdd(&hw[0][f[3 * p]], 1u);
+            atomicAdd(&hw[1][f[3 * p + 1]], 1u);
+            atomicAdd(&hw[2][f[3 * p + 2]], 1u);
+        } else {
+            int hh, ss, vv;
+            bgr2hsv(lut[0][f[3 * p]], lut[1][f[3 * p + 1]], lut[2][f[3 * p + 2]], sdiv, hdiv, hh, ss, vv);
+            atomicAdd(&hw[0][ss], 1u);
+            atomicAdd(&hw[1][vv], 1u);
+        }
+    }
+    __syncthreads();
+    const int nbins = PASS == 1 ? 768 : 512;
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < kBalWarps; ++w) s += (&h[w][0][0])[i];
+        if (!s) continue;
+        if (PASS == 1) {
+            atomicAdd(&T.hist[0][0] + i, s);
+            atomicAdd(&st[frame].hist_bgr[0][0] + i, s);
+        } else {
+            atomicAdd(&st[frame].hist_sv[0][0] + i, s);
+        }
+    }
+    if (last_block_of_frame(&st[frame].ticket[PASS - 1], gridDim.x * gridDim.y)) {
+        if (PASS == 1)
+            stats_bgr_block(st[frame], npx, prm, pow_quarter, sc, tiles + (size_t)frame * n_tiles, n_tiles, tile_px);
+        else
+            stats_sv_block(st[frame], npx, sc);
+    }
+}
+
+template <int MODE, int CODE>
+__global__ void __launch_bounds__(kBalThreads) final_tiled_kernel(const uint8_t *__restrict__ src, const BalFrame *__restrict__ st,
+                                                                  const BalTile *__restrict__ tiles, size_t npx, TileGeom tg,
+                                                                  BalOutputs out, const uint16_t *__restrict__ g_gamma,
+                                                                  const uint16_t *__restrict__ g_cbrt) {
+    __shared__ FinalSmem fs;
+    __shared__ SmemTabs tabs;
+    const int tile = blockIdx.y, frame = blockIdx.z, n_tiles = gridDim.y;
+    const BalTile &T = tiles[(size_t)frame * n_tiles + tile];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) (&fs.lut[0][0])[i] = (&T.lut[0][0])[i];
+    if (MODE == 2) {
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) (&fs.lut_sv[0][0])[i] = (&st[frame].lut_sv[0][0])[i];
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            fs.sdiv[i] = hsv_sdiv(i);
+            fs.hdiv[i] = hsv_hdiv(i);
+        }
+    }
+    init_tabs<CODE>(tabs, g_gamma, g_cbrt);
+    const size_t foff = (size_t)frame * npx;
+    const uint8_t *f = src + foff * 3;
+    const int vec_end = tg.width - (tg.width % 32);
+    constexpr bool kOne = CvtTraits<CODE>::kOneChannel;
+    const RangeTest bd = make_range_test(out.lo, out.hi);
+    const size_t tile_px = (size_t)tg.bw * tg.bh;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tile_px; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = tile_pixel(tg, tile, idx);
+        const int x = (int)(p % (size_t)tg.width);
+        const bool vec = x < vec_end;
+        const uint32_t px = balance_px<MODE>(f[3 * p], f[3 * p + 1], f[3 * p + 2], vec, fs);
+        const int b = (int)(px & 0xFF), gg = (int)((px >> 8) & 0xFF), r = (int)(px >> 16);
+        if (out.balanced) {
+            uint8_t *o = out.balanced + (foff + p) * 3;
+            o[0] = (uint8_t)b;
+            o[1] = (uint8_t)gg;
+            o[2] = (uint8_t)r;
+        }
+        int o0, o1, o2;
+        convert_px<CODE>(b, gg, r, vec, tabs, o0, o1, o2);
+        if (out.converted) {
+            if (kOne) {
+                out.converted[foff + p] = (uint8_t)o0;
+            } else {
+                uint8_t *o = out.converted + (foff + p) * 3;
+                o[0] = (uint8_t)o0;
+                o[1] = (uint8_t)o1;
+                o[2] = (uint8_t)o2;
+            }
+        }
+        if (out.mask) out.mask[foff + p] = in_range_px<CODE>(o0, o1, o2, bd) ? 255 : 0;
+    }
+}
+
+template <int MODE>
+static int dispatch_final_tiled(bv_ctx *ctx, const uint8_t *src, const BalFrame *st, const BalTile *tiles, dim3 grid,
+                                size_t npx, const TileGeom &tg, int code, const BalOutputs &out) {
+#define BV_FT(C)                                                                                               \
+    BV_LAUNCH(ctx, (final_tiled_kernel<MODE, C>), grid, kBalThreads, 0, src, st, tiles, npx, tg, out, ctx->d_lab_gamma, \
+              ctx->d_lab_cbrt);                                                                                \
+    return BV_OK
+    switch (code) {
+        case -1: BV_FT(-1);
+        case BV_BGR2HSV: BV_FT(BV_BGR2HSV);
+        case BV_BGR2LAB: BV_FT(BV_BGR2LAB);
+        case BV_BGR2GRAY: BV_FT(BV_BGR2GRAY);
+        case BV_BGR2YCRCB: BV_FT(BV_BGR2YCRCB);
+        case BV_BGR2HLS: BV_FT(BV_BGR2HLS);
+        default: set_error("stage: conversion code %d is not available in the fused pass", code); return BV_ERR_INVALID;
+    }
+#undef BV_FT
+}
+
+static int balance_run_tiled(bv_ctx *ctx, const uint8_t *src, int batch, int height, int width, const bv_balance_params &prm,
+                             int cvt_code, const BalOutputs &out, BalFrame *st) {
+    const int hb = prm.horizontal_blocks, vb = prm.vertical_blocks;
+    if (hb < 1 || vb < 1 || width % hb || height % vb) {
+        // the reference walks off the end of the row for non-divisible tilings (color_balance.cpp:442-464)
+        set_error("colour balance: horizontal/vertical_blocks must divide the frame (%dx%d into %dx%d tiles)", width, height, hb, vb);
+        return BV_ERR_UNSUPPORTED;
+    }
+    const int n_tiles = hb * vb;
+    if (n_tiles > 4096 || out.mask_bits) {
+        set_error("colour balance: too many tiles, or bit-packed mask requested with tiling");
+        return BV_ERR_UNSUPPORTED;
+    }
+    const size_t npx = (size_t)height * width;
+    BV_TRY(ensure_scratch(ctx, SCR_BAL_TILES, sizeof(BalTile) * (size_t)batch * n_tiles));
+    BalTile *tiles = (BalTile *)ctx->scratch[SCR_BAL_TILES];
+    BV_CUDA(cudaMemsetAsync(tiles, 0, sizeof(BalTile) * (size_t)batch * n_tiles, ctx->stream));
+    TileGeom tg{hb, vb, width / hb, height / vb, width, height};
+    const size_t tile_px = (size_t)tg.bw * tg.bh;
+    int bx = (int)((tile_px + kBalThreads * 16 - 1) / (kBalThreads * 16));
+    const int cap = (ctx->sm_count * 8 + n_tiles * batch - 1) / (n_tiles * batch);
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, n_tiles, batch);
+    BV_LAUNCH(ctx, hist_tiled_kernel<1>, grid, kBalThreads, 0, src, st, tiles, npx, tg, prm, ctx->d_pow_quarter);
+    if (prm.hsv_contrast_correct) {
+        BV_LAUNCH(ctx, hist_tiled_kernel<2>, grid, kBalThreads, 0, src, st, tiles, npx, tg, prm, ctx->d_pow_quarter);
+        return dispatch_final_tiled<2>(ctx, src, st, tiles, grid, npx, tg, cvt_code, out);
+    }
+    return dispatch_final_tiled<1>(ctx, src, st, tiles, grid, npx, tg, cvt_code, out);
+}
+
+// ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
 static int env_int(const char *name, int dflt) {
@@ -550,10 +762,7 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         set_error("colour balance: the HSI branch (color_balance.cpp:702-774) is not implemented");
         return BV_ERR_UNSUPPORTED;
     }
-    if (prm.horizontal_blocks != 1 || prm.vertical_blocks != 1) {
-        set_error("colour balance: tiled equalisation (horizontal/vertical_blocks > 1) is not implemented");
-        return BV_ERR_UNSUPPORTED;
-    }
+    const bool tiled = prm.horizontal_blocks != 1 || prm.vertical_blocks != 1;
     const size_t npx = (size_t)height * width;
     if (npx >= (1ull << 31)) {
         set_error("colour balance: frame too large for 32-bit histogram counters");
@@ -567,6 +776,15 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
     BV_TRY(ensure_scratch(ctx, SCR_BAL_STATE, sizeof(BalFrame) * (size_t)batch));
     BalFrame *st = (BalFrame *)ctx->scratch[SCR_BAL_STATE];
     BV_CUDA(cudaMemsetAsync(st, 0, sizeof(BalFrame) * (size_t)batch, ctx->stream));
+    if (tiled) {
+        BV_TRY(balance_run_tiled(ctx, src, batch, height, width, prm, cvt_code, out, st));
+        if (stats_host) {
+            BV_CUDA(cudaMemcpy2DAsync(stats_host, sizeof(bv_balance_stats), &st[0].stats, sizeof(BalFrame),
+                                      sizeof(bv_balance_stats), batch, cudaMemcpyDeviceToHost, ctx->stream));
+            BV_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        return BV_OK;
+    }
 
     // chunk the batch so that one chunk's input stays in L2 across the three passes; chunks are
     // independent and alternate over side streams so that their passes overlap on the SMs

@@ -14,6 +14,19 @@ struct BalFrame {
     bv_balance_stats stats;
 };
 
+// Tiled equalisation (horizontal_blocks x vertical_blocks > 1, color_balance.cpp:441-544): every
+// tile has its own local means, hence its own gains and composed tables.
+struct BalTile {
+    uint32_t hist[3][256];
+    uint8_t lut[3][256];
+};
+
+struct TileGeom {
+    int hb, vb;  // tiles across / down
+    int bw, bh;  // tile size in pixels (the tiling must divide the frame)
+    int width, height;
+};
+
 // What the final pass does with each balanced pixel.
 struct BalOutputs {
     uint8_t *balanced;   // BGR after balance (may be null)

@@ -51,6 +51,7 @@ void set_error(const char *fmt, ...);  // thread-local message, api.cu
 // ---- scratch slots ---------------------------------------------------------------------------
 enum ScratchSlot {
     SCR_BAL_STATE = 0,  // per-frame histograms, LUTs, stats of the colour balance
+    SCR_BAL_TILES,      // per-tile histograms and tables (tiled equalisation)
     SCR_BITS_A,         // bit-packed masks (ping)
     SCR_BITS_B,         // bit-packed masks (pong)
     SCR_CCL_PARENT,     // union-find parents, int32 per pixel

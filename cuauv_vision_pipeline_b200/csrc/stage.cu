@@ -63,7 +63,8 @@ int stage_run(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src, int ba
         tmp2 = tmp + words;
         const bool aligned = host_aligned16(src) && (!balanced || host_aligned16(balanced)) &&
                              (!converted || host_aligned16(converted)) && (!mask || host_aligned16(mask));
-        bits_direct = aligned && (width % 16 == 0);
+        const bool tiled = desc->do_balance && (desc->balance.horizontal_blocks != 1 || desc->balance.vertical_blocks != 1);
+        bits_direct = aligned && (width % 16 == 0) && !tiled;
         if (bits_direct) {
             if (width % 32 != 0) BV_CUDA(cudaMemsetAsync(bits, 0, words * 4, ctx->stream));
             out.mask_bits = (uint16_t *)bits;

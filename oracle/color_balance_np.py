@@ -115,7 +115,11 @@ def process_frame_np(img, equalize_rgb=True, rgb_contrast_correct=False,
                     lr = float(int(r2[sl].sum(dtype=np.int64))) / cnt
                     lg = float(int(g2[sl].sum(dtype=np.int64))) / cnt
                     lb = float(int(b2[sl].sum(dtype=np.int64))) / cnt
-                if abs(lr - r_avg) > r_avg / 6 or abs(lb - b_avg) > b_avg / 6 or abs(lg - g_avg) > g_avg / 6:  # 474
+                # 474: the unqualified abs() resolves to int abs(int) in the compiled reference (g++ 13,
+                # <cmath>/<cstdlib> only): the difference is truncated toward zero before the comparison
+                # (verified against oracle/_ref: a double fabs changes 18 683 bytes on a 4x2 tiling)
+                if abs(int(lr - r_avg)) > r_avg / 6 or abs(int(lb - b_avg)) > b_avg / 6 or \
+                        abs(int(lg - g_avg)) > g_avg / 6:
                     lr, lg, lb = r_avg, g_avg, b_avg
                 with np.errstate(divide="ignore", invalid="ignore"):
                     if lr > lg and lr > lb:                                # 480: red cast

@@ -52,9 +52,13 @@ def main():
              ("noclip_96x160", 96, 160, 15, dict(rgb_extrema_clipping=False)),
              ("rgbcc_96x160", 96, 160, 16, dict(rgb_contrast_correct=True)),
              ("adaptive_96x160", 96, 160, 17, dict(adaptive_cast_correction=True)),
-             ("noeq_96x160", 96, 160, 18, dict(equalize_rgb=False))]
+             ("noeq_96x160", 96, 160, 18, dict(equalize_rgb=False)),
+             ("tiles4x2_96x160", 96, 160, 19, dict(horizontal_blocks=4, vertical_blocks=2)),
+             ("tiles2x3_adaptive_96x160", 96, 160, 20, dict(horizontal_blocks=2, vertical_blocks=3, adaptive_cast_correction=True))]
     for name, h, w, seed, flags in cases:
         img = synth.gen_underwater(h, w, seed, targets=(name != "default_64x64_notargets"))
+        if name.startswith("tiles"):   # make one quadrant differ enough for the fall-back rule (line 474) to matter
+            img[:h // 2, :w // 2] = np.clip(img[:h // 2, :w // 2].astype(int) + np.array([25, 5, 0]), 0, 255).astype(np.uint8)
         out = ref_balance.balance(img, **flags)
         np.savez_compressed(os.path.join(OUT, "balance_%s.npz" % name), src=img, out=out,
                             flags=np.array(sorted(flags.items()), dtype=object) if flags else np.array([], dtype=object))

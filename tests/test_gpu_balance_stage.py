@@ -68,6 +68,33 @@ def test_balance_flag_combinations(ctx, flags):
     assert np.array_equal(got, oracle_balance(img, **flags))
 
 
+@pytest.mark.parametrize("hb,vb,flags", [(2, 2, {}), (4, 2, {}), (1, 3, {}), (8, 5, {}), (4, 4, dict(adaptive_cast_correction=True)),
+                                         (2, 2, dict(rgb_contrast_correct=True)), (5, 2, dict(hsv_contrast_correct=False)),
+                                         (16, 12, {})])
+def test_balance_tiled_equalisation(ctx, hb, vb, flags):
+    """horizontal/vertical_blocks > 1 (P1, color_balance.cpp:441-544): per-tile gains with the
+    fall-back-to-global rule of line 474."""
+    img = synth.gen_underwater(240, 320, 5)
+    img[:120, :160] = np.clip(img[:120, :160].astype(int) + np.array([25, 5, 0]), 0, 255).astype(np.uint8)
+    got = ctx.download(ctx.color_balance(ctx.upload(img), horizontal_blocks=hb, vertical_blocks=vb, **flags))
+    want = oracle_balance(img, horizontal_blocks=hb, vertical_blocks=vb, **flags)
+    assert np.array_equal(got, want)
+
+
+def test_balance_tiled_batch_and_stage(ctx):
+    frames = np.stack([synth.gen_underwater(240, 320, 60 + s) for s in range(3)])
+    frames[1, :120, :160] = np.clip(frames[1, :120, :160].astype(int) + np.array([30, 0, 0]), 0, 255).astype(np.uint8)
+    desc = ctx.make_stage(balance=dict(horizontal_blocks=4, vertical_blocks=2), cvt="bgr2hsv", lo=(0, 40, 60),
+                          hi=(179, 255, 255), morph=[("open", 5, 5, 1)])
+    out = ctx.stage(desc, ctx.upload(frames), want=("balanced", "mask"))
+    for i in range(3):
+        b_ref = oracle_balance(frames[i], horizontal_blocks=4, vertical_blocks=2)
+        assert np.array_equal(ctx.download(out["balanced"])[i], b_ref)
+        m_ref = cv2.morphologyEx(cv2.inRange(cv2.cvtColor(b_ref, cv2.COLOR_BGR2HSV), np.array([0, 40, 60]),
+                                             np.array([179, 255, 255])), cv2.MORPH_OPEN, cv_ops.rect_kernel(5))
+        assert np.array_equal(ctx.download(out["mask"])[i], m_ref)
+
+
 def test_balance_batch_of_distinct_frames_and_in_place(ctx):
     frames = np.stack([synth.gen_underwater(242, 368, 40 + s) for s in range(11)])
     d = ctx.upload(frames)
@@ -93,7 +120,7 @@ def test_balance_unsupported_flags_fail_loudly(ctx):
     with pytest.raises(bv.BVError):
         ctx.color_balance(d, hsi_contrast_correct=True)
     with pytest.raises(bv.BVError):
-        ctx.color_balance(d, horizontal_blocks=2)
+        ctx.color_balance(d, horizontal_blocks=3)       # 64 % 3 != 0: the reference walks off the row here
 
 
 def test_balance_degenerate_frame_is_defined(ctx):
