@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const uint32_t *__restric
     }
 }
 
+template <bool CONN8>
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint32_t *__restrict__ bits, int *__restrict__ parent,
                                                         int height, int width, int wpr, size_t total_words) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -120,8 +121,9 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint32_t *__restri
         if (wp.y == 0) continue;
         // (b) row above, 34-bit window: bit k <-> x = xbase + k - 1
         const uint32_t up = bits[i - wpr];
-        const uint32_t upl = wp.wx > 0 ? bits[i - wpr - 1] : 0u;
-        const uint32_t upr = wp.wx < wpr - 1 ? bits[i - wpr + 1] : 0u;
+        // 4-connectivity (background regions of an 8-connected foreground) has no diagonal contacts
+        const uint32_t upl = (CONN8 && wp.wx > 0) ? bits[i - wpr - 1] : 0u;
+        const uint32_t upr = (CONN8 && wp.wx < wpr - 1) ? bits[i - wpr + 1] : 0u;
         const unsigned long long U = ((unsigned long long)up << 1) | (unsigned long long)(upl >> 31) |
                                      ((unsigned long long)(upr & 1u) << 33);
         if (!U) continue;
@@ -133,9 +135,9 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint32_t *__restri
             const uint32_t above_s = w >> s;                       // run from bit s
             const int len = __ffs(~above_s) - 1;                   // ~above_s != 0 unless run spans to bit 31
             const int e = (len < 0) ? 31 : s + len - 1;            // __ffs(0) = 0 -> len = -1
-            // run occupies window bits s+1..e+1; its 8-neighbourhood above is s..e+2
-            const int nb = e - s + 3;
-            const unsigned long long dil = ((nb >= 64) ? ~0ull : ((1ull << nb) - 1ull)) << s;
+            // run occupies window bits s+1..e+1; its 8-neighbourhood above is s..e+2 (4-conn: s+1..e+1)
+            const int nb = CONN8 ? e - s + 3 : e - s + 1;
+            const unsigned long long dil = ((nb >= 64) ? ~0ull : ((1ull << nb) - 1ull)) << (CONN8 ? s : s + 1);
             unsigned long long T = U & dil;
             const int node = wp.y * width + xbase + s;
             while (T) {
@@ -231,13 +233,14 @@ __global__ void __launch_bounds__(1024) ccl_scan_kernel(const int *__restrict__ 
 // one warp per row: number the roots of the row in raster order, store -(label) in parent[root]
 __global__ void __launch_bounds__(256) ccl_rank_kernel(const uint32_t *__restrict__ bits, int *__restrict__ parent,
                                                        const int *__restrict__ row_off, int height, int width, int wpr,
-                                                       size_t total_rows) {
+                                                       size_t total_rows, int *__restrict__ root_px, int max_roots) {
     const int lane = threadIdx.x & 31;
     const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t row = warp0; row < total_rows; row += nwarps) {
         const int y = (int)(row % height);
         int *fp = parent + (row - y) * (size_t)width;
+        int *frame_roots = root_px ? root_px + ((row - y) / height) * (size_t)max_roots : nullptr;
         int next = row_off[row];  // labels handed out so far (0-based rank of the next root)
         for (int wbase = 0; wbase < wpr; wbase += 32) {
             const int wx = wbase + lane;
@@ -262,6 +265,7 @@ __global__ void __launch_bounds__(256) ccl_rank_kernel(const uint32_t *__restric
                 const int s = __ffs(roots) - 1;
                 roots &= roots - 1;
                 fp[y * width + wx * 32 + s] = -(rank + 1);
+                if (frame_roots && rank < max_roots) frame_roots[rank] = y * width + wx * 32 + s;
                 ++rank;
             }
             next += __shfl_sync(0xFFFFFFFFu, incl, 31);
@@ -425,8 +429,16 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restri
     }
 }
 
+static int label_bits_ex(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, int height, int width,
+                         bv_blob *blobs, int max_blobs, int32_t *n_blobs, int *root_px, int max_roots);
+
 int label_bits(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, int height, int width, bv_blob *blobs,
                int max_blobs, int32_t *n_blobs) {
+    return label_bits_ex(ctx, bits, labels, batch, height, width, blobs, max_blobs, n_blobs, nullptr, 0);
+}
+
+static int label_bits_ex(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, int height, int width,
+                         bv_blob *blobs, int max_blobs, int32_t *n_blobs, int *root_px, int max_roots) {
     const int wpr = words_per_row(width);
     const size_t total_words = (size_t)batch * height * wpr;
     const size_t total_rows = (size_t)batch * height;
@@ -443,10 +455,10 @@ int label_bits(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, in
     const int gw = grid_for(ctx, total_words, 256, 8);
     const int gr = grid_for(ctx, total_rows * 32, 256, 8);
     BV_LAUNCH(ctx, ccl_init_kernel, gw, 256, 0, bits, parent, height, width, wpr, total_words);
-    BV_LAUNCH(ctx, ccl_merge_kernel, gw, 256, 0, bits, parent, height, width, wpr, total_words);
+    BV_LAUNCH(ctx, ccl_merge_kernel<true>, gw, 256, 0, bits, parent, height, width, wpr, total_words);
     BV_LAUNCH(ctx, ccl_count_kernel, gr, 256, 0, bits, parent, row_count, height, width, wpr, total_rows);
     BV_LAUNCH(ctx, ccl_scan_kernel, batch, 1024, 0, row_count, row_off, nb, height);
-    BV_LAUNCH(ctx, ccl_rank_kernel, gr, 256, 0, bits, parent, row_off, height, width, wpr, total_rows);
+    BV_LAUNCH(ctx, ccl_rank_kernel, gr, 256, 0, bits, parent, row_off, height, width, wpr, total_rows, root_px, max_roots);
     if (blobs && max_blobs > 0) {
         dim3 g((unsigned)min(64, (max_blobs + 255) / 256), batch);
         BV_LAUNCH(ctx, ccl_blob_init_kernel, g, 256, 0, blobs, nb, max_blobs, height, width);
@@ -454,6 +466,184 @@ int label_bits(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, in
     if (labels || (blobs && max_blobs > 0))
         BV_LAUNCH(ctx, ccl_final_kernel, gw, 256, 0, bits, parent, labels, (max_blobs > 0 ? blobs : nullptr), max_blobs,
                   height, width, wpr, total_words);
+    return BV_OK;
+}
+
+
+// ----------------------------------------------------------------------------------------------
+// Outer borders as cv2.findContours(RETR_EXTERNAL) follows them, with the Green's-theorem sums of
+// cv2.moments(contour) -- the literal reference path outer_contours -> contour_centroid /
+// contour_area (utils/feature.py:5-21,240-265), SURVEY.md 8f rank 1.
+//
+//  * the start pixel of a component's outer border is its first pixel in raster order, i.e. the
+//    union-find root that the labelling already produces;
+//  * RETR_EXTERNAL drops components that lie inside a hole of another one: a component is external
+//    iff the background left of its start pixel belongs to a (4-connected) background region that
+//    reaches the image frame; background regions are labelled with the same union-find machinery
+//    on the inverted mask and the frame-touching ones are marked in a bitmap;
+//  * one thread walks one border with Suzuki's 8-neighbour rule (clockwise search for the first
+//    neighbour, then counter-clockwise from the direction it came from) and accumulates
+//    a00 = sum(x' y - x y'), a10 = sum(dxy (x' + x)), a01 = sum(dxy (y' + y)) in int64: exact, and
+//    independent of CHAIN_APPROX_SIMPLE (collinear points split a term into equal parts).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) invert_bits_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
+                                                          int width, int wpr, size_t total_words) {
+    const int tail = width - (wpr - 1) * 32;
+    const uint32_t tail_mask = tail == 32 ? 0xFFFFFFFFu : ((1u << tail) - 1u);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+        uint32_t w = ~src[i];
+        if ((int)(i % wpr) == wpr - 1) w &= tail_mask;
+        dst[i] = w;
+    }
+}
+
+// node (pixel index of the run start) of the set pixel (y, x) in a bit image
+__device__ __forceinline__ int node_of(const uint32_t *frame_bits, int wpr, int width, int y, int x) {
+    const uint32_t w = frame_bits[(size_t)y * wpr + (x >> 5)];
+    return y * width + (x & ~31) + run_start(w, x & 31);
+}
+
+// mark the background regions that touch the image frame: outer[root >> 5] |= 1 << (root & 31)
+__global__ void __launch_bounds__(256) bg_outer_kernel(const uint32_t *__restrict__ inv, const int *__restrict__ parent,
+                                                       uint32_t *__restrict__ outer, int height, int width, int wpr,
+                                                       int batch) {
+    const int per_frame = 2 * width + 2 * height;
+    const size_t total = (size_t)per_frame * batch;
+    const size_t words_per_frame = ((size_t)height * width + 31) / 32;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i / per_frame);
+        int k = (int)(i - (size_t)f * per_frame), x, y;
+        if (k < width) { y = 0; x = k; }
+        else if (k < 2 * width) { y = height - 1; x = k - width; }
+        else if (k < 2 * width + height) { x = 0; y = k - 2 * width; }
+        else { x = width - 1; y = k - 2 * width - height; }
+        const uint32_t *fb = inv + (size_t)f * height * wpr;
+        if (!((fb[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u)) continue;
+        const int *fp = parent + (size_t)f * height * width;
+        const int node = node_of(fb, wpr, width, y, x);
+        const int p = fp[node];
+        const int root = p;  // nodes were compressed to their root by ccl_count_kernel (roots point to themselves)
+        atomicOr(&outer[(size_t)f * words_per_frame + (root >> 5)], 1u << (root & 31));
+    }
+}
+
+__device__ __forceinline__ bool bit_at(const uint32_t *fb, int wpr, int width, int height, int x, int y) {
+    if ((unsigned)x >= (unsigned)width || (unsigned)y >= (unsigned)height) return false;
+    return (fb[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
+}
+
+__global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ inv,
+                                                      const int *__restrict__ parent_bg, const uint32_t *__restrict__ outer,
+                                                      const int *__restrict__ root_px, const int *__restrict__ n_blobs,
+                                                      bv_contour *__restrict__ out, int max_contours, int height, int width,
+                                                      int wpr) {
+    const int f = blockIdx.y;
+    const int n = min(n_blobs[f], max_contours);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const uint32_t *fb = bits + (size_t)f * height * wpr;
+    const int start = root_px[(size_t)f * max_contours + idx];
+    const int y0 = start / width, x0 = start - y0 * width;
+    bv_contour c;
+    c.label = idx + 1;
+    c.start_x = x0;
+    c.start_y = y0;
+    // external iff the background on the left reaches the frame (or the start pixel is on the frame)
+    int external = 1;
+    if (x0 > 0) {
+        const uint32_t *fi = inv + (size_t)f * height * wpr;
+        const int node = node_of(fi, wpr, width, y0, x0 - 1);
+        const int root = parent_bg[(size_t)f * height * width + node];
+        const size_t words_per_frame = ((size_t)height * width + 31) / 32;
+        external = (outer[(size_t)f * words_per_frame + (root >> 5)] >> (root & 31)) & 1u;
+    }
+    c.external = external;
+    // Suzuki border following, direction codes 0..7 = E, NE, N, NW, W, SW, S, SE (y grows downwards)
+    // dx = {1,1,0,-1,-1,-1,0,1}, dy = {0,-1,-1,-1,0,1,1,1} as nibble tables (value + 1), so that the
+    // dynamically indexed look-up stays in registers
+#define dx(s) ((int)((0x21000122u >> (4 * (s))) & 0xFu) - 1)
+#define dy(s) ((int)((0x22210001u >> (4 * (s))) & 0xFu) - 1)
+    long long a00 = 0, a10 = 0, a01 = 0;
+    int bx0 = x0, bx1 = x0, by0 = y0, by1 = y0, npts = 1;
+    int s = 4;
+    bool found = false;
+    for (int k = 0; k < 7; ++k) {  // clockwise from W: NW, N, NE, E, SE, S, SW
+        s = (s - 1) & 7;
+        if (bit_at(fb, wpr, width, height, x0 + dx(s), y0 + dy(s))) {
+            found = true;
+            break;
+        }
+    }
+    if (found) {
+        const int x1 = x0 + dx(s), y1 = y0 + dy(s);  // i1: the first neighbour, where the walk will end
+        int cx = x0, cy = y0;                        // i3
+        npts = 0;
+        for (;;) {
+            int nx, ny;
+            for (;;) {  // counter-clockwise, starting just after the direction we came from
+                s = (s + 1) & 7;
+                nx = cx + dx(s);
+                ny = cy + dy(s);
+                if (bit_at(fb, wpr, width, height, nx, ny)) break;
+            }
+            // polygon edge (cx,cy) -> (nx,ny)
+            const long long dxy = (long long)cx * ny - (long long)nx * cy;
+            a00 += dxy;
+            a10 += dxy * (cx + nx);
+            a01 += dxy * (cy + ny);
+            ++npts;
+            bx0 = min(bx0, cx); bx1 = max(bx1, cx); by0 = min(by0, cy); by1 = max(by1, cy);
+            if (nx == x0 && ny == y0 && cx == x1 && cy == y1) break;
+            cx = nx;
+            cy = ny;
+            s = (s + 4) & 7;
+        }
+    }
+    c.a00 = a00;
+    c.a10 = a10;
+    c.a01 = a01;
+    c.x0 = bx0; c.y0 = by0; c.x1 = bx1; c.y1 = by1;
+    c.n_points = npts;
+    c.reserved = 0;
+    out[(size_t)f * max_contours + idx] = c;
+#undef dx
+#undef dy
+}
+
+int outer_contours_bits(bv_ctx *ctx, const uint32_t *bits, int batch, int height, int width, bv_contour *contours,
+                        int max_contours, int32_t *n_contours) {
+    const int wpr = words_per_row(width);
+    const size_t total_words = (size_t)batch * height * wpr;
+    const size_t total_rows = (size_t)batch * height;
+    const size_t px = (size_t)height * width;
+    const size_t outer_words = (px + 31) / 32;
+    BV_TRY(ensure_scratch(ctx, SCR_CCL_ROOTS, (size_t)batch * max_contours * sizeof(int)));
+    BV_TRY(ensure_scratch(ctx, SCR_BITS_B, total_words * 8));
+    BV_TRY(ensure_scratch(ctx, SCR_CCL_PARENT2, total_rows * width * sizeof(int)));
+    BV_TRY(ensure_scratch(ctx, SCR_CCL_AUX2, (total_rows + (size_t)batch * outer_words) * sizeof(int)));
+    int *root_px = (int *)ctx->scratch[SCR_CCL_ROOTS];
+    uint32_t *inv = (uint32_t *)ctx->scratch[SCR_BITS_B];
+    int *parent_bg = (int *)ctx->scratch[SCR_CCL_PARENT2];
+    int *row_count_bg = (int *)ctx->scratch[SCR_CCL_AUX2];
+    uint32_t *outer = (uint32_t *)(row_count_bg + total_rows);
+    // foreground: labels are not needed, only the roots in raster order
+    BV_TRY(label_bits_ex(ctx, bits, nullptr, batch, height, width, nullptr, 0, n_contours, root_px, max_contours));
+    // background, 4-connected
+    const int gw = grid_for(ctx, total_words, 256, 8);
+    const int gr = grid_for(ctx, total_rows * 32, 256, 8);
+    BV_LAUNCH(ctx, invert_bits_kernel, gw, 256, 0, bits, inv, width, wpr, total_words);
+    BV_LAUNCH(ctx, ccl_init_kernel, gw, 256, 0, inv, parent_bg, height, width, wpr, total_words);
+    BV_LAUNCH(ctx, ccl_merge_kernel<false>, gw, 256, 0, inv, parent_bg, height, width, wpr, total_words);
+    BV_LAUNCH(ctx, ccl_count_kernel, gr, 256, 0, inv, parent_bg, row_count_bg, height, width, wpr, total_rows);
+    BV_CUDA(cudaMemsetAsync(outer, 0, (size_t)batch * outer_words * 4, ctx->stream));
+    BV_LAUNCH(ctx, bg_outer_kernel, grid_for(ctx, (size_t)batch * (2 * width + 2 * height), 256, 8), 256, 0, inv, parent_bg,
+              outer, height, width, wpr, batch);
+    // label_bits_ex wrote the blob count to n_contours (or its own scratch when NULL)
+    const int *nb = n_contours ? n_contours : (int *)ctx->scratch[SCR_CCL_AUX] + 2 * total_rows;
+    dim3 grid((max_contours + 127) / 128, batch);
+    BV_LAUNCH(ctx, contour_kernel, grid, 128, 0, bits, inv, parent_bg, outer, root_px, nb, contours, max_contours, height,
+              width, wpr);
     return BV_OK;
 }
 
@@ -472,4 +662,16 @@ extern "C" int bv_label(bv_ctx *ctx, const uint8_t *mask_dev, int32_t *labels_de
     uint32_t *bits = (uint32_t *)ctx->scratch[SCR_BITS_A];
     BV_TRY(mask_to_bits(ctx, mask_dev, bits, batch, height, width));
     return label_bits(ctx, bits, labels_dev, batch, height, width, blobs_dev, max_blobs, n_blobs_dev);
+}
+
+extern "C" int bv_outer_contours(bv_ctx *ctx, const uint8_t *mask_dev, int batch, int height, int width,
+                                 bv_contour *contours_dev, int max_contours, int32_t *n_contours_dev) {
+    BV_REQUIRE(ctx && mask_dev && contours_dev, "null argument");
+    BV_REQUIRE(batch > 0 && height > 0 && width > 0 && max_contours > 0, "sizes must be positive");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)batch * bits_frame_words(height, width);
+    BV_TRY(ensure_scratch(ctx, SCR_BITS_A, words * 4));
+    uint32_t *bits = (uint32_t *)ctx->scratch[SCR_BITS_A];
+    BV_TRY(mask_to_bits(ctx, mask_dev, bits, batch, height, width));
+    return outer_contours_bits(ctx, bits, batch, height, width, contours_dev, max_contours, n_contours_dev);
 }

@@ -56,6 +56,9 @@ enum ScratchSlot {
     SCR_BITS_B,         // bit-packed masks (pong)
     SCR_CCL_PARENT,     // union-find parents, int32 per pixel
     SCR_CCL_AUX,        // per-block root counts / offsets
+    SCR_CCL_PARENT2,    // union-find parents of the background regions (outer contours)
+    SCR_CCL_AUX2,       // background row counts + frame-touching bitmap
+    SCR_CCL_ROOTS,      // first pixel of every blob, raster order
     SCR_MORPH_TMP,      // intermediate image of multi-step grey morphology
     SCR_MORPH_TMP2,
     SCR_MORPH_SE,       // structuring-element offsets

@@ -29,6 +29,44 @@ def label_blobs(mat, max_blobs=4096, want_labels=True):
     return labels, out, int(n[0])
 
 
+class Contour(dict):
+    """One outer border (cv2.findContours RETR_EXTERNAL) reduced to its Green's-theorem sums."""
+
+
+def outer_contours(mat, max_contours=4096):
+    """utils/feature.py:5-21 on the GPU: the outermost 8-connected borders of `mat != 0`, in raster
+    order of their first pixel (cv2 returns the same set, in its own order).  Each record carries
+    what the reference consumes next (contour_centroid / contour_area below)."""
+    from .runtime import CONTOUR_DTYPE
+    ctx = ctx_for(mat)
+    table, nb = ctx.outer_contours(to_device(ctx, mat), max_contours=max_contours)
+    n = int(ctx.download(nb)[0])
+    raw = ctx.download(table)[0, :min(n, max_contours)].copy().view(CONTOUR_DTYPE).reshape(-1)
+    return [Contour({k: int(row[k]) for k in CONTOUR_DTYPE.names}) for row in raw if row["external"]]
+
+
+def _contour_moments(c):
+    """m00, m10, m01 exactly as cv2.moments(contour) scales its sums (contourMoments: multiply by
+    +-0.5 and +-1/6 in double)."""
+    a00, a10, a01 = float(c["a00"]), float(c["a10"]), float(c["a01"])
+    if abs(a00) <= 1.1920928955078125e-07:      # FLT_EPSILON: degenerate border, all moments 0
+        return 0.0, 0.0, 0.0
+    db1_2, db1_6 = (0.5, 0.16666666666666666666666666666667) if a00 > 0 else (-0.5, -0.16666666666666666666666666666667)
+    return a00 * db1_2, a10 * db1_6, a01 * db1_6
+
+
+def contour_centroid(contour):
+    """utils/feature.py:240-252."""
+    m00, m10, m01 = _contour_moments(contour)
+    m00 = max(1e-10, m00)
+    return int(m10 / m00), int(m01 / m00)
+
+
+def contour_area(contour):
+    """utils/feature.py:255-265 (cv2.contourArea, oriented=False)."""
+    return abs(float(contour["a00"]) * 0.5)
+
+
 def blob_centroid(blob):
     """Same rounding rule as contour_centroid (utils/feature.py:250-252): int(m10/m00), int(m01/m00)."""
     m00 = max(1e-10, float(blob["m00"]))

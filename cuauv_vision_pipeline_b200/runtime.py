@@ -25,6 +25,10 @@ THRESH = {"binary": lib.BV_THRESH_BINARY, "binary_inv": lib.BV_THRESH_BINARY_INV
 BLOB_DTYPE = np.dtype([(k, "<i8") for k in ("m00", "m10", "m01", "m20", "m11", "m02", "m30", "m21", "m12", "m03")] +
                       [(k, "<i4") for k in ("x0", "y0", "x1", "y1")])
 assert BLOB_DTYPE.itemsize == ffi.sizeof("bv_blob")
+CONTOUR_DTYPE = np.dtype([(k, "<i8") for k in ("a00", "a10", "a01")] +
+                         [(k, "<i4") for k in ("x0", "y0", "x1", "y1", "start_x", "start_y", "n_points", "label",
+                                               "external", "reserved")])
+assert CONTOUR_DTYPE.itemsize == ffi.sizeof("bv_contour")
 
 
 def _u8ptr(t):
@@ -247,6 +251,18 @@ class Context:
                            b, h, w, ffi.cast("bv_blob *", blobs.data_ptr()) if max_blobs else ffi.NULL, max_blobs,
                            ffi.cast("int32_t *", nb.data_ptr())))
         return labels, blobs, nb
+
+    def outer_contours(self, mask, max_contours=4096):
+        """Device mask [H,W] or [B,H,W] -> (structured device table as uint8 [B,max,64], count [B])."""
+        if mask.dim() == 2:
+            b, h, w = 1, mask.shape[0], mask.shape[1]
+        else:
+            b, h, w = mask.shape[0], mask.shape[1], mask.shape[2]
+        table = self.empty((b, max_contours, CONTOUR_DTYPE.itemsize), torch.uint8)
+        nb = self.empty((b,), torch.int32)
+        check(lib.bv_outer_contours(self.handle, _u8ptr(mask), b, h, w, ffi.cast("bv_contour *", table.data_ptr()),
+                                    max_contours, ffi.cast("int32_t *", nb.data_ptr())))
+        return table, nb
 
     def blobs_to_numpy(self, blobs, nb):
         """Device blob table -> list (per frame) of structured numpy arrays."""

@@ -194,6 +194,26 @@ int bv_morph(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, i
 int bv_label(bv_ctx *ctx, const uint8_t *mask_dev, int32_t *labels_dev, int batch, int height, int width,
              bv_blob *blobs_dev, int max_blobs, int32_t *n_blobs_dev);
 
+/* One outer border as cv2.findContours(mask, RETR_EXTERNAL, ...) follows it (utils/feature.py:5-21),
+ * reduced to what the reference consumes: the Green's-theorem sums of cv2.moments(contour)
+ * (contour_centroid, utils/feature.py:240-252) and cv2.contourArea (255-265):
+ *   m00 = |a00| / 2,   m10 = a10 / 6,   m01 = a01 / 6   (signs flipped when a00 < 0). */
+typedef struct bv_contour {
+    int64_t a00, a10, a01;
+    int32_t x0, y0, x1, y1;   /* bounding box of the border pixels (inclusive)                    */
+    int32_t start_x, start_y; /* first border pixel = the component's first pixel in raster order */
+    int32_t n_points;         /* border pixels visited (length of the CHAIN_APPROX_NONE contour)  */
+    int32_t label;            /* the component's label in bv_label's numbering                    */
+    int32_t external;         /* 1: reported by RETR_EXTERNAL; 0: lies inside another blob's hole */
+    int32_t reserved;
+} bv_contour;
+
+/* contours_dev: bv_contour[batch * max_contours], one record per 8-connected component in raster
+ * order of its first pixel (filter on .external for the RETR_EXTERNAL set); n_contours_dev:
+ * int32[batch] number of components (may exceed max_contours; may be NULL). */
+int bv_outer_contours(bv_ctx *ctx, const uint8_t *mask_dev, int batch, int height, int width,
+                      bv_contour *contours_dev, int max_contours, int32_t *n_contours_dev);
+
 /* ---- resize / YOLO input ------------------------------------------------------------------ */
 /* cv2.resize(..., INTER_LINEAR) on uint8 (utils/transform.py:179, modules/preprocessor.py:136-143). */
 int bv_resize_linear(bv_ctx *ctx, const uint8_t *src_dev, int src_h, int src_w, uint8_t *dst_dev, int dst_h,

@@ -240,3 +240,68 @@ def test_full_size_properties(ctx, shape):
     lat = synth.mask_lattice(h, w)
     _, _, nb = ctx.label(ctx.upload(lat), max_blobs=0, want_labels=False)
     assert int(ctx.download(nb)[0]) == (h // 2) * (w // 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# the literal reference path: outer contours + polygon centroid / area
+# ----------------------------------------------------------------------------------------------
+def check_contours(mask):
+    from cuauv_vision_pipeline_b200 import feature
+    ref = {}
+    for c in cv_ops.outer_contours(np.ascontiguousarray(mask)):
+        ref[(int(c[0, 0, 0]), int(c[0, 0, 1]))] = (cv_ops.contour_centroid(c), cv_ops.contour_area(c),
+                                                   cv2.boundingRect(c))
+    got = feature.outer_contours(mask, max_contours=max(16, 4 * len(ref) + 64))
+    assert len(got) == len(ref)
+    for g in got:
+        key = (g["start_x"], g["start_y"])
+        assert key in ref, key
+        centroid, area, (bx, by, bw, bh) = ref[key]
+        assert feature.contour_centroid(g) == centroid, key
+        assert feature.contour_area(g) == area, key
+        assert (g["x0"], g["y0"], g["x1"] - g["x0"] + 1, g["y1"] - g["y0"] + 1) == (bx, by, bw, bh), key
+    return len(ref)
+
+
+@pytest.mark.parametrize("shape,seed", [((270, 480), 3), ((479, 641), 4), ((1080, 1920), 5), ((65, 33), 6)])
+def test_outer_contours_match_findcontours(ctx, shape, seed):
+    assert check_contours(synth.mask_blobs(shape[0], shape[1], seed, sigma=5.0)) > 0
+
+
+def test_outer_contours_nested_rings_report_only_the_outermost(ctx):
+    assert check_contours(synth.mask_rings(301, 403)) == 1
+
+
+@pytest.mark.parametrize("density", [0.2, 0.5, 0.7])
+def test_outer_contours_noise(ctx, density):
+    check_contours(synth.mask_random(150, 211, 21, density))
+
+
+def test_outer_contours_special_shapes(ctx):
+    m = np.zeros((40, 70), np.uint8)
+    m[3, 5] = 255                               # single pixel
+    m[8, 10:30] = 255                           # 1-px horizontal line
+    m[12:30, 40] = 255                          # 1-px vertical line
+    for k in range(10):
+        m[15 + k, 5 + k] = 255                  # diagonal
+    m[32:38, 50:60] = 255
+    m[34:36, 53:57] = 0                         # a hole
+    m[0, 0] = m[39, 69] = m[0, 69] = 255        # frame corners
+    m[20:26, 60:70] = 255                       # touches the right edge
+    m[22:24, 62:66] = 0
+    m[22, 63] = 255                             # island inside the hole: must not be reported
+    check_contours(m)
+    check_contours(synth.mask_serpentine(41, 53))
+    check_contours(synth.mask_diagonals(60, 90))
+    check_contours(np.full((30, 40), 255, np.uint8))
+    assert check_contours(np.zeros((30, 40), np.uint8)) == 0
+
+
+def test_bins_module_pipeline_with_reference_contours(ctx):
+    """modules/bins.py:13-27 end to end: threshold -> OPEN -> outer contours, centroid and area of every contour."""
+    img = synth.gen_underwater(480, 640, 77)
+    _, cleaned = cv_ops.bins_mask(img)
+    desc = ctx.make_stage(cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255), morph=[("open", 5, 5, 1)])
+    mask = ctx.stage(desc, ctx.upload(img), want=("mask",))["mask"]
+    assert np.array_equal(ctx.download(mask), cleaned)
+    check_contours(cleaned)
