@@ -92,6 +92,7 @@ class BuoyLABGPU(ModuleBase):
         self.ctx = default_context(device)
         self.thresh = (thresh_min, thresh_max)
         self.result = None
+        self.contour_result = None
 
     def process(self, direction, image):
         self._shape = image.shape[:2]
@@ -101,7 +102,8 @@ class BuoyLABGPU(ModuleBase):
         threshed_desc = self.ctx.make_stage(cvt="bgr2lab", lo=(0, lo, 0), hi=(255, hi, 255))
         cleaned_desc = self.ctx.make_stage(cvt="bgr2lab", lo=(0, lo, 0), hi=(255, hi, 255),
                                            morph=[("open", 5, 5, 1), ("close", 5, 5, 1)], label=True)
-        self.post("threshed", self.ctx.stage_host(threshed_desc, image, want=("mask",))["mask"], "GRAY")
+        threshed = self.ctx.stage_host(threshed_desc, image, want=("mask",))["mask"]
+        self.post("threshed", threshed, "GRAY")
         out = self.ctx.stage_host(cleaned_desc, image, want=("mask", "blobs"), max_blobs=1024)
         self.post("threshed_cleaned", out["mask"], "GRAY")
         n = min(int(out["n_blobs"][0]), 1024)
@@ -112,6 +114,16 @@ class BuoyLABGPU(ModuleBase):
             x, y = feature.blob_centroid(best)
             ny, nx = self.normalize((y, x))
             self.result = dict(center_x=nx, center_y=ny, area=float(best["m00"]), pixel=(x, y))
+        # the literal reference path (red_buoy.py:38-44): outer contours of the UN-cleaned mask, polygon
+        # centroid and area; "most likely contour" (line 40, logic omitted upstream) = largest area here
+        contours = feature.outer_contours(threshed)
+        if contours:
+            c = max(contours, key=feature.contour_area)
+            cx, cy = feature.contour_centroid(c)
+            cny, cnx = self.normalize((cy, cx))
+            self.contour_result = dict(center_x=cnx, center_y=cny, area=feature.contour_area(c), pixel=(cx, cy))
+        else:
+            self.contour_result = None
         return self.result
 
 

@@ -341,5 +341,10 @@ def test_drop_in_modules(ctx):
         assert res["area"] == float(tab["m00"][i])
     else:
         assert res is None
+    ref_contours = cv_ops.outer_contours(th)                      # red_buoy.py:38 (un-cleaned mask)
+    if ref_contours:
+        best = max(ref_contours, key=cv_ops.contour_area)
+        assert buoy.contour_result["pixel"] == cv_ops.contour_centroid(best)
+        assert buoy.contour_result["area"] == cv_ops.contour_area(best)
     cbm = ColorBalanceGPU(["forward"])
     assert np.array_equal(cbm.process("forward", img), oracle_balance(img))
