@@ -74,25 +74,27 @@ __device__ __forceinline__ int run_start(uint32_t w, int pos) {
 
 struct WordPos {
     int wx, y;
-    size_t row;  // frame * height + y
+    uint32_t row;  // frame * height + y
 };
 
-__device__ __forceinline__ WordPos word_pos(size_t i, int wpr, int height) {
+// 32-bit index math throughout the word-indexed kernels (64-bit div/mod costs ~10x; the host
+// refuses batches of 2^31 words or more)
+__device__ __forceinline__ WordPos word_pos(uint32_t i, int wpr, int height) {
     WordPos p;
-    p.wx = (int)(i % wpr);
-    p.row = i / wpr;
-    p.y = (int)(p.row % height);
+    p.wx = (int)(i % (uint32_t)wpr);
+    p.row = i / (uint32_t)wpr;
+    p.y = (int)(p.row % (uint32_t)height);
     return p;
 }
 
 __global__ void __launch_bounds__(256) ccl_init_kernel(const uint32_t *__restrict__ bits, int *__restrict__ parent,
-                                                       int height, int width, int wpr, size_t total_words) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+                                                       int height, int width, int wpr, uint32_t total_words) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
         const uint32_t w = bits[i];
         if (!w) continue;
         const WordPos wp = word_pos(i, wpr, height);
-        int *fp = parent + (wp.row - wp.y) * (size_t)width;  // this frame's parent array
+        int *fp = parent + (size_t)(wp.row - wp.y) * width;  // this frame's parent array
         uint32_t starts = w & ~(w << 1);
         while (starts) {
             const int s = __ffs(starts) - 1;
@@ -105,13 +107,13 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const uint32_t *__restric
 
 template <bool CONN8>
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint32_t *__restrict__ bits, int *__restrict__ parent,
-                                                        int height, int width, int wpr, size_t total_words) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+                                                        int height, int width, int wpr, uint32_t total_words) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
         const uint32_t w = bits[i];
         if (!w) continue;
         const WordPos wp = word_pos(i, wpr, height);
-        int *fp = parent + (wp.row - wp.y) * (size_t)width;
+        int *fp = parent + (size_t)(wp.row - wp.y) * width;
         const int xbase = wp.wx * 32;
         // (a) continuation of the previous word's last run
         if ((w & 1u) && wp.wx > 0) {
@@ -343,19 +345,30 @@ __device__ __forceinline__ void blob_atomic_add(bv_blob *b, const RunSums &r) {
 __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ parent,
                                                         int *__restrict__ labels, bv_blob *__restrict__ blobs,
                                                         int max_blobs, int height, int width, int wpr,
-                                                        size_t total_words) {
+                                                        uint32_t total_words) {
     __shared__ int tile[8][32][33];
     const int lane = threadIdx.x & 31;
+    const bool full_words = (width & 31) == 0;
     int(*my_tile)[33] = tile[threadIdx.x >> 5];
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t rounded = (total_words + 31) / 32 * 32;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounded = (total_words + 31u) / 32u * 32u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
         const bool valid = i < total_words;
         const uint32_t w = valid ? bits[i] : 0u;
         const WordPos wp = word_pos(valid ? i : 0, wpr, height);
-        const size_t frame = (wp.row - wp.y) / height;
-        const int *fp = parent + (wp.row - wp.y) * (size_t)width;
+        const size_t frame = (wp.row - wp.y) / (uint32_t)height;
+        const int *fp = parent + (size_t)(wp.row - wp.y) * width;
         const int xbase = wp.wx * 32;
+        if (labels && full_words && !__any_sync(0xFFFFFFFFu, w != 0)) {
+            // empty warp (the common case on sparse masks): 4 KB of zeros, 128-bit coalesced stores
+            const uint32_t warp_first = i - lane;
+            if (warp_first + 32 <= total_words) {
+                int4 *base = reinterpret_cast<int4 *>(labels + (size_t)warp_first * 32);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) base[k * 32 + lane] = make_int4(0, 0, 0, 0);
+                continue;
+            }
+        }
         uint32_t rest = w;
         int written = 0;  // pixels of this word already staged
         while (__any_sync(0xFFFFFFFFu, rest != 0)) {
@@ -414,15 +427,22 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restri
         if (labels) {
             for (int x = written; x < 32; ++x) my_tile[lane][x] = 0;
             __syncwarp();
-            const size_t warp_first = i - lane;  // word index owned by lane 0
+            const uint32_t warp_first = i - lane;  // word index owned by lane 0
+            if (full_words) {  // width % 32 == 0: the label image is linear in the word index
+                int *base = labels + (size_t)warp_first * 32;
+                const int nk = min(32u, total_words - warp_first);
 #pragma unroll 4
-            for (int k = 0; k < 32; ++k) {
-                const size_t wi = warp_first + k;
-                if (wi >= total_words) break;
-                const int kwx = (int)(wi % wpr);
-                const size_t krow = wi / wpr;
-                const int x = kwx * 32 + lane;
-                if (x < width) labels[krow * (size_t)width + x] = my_tile[k][lane];
+                for (int k = 0; k < nk; ++k) base[k * 32 + lane] = my_tile[k][lane];
+            } else {
+#pragma unroll 4
+                for (int k = 0; k < 32; ++k) {
+                    const uint32_t wi = warp_first + k;
+                    if (wi >= total_words) break;
+                    const int kwx = (int)(wi % (uint32_t)wpr);
+                    const uint32_t krow = wi / (uint32_t)wpr;
+                    const int x = kwx * 32 + lane;
+                    if (x < width) labels[(size_t)krow * width + x] = my_tile[k][lane];
+                }
             }
             __syncwarp();
         }
@@ -442,8 +462,8 @@ static int label_bits_ex(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int
     const int wpr = words_per_row(width);
     const size_t total_words = (size_t)batch * height * wpr;
     const size_t total_rows = (size_t)batch * height;
-    if ((size_t)height * width >= (1ull << 31)) {
-        set_error("bv_label: frame too large for 32-bit pixel indices");
+    if ((size_t)height * width >= (1ull << 31) || total_words >= (1ull << 31)) {
+        set_error("bv_label: frame or batch too large for 32-bit indices");
         return BV_ERR_INVALID;
     }
     BV_TRY(ensure_scratch(ctx, SCR_CCL_PARENT, total_rows * width * sizeof(int)));
@@ -454,8 +474,8 @@ static int label_bits_ex(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int
     int *nb = n_blobs ? n_blobs : row_off + total_rows;
     const int gw = grid_for(ctx, total_words, 256, 8);
     const int gr = grid_for(ctx, total_rows * 32, 256, 8);
-    BV_LAUNCH(ctx, ccl_init_kernel, gw, 256, 0, bits, parent, height, width, wpr, total_words);
-    BV_LAUNCH(ctx, ccl_merge_kernel<true>, gw, 256, 0, bits, parent, height, width, wpr, total_words);
+    BV_LAUNCH(ctx, ccl_init_kernel, gw, 256, 0, bits, parent, height, width, wpr, (uint32_t)total_words);
+    BV_LAUNCH(ctx, ccl_merge_kernel<true>, gw, 256, 0, bits, parent, height, width, wpr, (uint32_t)total_words);
     BV_LAUNCH(ctx, ccl_count_kernel, gr, 256, 0, bits, parent, row_count, height, width, wpr, total_rows);
     BV_LAUNCH(ctx, ccl_scan_kernel, batch, 1024, 0, row_count, row_off, nb, height);
     BV_LAUNCH(ctx, ccl_rank_kernel, gr, 256, 0, bits, parent, row_off, height, width, wpr, total_rows, root_px, max_roots);
@@ -465,7 +485,7 @@ static int label_bits_ex(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int
     }
     if (labels || (blobs && max_blobs > 0))
         BV_LAUNCH(ctx, ccl_final_kernel, gw, 256, 0, bits, parent, labels, (max_blobs > 0 ? blobs : nullptr), max_blobs,
-                  height, width, wpr, total_words);
+                  height, width, wpr, (uint32_t)total_words);
     return BV_OK;
 }
 
@@ -487,13 +507,13 @@ static int label_bits_ex(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int
 //    independent of CHAIN_APPROX_SIMPLE (collinear points split a term into equal parts).
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) invert_bits_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
-                                                          int width, int wpr, size_t total_words) {
+                                                          int width, int wpr, uint32_t total_words) {
     const int tail = width - (wpr - 1) * 32;
     const uint32_t tail_mask = tail == 32 ? 0xFFFFFFFFu : ((1u << tail) - 1u);
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
         uint32_t w = ~src[i];
-        if ((int)(i % wpr) == wpr - 1) w &= tail_mask;
+        if ((int)(i % (uint32_t)wpr) == wpr - 1) w &= tail_mask;
         dst[i] = w;
     }
 }
@@ -632,9 +652,9 @@ int outer_contours_bits(bv_ctx *ctx, const uint32_t *bits, int batch, int height
     // background, 4-connected
     const int gw = grid_for(ctx, total_words, 256, 8);
     const int gr = grid_for(ctx, total_rows * 32, 256, 8);
-    BV_LAUNCH(ctx, invert_bits_kernel, gw, 256, 0, bits, inv, width, wpr, total_words);
-    BV_LAUNCH(ctx, ccl_init_kernel, gw, 256, 0, inv, parent_bg, height, width, wpr, total_words);
-    BV_LAUNCH(ctx, ccl_merge_kernel<false>, gw, 256, 0, inv, parent_bg, height, width, wpr, total_words);
+    BV_LAUNCH(ctx, invert_bits_kernel, gw, 256, 0, bits, inv, width, wpr, (uint32_t)total_words);
+    BV_LAUNCH(ctx, ccl_init_kernel, gw, 256, 0, inv, parent_bg, height, width, wpr, (uint32_t)total_words);
+    BV_LAUNCH(ctx, ccl_merge_kernel<false>, gw, 256, 0, inv, parent_bg, height, width, wpr, (uint32_t)total_words);
     BV_LAUNCH(ctx, ccl_count_kernel, gr, 256, 0, inv, parent_bg, row_count_bg, height, width, wpr, total_rows);
     BV_CUDA(cudaMemsetAsync(outer, 0, (size_t)batch * outer_words * 4, ctx->stream));
     BV_LAUNCH(ctx, bg_outer_kernel, grid_for(ctx, (size_t)batch * (2 * width + 2 * height), 256, 8), 256, 0, inv, parent_bg,

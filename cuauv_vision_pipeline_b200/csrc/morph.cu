@@ -21,12 +21,12 @@ namespace bv {
 // uint8 mask <-> bits
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mask_to_bits_kernel(const uint8_t *__restrict__ mask, uint32_t *__restrict__ bits,
-                                                           int height, int width, int wpr, size_t total_words) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
-        const int wx = (int)(i % wpr);
-        const size_t row = i / wpr;  // frame * height + y
-        const uint8_t *p = mask + row * (size_t)width + (size_t)wx * 32;
+                                                           int height, int width, int wpr, uint32_t total_words) {
+    const uint32_t stride = gridDim.x * blockDim.x;  // 32-bit index math: 64-bit div/mod costs ~10x
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+        const int wx = (int)(i % (uint32_t)wpr);
+        const uint32_t row = i / (uint32_t)wpr;  // frame * height + y
+        const uint8_t *p = mask + (size_t)row * width + (size_t)wx * 32;
         const int n = min(32, width - wx * 32);
         uint32_t w = 0;
         if (n == 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
@@ -45,12 +45,12 @@ __global__ void __launch_bounds__(256) mask_to_bits_kernel(const uint8_t *__rest
 }
 
 __global__ void __launch_bounds__(256) bits_to_mask_kernel(const uint32_t *__restrict__ bits, uint8_t *__restrict__ mask,
-                                                           int height, int width, int wpr, size_t total_words) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
-        const int wx = (int)(i % wpr);
-        const size_t row = i / wpr;
-        uint8_t *p = mask + row * (size_t)width + (size_t)wx * 32;
+                                                           int height, int width, int wpr, uint32_t total_words) {
+    const uint32_t stride = gridDim.x * blockDim.x;  // 32-bit index math: 64-bit div/mod costs ~10x
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+        const int wx = (int)(i % (uint32_t)wpr);
+        const uint32_t row = i / (uint32_t)wpr;
+        uint8_t *p = mask + (size_t)row * width + (size_t)wx * 32;
         const int n = min(32, width - wx * 32);
         const uint32_t w = bits[i];
         if (n == 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
@@ -69,17 +69,26 @@ __global__ void __launch_bounds__(256) bits_to_mask_kernel(const uint32_t *__res
     }
 }
 
+static int check_words(size_t total) {
+    if (total >= (1ull << 31)) {
+        set_error("bit-packed batch too large (%zu words): split the batch", total);
+        return BV_ERR_INVALID;
+    }
+    return BV_OK;
+}
+
 int mask_to_bits(bv_ctx *ctx, const uint8_t *mask, uint32_t *bits, int batch, int height, int width) {
     const int wpr = words_per_row(width);
     const size_t total = (size_t)batch * height * wpr;
-    BV_LAUNCH(ctx, mask_to_bits_kernel, grid_for(ctx, total, 256, 8), 256, 0, mask, bits, height, width, wpr, total);
+    BV_TRY(check_words(total));
+    BV_LAUNCH(ctx, mask_to_bits_kernel, grid_for(ctx, total, 256, 8), 256, 0, mask, bits, height, width, wpr, (uint32_t)total);
     return BV_OK;
 }
 
 int bits_to_mask(bv_ctx *ctx, const uint32_t *bits, uint8_t *mask, int batch, int height, int width) {
     const int wpr = words_per_row(width);
     const size_t total = (size_t)batch * height * wpr;
-    BV_LAUNCH(ctx, bits_to_mask_kernel, grid_for(ctx, total, 256, 8), 256, 0, bits, mask, height, width, wpr, total);
+    BV_LAUNCH(ctx, bits_to_mask_kernel, grid_for(ctx, total, 256, 8), 256, 0, bits, mask, height, width, wpr, (uint32_t)total);
     return BV_OK;
 }
 
@@ -88,18 +97,18 @@ int bits_to_mask(bv_ctx *ctx, const uint32_t *bits, uint8_t *mask, int batch, in
 // ----------------------------------------------------------------------------------------------
 template <bool ERODE>
 __global__ void __launch_bounds__(256) morph_bits_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
-                                                         int height, int width, int wpr, size_t total_words, int L, int R,
+                                                         int height, int width, int wpr, uint32_t total_words, int L, int R,
                                                          int U, int D) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint32_t stride = gridDim.x * blockDim.x;  // 32-bit index math: 64-bit div/mod costs ~10x
     const uint32_t neutral = ERODE ? 0xFFFFFFFFu : 0u;
     const int last = wpr - 1;
     const int tail = width - last * 32;  // valid bits in the last word of a row
     const uint32_t tail_mask = tail == 32 ? 0xFFFFFFFFu : ((1u << tail) - 1u);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
-        const int wx = (int)(i % wpr);
-        const size_t row = i / wpr;
-        const int y = (int)(row % height);
-        const uint32_t *frame_row0 = src + (row - y) * (size_t)wpr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+        const int wx = (int)(i % (uint32_t)wpr);
+        const uint32_t row = i / (uint32_t)wpr;
+        const int y = (int)(row % (uint32_t)height);
+        const uint32_t *frame_row0 = src + (size_t)(row - y) * wpr;
         uint32_t acc = neutral;
         for (int yy = max(0, y - U); yy <= min(height - 1, y + D); ++yy) {
             const uint32_t *r = frame_row0 + (size_t)yy * wpr;
@@ -152,9 +161,9 @@ static int morph_bits_basic(bv_ctx *ctx, const uint32_t *src, uint32_t *dst, uin
         L -= l; R -= r; U -= u; D -= d;
         uint32_t *out = ((passes - k) % 2 == 0) ? dst : tmp;
         if (erode)
-            BV_LAUNCH(ctx, morph_bits_kernel<true>, grid, 256, 0, cur, out, height, width, wpr, total, l, r, u, d);
+            BV_LAUNCH(ctx, morph_bits_kernel<true>, grid, 256, 0, cur, out, height, width, wpr, (uint32_t)total, l, r, u, d);
         else
-            BV_LAUNCH(ctx, morph_bits_kernel<false>, grid, 256, 0, cur, out, height, width, wpr, total, l, r, u, d);
+            BV_LAUNCH(ctx, morph_bits_kernel<false>, grid, 256, 0, cur, out, height, width, wpr, (uint32_t)total, l, r, u, d);
         cur = out;
     }
     return BV_OK;
