@@ -171,8 +171,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C2: 2208x1242 balance(default flags) + BGR2LAB, CPU reference, %d frames per step"
-                               % per_step, "frames_per_step": per_step},
+        "config": {"workload": "C2: ZED 2208x1242 stereo frames, balance() default flags -> BGR2LAB image "
+                               "(BASELINE.json configs[1])",
+                   "reference_sample": "each step = %d frames on the host cores (compiled reference process_frame + "
+                                       "cv2.cvtColor), one frame per thread" % per_step,
+                   "frames_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores,
                          "kind": "reference" if ref_balance.available() else "port",
                          "sample": "%d steps x %d frames, one frame per thread over %d threads" % (args.steps, per_step, cores)},
@@ -228,7 +231,7 @@ def side_workloads(ctx, peak_gbs):
         lambda s: o3.update(ctx.stage(d3, ring3, want=("mask", "labels", "blobs"), max_blobs=4096, out=o3)), 16, 8 * 1080 * 1920)
     # C5: 3840x2160 balance -> HSV -> inRange -> OPEN -> label (8 B/px), 8 streams
     ring5 = ctx.upload(np.stack([synth.gen_underwater(2160, 3840, 3200 + i) for i in range(8)]))
-    d5 = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=(0, 40, 60), hi=(179, 255, 255), morph=[("open", 5, 5, 1)], label=True)
+    d5 = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255), morph=[("open", 5, 5, 1)], label=True)
     o5 = {}
     fps("c5_balance_threshold_label_3840x2160",
         lambda s: o5.update(ctx.stage(d5, ring5, want=("mask", "labels", "blobs"), max_blobs=8192, out=o5)), 8, 8 * 2160 * 3840)
@@ -318,8 +321,17 @@ def run_ours(args):
     chunk_frames = min(chunk_frames, BATCH)
     dom_ms = prof[dom]["ms"] / prof[dom]["launches"]
     achieved = BPP_C2 * H * W * chunk_frames / (dom_ms / 1e3) / 1e9
+    traffic, traffic_src = None, None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        if dom in t["kernels"]:
+            per_frame = t["kernels"][dom]["dram_bytes_per_launch"] / t["kernels"][dom]["frames_per_launch"]
+            traffic, traffic_src = per_frame * chunk_frames, t["source"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel_ms_per_launch": dom_ms, "kernel_share_of_step": prof[dom]["ms"] / total_ms,
                 "algorithmic_bytes_per_launch": BPP_C2 * H * W * chunk_frames,
                 "note": "achieved = 6 B/px (BGR in + LAB out) x frames in one launch / that kernel's CUDA-event time"}
