@@ -352,6 +352,11 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restri
     int(*my_tile)[33] = tile[threadIdx.x >> 5];
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounded = (total_words + 31u) / 32u * 32u;
+    long long carry_key = 0;  // (frame << 32) | label of the blob this warp accumulates in registers
+    RunSums carry;
+    carry.m00 = carry.m10 = carry.m01 = carry.m20 = carry.m11 = carry.m02 = carry.m30 = carry.m21 = carry.m12 = carry.m03 = 0;
+    carry.x0 = carry.y0 = 0x7FFFFFFF;
+    carry.x1 = carry.y1 = -1;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
         const bool valid = i < total_words;
         const uint32_t w = valid ? bits[i] : 0u;
@@ -421,7 +426,58 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restri
                         rs.y1 = max(rs.y1, oy1);
                     }
                 }
-                if (head && lab && lab <= max_blobs) blob_atomic_add(&blobs[frame * (size_t)max_blobs + (lab - 1)], rs);
+                // Warp-level carry: the segment with the most pixels in this step designates the
+                // "carried" blob; all segments of that blob are summed across the warp into registers
+                // and only flushed (one set of global atomics) when another blob takes over or the
+                // kernel ends.  A blob that covers much of the frame therefore costs a handful of
+                // atomic sets per WARP instead of one per 1024-pixel segment (they all hit the same
+                // addresses and serialise in L2).  Everything else goes to the table directly.
+                const bool counted = head && lab && lab <= max_blobs;
+                long long best = counted ? rs.m00 : 0;
+                long long best_key = counted ? key : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
+                    const long long ok = __shfl_xor_sync(0xFFFFFFFFu, best_key, d);
+                    if (ob > best || (ob == best && ok > best_key)) {
+                        best = ob;
+                        best_key = ok;
+                    }
+                }
+                if (best_key != 0) {
+                    if (best_key != carry_key) {
+                        if (carry_key != 0 && lane == 0)
+                            blob_atomic_add(&blobs[(size_t)(carry_key >> 32) * max_blobs + ((int)(carry_key & 0xFFFFFFFFll) - 1)], carry);
+                        carry_key = best_key;
+                        carry.m00 = carry.m10 = carry.m01 = carry.m20 = carry.m11 = carry.m02 = 0;
+                        carry.m30 = carry.m21 = carry.m12 = carry.m03 = 0;
+                        carry.x0 = carry.y0 = 0x7FFFFFFF;
+                        carry.x1 = carry.y1 = -1;
+                    }
+                    const bool mine = counted && key == carry_key;
+                    RunSums t = rs;
+                    if (!mine) {
+                        t.m00 = t.m10 = t.m01 = t.m20 = t.m11 = t.m02 = t.m30 = t.m21 = t.m12 = t.m03 = 0;
+                        t.x0 = t.y0 = 0x7FFFFFFF;
+                        t.x1 = t.y1 = -1;
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+#define BV_ALL_ADD(field) t.field += __shfl_xor_sync(0xFFFFFFFFu, t.field, d);
+                        BV_ALL_ADD(m00) BV_ALL_ADD(m10) BV_ALL_ADD(m01) BV_ALL_ADD(m20) BV_ALL_ADD(m11)
+                        BV_ALL_ADD(m02) BV_ALL_ADD(m30) BV_ALL_ADD(m21) BV_ALL_ADD(m12) BV_ALL_ADD(m03)
+#undef BV_ALL_ADD
+                        t.x0 = min(t.x0, __shfl_xor_sync(0xFFFFFFFFu, t.x0, d));
+                        t.y0 = min(t.y0, __shfl_xor_sync(0xFFFFFFFFu, t.y0, d));
+                        t.x1 = max(t.x1, __shfl_xor_sync(0xFFFFFFFFu, t.x1, d));
+                        t.y1 = max(t.y1, __shfl_xor_sync(0xFFFFFFFFu, t.y1, d));
+                    }
+                    carry.m00 += t.m00; carry.m10 += t.m10; carry.m01 += t.m01; carry.m20 += t.m20; carry.m11 += t.m11;
+                    carry.m02 += t.m02; carry.m30 += t.m30; carry.m21 += t.m21; carry.m12 += t.m12; carry.m03 += t.m03;
+                    carry.x0 = min(carry.x0, t.x0); carry.y0 = min(carry.y0, t.y0);
+                    carry.x1 = max(carry.x1, t.x1); carry.y1 = max(carry.y1, t.y1);
+                    if (counted && !mine) blob_atomic_add(&blobs[frame * (size_t)max_blobs + (lab - 1)], rs);
+                }
             }
         }
         if (labels) {
@@ -447,6 +503,8 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restri
             __syncwarp();
         }
     }
+    if (blobs && carry_key != 0 && lane == 0)
+        blob_atomic_add(&blobs[(size_t)(carry_key >> 32) * max_blobs + ((int)(carry_key & 0xFFFFFFFFll) - 1)], carry);
 }
 
 static int label_bits_ex(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, int height, int width,
