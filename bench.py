@@ -358,12 +358,23 @@ def run_ours(args):
         t = torch.tensor([e2e_dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
+    # single-frame latency of the drop-in call (what a module's process() pays per frame)
+    one_out = {"converted": pin_out.array[:1]}
+    for s in range(3):
+        ctx.stage_host(desc, pin_in.array[0][:1], want=("converted",), out=one_out)
+    t0 = time.perf_counter()
+    for s in range(20):
+        ctx.stage_host(desc, pin_in.array[0][s % BATCH:s % BATCH + 1], want=("converted",), out=one_out)
+    single_ms = (time.perf_counter() - t0) / 20 * 1e3
     clocks = sampler.stop(mark_a, None) if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "device-resident timed region + per-kernel profile + end-to-end leg"
     e2e = {"value": world * BATCH * e2e_steps / e2e_dt, "unit": "frames/s",
            "h2d_bytes_per_step": BATCH * H * W * 3, "d2h_bytes_per_step": BATCH * H * W * 3,
-           "api": "bv_stage_host (C ABI, pinned host buffers, blocking)", "steps": e2e_steps}
+           "api": "bv_stage_host (C ABI, pinned host buffers, blocking)", "steps": e2e_steps,
+           "single_frame_latency_ms": single_ms,
+           "pcie_note": "8.23 MB in + 8.23 MB out per frame; this pool's boxes copy ~81 GB/s with both directions busy "
+                        "(profiles/r01_e2e_pcie.log), i.e. a ceiling of ~4.9 k frames/s per GPU"}
 
     if rank == 0:
         cores = os.cpu_count() or 1

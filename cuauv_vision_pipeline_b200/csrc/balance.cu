@@ -684,12 +684,20 @@ static int env_int(const char *name, int dflt) {
     return v > 0 ? v : dflt;
 }
 // blocks per SM of the histogram passes and of the final pass (tuning knobs)
-static int hist_blocks_per_sm() { static int v = env_int("BV_HIST_BPS", 2); return v; }
+// With side streams the passes of different chunks share the SMs, so each kernel takes a small
+// persistent grid (2 blocks/SM); a lone chunk (single frame, or profiling) gets the whole machine.
+static int hist_blocks_per_sm(bool overlapped) {
+    static int v = getenv("BV_HIST_BPS") ? env_int("BV_HIST_BPS", 2) : 0;
+    return v ? v : (overlapped ? 2 : 4);
+}
 static int side_streams() {
     static int v = env_int("BV_SIDE_STREAMS", 4);
     return v > BV_MAX_SIDE ? BV_MAX_SIDE : v;
 }
-static int final_blocks_per_sm() { static int v = env_int("BV_FINAL_BPS", 2); return v; }
+static int final_blocks_per_sm(bool overlapped) {
+    static int v = getenv("BV_FINAL_BPS") ? env_int("BV_FINAL_BPS", 2) : 0;
+    return v ? v : (overlapped ? 2 : 8);
+}
 
 static bool vec_ok(const void *p, size_t npx, int batch, int bytes_per_px) {
     (void)bytes_per_px;
@@ -699,7 +707,7 @@ static bool vec_ok(const void *p, size_t npx, int batch, int bytes_per_px) {
 template <int MODE, int CODE>
 static int launch_final(bv_ctx *ctx, const uint8_t *src, const BalFrame *st, int batch, size_t npx, int width,
                         const BalOutputs &out, bool vec) {
-    int bpf = (ctx->sm_count * final_blocks_per_sm() + batch - 1) / batch;
+    int bpf = (ctx->sm_count * final_blocks_per_sm(ctx->overlapped != 0) + batch - 1) / batch;
     const size_t need = (npx / 16 + kBalThreads - 1) / kBalThreads;
     if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
     dim3 grid(bpf, batch);
@@ -749,6 +757,7 @@ static bool all_vec(const uint8_t *src, const BalOutputs &out, size_t npx, int b
 int convert_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int width, int cvt_code, const BalOutputs &out) {
     const size_t npx = (size_t)height * width;
     const bool vec = all_vec(src, out, npx, batch);
+    ctx->overlapped = 0;
     if (out.mask_bits && !(vec && width % 16 == 0)) {
         set_error("convert_run: bit-packed mask needs 16-byte aligned buffers and width %% 16 == 0");
         return BV_ERR_INVALID;
@@ -795,6 +804,7 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
     if (nside > nchunks) nside = nchunks;
     if (ctx->prof) nside = 1;  // per-kernel timing wants serialised launches
     cudaStream_t main_stream = ctx->stream;
+    ctx->overlapped = nside > 1;
     if (nside > 1) {
         BV_CUDA(cudaEventRecord(ctx->ev_fork, main_stream));
         for (int i = 0; i < nside; ++i) BV_CUDA(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
@@ -809,7 +819,7 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         const int nf = batch - f0 < chunk ? batch - f0 : chunk;
         const uint8_t *csrc = src + (size_t)f0 * npx * 3;
         BalFrame *cst = st + f0;
-        int bpf = (ctx->sm_count * hist_blocks_per_sm() + nf - 1) / nf;
+        int bpf = (ctx->sm_count * hist_blocks_per_sm(ctx->overlapped != 0) + nf - 1) / nf;
         const size_t need = (npx / 16 + kBalThreads - 1) / kBalThreads;
         if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
         dim3 grid(bpf, nf);

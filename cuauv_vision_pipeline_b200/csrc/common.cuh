@@ -93,6 +93,7 @@ struct bv_ctx {
     // host-memory pipeline (bv_stage_host): copy streams and per-chunk events
     cudaStream_t copy_in, copy_out;
     cudaEvent_t ev_in[BV_MAX_CHUNKS], ev_done[BV_MAX_CHUNKS];
+    int overlapped;  // the current call spreads its chunks over side streams (small grids per kernel)
     void *prof;  // per-kernel CUDA-event timing, only while bv_profile_enable(ctx, 1)
     // side streams: independent chunks of one call run concurrently so that the issue-bound final
     // pass of one chunk overlaps the atomics-bound histogram passes of the next
