@@ -611,39 +611,53 @@ __device__ __forceinline__ bool bit_at(const uint32_t *fb, int wpr, int width, i
     return (fb[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
 }
 
+// WRITE = false: first walk (sums, counts, externality).  WRITE = true: second walk of the external
+// borders that got a slot in the point list, emitting the CHAIN_APPROX_SIMPLE vertices.
+template <bool WRITE>
 __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ inv,
                                                       const int *__restrict__ parent_bg, const uint32_t *__restrict__ outer,
                                                       const int *__restrict__ root_px, const int *__restrict__ n_blobs,
                                                       bv_contour *__restrict__ out, int max_contours, int height, int width,
-                                                      int wpr) {
+                                                      int wpr, int *__restrict__ points, int max_points) {
     const int f = blockIdx.y;
     const int n = min(n_blobs[f], max_contours);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
     const uint32_t *fb = bits + (size_t)f * height * wpr;
-    const int start = root_px[(size_t)f * max_contours + idx];
-    const int y0 = start / width, x0 = start - y0 * width;
     bv_contour c;
-    c.label = idx + 1;
-    c.start_x = x0;
-    c.start_y = y0;
-    // external iff the background on the left reaches the frame (or the start pixel is on the frame)
-    int external = 1;
-    if (x0 > 0) {
-        const uint32_t *fi = inv + (size_t)f * height * wpr;
-        const int node = node_of(fi, wpr, width, y0, x0 - 1);
-        const int root = parent_bg[(size_t)f * height * width + node];
-        const size_t words_per_frame = ((size_t)height * width + 31) / 32;
-        external = (outer[(size_t)f * words_per_frame + (root >> 5)] >> (root & 31)) & 1u;
+    int *pts = nullptr;
+    int x0, y0;
+    if (WRITE) {
+        c = out[(size_t)f * max_contours + idx];
+        if (!c.external || c.point_offset < 0) return;
+        pts = points + ((size_t)f * max_points + c.point_offset) * 2;
+        x0 = c.start_x;
+        y0 = c.start_y;
+    } else {
+        const int start = root_px[(size_t)f * max_contours + idx];
+        y0 = start / width;
+        x0 = start - y0 * width;
+        c.label = idx + 1;
+        c.start_x = x0;
+        c.start_y = y0;
+        // external iff the background on the left reaches the frame (or the start pixel is on the frame)
+        int external = 1;
+        if (x0 > 0) {
+            const uint32_t *fi = inv + (size_t)f * height * wpr;
+            const int node = node_of(fi, wpr, width, y0, x0 - 1);
+            const int root = parent_bg[(size_t)f * height * width + node];
+            const size_t words_per_frame = ((size_t)height * width + 31) / 32;
+            external = (outer[(size_t)f * words_per_frame + (root >> 5)] >> (root & 31)) & 1u;
+        }
+        c.external = external;
     }
-    c.external = external;
     // Suzuki border following, direction codes 0..7 = E, NE, N, NW, W, SW, S, SE (y grows downwards)
     // dx = {1,1,0,-1,-1,-1,0,1}, dy = {0,-1,-1,-1,0,1,1,1} as nibble tables (value + 1), so that the
     // dynamically indexed look-up stays in registers
 #define dx(s) ((int)((0x21000122u >> (4 * (s))) & 0xFu) - 1)
 #define dy(s) ((int)((0x22210001u >> (4 * (s))) & 0xFu) - 1)
     long long a00 = 0, a10 = 0, a01 = 0;
-    int bx0 = x0, bx1 = x0, by0 = y0, by1 = y0, npts = 1;
+    int bx0 = x0, bx1 = x0, by0 = y0, by1 = y0, npts = 1, nsimple = 1;
     int s = 4;
     bool found = false;
     for (int k = 0; k < 7; ++k) {  // clockwise from W: NW, N, NE, E, SE, S, SW
@@ -653,10 +667,17 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
             break;
         }
     }
-    if (found) {
+    if (!found) {
+        if (WRITE) {
+            pts[0] = x0;
+            pts[1] = y0;
+        }
+    } else {
         const int x1 = x0 + dx(s), y1 = y0 + dy(s);  // i1: the first neighbour, where the walk will end
         int cx = x0, cy = y0;                        // i3
+        int prev_s = s ^ 4;                          // CHAIN_APPROX_SIMPLE: keep a point when the direction turns
         npts = 0;
+        nsimple = 0;
         for (;;) {
             int nx, ny;
             for (;;) {  // counter-clockwise, starting just after the direction we came from
@@ -665,32 +686,87 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
                 ny = cy + dy(s);
                 if (bit_at(fb, wpr, width, height, nx, ny)) break;
             }
-            // polygon edge (cx,cy) -> (nx,ny)
-            const long long dxy = (long long)cx * ny - (long long)nx * cy;
-            a00 += dxy;
-            a10 += dxy * (cx + nx);
-            a01 += dxy * (cy + ny);
+            if (s != prev_s) {
+                if (WRITE) {
+                    pts[2 * nsimple] = cx;
+                    pts[2 * nsimple + 1] = cy;
+                }
+                ++nsimple;
+                prev_s = s;
+            }
+            if (!WRITE) {
+                // polygon edge (cx,cy) -> (nx,ny)
+                const long long dxy = (long long)cx * ny - (long long)nx * cy;
+                a00 += dxy;
+                a10 += dxy * (cx + nx);
+                a01 += dxy * (cy + ny);
+                bx0 = min(bx0, cx); bx1 = max(bx1, cx); by0 = min(by0, cy); by1 = max(by1, cy);
+            }
             ++npts;
-            bx0 = min(bx0, cx); bx1 = max(bx1, cx); by0 = min(by0, cy); by1 = max(by1, cy);
             if (nx == x0 && ny == y0 && cx == x1 && cy == y1) break;
             cx = nx;
             cy = ny;
             s = (s + 4) & 7;
         }
     }
+#undef dx
+#undef dy
+    if (WRITE) return;
     c.a00 = a00;
     c.a10 = a10;
     c.a01 = a01;
     c.x0 = bx0; c.y0 = by0; c.x1 = bx1; c.y1 = by1;
     c.n_points = npts;
+    c.n_simple = nsimple;
+    c.point_offset = -1;
     c.reserved = 0;
     out[(size_t)f * max_contours + idx] = c;
-#undef dx
-#undef dy
+}
+
+// one block per frame: hand every external contour its slice of the frame's point list
+// (exclusive scan of n_simple in raster order; sequential over chunks of blockDim contours)
+__global__ void __launch_bounds__(1024) contour_offsets_kernel(bv_contour *__restrict__ contours, const int *__restrict__ n_blobs,
+                                                               int max_contours, int max_points, int *__restrict__ n_points) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int f = blockIdx.x;
+    const int n = min(n_blobs[f], max_contours);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    bv_contour *fc = contours + (size_t)f * max_contours;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = (i < n && fc[i].external) ? fc[i].n_simple : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int ws = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xFFFFFFFFu, ws, d);
+                if (lane >= d) ws += o;
+            }
+            warp_sums[lane] = ws;
+        }
+        __syncthreads();
+        const int before = carry + (wid ? warp_sums[wid - 1] : 0) + incl - v;
+        if (i < n && v > 0 && before + v <= max_points) fc[i].point_offset = before;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && n_points) n_points[f] = carry;
 }
 
 int outer_contours_bits(bv_ctx *ctx, const uint32_t *bits, int batch, int height, int width, bv_contour *contours,
-                        int max_contours, int32_t *n_contours) {
+                        int max_contours, int32_t *n_contours, int32_t *points, int max_points, int32_t *n_points) {
     const int wpr = words_per_row(width);
     const size_t total_words = (size_t)batch * height * wpr;
     const size_t total_rows = (size_t)batch * height;
@@ -720,8 +796,13 @@ int outer_contours_bits(bv_ctx *ctx, const uint32_t *bits, int batch, int height
     // label_bits_ex wrote the blob count to n_contours (or its own scratch when NULL)
     const int *nb = n_contours ? n_contours : (int *)ctx->scratch[SCR_CCL_AUX] + 2 * total_rows;
     dim3 grid((max_contours + 127) / 128, batch);
-    BV_LAUNCH(ctx, contour_kernel, grid, 128, 0, bits, inv, parent_bg, outer, root_px, nb, contours, max_contours, height,
-              width, wpr);
+    BV_LAUNCH(ctx, contour_kernel<false>, grid, 128, 0, bits, inv, parent_bg, outer, root_px, nb, contours, max_contours,
+              height, width, wpr, nullptr, 0);
+    if (points && max_points > 0) {
+        BV_LAUNCH(ctx, contour_offsets_kernel, batch, 1024, 0, contours, nb, max_contours, max_points, n_points);
+        BV_LAUNCH(ctx, contour_kernel<true>, grid, 128, 0, bits, inv, parent_bg, outer, root_px, nb, contours, max_contours,
+                  height, width, wpr, points, max_points);
+    }
     return BV_OK;
 }
 
@@ -743,7 +824,8 @@ extern "C" int bv_label(bv_ctx *ctx, const uint8_t *mask_dev, int32_t *labels_de
 }
 
 extern "C" int bv_outer_contours(bv_ctx *ctx, const uint8_t *mask_dev, int batch, int height, int width,
-                                 bv_contour *contours_dev, int max_contours, int32_t *n_contours_dev) {
+                                 bv_contour *contours_dev, int max_contours, int32_t *n_contours_dev, int32_t *points_dev,
+                                 int max_points, int32_t *n_points_dev) {
     BV_REQUIRE(ctx && mask_dev && contours_dev, "null argument");
     BV_REQUIRE(batch > 0 && height > 0 && width > 0 && max_contours > 0, "sizes must be positive");
     BV_CUDA(cudaSetDevice(ctx->device));
@@ -751,5 +833,6 @@ extern "C" int bv_outer_contours(bv_ctx *ctx, const uint8_t *mask_dev, int batch
     BV_TRY(ensure_scratch(ctx, SCR_BITS_A, words * 4));
     uint32_t *bits = (uint32_t *)ctx->scratch[SCR_BITS_A];
     BV_TRY(mask_to_bits(ctx, mask_dev, bits, batch, height, width));
-    return outer_contours_bits(ctx, bits, batch, height, width, contours_dev, max_contours, n_contours_dev);
+    return outer_contours_bits(ctx, bits, batch, height, width, contours_dev, max_contours, n_contours_dev, points_dev,
+                               points_dev ? max_points : 0, n_points_dev);
 }

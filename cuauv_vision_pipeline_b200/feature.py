@@ -33,16 +33,29 @@ class Contour(dict):
     """One outer border (cv2.findContours RETR_EXTERNAL) reduced to its Green's-theorem sums."""
 
 
-def outer_contours(mat, max_contours=4096):
+def outer_contours(mat, max_contours=4096, points=False, max_points=None):
     """utils/feature.py:5-21 on the GPU: the outermost 8-connected borders of `mat != 0`, in raster
     order of their first pixel (cv2 returns the same set, in its own order).  Each record carries
-    what the reference consumes next (contour_centroid / contour_area below)."""
+    what the reference consumes next (contour_centroid / contour_area below); with `points=True`
+    also the CHAIN_APPROX_SIMPLE vertices as an int32 [n,1,2] array, exactly the array cv2 returns
+    (ready for cv2.minAreaRect as in modules/bins.py:60)."""
     from .runtime import CONTOUR_DTYPE
     ctx = ctx_for(mat)
-    table, nb = ctx.outer_contours(to_device(ctx, mat), max_contours=max_contours)
+    h, w = mat.shape[-2], mat.shape[-1]
+    if points and max_points is None:
+        max_points = 4 * (h + w) + h * w // 4        # generous: borders of a very ragged mask
+    table, nb, pts, npts = ctx.outer_contours(to_device(ctx, mat), max_contours=max_contours,
+                                              max_points=max_points if points else 0)
     n = int(ctx.download(nb)[0])
     raw = ctx.download(table)[0, :min(n, max_contours)].copy().view(CONTOUR_DTYPE).reshape(-1)
-    return [Contour({k: int(row[k]) for k in CONTOUR_DTYPE.names}) for row in raw if row["external"]]
+    out = [Contour({k: int(row[k]) for k in CONTOUR_DTYPE.names}) for row in raw if row["external"]]
+    if points:
+        needed = int(ctx.download(npts)[0])
+        host = ctx.download(pts)[0, :min(needed, max_points)]
+        for c in out:
+            off = c["point_offset"]
+            c["points"] = host[off:off + c["n_simple"]].reshape(-1, 1, 2).copy() if off >= 0 else None
+    return out
 
 
 def _contour_moments(c):

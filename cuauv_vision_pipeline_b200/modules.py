@@ -48,10 +48,12 @@ class BinDetectorGPU(ModuleBase):
     lower_beige = (10, 20, 60)
     upper_beige = (30, 100, 255)
 
-    def __init__(self, *a, device=0, overlay=False, **kw):
+    def __init__(self, *a, device=0, overlay=False, want_contours=True, **kw):
         super().__init__(*a, **kw)
         self.ctx = default_context(device)
         self.overlay = overlay
+        self.want_contours = want_contours
+        self.contours = []
         self.desc = self.ctx.make_stage(cvt="bgr2hsv", lo=self.lower_beige, hi=self.upper_beige,
                                         morph=[("open", 5, 5, 1)], label=True)
         self.blobs = []
@@ -73,6 +75,9 @@ class BinDetectorGPU(ModuleBase):
                 b["label"] = i + 1
                 self.blobs.append(b)
         cleaned = out["mask"]
+        # the reference's own next step (bins.py:27): outer contours of the cleaned mask, as the exact
+        # vertex arrays cv2.findContours returns -- ready for cv2.minAreaRect (bins.py:60) on the host
+        self.contours = feature.outer_contours(cleaned, points=True) if self.want_contours else []
         if self.overlay:
             vis = np.repeat(cleaned[..., None], 3, axis=2)
             overlayed = np.clip(np.rint(img * 0.7 + vis * 0.3), 0, 255).astype(np.uint8)   # bins.py:19-20

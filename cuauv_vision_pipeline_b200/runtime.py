@@ -26,8 +26,8 @@ BLOB_DTYPE = np.dtype([(k, "<i8") for k in ("m00", "m10", "m01", "m20", "m11", "
                       [(k, "<i4") for k in ("x0", "y0", "x1", "y1")])
 assert BLOB_DTYPE.itemsize == ffi.sizeof("bv_blob")
 CONTOUR_DTYPE = np.dtype([(k, "<i8") for k in ("a00", "a10", "a01")] +
-                         [(k, "<i4") for k in ("x0", "y0", "x1", "y1", "start_x", "start_y", "n_points", "label",
-                                               "external", "reserved")])
+                         [(k, "<i4") for k in ("x0", "y0", "x1", "y1", "start_x", "start_y", "n_points", "n_simple",
+                                               "label", "external", "point_offset", "reserved")])
 assert CONTOUR_DTYPE.itemsize == ffi.sizeof("bv_contour")
 
 
@@ -252,17 +252,22 @@ class Context:
                            ffi.cast("int32_t *", nb.data_ptr())))
         return labels, blobs, nb
 
-    def outer_contours(self, mask, max_contours=4096):
-        """Device mask [H,W] or [B,H,W] -> (structured device table as uint8 [B,max,64], count [B])."""
+    def outer_contours(self, mask, max_contours=4096, max_points=0):
+        """Device mask [H,W] or [B,H,W] -> (contour table as uint8 [B,max,72], count [B], points
+        int32 [B,max_points,2] or None, points needed [B] or None)."""
         if mask.dim() == 2:
             b, h, w = 1, mask.shape[0], mask.shape[1]
         else:
             b, h, w = mask.shape[0], mask.shape[1], mask.shape[2]
         table = self.empty((b, max_contours, CONTOUR_DTYPE.itemsize), torch.uint8)
         nb = self.empty((b,), torch.int32)
+        points = self.empty((b, max_points, 2), torch.int32) if max_points else None
+        npts = self.empty((b,), torch.int32) if max_points else None
         check(lib.bv_outer_contours(self.handle, _u8ptr(mask), b, h, w, ffi.cast("bv_contour *", table.data_ptr()),
-                                    max_contours, ffi.cast("int32_t *", nb.data_ptr())))
-        return table, nb
+                                    max_contours, ffi.cast("int32_t *", nb.data_ptr()),
+                                    ffi.cast("int32_t *", points.data_ptr()) if max_points else ffi.NULL, max_points,
+                                    ffi.cast("int32_t *", npts.data_ptr()) if max_points else ffi.NULL))
+        return table, nb, points, npts
 
     def blobs_to_numpy(self, blobs, nb):
         """Device blob table -> list (per frame) of structured numpy arrays."""

@@ -203,16 +203,24 @@ typedef struct bv_contour {
     int32_t x0, y0, x1, y1;   /* bounding box of the border pixels (inclusive)                    */
     int32_t start_x, start_y; /* first border pixel = the component's first pixel in raster order */
     int32_t n_points;         /* border pixels visited (length of the CHAIN_APPROX_NONE contour)  */
+    int32_t n_simple;         /* vertices kept by CHAIN_APPROX_SIMPLE (utils/feature.py:20)       */
     int32_t label;            /* the component's label in bv_label's numbering                    */
     int32_t external;         /* 1: reported by RETR_EXTERNAL; 0: lies inside another blob's hole */
+    int32_t point_offset;     /* index of its first vertex in the frame's point list, -1 if the   */
+                              /* list was not requested or is full                                */
     int32_t reserved;
 } bv_contour;
 
 /* contours_dev: bv_contour[batch * max_contours], one record per 8-connected component in raster
  * order of its first pixel (filter on .external for the RETR_EXTERNAL set); n_contours_dev:
- * int32[batch] number of components (may exceed max_contours; may be NULL). */
+ * int32[batch] number of components (may exceed max_contours; may be NULL).
+ * points_dev (optional): int32[batch][max_points][2] receiving the CHAIN_APPROX_SIMPLE vertices
+ * (x, y) of the external contours in cv2's order, contour after contour; n_points_dev (optional):
+ * int32[batch] vertices needed per frame (may exceed max_points: contours that do not fit get
+ * point_offset = -1). */
 int bv_outer_contours(bv_ctx *ctx, const uint8_t *mask_dev, int batch, int height, int width,
-                      bv_contour *contours_dev, int max_contours, int32_t *n_contours_dev);
+                      bv_contour *contours_dev, int max_contours, int32_t *n_contours_dev, int32_t *points_dev,
+                      int max_points, int32_t *n_points_dev);
 
 /* ---- resize / YOLO input ------------------------------------------------------------------ */
 /* cv2.resize(..., INTER_LINEAR) on uint8 (utils/transform.py:179, modules/preprocessor.py:136-143). */

@@ -330,6 +330,17 @@ def test_drop_in_modules(ctx):
     h = tab["y1"] - tab["y0"] + 1
     keep = (w * h >= 500) & (np.maximum(w, h) / np.minimum(w, h) <= 3.0)
     assert [b["label"] for b in blobs] == (np.flatnonzero(keep) + 1).tolist()
+    # bins.py:27,60-69 literally: cv2.minAreaRect on the contour vertex arrays, same accepted rectangles
+    def valid_rects(contours):
+        keep = []
+        for c in contours:
+            (center, (w, h), angle) = cv2.minAreaRect(c)
+            if w * h < 500:
+                continue
+            if 1.0 <= max(w, h) / min(w, h) <= 3.0:
+                keep.append((center, (w, h), angle))
+        return sorted(keep)
+    assert valid_rects([c["points"] for c in mod.contours]) == valid_rects(cv_ops.outer_contours(cleaned))
     buoy = BuoyLABGPU(["zed"], thresh_min=150, thresh_max=255)
     res = buoy.process("zed", img)
     th, cl = cv_ops.buoy_mask(img, 150, 255)

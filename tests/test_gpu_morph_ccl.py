@@ -251,8 +251,13 @@ def check_contours(mask):
     for c in cv_ops.outer_contours(np.ascontiguousarray(mask)):
         ref[(int(c[0, 0, 0]), int(c[0, 0, 1]))] = (cv_ops.contour_centroid(c), cv_ops.contour_area(c),
                                                    cv2.boundingRect(c))
-    got = feature.outer_contours(mask, max_contours=max(16, 4 * len(ref) + 64))
+    ref_pts = {(int(c[0, 0, 0]), int(c[0, 0, 1])): c for c in cv_ops.outer_contours(np.ascontiguousarray(mask))}
+    got = feature.outer_contours(mask, max_contours=max(16, 4 * len(ref) + 64), points=True)
     assert len(got) == len(ref)
+    for g in got:   # the vertex lists are the arrays cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) returns
+        want = ref_pts[(g["start_x"], g["start_y"])]
+        assert g["points"] is not None and g["points"].shape == want.shape and np.array_equal(g["points"], want)
+        assert cv2.minAreaRect(g["points"]) == cv2.minAreaRect(want)       # modules/bins.py:60
     for g in got:
         key = (g["start_x"], g["start_y"])
         assert key in ref, key
