@@ -6,6 +6,7 @@
 // linear_vblend), so the uint8 result is bit-identical to cv2.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -93,6 +94,204 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxImg *__re
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Letterbox with TMA-staged source rows.  A work item is one output row of one image: the two
+// source rows that row interpolates between (2 x W x 3 bytes, e.g. 13 KB at 2208 px) are pulled
+// into shared memory by a single elected thread with cp.async.bulk (the TMA engine; SASS: UBLKCP)
+// signalling an mbarrier, so HBM sees two long sequential bursts per block instead of 12 scattered
+// byte loads per output pixel; all threads then gather their taps from shared memory.
+// Rows whose byte size or address is not 16-byte aligned are staged with ordinary loads instead.
+// ----------------------------------------------------------------------------------------------
+constexpr int kLbMaxRowBytes = 11520;  // up to 3840 px wide sources (2 stages x 2 rows = 45 KB of shared memory)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LB_DONE;\n"
+        "bra LB_WAIT;\n"
+        "LB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// horizontal taps of one output column
+struct LbCoef {
+    short o0, o1;  // byte offsets of the two taps inside a source row; o0 < 0: padding column
+    short w0, w1;
+};
+
+__device__ __forceinline__ LbCoef lb_coef(const LetterboxImg &im, bool identity, int x) {
+    LbCoef c;
+    const int ux = x - im.left;
+    if (ux < 0 || ux >= im.uw) {
+        c.o0 = c.o1 = -1;
+        c.w0 = c.w1 = 0;
+    } else if (identity) {
+        c.o0 = c.o1 = (short)(ux * 3);
+        c.w0 = 2048;
+        c.w1 = 0;
+    } else {
+        const LinCoef cx = linear_coef(ux, im.sw, im.scale_x, true);
+        c.o0 = (short)(cx.i0 * 3);
+        c.o1 = (short)(cx.i1 * 3);
+        c.w0 = (short)cx.w0;
+        c.w1 = (short)cx.w1;
+    }
+    return c;
+}
+
+struct LbItem {
+    LetterboxImg im;
+    int img, y, uy;
+    bool inside_y, identity, tma_ok;
+    uint32_t row_bytes;
+    LinCoef cy;
+    const uint8_t *g0, *g1;
+};
+
+__device__ __forceinline__ LbItem lb_item(const LetterboxImg *__restrict__ imgs, int item, int oh) {
+    LbItem t;
+    t.img = item / oh;
+    t.y = item - t.img * oh;
+    t.im = imgs[t.img];
+    t.uy = t.y - t.im.top;
+    t.inside_y = t.uy >= 0 && t.uy < t.im.uh;
+    t.identity = t.im.uw == t.im.sw && t.im.uh == t.im.sh;
+    t.row_bytes = (uint32_t)t.im.sw * 3u;
+    t.cy.i0 = t.cy.i1 = t.uy;
+    t.cy.w0 = 2048;
+    t.cy.w1 = 0;
+    if (t.inside_y && !t.identity) t.cy = linear_coef(t.uy, t.im.sh, t.im.scale_y, false);
+    t.g0 = t.g1 = t.im.src;
+    t.tma_ok = false;
+    if (t.inside_y) {
+        t.g0 = t.im.src + (size_t)t.cy.i0 * t.row_bytes;
+        t.g1 = t.im.src + (size_t)t.cy.i1 * t.row_bytes;
+        t.tma_ok = (t.row_bytes % 16u == 0) && ((reinterpret_cast<uintptr_t>(t.g0) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(t.g1) & 15) == 0);
+    }
+    return t;
+}
+
+// Persistent blocks, two-stage pipeline: while the threads interpolate output row k out of stage
+// k&1, the TMA engine is already filling the other stage with the source rows of item k+1.
+template <bool FP16>
+__global__ void __launch_bounds__(256) letterbox_tma_kernel(const LetterboxImg *__restrict__ imgs, void *__restrict__ out, int oh,
+                                                            int ow, int pad, int n_items) {
+    __shared__ __align__(128) uint8_t rows[2][2][kLbMaxRowBytes];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ float norm[256];  // v / 255 in float32 (IEEE division once per value instead of per pixel)
+    __shared__ LbItem sitem[2];  // the item of each stage, worked out once by thread 0 (not by all 256 threads)
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) norm[k] = __fdiv_rn((float)k, 255.f);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+    }
+    __syncthreads();
+    auto issue = [&](int item, int stage) {  // thread 0 only
+        if (item >= n_items) return;
+        const LbItem t = lb_item(imgs, item, oh);
+        sitem[stage] = t;
+        if (!t.tma_ok) return;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this stage are done
+        mbar_expect_tx(&bar[stage], t.identity ? t.row_bytes : 2u * t.row_bytes);
+        bulk_g2s(rows[stage][0], t.g0, t.row_bytes, &bar[stage]);
+        if (!t.identity) bulk_g2s(rows[stage][1], t.g1, t.row_bytes, &bar[stage]);
+    };
+    if (threadIdx.x == 0) {
+        issue(blockIdx.x, 0);
+        issue(blockIdx.x + gridDim.x, 1);
+    }
+    __syncthreads();  // sitem[] of the first two items is visible
+    uint32_t phase[2] = {0, 0};
+    const size_t plane = (size_t)oh * ow;
+    int k = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+        const int stage = k & 1;
+        const LbItem &t = sitem[stage];
+        const uint8_t *r0 = rows[stage][0];
+        const uint8_t *r1 = rows[stage][1];
+        if (t.inside_y) {  // block-uniform
+            if (t.tma_ok) {
+                mbar_wait(&bar[stage], phase[stage]);
+                phase[stage] ^= 1;
+            } else {  // unaligned source rows: ordinary loads
+                for (uint32_t q = threadIdx.x; q < t.row_bytes; q += blockDim.x) {
+                    rows[stage][0][q] = t.g0[q];
+                    if (!t.identity) rows[stage][1][q] = t.g1[q];
+                }
+                __syncthreads();
+            }
+        }
+        const size_t obase = (size_t)t.img * 3 * plane + (size_t)t.y * ow;
+        if (t.identity) r1 = r0;  // single staged row; weights (2048, 0) make the blend an exact copy
+        const bool inside_y = t.inside_y;
+        const int cw0 = t.cy.w0, cw1 = t.cy.w1;
+        // three output pixels per thread and step, coefficient loads issued together (independent
+        // L2 round trips overlap instead of serialising over the short per-row loop)
+        for (int xb = 0; xb < ow; xb += 3 * 256) {
+            LbCoef cx[3];
+            int xs[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                xs[u] = xb + u * 256 + threadIdx.x;
+                cx[u] = lb_coef(t.im, t.identity, xs[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                if (xs[u] >= ow) continue;
+                int b = pad, g = pad, r = pad;
+                if (inside_y && cx[u].o0 >= 0) {
+                    int v[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int h0 = r0[cx[u].o0 + c] * cx[u].w0 + r0[cx[u].o1 + c] * cx[u].w1;
+                        const int h1 = r1[cx[u].o0 + c] * cx[u].w0 + r1[cx[u].o1 + c] * cx[u].w1;
+                        v[c] = linear_vblend(h0, h1, cw0, cw1);
+                    }
+                    b = v[0];
+                    g = v[1];
+                    r = v[2];
+                }
+                const float fr = norm[r], fg = norm[g], fb = norm[b];
+                const int x = xs[u];
+                if (FP16) {
+                    __half *q = reinterpret_cast<__half *>(out);
+                    q[obase + x] = __float2half_rn(fr);
+                    q[obase + x + plane] = __float2half_rn(fg);
+                    q[obase + x + 2 * plane] = __float2half_rn(fb);
+                } else {
+                    float *q = reinterpret_cast<float *>(out);
+                    q[obase + x] = fr;
+                    q[obase + x + plane] = fg;
+                    q[obase + x + 2 * plane] = fb;
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with this stage: refill it for the item after next
+        if (threadIdx.x == 0) issue(item + 2 * gridDim.x, stage);
+    }
+}
+
 }  // namespace bv
 
 using namespace bv;
@@ -144,6 +343,19 @@ extern "C" int bv_letterbox(bv_ctx *ctx, const uint8_t *const *srcs_host, const 
     BV_TRY(ensure_scratch(ctx, SCR_LETTERBOX, sizeof(LetterboxImg) * 256));
     LetterboxImg *d_descs = (LetterboxImg *)ctx->scratch[SCR_LETTERBOX];
     BV_CUDA(cudaMemcpyAsync(d_descs, descs, sizeof(LetterboxImg) * n, cudaMemcpyHostToDevice, ctx->stream));
+    bool fits = true;  // the staged kernel holds two source rows in shared memory
+    for (int i = 0; i < n; ++i) fits = fits && (size_t)widths_host[i] * 3 <= (size_t)kLbMaxRowBytes;
+    static const bool use_tma = getenv("BV_LETTERBOX_GATHER") == nullptr;
+    if (fits && use_tma) {
+        const int n_items = out_h * n;
+        int grid = ctx->sm_count * 4;  // persistent: 4 blocks of 45 KB per SM
+        if (grid > n_items) grid = n_items;
+        if (out_fp16)
+            BV_LAUNCH(ctx, letterbox_tma_kernel<true>, grid, 256, 0, d_descs, out_dev, out_h, out_w, pad_value, n_items);
+        else
+            BV_LAUNCH(ctx, letterbox_tma_kernel<false>, grid, 256, 0, d_descs, out_dev, out_h, out_w, pad_value, n_items);
+        return BV_OK;
+    }
     dim3 grid((out_w + 255) / 256, out_h, n);
     if (out_fp16)
         BV_LAUNCH(ctx, letterbox_kernel<true>, grid, 256, 0, d_descs, out_dev, out_h, out_w, pad_value);

@@ -293,7 +293,7 @@ class Context:
         check(lib.bv_resize_linear(self.handle, _u8ptr(src), sh, sw, _u8ptr(dst), height, width, c, b))
         return dst
 
-    def letterbox(self, images, out_h=640, out_w=640, pad=114, half=True):
+    def letterbox(self, images, out_h=640, out_w=640, pad=114, half=True, out=None):
         n = len(images)
         for im in images:
             if im.dim() != 3 or im.shape[2] != 3 or im.dtype != torch.uint8 or not im.is_cuda:
@@ -301,7 +301,8 @@ class Context:
         srcs = ffi.new("uint8_t *[]", [_u8ptr(im) for im in images])
         hs = ffi.new("int32_t[]", [int(im.shape[0]) for im in images])
         ws = ffi.new("int32_t[]", [int(im.shape[1]) for im in images])
-        out = self.empty((n, 3, out_h, out_w), torch.float16 if half else torch.float32)
+        if out is None:
+            out = self.empty((n, 3, out_h, out_w), torch.float16 if half else torch.float32)
         check(lib.bv_letterbox(self.handle, ffi.cast("const uint8_t *const *", srcs), hs, ws, n,
                                ffi.cast("void *", out.data_ptr()), out_h, out_w, pad, 1 if half else 0))
         return out
