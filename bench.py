@@ -34,7 +34,7 @@ H, W = 1242, 2208
 BATCH = 16
 RING = 64
 BPP_C2 = 6          # BGR in (3) + LAB image out (3)
-METRIC = "frames/sec at 2208x1242 (balance + BGR2LAB), device-resident"
+METRIC = "frames/sec at 2208x1242"
 
 
 def read_peaks():
@@ -242,7 +242,18 @@ def side_workloads(ctx, peak_gbs):
     res["c4_letterbox_16x2208x1242_to_640_fp16"] = {"images_per_s": 160 / dt, "ms_per_step": 1e2 * dt,
                                                    "algorithmic_gbs": bytes_batch * 10 / dt / 1e9,
                                                    "frac_of_hbm": bytes_batch * 10 / dt / 1e9 / peak_gbs}
-    del ring, ring3, ring5, imgs
+    # pure streaming kernels (what the HBM roofline looks like on this path when the arithmetic is light)
+    rgba = ctx.upload(np.random.default_rng(0).integers(0, 256, (16, H, W, 4), dtype=np.uint8))
+    gray_out = {}
+    dt = time_device(ctx, lambda s: ctx.rgba_to_rgb(rgba), 10, 3)
+    res["stream_rgba_to_rgb_16x2208x1242"] = {"frames_per_s": 160 / dt, "ms_per_step": 1e2 * dt,
+                                              "algorithmic_gbs": 7 * H * W * 160 / dt / 1e9,
+                                              "frac_of_hbm": 7 * H * W * 160 / dt / 1e9 / peak_gbs}
+    dt = time_device(ctx, lambda s: ctx.cvt_color(ring, "bgr2gray"), 10, 3)
+    res["stream_bgr2gray_16x2208x1242"] = {"frames_per_s": 160 / dt, "ms_per_step": 1e2 * dt,
+                                           "algorithmic_gbs": 4 * H * W * 160 / dt / 1e9,
+                                           "frac_of_hbm": 4 * H * W * 160 / dt / 1e9 / peak_gbs}
+    del ring, ring3, ring5, imgs, rgba
     torch.cuda.empty_cache()
     return res
 

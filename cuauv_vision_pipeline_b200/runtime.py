@@ -307,6 +307,33 @@ class Context:
                                ffi.cast("void *", out.data_ptr()), out_h, out_w, pad, 1 if half else 0))
         return out
 
+    # -- ZED auxiliary planes --------------------------------------------------------------------
+    def rgba_to_rgb(self, src):
+        dst = self.empty(tuple(src.shape[:-1]) + (3,))
+        check(lib.bv_rgba_to_rgb(self.handle, _u8ptr(src), _u8ptr(dst), src.numel() // 4))
+        return dst
+
+    def normals_to_rgb01(self, src):
+        dst = self.empty(tuple(src.shape[:-1]) + (3,), torch.float32)
+        check(lib.bv_normals_to_rgb01(self.handle, ffi.cast("float *", src.data_ptr()), ffi.cast("float *", dst.data_ptr()),
+                                      src.numel() // 4))
+        return dst
+
+    def f32_to_u8(self, src, sub=None, div=None, clip_before_scale=False):
+        dst = self.empty(tuple(src.shape))
+        affine = sub is not None
+        check(lib.bv_f32_to_u8(self.handle, ffi.cast("float *", src.data_ptr()), _u8ptr(dst), src.numel(), 1 if affine else 0,
+                               float(sub or 0.0), float(div if div is not None else 1.0), 1 if clip_before_scale else 0))
+        return dst
+
+    def channel_means(self, src):
+        """np.mean(img, axis=(0, 1)) of a uint8 [H,W,C] device image: exact integer sums / count."""
+        c = src.shape[-1] if src.dim() == 3 else 1
+        sums = self.empty((c,), torch.int64)
+        npx = src.numel() // c
+        check(lib.bv_channel_sums(self.handle, _u8ptr(src), npx, c, ffi.cast("uint64_t *", sums.data_ptr())))
+        return self.download(sums).astype(np.float64) / npx
+
     # -- fused stage ---------------------------------------------------------------------------
     @staticmethod
     def make_stage(balance=None, cvt=None, lo=(0, 0, 0), hi=(255, 255, 255), morph=(), label=False):

@@ -233,6 +233,21 @@ int bv_letterbox(bv_ctx *ctx, const uint8_t *const *srcs_host, const int32_t *he
                  const int32_t *widths_host, int n, void *out_dev, int out_h, int out_w, int pad_value,
                  int out_fp16);
 
+/* ---- ZED auxiliary planes (capture_sources/zed.{py,cpp}, modules/poster.py, modules/record.py) ----- */
+/* Drop the alpha byte (cv2.cvtColor(RGBA2RGB), capture_sources/zed.py:49-50; zed.cpp:54-71). */
+int bv_rgba_to_rgb(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, size_t n_pixels);
+/* float4 normals -> 3 floats (v + 1) * 0.5 (capture_sources/zed.cpp:73-91). */
+int bv_normals_to_rgb01(bv_ctx *ctx, const float *src_xyzw_dev, float *dst_rgb_dev, size_t n_pixels);
+/* float32 plane -> uint8 for display.  y = apply_affine ? (x - sub) / div : x, then
+ * clip_before_scale == 0: clip(y * 255, 0, 255)   (modules/poster.py:41-47, modules/calibrate.py:111)
+ * clip_before_scale != 0: clip(y, 0, 1) * 255      (modules/record.py:106-109)
+ * truncated to uint8 like numpy's astype.  NaN -> 0 (undefined in numpy). */
+int bv_f32_to_u8(bv_ctx *ctx, const float *src_dev, uint8_t *dst_dev, size_t n, int apply_affine, float sub, float div,
+                 int clip_before_scale);
+/* Exact per-channel sums of an interleaved uint8 image: the numerators of np.mean(img, axis=(0,1))
+ * (modules/auto_calibrate_zed.py:82).  sums_dev: uint64[channels]. */
+int bv_channel_sums(bv_ctx *ctx, const uint8_t *src_dev, size_t n_pixels, int channels, uint64_t *sums_dev);
+
 /* ---- fused stage --------------------------------------------------------------------------- */
 /* Any output pointer may be NULL to skip it.  balanced_dev: BGR after colour balance;
  * converted_dev: image after desc->cvt_code; mask_dev: uint8 0/255 after the morphology steps;
