@@ -11,9 +11,12 @@
 //           dominant channel + gains in double (480-544), optional RGB contrast stretch
 //           (546-645) -> ONE composed 256-entry table per channel
 //   pass 2  hist_sv     table -> BGR2HSV -> histograms of S and V          (re-reads 3 B/px, L2)
+//                       and keeps H,S,V (3 B/px) in an L2-resident scratch image
 //   stats2  (last block of pass 2) S/V percentile bounds (671-681) -> stretch tables (683-686)
-//   pass 3  final       table -> BGR2HSV -> S/V tables -> HSV2BGR -> [convert -> inRange]
+//   pass 3  final       H,S,V scratch -> S/V tables -> HSV2BGR -> [convert -> inRange]
 //                       writes balanced BGR and/or converted image and/or mask
+//           or mask_from_hsv (HSV inRange mask only): H,S,V scratch -> S/V tables -> one look-up
+//                       in a 128 KB shared-memory table of hue intervals (see "hue-interval table")
 //
 // Because clipping, equalisation and the contrast stretch are all per-channel point operations
 // that depend only on global statistics, they collapse into look-up tables computed once per frame;
@@ -292,12 +295,45 @@ __global__ void __launch_bounds__(kBalThreads) hist_bgr_kernel(const uint8_t *__
     if (last_block_of_frame(&st[frame].ticket[0], gridDim.x)) stats_bgr_block(st[frame], npx, prm, pow_quarter, sc, nullptr, 1, npx);
 }
 
+// insert the 24-bit packed pixel J (0..15) into the 12-word output buffer
+template <int J>
+__device__ __forceinline__ void put_px(uint32_t (&w)[12], uint32_t p) {
+    constexpr int o = 3 * J, wi = o >> 2, sh = 8 * (o & 3);
+    w[wi] |= p << sh;
+    if constexpr (sh > 8) w[wi + 1] |= p >> (32 - sh);
+}
+
+// pixels J..15 of a 16-pixel group of pass 2: tables -> BGR2HSV -> S and V counted, H,S,V packed
+template <int J>
+__device__ __forceinline__ void hsv_group(const Px16 &in, const uint8_t (*lut)[256], const int *sdiv, const int *hdiv,
+                                          uint32_t (*hw)[256], Px16 &o) {
+    if constexpr (J < 16) {
+        int hh, ss, vv;
+        bgr2hsv(lut[0][BV_GETB(in.w, 3 * J)], lut[1][BV_GETB(in.w, 3 * J + 1)], lut[2][BV_GETB(in.w, 3 * J + 2)], sdiv, hdiv, hh,
+                ss, vv);
+        atomicAdd(&hw[0][ss], 1u);
+        atomicAdd(&hw[1][vv], 1u);
+        put_px<J>(o.w, (uint32_t)hh | ((uint32_t)ss << 8) | ((uint32_t)vv << 16));
+        hsv_group<J + 1>(in, lut, sdiv, hdiv, hw, o);
+    }
+}
+
+// ordinary (L2 write-back) 48-byte store: the scratch image is re-read by pass 3
+__device__ __forceinline__ void store_px16_keep(uint8_t *base, size_t group, const Px16 &p) {
+    uint4 *q = reinterpret_cast<uint4 *>(base) + group * 3;
+    q[0] = make_uint4(p.w[0], p.w[1], p.w[2], p.w[3]);
+    q[1] = make_uint4(p.w[4], p.w[5], p.w[6], p.w[7]);
+    q[2] = make_uint4(p.w[8], p.w[9], p.w[10], p.w[11]);
+}
+
 // ----------------------------------------------------------------------------------------------
 // pass 2: S and V histograms of the table-corrected frame (+ statistics in the last block)
 // ----------------------------------------------------------------------------------------------
+// The full H,S,V of every pixel is kept in `hsv` (frame stride hsv_stride bytes, 16-byte aligned):
+// pass 3 starts from it instead of repeating the three table look-ups and the conversion.
 template <bool VEC>
 __global__ void __launch_bounds__(kBalThreads) hist_sv_kernel(const uint8_t *__restrict__ src, BalFrame *__restrict__ st,
-                                                              size_t npx) {
+                                                              size_t npx, uint8_t *__restrict__ hsv, size_t hsv_stride) {
     __shared__ uint32_t h[kBalWarps][2][256];
     __shared__ uint8_t lut[3][256];
     __shared__ int sdiv[256], hdiv[256];
@@ -314,23 +350,23 @@ __global__ void __launch_bounds__(kBalThreads) hist_sv_kernel(const uint8_t *__r
     uint32_t(*hw)[256] = h[threadIdx.x >> 5];
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t ngroups = VEC ? npx / 16 : 0;
+    uint8_t *hf = hsv + (size_t)frame * hsv_stride;
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
-        Px16 in;
+        Px16 in, o;
         load_px16<true>(f, g, in);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            int hh, ss, vv;
-            bgr2hsv(lut[0][BV_GETB(in.w, 3 * j)], lut[1][BV_GETB(in.w, 3 * j + 1)], lut[2][BV_GETB(in.w, 3 * j + 2)], sdiv,
-                    hdiv, hh, ss, vv);
-            atomicAdd(&hw[0][ss], 1u);
-            atomicAdd(&hw[1][vv], 1u);
-        }
+        for (int k = 0; k < 12; ++k) o.w[k] = 0;
+        hsv_group<0>(in, lut, sdiv, hdiv, hw, o);
+        store_px16_keep(hf, g, o);
     }
     for (size_t p = ngroups * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += stride) {
         int hh, ss, vv;
         bgr2hsv(lut[0][f[3 * p]], lut[1][f[3 * p + 1]], lut[2][f[3 * p + 2]], sdiv, hdiv, hh, ss, vv);
         atomicAdd(&hw[0][ss], 1u);
         atomicAdd(&hw[1][vv], 1u);
+        hf[3 * p] = (uint8_t)hh;
+        hf[3 * p + 1] = (uint8_t)ss;
+        hf[3 * p + 2] = (uint8_t)vv;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 512; i += blockDim.x) {
@@ -344,8 +380,9 @@ __global__ void __launch_bounds__(kBalThreads) hist_sv_kernel(const uint8_t *__r
 
 // ----------------------------------------------------------------------------------------------
 // pass 3: everything per pixel.  MODE 0: no balance (pure conversion); 1: BGR tables only
-// (hsv_contrast_correct = 0); 2: tables + HSV stretch round trip.  CODE: conversion applied to
-// the balanced pixel for the converted / mask outputs (-1: none).
+// (hsv_contrast_correct = 0); 2: tables + HSV stretch round trip from the BGR frame (tiled
+// equalisation); 3: the input IS pass 2's H,S,V scratch image -> S/V tables -> HSV2BGR.
+// CODE: conversion applied to the balanced pixel for the converted / mask outputs (-1: none).
 // ----------------------------------------------------------------------------------------------
 struct FinalSmem {
     uint8_t lut[3][256];
@@ -356,6 +393,7 @@ struct FinalSmem {
 // returns the balanced pixel packed as b | g<<8 | r<<16
 template <int MODE>
 __device__ __forceinline__ uint32_t balance_px(uint32_t b, uint32_t g, uint32_t r, bool vec, const FinalSmem &fs) {
+    if (MODE == 3) return hsv2bgr_packed((int)b, fs.lut_sv[0][g], fs.lut_sv[1][r], vec);  // (b, g, r) hold (h, s, v)
     if (MODE >= 1) {
         b = fs.lut[0][b];
         g = fs.lut[1][g];
@@ -367,14 +405,6 @@ __device__ __forceinline__ uint32_t balance_px(uint32_t b, uint32_t g, uint32_t 
         return hsv2bgr_packed(h, fs.lut_sv[0][s], fs.lut_sv[1][v], vec);
     }
     return b | (g << 8) | (r << 16);
-}
-
-// insert the 24-bit packed pixel J (0..15) into the 12-word output buffer
-template <int J>
-__device__ __forceinline__ void put_px(uint32_t (&w)[12], uint32_t p) {
-    constexpr int o = 3 * J, wi = o >> 2, sh = 8 * (o & 3);
-    w[wi] |= p << sh;
-    if constexpr (sh > 8) w[wi + 1] |= p >> (32 - sh);
 }
 
 // one group of 16 pixels.  TRACK_X: the group touches the row tail (width % 32 columns), where
@@ -411,17 +441,18 @@ struct GroupBody<MODE, CODE, TRACK_X, NEED_MASK, 16> {
 };
 
 template <int MODE, int CODE, bool VEC, bool NEED_MASK>
-__global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__restrict__ src, const BalFrame *__restrict__ st,
-                                                            size_t npx, int width, BalOutputs out,
-                                                            const uint16_t *__restrict__ g_gamma,
+__global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__restrict__ src, size_t src_stride,
+                                                            const BalFrame *__restrict__ st, size_t npx, int width,
+                                                            BalOutputs out, const uint16_t *__restrict__ g_gamma,
                                                             const uint16_t *__restrict__ g_cbrt) {
     __shared__ FinalSmem fs;
     __shared__ SmemTabs tabs;
     const int frame = blockIdx.y;
-    if (MODE >= 1)
+    if (MODE == 1 || MODE == 2)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) (&fs.lut[0][0])[i] = (&st[frame].lut_bgr[0][0])[i];
-    if (MODE == 2) {
+    if (MODE >= 2)
         for (int i = threadIdx.x; i < 512; i += blockDim.x) (&fs.lut_sv[0][0])[i] = (&st[frame].lut_sv[0][0])[i];
+    if (MODE == 2) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) {
             fs.sdiv[i] = hsv_sdiv(i);
             fs.hdiv[i] = hsv_hdiv(i);
@@ -429,10 +460,10 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
     }
     init_tabs<CODE>(tabs, g_gamma, g_cbrt);  // ends with __syncthreads()
     const size_t foff = (size_t)frame * npx;
-    const uint8_t *f = src + foff * 3;
+    const uint8_t *f = src + (size_t)frame * src_stride;  // BGR frame, or pass 2's H,S,V scratch (MODE 3)
     const int vec_end = width - (width % 32);
     constexpr bool kOne = CvtTraits<CODE>::kOneChannel;
-    constexpr bool kNeedX = (MODE == 2) || CvtTraits<CODE>::kNeedsX;
+    constexpr bool kNeedX = (MODE >= 2) || CvtTraits<CODE>::kNeedsX;
     const RangeTest bd = make_range_test(out.lo, out.hi);
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t ngroups = VEC ? (uint32_t)(npx / 16) : 0u;  // npx < 2^31 (checked on the host)
@@ -503,6 +534,175 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
         }
         if (out.mask) out.mask[foff + p] = in_range_px<CODE>(o0, o1, o2, bd) ? 255 : 0;
     }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Hue-interval table: the HSV inRange mask of a balanced frame without the HSV -> BGR -> HSV
+// round trip.
+//
+// With hsv_contrast_correct the balanced pixel is HSV2BGR(H, S', V') (color_balance.cpp:693) and
+// modules/bins.py:13-16 immediately converts it back to HSV and thresholds it.  That composite
+//     (H, S', V')  ->  HSV2BGR  ->  BGR2HSV  ->  inRange(lo, hi)
+// does not depend on the frame, only on the bounds.  HSV2BGR yields max = trunc(v*255),
+// min = trunc(v(1-s)*255) and a middle value that alone depends on H; so S2 and V2 of the round
+// trip are functions of (S', V') and, for every (S', V'), the hues that pass are one cyclic
+// interval of [0,180).  The table stores that interval for each of the 65536 (S', V') pairs as
+// (first hue, span mod 256); a pixel passes iff ((H - first) & 255) <= span.  It is filled by the
+// exact per-pixel arithmetic (all 180 x 65536 combinations) once per distinct bounds set, the
+// build verifies the single-interval property for every pair (otherwise the generic pass 3 is
+// used), and it lives in shared memory (128 KB, brought in with one TMA bulk copy per block).
+// Valid for whole 32-pixel groups of a row only (cv2's vector HSV2BGR rounding): width % 32 == 0.
+// ----------------------------------------------------------------------------------------------
+constexpr int kIvlEntries = 65536;
+constexpr uint32_t kIvlBytes = kIvlEntries * 2;
+constexpr int kIvlEmpty = 200;  // first = 200, span = 0: no hue in [0,180) passes
+
+__global__ void __launch_bounds__(256) ivl_build_kernel(uint16_t *__restrict__ table, int *__restrict__ bad, Bounds3 bd) {
+    __shared__ int sdiv[256], hdiv[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sdiv[i] = hsv_sdiv(i);
+        hdiv[i] = hsv_hdiv(i);
+    }
+    __syncthreads();
+    const RangeTest rt = make_range_test(bd.lo, bd.hi);
+    const int lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // S' * 256 + V'
+    const int S = pair >> 8, V = pair & 255;
+    auto passes = [&](int H) {
+        const uint32_t p = hsv2bgr_packed(H, S, V, true);
+        int h2, s2, v2;
+        bgr2hsv((int)(p & 0xFF), (int)((p >> 8) & 0xFF), (int)(p >> 16), sdiv, hdiv, h2, s2, v2);
+        return in_range_px<BV_BGR2HSV>(h2, s2, v2, rt);
+    };
+    int n_in = 0, n_rise = 0, first = 0;
+    for (int it = 0; it < 6; ++it) {
+        const int H = it * 32 + lane;
+        bool in = false, rise = false;
+        if (H < 180) {
+            in = passes(H);
+            rise = in && !passes(H == 0 ? 179 : H - 1);
+        }
+        const uint32_t bi = __ballot_sync(0xFFFFFFFFu, in), br = __ballot_sync(0xFFFFFFFFu, rise);
+        n_in += __popc(bi);
+        n_rise += __popc(br);
+        if (br) first = it * 32 + __ffs(br) - 1;
+    }
+    if (lane == 0) {
+        int lo = kIvlEmpty, span = 0;
+        if (n_in == 180) {
+            lo = 0;
+            span = 179;
+        } else if (n_in > 0) {
+            if (n_rise != 1) atomicOr(bad, 1);
+            const int last = (first + n_in - 1) % 180;
+            lo = first;
+            span = (last - first) & 0xFF;
+        }
+        table[pair] = (uint16_t)(lo | (span << 8));
+    }
+}
+
+struct IvlSmem {
+    uint16_t tab[kIvlEntries];
+    uint8_t lsv[2][256];
+    uint64_t bar;
+};
+
+// pass 3 of the fast path: H,S,V scratch -> S/V stretch tables -> hue interval -> mask
+__global__ void __launch_bounds__(1024, 1) mask_from_hsv_kernel(const uint8_t *__restrict__ hsv, size_t hsv_stride,
+                                                                const BalFrame *__restrict__ st,
+                                                                const uint16_t *__restrict__ table, size_t npx, int width,
+                                                                BalOutputs out) {
+    extern __shared__ __align__(128) unsigned char ivl_raw[];
+    IvlSmem &sm = *reinterpret_cast<IvlSmem *>(ivl_raw);
+    const int frame = blockIdx.y;
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bar, 1);
+        mbar_expect_tx(&sm.bar, kIvlBytes);
+        for (uint32_t o = 0; o < kIvlBytes; o += 32768u)
+            bulk_g2s(reinterpret_cast<unsigned char *>(sm.tab) + o, reinterpret_cast<const unsigned char *>(table) + o, 32768u, &sm.bar);
+    }
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sm.lsv[0][0])[i] = (&st[frame].lut_sv[0][0])[i];
+    __syncthreads();
+    mbar_wait(&sm.bar, 0);
+    const uint8_t *f = hsv + (size_t)frame * hsv_stride;
+    const size_t foff = (size_t)frame * npx;
+    const uint32_t stride = gridDim.x * blockDim.x, ngroups = (uint32_t)(npx / 16);
+    const uint32_t height = (uint32_t)(npx / (size_t)width);
+    const int wp2 = ((width + 31) / 32) * 2;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+        Px16 in;
+        load_px16<false>(f, g, in);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t h = BV_GETB(in.w, 3 * j);
+            const uint32_t s = sm.lsv[0][BV_GETB(in.w, 3 * j + 1)], v = sm.lsv[1][BV_GETB(in.w, 3 * j + 2)];
+            const uint32_t e = sm.tab[(s << 8) | v];
+            if (((h - (e & 0xFFu)) & 0xFFu) <= (e >> 8)) bits |= 1u << j;
+        }
+        if (out.mask) {
+            uint32_t m[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t nib = (bits >> (4 * k)) & 0xF;
+                m[k] = ((nib & 1) * 0xFFu) | (((nib >> 1) & 1) * 0xFF00u) | (((nib >> 2) & 1) * 0xFF0000u) |
+                       (((nib >> 3) & 1) * 0xFF000000u);
+            }
+            st_stream(reinterpret_cast<uint4 *>(out.mask + foff) + g, make_uint4(m[0], m[1], m[2], m[3]));
+        }
+        if (out.mask_bits) {
+            const uint32_t p0 = g * 16u, y = p0 / (uint32_t)width, x0 = p0 - y * (uint32_t)width;
+            out.mask_bits[((size_t)frame * height + y) * wp2 + (x0 >> 4)] = (uint16_t)bits;
+        }
+    }
+}
+
+// Table for these bounds, building it on first use (one build + one flag read-back per distinct
+// bounds set; tuner changes are rare).  *table = nullptr when the fast path cannot be used.
+static int ivl_table(bv_ctx *ctx, const uint8_t lo[3], const uint8_t hi[3], const uint16_t **table) {
+    *table = nullptr;
+    static int disabled = getenv("BV_NO_HUE_TABLE") ? 1 : 0;
+    if (disabled) return BV_OK;
+    uint8_t key[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+    for (int i = 0; i < BV_IVL_SLOTS; ++i)
+        if (ctx->ivl[i].state && !memcmp(ctx->ivl[i].key, key, 6)) {
+            if (ctx->ivl[i].state == 1) *table = ctx->ivl[i].table;
+            return BV_OK;
+        }
+    const int slot = ctx->ivl_next;
+    ctx->ivl_next = (slot + 1) % BV_IVL_SLOTS;
+    if (ctx->ivl[slot].state) BV_CUDA(cudaStreamSynchronize(ctx->stream));  // the evicted table may still be in use
+    if (!ctx->ivl[slot].table) BV_CUDA(cudaMalloc(&ctx->ivl[slot].table, kIvlBytes));
+    if (!ctx->d_ivl_flag) BV_CUDA(cudaMalloc(&ctx->d_ivl_flag, sizeof(int)));
+    ctx->ivl[slot].state = 0;
+    BV_CUDA(cudaMemsetAsync(ctx->d_ivl_flag, 0, sizeof(int), ctx->stream));
+    Bounds3 bd;
+    for (int k = 0; k < 3; ++k) {
+        bd.lo[k] = lo[k];
+        bd.hi[k] = hi[k];
+    }
+    BV_LAUNCH(ctx, ivl_build_kernel, kIvlEntries / 8, 256, 0, ctx->ivl[slot].table, ctx->d_ivl_flag, bd);
+    int bad = 0;
+    BV_CUDA(cudaMemcpyAsync(&bad, ctx->d_ivl_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    BV_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->ivl[slot].key, key, 6);
+    ctx->ivl[slot].state = bad ? 2 : 1;
+    if (!bad) *table = ctx->ivl[slot].table;
+    return BV_OK;
+}
+
+static int launch_mask_from_hsv(bv_ctx *ctx, const uint8_t *hsv, size_t hsv_stride, const BalFrame *st, int batch, size_t npx,
+                                int width, const uint16_t *table, const BalOutputs &out) {
+    if (!ctx->ivl_attr_set) {  // per device
+        BV_CUDA(cudaFuncSetAttribute(mask_from_hsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IvlSmem)));
+        ctx->ivl_attr_set = 1;
+    }
+    int bpf = (ctx->sm_count + batch - 1) / batch;  // one 1024-thread block per SM
+    const size_t need = (npx / 16 + 1023) / 1024;
+    if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
+    BV_LAUNCH(ctx, mask_from_hsv_kernel, dim3(bpf, batch), 1024, sizeof(IvlSmem), hsv, hsv_stride, st, table, npx, width, out);
+    return BV_OK;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -705,16 +905,16 @@ static bool vec_ok(const void *p, size_t npx, int batch, int bytes_per_px) {
 }
 
 template <int MODE, int CODE>
-static int launch_final(bv_ctx *ctx, const uint8_t *src, const BalFrame *st, int batch, size_t npx, int width,
-                        const BalOutputs &out, bool vec) {
+static int launch_final(bv_ctx *ctx, const uint8_t *src, size_t src_stride, const BalFrame *st, int batch, size_t npx,
+                        int width, const BalOutputs &out, bool vec) {
     int bpf = (ctx->sm_count * final_blocks_per_sm(ctx->overlapped != 0) + batch - 1) / batch;
     const size_t need = (npx / 16 + kBalThreads - 1) / kBalThreads;
     if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
     dim3 grid(bpf, batch);
     const bool need_mask = out.mask || out.mask_bits;
 #define BV_FINAL(V, M)                                                                                              \
-    BV_LAUNCH(ctx, (final_kernel<MODE, CODE, V, M>), grid, kBalThreads, 0, src, st, npx, width, out, ctx->d_lab_gamma, \
-              ctx->d_lab_cbrt)
+    BV_LAUNCH(ctx, (final_kernel<MODE, CODE, V, M>), grid, kBalThreads, 0, src, src_stride, st, npx, width, out,    \
+              ctx->d_lab_gamma, ctx->d_lab_cbrt)
     if (vec) {
         if (need_mask) BV_FINAL(true, true); else BV_FINAL(true, false);
     } else {
@@ -725,15 +925,15 @@ static int launch_final(bv_ctx *ctx, const uint8_t *src, const BalFrame *st, int
 }
 
 template <int MODE>
-static int dispatch_final(bv_ctx *ctx, const uint8_t *src, const BalFrame *st, int batch, size_t npx, int width,
-                          int code, const BalOutputs &out, bool vec) {
+static int dispatch_final(bv_ctx *ctx, const uint8_t *src, size_t src_stride, const BalFrame *st, int batch, size_t npx,
+                          int width, int code, const BalOutputs &out, bool vec) {
     switch (code) {
-        case -1: return launch_final<MODE, -1>(ctx, src, st, batch, npx, width, out, vec);
-        case BV_BGR2HSV: return launch_final<MODE, BV_BGR2HSV>(ctx, src, st, batch, npx, width, out, vec);
-        case BV_BGR2LAB: return launch_final<MODE, BV_BGR2LAB>(ctx, src, st, batch, npx, width, out, vec);
-        case BV_BGR2GRAY: return launch_final<MODE, BV_BGR2GRAY>(ctx, src, st, batch, npx, width, out, vec);
-        case BV_BGR2YCRCB: return launch_final<MODE, BV_BGR2YCRCB>(ctx, src, st, batch, npx, width, out, vec);
-        case BV_BGR2HLS: return launch_final<MODE, BV_BGR2HLS>(ctx, src, st, batch, npx, width, out, vec);
+        case -1: return launch_final<MODE, -1>(ctx, src, src_stride, st, batch, npx, width, out, vec);
+        case BV_BGR2HSV: return launch_final<MODE, BV_BGR2HSV>(ctx, src, src_stride, st, batch, npx, width, out, vec);
+        case BV_BGR2LAB: return launch_final<MODE, BV_BGR2LAB>(ctx, src, src_stride, st, batch, npx, width, out, vec);
+        case BV_BGR2GRAY: return launch_final<MODE, BV_BGR2GRAY>(ctx, src, src_stride, st, batch, npx, width, out, vec);
+        case BV_BGR2YCRCB: return launch_final<MODE, BV_BGR2YCRCB>(ctx, src, src_stride, st, batch, npx, width, out, vec);
+        case BV_BGR2HLS: return launch_final<MODE, BV_BGR2HLS>(ctx, src, src_stride, st, batch, npx, width, out, vec);
         default: set_error("stage: conversion code %d is not available in the fused pass", code); return BV_ERR_INVALID;
     }
 }
@@ -762,7 +962,7 @@ int convert_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         set_error("convert_run: bit-packed mask needs 16-byte aligned buffers and width %% 16 == 0");
         return BV_ERR_INVALID;
     }
-    return dispatch_final<0>(ctx, src, nullptr, batch, npx, width, cvt_code, out, vec);
+    return dispatch_final<0>(ctx, src, npx * 3, nullptr, batch, npx, width, cvt_code, out, vec);
 }
 
 int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int width, const bv_balance_params &prm,
@@ -795,6 +995,19 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         return BV_OK;
     }
 
+    // pass 2 leaves H,S,V of every pixel in a scratch image for pass 3 (frame stride padded to 16 bytes)
+    const size_t hsv_stride = (npx * 3 + 15) & ~(size_t)15;
+    uint8_t *hsv = nullptr;
+    const uint16_t *ivl = nullptr;
+    if (prm.hsv_contrast_correct) {
+        BV_TRY(ensure_scratch(ctx, SCR_BAL_HSV, hsv_stride * (size_t)batch));
+        hsv = (uint8_t *)ctx->scratch[SCR_BAL_HSV];
+        // HSV inRange mask as the only output, whole 32-pixel groups per row: hue-interval table
+        if (cvt_code == BV_BGR2HSV && !out.balanced && !out.converted && (out.mask || out.mask_bits) && vec && npx % 16 == 0 &&
+            width % 32 == 0)
+            BV_TRY(ivl_table(ctx, out.lo, out.hi, &ivl));
+    }
+
     // chunk the batch so that one chunk's input stays in L2 across the three passes; chunks are
     // independent and alternate over side streams so that their passes overlap on the SMs
     int chunk = (int)(l2_chunk_bytes() / (npx * 3));
@@ -819,6 +1032,7 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         const int nf = batch - f0 < chunk ? batch - f0 : chunk;
         const uint8_t *csrc = src + (size_t)f0 * npx * 3;
         BalFrame *cst = st + f0;
+        uint8_t *chsv = hsv ? hsv + (size_t)f0 * hsv_stride : nullptr;
         int bpf = (ctx->sm_count * hist_blocks_per_sm(ctx->overlapped != 0) + nf - 1) / nf;
         const size_t need = (npx / 16 + kBalThreads - 1) / kBalThreads;
         if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
@@ -829,19 +1043,21 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
             BV_LAUNCH(ctx, hist_bgr_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx, prm, ctx->d_pow_quarter);
         if (prm.hsv_contrast_correct) {
             if (vec)
-                BV_LAUNCH(ctx, hist_sv_kernel<true>, grid, kBalThreads, 0, csrc, cst, npx);
+                BV_LAUNCH(ctx, hist_sv_kernel<true>, grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
             else
-                BV_LAUNCH(ctx, hist_sv_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx);
+                BV_LAUNCH(ctx, hist_sv_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
         }
         BalOutputs co = out;
         if (co.balanced) co.balanced += (size_t)f0 * npx * 3;
         if (co.converted) co.converted += (size_t)f0 * npx * (cvt_code == BV_BGR2GRAY ? 1 : 3);
         if (co.mask) co.mask += (size_t)f0 * npx;
         if (co.mask_bits) co.mask_bits += (size_t)f0 * height * (((width + 31) / 32) * 2);
-        if (prm.hsv_contrast_correct)
-            BV_TRY(dispatch_final<2>(ctx, csrc, cst, nf, npx, width, cvt_code, co, vec));
+        if (ivl)
+            BV_TRY(launch_mask_from_hsv(ctx, chsv, hsv_stride, cst, nf, npx, width, ivl, co));
+        else if (prm.hsv_contrast_correct)
+            BV_TRY(dispatch_final<3>(ctx, chsv, hsv_stride, cst, nf, npx, width, cvt_code, co, vec));
         else
-            BV_TRY(dispatch_final<1>(ctx, csrc, cst, nf, npx, width, cvt_code, co, vec));
+            BV_TRY(dispatch_final<1>(ctx, csrc, npx * 3, cst, nf, npx, width, cvt_code, co, vec));
     }
     ctx->stream = main_stream;
     if (nside > 1)

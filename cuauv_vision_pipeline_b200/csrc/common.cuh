@@ -52,6 +52,7 @@ void set_error(const char *fmt, ...);  // thread-local message, api.cu
 enum ScratchSlot {
     SCR_BAL_STATE = 0,  // per-frame histograms, LUTs, stats of the colour balance
     SCR_BAL_TILES,      // per-tile histograms and tables (tiled equalisation)
+    SCR_BAL_HSV,        // H,S,V image written by pass 2 and read by pass 3 (L2 resident per chunk)
     SCR_BITS_A,         // bit-packed masks (ping)
     SCR_BITS_B,         // bit-packed masks (pong)
     SCR_CCL_PARENT,     // union-find parents, int32 per pixel
@@ -78,6 +79,7 @@ enum ScratchSlot {
 
 #define BV_MAX_CHUNKS 64
 #define BV_MAX_SIDE 4
+#define BV_IVL_SLOTS 4
 
 struct bv_ctx {
     int device;
@@ -99,6 +101,15 @@ struct bv_ctx {
     // pass of one chunk overlaps the atomics-bound histogram passes of the next
     cudaStream_t side[BV_MAX_SIDE];
     cudaEvent_t ev_fork, ev_join[BV_MAX_SIDE];
+    // hue-interval tables of the HSV inRange fast path (balance.cu), one per distinct bounds set
+    struct {
+        uint8_t key[6];
+        int state;         // 0 empty, 1 usable, 2 built but not representable (generic pass is used)
+        uint16_t *table;   // 65536 entries, device
+    } ivl[BV_IVL_SLOTS];
+    int ivl_next;
+    int ivl_attr_set;
+    int *d_ivl_flag;
 };
 
 namespace bv {
@@ -159,6 +170,35 @@ __device__ __forceinline__ void store_px16(uint8_t *base, size_t group, const Px
 // byte k (compile-time constant after unrolling) of a packed word array
 #define BV_GETB(W, k) (((W)[(k) >> 2] >> (8 * ((k)&3))) & 0xFFu)
 #define BV_PUTB(W, k, v) ((W)[(k) >> 2] |= ((uint32_t)(v)) << (8 * ((k)&3)))
+
+// ---- TMA bulk copy (cp.async.bulk, SASS: UBLKCP) completing on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LB_DONE_%=;\n"
+        "bra LB_WAIT_%=;\n"
+        "LB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
 
 __device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 

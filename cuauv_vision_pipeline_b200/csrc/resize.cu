@@ -105,34 +105,6 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxImg *__re
 // ----------------------------------------------------------------------------------------------
 constexpr int kLbMaxRowBytes = 11520;  // up to 3840 px wide sources (2 stages x 2 rows = 45 KB of shared memory)
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LB_DONE;\n"
-        "bra LB_WAIT;\n"
-        "LB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(phase)
-        : "memory");
-}
-
 // horizontal taps of one output column
 struct LbCoef {
     short o0, o1;  // byte offsets of the two taps inside a source row; o0 < 0: padding column

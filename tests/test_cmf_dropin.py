@@ -47,8 +47,8 @@ def test_modules_fed_through_the_reference_transport(ctx):
 
     def capture_source():  # role of capture_sources/image_directory.py:30-36 + core/capture_source.py:183-234
         i = 0
-        while not stop.is_set() and i < len(frames):
-            writer.write(1000 + i, frames[i])
+        while not stop.is_set() and i < 400:                  # keeps cycling: a cold first call may take a while
+            writer.write(1000 + i, frames[i % len(frames)])
             i += 1
             time.sleep(0.05)
 
@@ -66,7 +66,7 @@ def test_modules_fed_through_the_reference_transport(ctx):
             if st != cmf.lib().SUCCESS:
                 time.sleep(0.005)
                 continue
-            idx = t - 1000
+            idx = (t - 1000) % len(frames)
             # zero-copy ingest: pin the reader's buffer once, hand the pointer straight to the C ABI
             if pinned_ptr != reader.data_pointer():
                 if pinned_ptr is not None:

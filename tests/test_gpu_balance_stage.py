@@ -359,3 +359,49 @@ def test_drop_in_modules(ctx):
         assert buoy.contour_result["area"] == cv_ops.contour_area(best)
     cbm = ColorBalanceGPU(["forward"])
     assert np.array_equal(cbm.process("forward", img), oracle_balance(img))
+
+
+HUE_TABLE_BOUNDS = [((10, 20, 60), (30, 100, 255)),      # modules/bins.py:14-15
+                    ((0, 40, 60), (179, 255, 255)),
+                    ((0, 0, 0), (5, 255, 255)),           # hue interval touching 0
+                    ((170, 0, 0), (179, 255, 255)),       # ... and 179 (round trip may wrap)
+                    ((0, 0, 0), (179, 30, 40)),           # dark / grey pixels: hue is unstable there
+                    ((50, 0, 0), (40, 255, 255)),         # empty range
+                    ((0, 0, 0), (255, 255, 255)),
+                    ((90, 100, 100), (90, 200, 200))]
+
+
+@pytest.mark.parametrize("lo,hi", HUE_TABLE_BOUNDS)
+def test_stage_mask_only_hue_interval_table(ctx, lo, hi):
+    """Mask-only HSV threshold of a balanced frame (the shared-memory hue-interval table instead of the
+    HSV -> BGR -> HSV round trip) == balance() -> cv2.cvtColor(BGR2HSV) -> cv2.inRange -> OPEN."""
+    frames = np.stack([synth.gen_underwater(480, 640, 90 + s) for s in range(3)] + [synth.gen_random_bgr(480, 640, 5)])
+    desc = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=lo, hi=hi)
+    mask = ctx.download(ctx.stage(desc, ctx.upload(frames), want=("mask",))["mask"])
+    desc_m = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=lo, hi=hi, morph=[("open", 5, 5, 1)], label=True)
+    out = ctx.stage(desc_m, ctx.upload(frames), want=("mask", "labels", "blobs"), max_blobs=4096)
+    opened, lab = ctx.download(out["mask"]), ctx.download(out["labels"])
+    for i in range(frames.shape[0]):
+        hsv_ref = cv2.cvtColor(oracle_balance(frames[i]), cv2.COLOR_BGR2HSV)
+        m_ref = cv2.inRange(hsv_ref, np.array(lo), np.array(hi))
+        assert np.array_equal(mask[i], m_ref)
+        o_ref = cv2.morphologyEx(m_ref, cv2.MORPH_OPEN, cv_ops.rect_kernel(5))
+        assert np.array_equal(opened[i], o_ref)
+        assert np.array_equal(lab[i], ccl.label_and_moments(o_ref)[1])
+
+
+def test_stage_mask_only_many_bounds_reuse_and_evict_tables(ctx):
+    """More distinct bounds than table slots, revisited: cached, evicted and rebuilt tables all agree
+    with the full-output pass (which does the round trip arithmetically)."""
+    frames = np.stack([synth.gen_underwater(352, 640, 120 + s) for s in range(2)])
+    dev = ctx.upload(frames)
+    rng = np.random.default_rng(11)
+    bounds = []
+    for _ in range(6):
+        a, b = rng.integers(0, 180, 2), rng.integers(0, 256, (2, 2))
+        bounds.append(((int(min(a)), int(b[:, 0].min()), int(b[:, 1].min())), (int(max(a)), int(b[:, 0].max()), int(b[:, 1].max()))))
+    for lo, hi in bounds + bounds[:3]:
+        desc = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=lo, hi=hi)
+        fast = ctx.download(ctx.stage(desc, dev, want=("mask",))["mask"])
+        full = ctx.download(ctx.stage(desc, dev, want=("mask", "converted"))["mask"])
+        assert np.array_equal(fast, full), (lo, hi)

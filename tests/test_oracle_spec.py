@@ -108,3 +108,22 @@ def test_color_distance_restatement_matches_reference_function_golden():
     for k, kw in enumerate(cases):
         m, d = cv_ops.thresh_color_distance(split, **kw)
         assert np.array_equal(m, z["tcd%d_mask" % k]) and np.array_equal(d, z["tcd%d_dist" % k])
+
+
+def test_hue_interval_property_of_the_hsv_round_trip():
+    """The property the CUDA fast path for `balance -> BGR2HSV -> inRange` rests on (balance.cu, "hue-interval
+    table"), pinned on cv2 itself: for every (S, V) the hues H for which
+    inRange(BGR2HSV(HSV2BGR(H, S, V))) passes form ONE cyclic interval of [0, 180), and S2, V2 of the
+    round trip do not depend on H."""
+    cube = np.empty((180, 65536, 3), np.uint8)
+    cube[..., 0] = np.arange(180, dtype=np.uint8)[:, None]
+    sv = np.arange(65536)
+    cube[..., 1] = (sv >> 8).astype(np.uint8)[None, :]
+    cube[..., 2] = (sv & 255).astype(np.uint8)[None, :]
+    back = cv2.cvtColor(cv2.cvtColor(cube, cv2.COLOR_HSV2BGR), cv2.COLOR_BGR2HSV)     # width 65536: vector path throughout
+    assert (back[..., 1] == back[0:1, :, 1]).all() and (back[..., 2] == back[0:1, :, 2]).all()
+    for lo, hi in [((10, 20, 60), (30, 100, 255)), ((0, 0, 0), (5, 255, 255)), ((170, 0, 0), (179, 255, 255)),
+                   ((0, 0, 0), (179, 30, 40)), ((37, 5, 9), (121, 250, 251)), ((90, 0, 0), (90, 255, 255))]:
+        m = cv2.inRange(back, np.array(lo), np.array(hi)) > 0                          # [180, 65536]
+        rises = (m & ~np.roll(m, 1, axis=0)).sum(axis=0)
+        assert int(rises.max()) <= 1, (lo, hi)
