@@ -219,7 +219,20 @@ extern "C" int bv_create(int device, bv_ctx **out) {
         bv_destroy(ctx);
         return BV_ERR_CUDA;
     }
+    static const char *const opt_env[BV_OPT_COUNT] = {"BV_HIST_BPS", "BV_FINAL_BPS", "BV_SIDE_STREAMS", "BV_L2_CHUNK_MB",
+                                                      "BV_NO_HUE_TABLE"};
+    for (int i = 0; i < BV_OPT_COUNT; ++i) {
+        const char *v = getenv(opt_env[i]);
+        ctx->opt[i] = v ? atoi(v) : 0;
+    }
     *out = ctx;
+    return BV_OK;
+}
+
+extern "C" int bv_set_option(bv_ctx *ctx, int option, int value) {
+    BV_REQUIRE(ctx, "null context");
+    BV_REQUIRE(option >= 0 && option < BV_OPT_COUNT, "unknown option");
+    ctx->opt[option] = value > 0 ? value : 0;
     return BV_OK;
 }
 

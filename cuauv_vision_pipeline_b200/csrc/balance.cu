@@ -274,11 +274,16 @@ __global__ void __launch_bounds__(kBalThreads) hist_bgr_kernel(const uint8_t *__
     uint32_t(*hw)[256] = h[threadIdx.x >> 5];
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t ngroups = VEC ? npx / 16 : 0;
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
-        Px16 in;
-        load_px16<true>(f, g, in);
+    // the next group's 48 bytes are requested before the current group's 48 atomics are issued, so
+    // HBM latency overlaps the shared-memory atomics of the same warp
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Px16 in, nxt;
+    if (g < ngroups) load_px16<true>(f, g, in);
+    for (; g < ngroups; g += stride) {
+        if (g + stride < ngroups) load_px16<true>(f, g + stride, nxt);
 #pragma unroll
         for (int k = 0; k < 48; ++k) atomicAdd(&hw[k % 3][BV_GETB(in.w, k)], 1u);
+        in = nxt;
     }
     for (size_t p = ngroups * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += stride) {
         atomicAdd(&hw[0][f[3 * p]], 1u);
@@ -351,13 +356,17 @@ __global__ void __launch_bounds__(kBalThreads) hist_sv_kernel(const uint8_t *__r
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t ngroups = VEC ? npx / 16 : 0;
     uint8_t *hf = hsv + (size_t)frame * hsv_stride;
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
-        Px16 in, o;
-        load_px16<true>(f, g, in);
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Px16 in, nxt;
+    if (g < ngroups) load_px16<true>(f, g, in);
+    for (; g < ngroups; g += stride) {
+        if (g + stride < ngroups) load_px16<true>(f, g + stride, nxt);  // prefetch, see pass 1
+        Px16 o;
 #pragma unroll
         for (int k = 0; k < 12; ++k) o.w[k] = 0;
         hsv_group<0>(in, lut, sdiv, hdiv, hw, o);
         store_px16_keep(hf, g, o);
+        in = nxt;
     }
     for (size_t p = ngroups * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += stride) {
         int hh, ss, vv;
@@ -630,9 +639,11 @@ __global__ void __launch_bounds__(1024, 1) mask_from_hsv_kernel(const uint8_t *_
     const uint32_t stride = gridDim.x * blockDim.x, ngroups = (uint32_t)(npx / 16);
     const uint32_t height = (uint32_t)(npx / (size_t)width);
     const int wp2 = ((width + 31) / 32) * 2;
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
-        Px16 in;
-        load_px16<false>(f, g, in);
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    Px16 in, nxt;
+    if (g < ngroups) load_px16<false>(f, g, in);
+    for (; g < ngroups; g += stride) {
+        if (g + stride < ngroups) load_px16<false>(f, g + stride, nxt);  // prefetch the next group
         uint32_t bits = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -655,6 +666,7 @@ __global__ void __launch_bounds__(1024, 1) mask_from_hsv_kernel(const uint8_t *_
             const uint32_t p0 = g * 16u, y = p0 / (uint32_t)width, x0 = p0 - y * (uint32_t)width;
             out.mask_bits[((size_t)frame * height + y) * wp2 + (x0 >> 4)] = (uint16_t)bits;
         }
+        in = nxt;
     }
 }
 
@@ -662,8 +674,7 @@ __global__ void __launch_bounds__(1024, 1) mask_from_hsv_kernel(const uint8_t *_
 // bounds set; tuner changes are rare).  *table = nullptr when the fast path cannot be used.
 static int ivl_table(bv_ctx *ctx, const uint8_t lo[3], const uint8_t hi[3], const uint16_t **table) {
     *table = nullptr;
-    static int disabled = getenv("BV_NO_HUE_TABLE") ? 1 : 0;
-    if (disabled) return BV_OK;
+    if (ctx->opt[BV_OPT_NO_HUE_TABLE] > 0) return BV_OK;
     uint8_t key[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
     for (int i = 0; i < BV_IVL_SLOTS; ++i)
         if (ctx->ivl[i].state && !memcmp(ctx->ivl[i].key, key, 6)) {
@@ -878,26 +889,17 @@ static int balance_run_tiled(bv_ctx *ctx, const uint8_t *src, int batch, int hei
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
-static int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    const int v = e ? atoi(e) : dflt;
-    return v > 0 ? v : dflt;
-}
-// blocks per SM of the histogram passes and of the final pass (tuning knobs)
-// With side streams the passes of different chunks share the SMs, so each kernel takes a small
-// persistent grid (2 blocks/SM); a lone chunk (single frame, or profiling) gets the whole machine.
-static int hist_blocks_per_sm(bool overlapped) {
-    static int v = getenv("BV_HIST_BPS") ? env_int("BV_HIST_BPS", 2) : 0;
-    return v ? v : (overlapped ? 2 : 4);
-}
-static int side_streams() {
-    static int v = env_int("BV_SIDE_STREAMS", 4);
+// Tuning knobs (bv_set_option / BV_* environment variables read at bv_create, see api.cu):
+// blocks per SM of the histogram passes and of the final pass.  With side streams the passes of
+// different chunks share the SMs, so each kernel takes a small persistent grid (2 blocks/SM); a
+// lone chunk (single frame, or profiling) gets the whole machine.
+static int hist_blocks_per_sm(const bv_ctx *ctx) { return ctx->opt[BV_OPT_HIST_BPS] > 0 ? ctx->opt[BV_OPT_HIST_BPS] : (ctx->overlapped ? 2 : 4); }
+static int final_blocks_per_sm(const bv_ctx *ctx) { return ctx->opt[BV_OPT_FINAL_BPS] > 0 ? ctx->opt[BV_OPT_FINAL_BPS] : (ctx->overlapped ? 2 : 8); }
+static int side_streams(const bv_ctx *ctx) {
+    const int v = ctx->opt[BV_OPT_SIDE_STREAMS] > 0 ? ctx->opt[BV_OPT_SIDE_STREAMS] : 4;
     return v > BV_MAX_SIDE ? BV_MAX_SIDE : v;
 }
-static int final_blocks_per_sm(bool overlapped) {
-    static int v = getenv("BV_FINAL_BPS") ? env_int("BV_FINAL_BPS", 2) : 0;
-    return v ? v : (overlapped ? 2 : 8);
-}
+static size_t l2_chunk_bytes(const bv_ctx *ctx) { return (size_t)(ctx->opt[BV_OPT_L2_CHUNK_MB] > 0 ? ctx->opt[BV_OPT_L2_CHUNK_MB] : 33) << 20; }
 
 static bool vec_ok(const void *p, size_t npx, int batch, int bytes_per_px) {
     (void)bytes_per_px;
@@ -907,7 +909,7 @@ static bool vec_ok(const void *p, size_t npx, int batch, int bytes_per_px) {
 template <int MODE, int CODE>
 static int launch_final(bv_ctx *ctx, const uint8_t *src, size_t src_stride, const BalFrame *st, int batch, size_t npx,
                         int width, const BalOutputs &out, bool vec) {
-    int bpf = (ctx->sm_count * final_blocks_per_sm(ctx->overlapped != 0) + batch - 1) / batch;
+    int bpf = (ctx->sm_count * final_blocks_per_sm(ctx) + batch - 1) / batch;
     const size_t need = (npx / 16 + kBalThreads - 1) / kBalThreads;
     if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
     dim3 grid(bpf, batch);
@@ -938,17 +940,6 @@ static int dispatch_final(bv_ctx *ctx, const uint8_t *src, size_t src_stride, co
     }
 }
 
-static size_t l2_chunk_bytes() {
-    static size_t v = 0;
-    if (!v) {
-        const char *e = getenv("BV_L2_CHUNK_MB");
-        long mb = e ? atol(e) : 33;
-        if (mb < 1) mb = 1;
-        v = (size_t)mb << 20;
-    }
-    return v;
-}
-
 static bool all_vec(const uint8_t *src, const BalOutputs &out, size_t npx, int batch) {
     return vec_ok(src, npx, batch, 3) && vec_ok(out.balanced, npx, batch, 3) && vec_ok(out.converted, npx, batch, 3) &&
            vec_ok(out.mask, npx, batch, 1);
@@ -966,7 +957,7 @@ int convert_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
 }
 
 int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int width, const bv_balance_params &prm,
-                int cvt_code, const BalOutputs &out, bv_balance_stats *stats_host) {
+                int cvt_code, const BalOutputs &out, bv_balance_stats *stats_host, const ChunkHook *after_chunk) {
     if (prm.hsi_contrast_correct) {
         set_error("colour balance: the HSI branch (color_balance.cpp:702-774) is not implemented");
         return BV_ERR_UNSUPPORTED;
@@ -1010,10 +1001,10 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
 
     // chunk the batch so that one chunk's input stays in L2 across the three passes; chunks are
     // independent and alternate over side streams so that their passes overlap on the SMs
-    int chunk = (int)(l2_chunk_bytes() / (npx * 3));
+    int chunk = (int)(l2_chunk_bytes(ctx) / (npx * 3));
     if (chunk < 1) chunk = 1;
     const int nchunks = (batch + chunk - 1) / chunk;
-    int nside = side_streams();
+    int nside = side_streams(ctx);
     if (nside > nchunks) nside = nchunks;
     if (ctx->prof) nside = 1;  // per-kernel timing wants serialised launches
     cudaStream_t main_stream = ctx->stream;
@@ -1033,7 +1024,7 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         const uint8_t *csrc = src + (size_t)f0 * npx * 3;
         BalFrame *cst = st + f0;
         uint8_t *chsv = hsv ? hsv + (size_t)f0 * hsv_stride : nullptr;
-        int bpf = (ctx->sm_count * hist_blocks_per_sm(ctx->overlapped != 0) + nf - 1) / nf;
+        int bpf = (ctx->sm_count * hist_blocks_per_sm(ctx) + nf - 1) / nf;
         const size_t need = (npx / 16 + kBalThreads - 1) / kBalThreads;
         if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
         dim3 grid(bpf, nf);
@@ -1058,6 +1049,7 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
             BV_TRY(dispatch_final<3>(ctx, chsv, hsv_stride, cst, nf, npx, width, cvt_code, co, vec));
         else
             BV_TRY(dispatch_final<1>(ctx, csrc, npx * 3, cst, nf, npx, width, cvt_code, co, vec));
+        if (after_chunk) BV_TRY(after_chunk->fn(after_chunk->self, ctx, f0, nf));
     }
     ctx->stream = main_stream;
     if (nside > 1)

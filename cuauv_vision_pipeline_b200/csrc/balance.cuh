@@ -37,8 +37,16 @@ struct BalOutputs {
 };
 
 // Enqueues the complete colour balance of `batch` frames.  `out.balanced == src` is allowed.
+// `after_chunk`, if given, is called for every chunk of frames [f0, f0 + nf) right after its last
+// pass has been enqueued, with ctx->stream set to the stream that chunk runs on: work the caller
+// enqueues there (morphology on the chunk's mask bits) overlaps the other chunks' passes.  It is
+// not called for tiled equalisation.
+struct ChunkHook {
+    int (*fn)(void *self, bv_ctx *ctx, int f0, int nf);
+    void *self;
+};
 int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int width, const bv_balance_params &prm,
-                int cvt_code, const BalOutputs &out, bv_balance_stats *stats_host);
+                int cvt_code, const BalOutputs &out, bv_balance_stats *stats_host, const ChunkHook *after_chunk = nullptr);
 
 // Convert (+inRange) without balance, writing any of converted / mask / mask_bits.
 int convert_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int width, int cvt_code,

@@ -213,6 +213,185 @@ int morph_bits_rect(bv_ctx *ctx, uint32_t *bits, uint32_t *tmp, uint32_t *tmp2, 
 }
 
 // ----------------------------------------------------------------------------------------------
+// A whole chain of binary erosions / dilations (OPEN = erode, dilate; CLOSE = dilate, erode; ...)
+// in ONE launch: a block stages a tile of 32 output rows plus the halo rows the chain needs in
+// shared memory (bits: a 2208-px row is 276 bytes; 32 warps, one row each per round), runs every step there as a horizontal pass
+// (funnel shifts) and a vertical pass, and writes the final bits and/or the uint8 0/255 mask.
+// Replaces one launch per elementary step plus the bits -> bytes expansion, each of which went
+// through L2 with 15 dependent loads per word.
+// ----------------------------------------------------------------------------------------------
+constexpr int kChainMaxOps = 8;
+constexpr int kChainThreads = 1024;  // 32 warps, one shared-memory row each per round
+struct MorphChain {
+    int n;
+    int halo_up, halo_down;  // sum of the vertical extents
+    struct {
+        int erode, L, R, U, D;
+    } op[kChainMaxOps];
+};
+
+// horizontal erosion / dilation of one word by taps x-L .. x+R (L, R <= 31); the common small
+// symmetric extents are fully unrolled
+template <bool ERODE>
+__device__ __forceinline__ uint32_t hpass_word(uint32_t l, uint32_t c, uint32_t n, int L, int R) {
+    uint32_t h = c;
+#define BV_TAP_L(d) { const uint32_t s_ = __funnelshift_l(l, c, (d)); h = ERODE ? (h & s_) : (h | s_); }
+#define BV_TAP_R(d) { const uint32_t s_ = __funnelshift_r(c, n, (d)); h = ERODE ? (h & s_) : (h | s_); }
+    if (L == R && L <= 3) {
+        if (L >= 1) { BV_TAP_L(1) BV_TAP_R(1) }
+        if (L >= 2) { BV_TAP_L(2) BV_TAP_R(2) }
+        if (L >= 3) { BV_TAP_L(3) BV_TAP_R(3) }
+    } else {
+        for (int d = 1; d <= L; ++d) BV_TAP_L(d)
+        for (int d = 1; d <= R; ++d) BV_TAP_R(d)
+    }
+#undef BV_TAP_L
+#undef BV_TAP_R
+    return h;
+}
+
+// 4 mask bits -> 4 bytes of 0x00 / 0xFF
+__device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xFFu; }
+
+template <bool ERODE>
+__device__ __forceinline__ void chain_step(uint32_t *A, uint32_t *B, int rows, int wpr, int ybase, int height, int L, int R,
+                                           int U, int D, uint32_t tail_mask) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int last = wpr - 1;
+    const uint32_t neutral = ERODE ? 0xFFFFFFFFu : 0u;
+    // horizontal pass A -> B (taps x-L .. x+R)
+    for (int r = warp; r < rows; r += nwarps) {
+        const uint32_t *a = A + r * wpr;
+        for (int wx = lane; wx < wpr; wx += 32) {
+            uint32_t c = a[wx];
+            const uint32_t l = wx > 0 ? a[wx - 1] : neutral;
+            uint32_t n = wx < last ? a[wx + 1] : neutral;
+            if (ERODE) {  // pixels beyond the right image edge count as set
+                if (wx == last) c |= ~tail_mask;
+                if (wx + 1 == last) n |= ~tail_mask;
+            }
+            B[r * wpr + wx] = hpass_word<ERODE>(l, c, n, L, R);
+        }
+    }
+    __syncthreads();
+    // vertical pass B -> A (rows y-U .. y+D; rows outside the image are ignored)
+    for (int r = warp; r < rows; r += nwarps) {
+        const int y = ybase + r;
+        if (y < 0 || y >= height) continue;
+        // rows the tile does not hold only feed halo rows that are discarded before the output
+        const int r0 = max(max(0, y - U) - ybase, 0), r1 = min(min(height - 1, y + D) - ybase, rows - 1);
+        for (int wx = lane; wx < wpr; wx += 32) {
+            uint32_t acc = neutral;
+            for (int rr = r0; rr <= r1; ++rr) {
+                const uint32_t v = B[rr * wpr + wx];
+                acc = ERODE ? (acc & v) : (acc | v);
+            }
+            if (wx == last) acc &= tail_mask;
+            A[r * wpr + wx] = acc;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kChainThreads) morph_chain_kernel(const uint32_t *__restrict__ src,
+                                                                    uint32_t *__restrict__ dst_bits, uint8_t *__restrict__ mask,
+                                                                    int height, int width, int wpr, int tiles_per_frame,
+                                                                    int tile_rows, MorphChain ch) {
+    extern __shared__ uint32_t chain_smem[];
+    const int frame = blockIdx.x / tiles_per_frame, tile = blockIdx.x - frame * tiles_per_frame;
+    const int rows = tile_rows + ch.halo_up + ch.halo_down;
+    const int ybase = tile * tile_rows - ch.halo_up;  // image row of shared-memory row 0
+    uint32_t *A = chain_smem, *B = chain_smem + rows * wpr;
+    const uint32_t *fsrc = src + (size_t)frame * height * wpr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < rows; r += nwarps) {
+        const int y = ybase + r;
+        const bool inside = y >= 0 && y < height;
+        for (int wx = lane; wx < wpr; wx += 32) A[r * wpr + wx] = inside ? __ldg(fsrc + (size_t)y * wpr + wx) : 0u;
+    }
+    __syncthreads();
+    const int last = wpr - 1;
+    const int tail = width - last * 32;
+    const uint32_t tail_mask = tail == 32 ? 0xFFFFFFFFu : ((1u << tail) - 1u);
+    for (int k = 0; k < ch.n; ++k) {
+        if (ch.op[k].erode)
+            chain_step<true>(A, B, rows, wpr, ybase, height, ch.op[k].L, ch.op[k].R, ch.op[k].U, ch.op[k].D, tail_mask);
+        else
+            chain_step<false>(A, B, rows, wpr, ybase, height, ch.op[k].L, ch.op[k].R, ch.op[k].U, ch.op[k].D, tail_mask);
+    }
+    // output rows
+    const int y_first = tile * tile_rows;
+    const int n_rows = min(tile_rows, height - y_first);
+    const bool wide_ok = (width % 16 == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+    for (int r = warp; r < n_rows; r += nwarps) {
+        const size_t row = (size_t)frame * height + y_first + r;
+        for (int wx = lane; wx < wpr; wx += 32) {
+            const uint32_t w = A[(r + ch.halo_up) * wpr + wx];
+            if (dst_bits) dst_bits[row * wpr + wx] = w;
+            if (mask) {
+                uint8_t *p = mask + row * width + (size_t)wx * 32;
+                const int n = min(32, width - wx * 32);
+                if (n == 32 && wide_ok) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = nibble_to_bytes((w >> (4 * q)) & 0xFu);
+                    st_stream(reinterpret_cast<uint4 *>(p), make_uint4(v[0], v[1], v[2], v[3]));
+                    st_stream(reinterpret_cast<uint4 *>(p) + 1, make_uint4(v[4], v[5], v[6], v[7]));
+                } else {
+                    for (int q = 0; q < n; ++q) p[q] = ((w >> q) & 1) ? 255 : 0;
+                }
+            }
+        }
+    }
+}
+
+// All steps as one chain, if they fit (erode / dilate / open / close with rectangles, horizontal
+// extents <= 31 per elementary step, shared memory for tile + halos).  *done = false: use the
+// step-by-step path.
+int morph_bits_chain(bv_ctx *ctx, const uint32_t *bits, uint32_t *dst_bits, uint8_t *mask, int batch, int height, int width,
+                     int n_steps, const int *ops, const int *kws, const int *khs, const int *iters, bool *done) {
+    *done = false;
+    MorphChain ch;
+    memset(&ch, 0, sizeof(ch));
+    for (int s = 0; s < n_steps; ++s) {
+        if (iters[s] < 1 || (kws[s] == 1 && khs[s] == 1 && ops[s] != BV_MORPH_GRADIENT)) continue;  // identity
+        if (ops[s] == BV_MORPH_GRADIENT) return BV_OK;
+        const int ax = kws[s] / 2, ay = khs[s] / 2;
+        const int L = ax * iters[s], R = (kws[s] - 1 - ax) * iters[s], U = ay * iters[s], D = (khs[s] - 1 - ay) * iters[s];
+        if (L > 31 || R > 31) return BV_OK;
+        const int first_erode = (ops[s] == BV_MORPH_ERODE || ops[s] == BV_MORPH_OPEN) ? 1 : 0;
+        const int n_el = (ops[s] == BV_MORPH_OPEN || ops[s] == BV_MORPH_CLOSE) ? 2 : 1;
+        for (int e = 0; e < n_el; ++e) {
+            if (ch.n == kChainMaxOps) return BV_OK;
+            ch.op[ch.n].erode = e == 0 ? first_erode : !first_erode;
+            ch.op[ch.n].L = L; ch.op[ch.n].R = R; ch.op[ch.n].U = U; ch.op[ch.n].D = D;
+            // output row y of step k reads rows y-U .. y+D of step k-1
+            ch.halo_up += U;
+            ch.halo_down += D;
+            ++ch.n;
+        }
+    }
+    const int wpr = words_per_row(width);
+    // shared-memory rows = a multiple of the 32 warps: 32 rows while the halo leaves at least half of
+    // them as output rows, more otherwise
+    const int halo = ch.halo_up + ch.halo_down;
+    int rows = 32;
+    while (rows - halo < rows / 2) rows += 32;
+    const int tile_rows = rows - halo;
+    const size_t smem = (size_t)2 * rows * wpr * sizeof(uint32_t);
+    if (rows > 256 || smem > 200 * 1024) return BV_OK;
+    if (smem > 48 * 1024 && smem > (size_t)ctx->chain_smem_set) {
+        BV_CUDA(cudaFuncSetAttribute(morph_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->chain_smem_set = (int)smem;
+    }
+    const int tiles = (height + tile_rows - 1) / tile_rows;
+    BV_LAUNCH(ctx, morph_chain_kernel, batch * tiles, kChainThreads, smem, bits, dst_bits, mask, height, width, wpr, tiles,
+              tile_rows, ch);
+    *done = true;
+    return BV_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
 // grey morphology, arbitrary SE as horizontal runs
 // ----------------------------------------------------------------------------------------------
 constexpr int kMaxRuns = 256;

@@ -18,4 +18,10 @@ int bits_to_mask(bv_ctx *ctx, const uint32_t *bits, uint8_t *mask, int batch, in
 int morph_bits_rect(bv_ctx *ctx, uint32_t *bits, uint32_t *tmp, uint32_t *tmp2, int batch, int height, int width, int op,
                     int kw, int kh, int iterations);
 
+// The whole list of steps in one launch (tile + halo in shared memory), writing the final bits
+// (dst_bits, may be null, must differ from bits) and/or the uint8 mask (may be null).  *done = false
+// when the chain does not qualify; nothing was launched then.
+int morph_bits_chain(bv_ctx *ctx, const uint32_t *bits, uint32_t *dst_bits, uint8_t *mask, int batch, int height, int width,
+                     int n_steps, const int *ops, const int *kws, const int *khs, const int *iters, bool *done);
+
 }  // namespace bv

@@ -81,18 +81,51 @@ int stage_run(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src, int ba
     } else {
         out.mask = mask;
     }
+    // Morphology of a chunk right behind its threshold pass, on the chunk's own stream
+    struct ChainPerChunk {
+        const bv_stage_desc *desc;
+        uint32_t *bits, *dst_bits;
+        uint8_t *mask;
+        int height, width;
+        bool all_done;
+        static int run(void *self, bv_ctx *c, int f0, int nf) {
+            ChainPerChunk *h = (ChainPerChunk *)self;
+            const size_t fw = bits_frame_words(h->height, h->width), fpx = (size_t)h->height * h->width;
+            bool done = false;
+            BV_TRY(morph_bits_chain(c, h->bits + f0 * fw, h->dst_bits ? h->dst_bits + f0 * fw : nullptr,
+                                    h->mask ? h->mask + f0 * fpx : nullptr, nf, h->height, h->width, h->desc->n_morph,
+                                    h->desc->morph_op, h->desc->morph_kw, h->desc->morph_kh, h->desc->morph_iters, &done));
+            h->all_done = h->all_done && done;
+            return BV_OK;
+        }
+    } per_chunk{desc, bits, want_label ? tmp : nullptr, mask, height, width, true};
+    const bool tiled_bal = desc->do_balance && (desc->balance.horizontal_blocks != 1 || desc->balance.vertical_blocks != 1);
+    const bool use_hook = desc->do_balance && !tiled_bal && bits_direct && desc->n_morph > 0;
+    ChunkHook hook{&ChainPerChunk::run, &per_chunk};
     if (out.balanced || out.converted || out.mask || out.mask_bits) {
         if (desc->do_balance)
-            BV_TRY(balance_run(ctx, src, batch, height, width, desc->balance, desc->cvt_code, out, nullptr));
+            BV_TRY(balance_run(ctx, src, batch, height, width, desc->balance, desc->cvt_code, out, nullptr, use_hook ? &hook : nullptr));
         else
             BV_TRY(convert_run(ctx, src, batch, height, width, desc->cvt_code, out));
     }
     if (!need_bits) return BV_OK;
     if (!bits_direct) BV_TRY(mask_to_bits(ctx, out.mask, bits, batch, height, width));
-    for (int i = 0; i < desc->n_morph; ++i)
-        BV_TRY(morph_bits_rect(ctx, bits, tmp, tmp2, batch, height, width, desc->morph_op[i], desc->morph_kw[i],
-                               desc->morph_kh[i], desc->morph_iters[i]));
-    if (mask && (desc->n_morph > 0)) BV_TRY(bits_to_mask(ctx, bits, mask, batch, height, width));
+    bool chained = false;
+    if (use_hook && per_chunk.all_done) {  // the chunks already went through the chain
+        chained = true;
+        if (want_label) bits = tmp;
+    } else if (desc->n_morph > 0) {
+        // one launch for the whole chain; it also expands the final bits into the uint8 mask
+        BV_TRY(morph_bits_chain(ctx, bits, want_label ? tmp : nullptr, mask, batch, height, width, desc->n_morph, desc->morph_op,
+                                desc->morph_kw, desc->morph_kh, desc->morph_iters, &chained));
+        if (chained && want_label) bits = tmp;
+    }
+    if (!chained) {
+        for (int i = 0; i < desc->n_morph; ++i)
+            BV_TRY(morph_bits_rect(ctx, bits, tmp, tmp2, batch, height, width, desc->morph_op[i], desc->morph_kw[i],
+                                   desc->morph_kh[i], desc->morph_iters[i]));
+        if (mask && (desc->n_morph > 0)) BV_TRY(bits_to_mask(ctx, bits, mask, batch, height, width));
+    }
     if (want_label) BV_TRY(label_bits(ctx, bits, labels, batch, height, width, blobs, max_blobs, n_blobs));
     return BV_OK;
 }

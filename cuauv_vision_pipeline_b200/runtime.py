@@ -80,6 +80,12 @@ class Context:
     def launches(self):
         return int(lib.bv_launch_count(self.handle))
 
+    OPTIONS = {"hist_bps": 0, "final_bps": 1, "side_streams": 2, "l2_chunk_mb": 3, "no_hue_table": 4}
+
+    def set_option(self, name, value):
+        """Tuning knob of the colour-balance passes (include/b200vision.h, BV_OPT_*); 0 = default."""
+        check(lib.bv_set_option(self.handle, self.OPTIONS[name], int(value)))
+
     def profile(self, on=True):
         """Bracket every kernel launch with CUDA events on the context's stream."""
         check(lib.bv_profile_enable(self.handle, 1 if on else 0))

@@ -139,6 +139,19 @@ void *bv_stream(bv_ctx *ctx);
 int bv_set_stream(bv_ctx *ctx, void *cuda_stream);
 /* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
 uint64_t bv_launch_count(const bv_ctx *ctx);
+
+/* Tuning knobs of the colour-balance passes (no reference counterpart).  value <= 0 restores the
+ * built-in default.  Each knob is also read once, at bv_create, from the environment variable of
+ * the same name (BV_HIST_BPS, BV_FINAL_BPS, BV_SIDE_STREAMS, BV_L2_CHUNK_MB, BV_NO_HUE_TABLE). */
+enum {
+    BV_OPT_HIST_BPS = 0,     /* blocks per SM of the histogram passes */
+    BV_OPT_FINAL_BPS = 1,    /* blocks per SM of the final pass */
+    BV_OPT_SIDE_STREAMS = 2, /* independent chunks of one call in flight (1..4) */
+    BV_OPT_L2_CHUNK_MB = 3,  /* input bytes per chunk: the chunk and its H,S,V scratch stay in L2 across the passes */
+    BV_OPT_NO_HUE_TABLE = 4, /* 1: always do the HSV round trip arithmetically (testing) */
+    BV_OPT_COUNT = 5
+};
+int bv_set_option(bv_ctx *ctx, int option, int value);
 void bv_balance_default(bv_balance_params *p);
 /* Per-kernel timing: while enabled, every kernel launch is bracketed by CUDA events on the
  * context's stream.  bv_profile_dump synchronises, writes a JSON object

@@ -310,3 +310,22 @@ def test_bins_module_pipeline_with_reference_contours(ctx):
     mask = ctx.stage(desc, ctx.upload(img), want=("mask",))["mask"]
     assert np.array_equal(ctx.download(mask), cleaned)
     check_contours(cleaned)
+
+
+@pytest.mark.parametrize("shape", [(301, 333), (270, 496), (64, 2208)])
+def test_morphology_chain_of_four_steps_with_labels(ctx, shape):
+    """Four steps (8 elementary erosions / dilations, halo 13 rows) in the single shared-memory chain launch,
+    batch of 3, final bits feeding the labelling."""
+    frames = np.stack([synth.gen_underwater(shape[0], shape[1], 40 + i) for i in range(3)])
+    steps = [("open", 5, 5, 1), ("close", 7, 3, 1), ("dilate", 3, 3, 2), ("erode", 9, 1, 1)]
+    desc = ctx.make_stage(cvt="bgr2hsv", lo=(0, 40, 60), hi=(179, 255, 255), morph=steps, label=True)
+    out = ctx.stage(desc, ctx.upload(frames), want=("mask", "labels", "blobs"), max_blobs=4096)
+    mask, lab = ctx.download(out["mask"]), ctx.download(out["labels"])
+    for i in range(3):
+        m = cv2.inRange(cv2.cvtColor(frames[i], cv2.COLOR_BGR2HSV), np.array([0, 40, 60]), np.array([179, 255, 255]))
+        m = cv2.morphologyEx(m, cv2.MORPH_OPEN, np.ones((5, 5), np.uint8))
+        m = cv2.morphologyEx(m, cv2.MORPH_CLOSE, np.ones((3, 7), np.uint8))
+        m = cv2.dilate(m, np.ones((3, 3), np.uint8), iterations=2)
+        m = cv2.erode(m, np.ones((1, 9), np.uint8))
+        assert np.array_equal(mask[i], m)
+        assert np.array_equal(lab[i], ccl.label_and_moments(m)[1])
