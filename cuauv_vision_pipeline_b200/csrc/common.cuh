@@ -109,6 +109,7 @@ struct bv_ctx {
     } ivl[BV_IVL_SLOTS];
     int ivl_next;
     int ivl_attr_set;
+    int lb_smem_set;     // same for letterbox_tma_kernel
     int chain_smem_set;  // largest dynamic shared-memory size already enabled for morph_chain_kernel
     int opt[BV_OPT_COUNT];  // tuning knobs, 0 = built-in default (bv_set_option)
     int *d_ivl_flag;

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxImg *__re
 // byte loads per output pixel; all threads then gather their taps from shared memory.
 // Rows whose byte size or address is not 16-byte aligned are staged with ordinary loads instead.
 // ----------------------------------------------------------------------------------------------
-constexpr int kLbMaxRowBytes = 11520;  // up to 3840 px wide sources (2 stages x 2 rows = 45 KB of shared memory)
+constexpr int kLbMaxRowBytes = 11520;  // up to 3840 px wide sources (4 stages x 2 rows = 92 KB of shared memory)
 
 // horizontal taps of one output column
 struct LbCoef {
@@ -164,103 +164,174 @@ __device__ __forceinline__ LbItem lb_item(const LetterboxImg *__restrict__ imgs,
     return t;
 }
 
-// Persistent blocks, two-stage pipeline: while the threads interpolate output row k out of stage
-// k&1, the TMA engine is already filling the other stage with the source rows of item k+1.
+// The horizontal taps depend on (image, output column) only: worked out once per call (float64
+// coordinate arithmetic, ~40 instructions) instead of once per output pixel.
+__global__ void __launch_bounds__(256) letterbox_coef_kernel(const LetterboxImg *__restrict__ imgs, LbCoef *__restrict__ coefs, int ow,
+                                                             int total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int img = i / ow, x = i - img * ow;
+    const LetterboxImg im = imgs[img];
+    coefs[i] = lb_coef(im, im.uw == im.sw && im.uh == im.sh, x);
+}
+
+__device__ __forceinline__ LbCoef coef_from_words(uint32_t a, uint32_t b) {
+    LbCoef c;
+    c.o0 = (short)(a & 0xFFFFu);
+    c.o1 = (short)(a >> 16);
+    c.w0 = (short)(b & 0xFFFFu);
+    c.w1 = (short)(b >> 16);
+    return c;
+}
+
+// Persistent, warp-specialised blocks: warp 8 is the producer -- one lane works out the next item
+// (which image, which two source rows) and hands the copy to the TMA engine as soon as a stage is
+// free; warps 0-7 only ever wait for a filled stage, interpolate one output row out of it and
+// release it.  kLbStages rows-pairs are in flight per block, so neither the descriptor arithmetic
+// nor the HBM latency of a row sits on the consumers' critical path.
+constexpr int kLbStages = 2;  // per block; 5-6 blocks per SM keep ~12 row pairs in flight per SM
+constexpr int kLbConsumers = 256;
+constexpr int kLbMaxImgs = 256;
+constexpr int kLbSmemImgs = 64;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kLbConsumers) : "memory"); }
+
 template <bool FP16>
-__global__ void __launch_bounds__(256) letterbox_tma_kernel(const LetterboxImg *__restrict__ imgs, void *__restrict__ out, int oh,
-                                                            int ow, int pad, int n_items) {
-    __shared__ __align__(128) uint8_t rows[2][2][kLbMaxRowBytes];
-    __shared__ __align__(8) uint64_t bar[2];
+__global__ void __launch_bounds__(kLbConsumers + 32) letterbox_tma_kernel(const LetterboxImg *__restrict__ imgs, int n_imgs,
+                                                                         const LbCoef *__restrict__ coefs, void *__restrict__ out,
+                                                                         int oh, int ow, int pad, int n_items, int row_stride) {
+    extern __shared__ __align__(128) uint8_t lb_rows[];  // [kLbStages][2][row_stride], then LbCoef[ow] of the current image
+    __shared__ __align__(8) uint64_t full[kLbStages], empty[kLbStages];
     __shared__ float norm[256];  // v / 255 in float32 (IEEE division once per value instead of per pixel)
-    __shared__ LbItem sitem[2];  // the item of each stage, worked out once by thread 0 (not by all 256 threads)
+    __shared__ LbItem sitem[kLbStages];
+    __shared__ LetterboxImg simgs[kLbSmemImgs];  // descriptors of the first images (3 KB); larger batches read the rest from L2
     for (int k = threadIdx.x; k < 256; k += blockDim.x) norm[k] = __fdiv_rn((float)k, 255.f);
+    for (int k = threadIdx.x; k < n_imgs && k < kLbSmemImgs; k += blockDim.x) simgs[k] = imgs[k];
     if (threadIdx.x == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        for (int s = 0; s < kLbStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kLbConsumers / 32);
+        }
     }
     __syncthreads();
-    auto issue = [&](int item, int stage) {  // thread 0 only
-        if (item >= n_items) return;
-        const LbItem t = lb_item(imgs, item, oh);
-        sitem[stage] = t;
-        if (!t.tma_ok) return;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this stage are done
-        mbar_expect_tx(&bar[stage], t.identity ? t.row_bytes : 2u * t.row_bytes);
-        bulk_g2s(rows[stage][0], t.g0, t.row_bytes, &bar[stage]);
-        if (!t.identity) bulk_g2s(rows[stage][1], t.g1, t.row_bytes, &bar[stage]);
-    };
-    if (threadIdx.x == 0) {
-        issue(blockIdx.x, 0);
-        issue(blockIdx.x + gridDim.x, 1);
-    }
-    __syncthreads();  // sitem[] of the first two items is visible
-    uint32_t phase[2] = {0, 0};
-    const size_t plane = (size_t)oh * ow;
-    int k = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
-        const int stage = k & 1;
-        const LbItem &t = sitem[stage];
-        const uint8_t *r0 = rows[stage][0];
-        const uint8_t *r1 = rows[stage][1];
-        if (t.inside_y) {  // block-uniform
-            if (t.tma_ok) {
-                mbar_wait(&bar[stage], phase[stage]);
-                phase[stage] ^= 1;
-            } else {  // unaligned source rows: ordinary loads
-                for (uint32_t q = threadIdx.x; q < t.row_bytes; q += blockDim.x) {
-                    rows[stage][0][q] = t.g0[q];
-                    if (!t.identity) rows[stage][1][q] = t.g1[q];
-                }
-                __syncthreads();
+    // a block takes a contiguous range of output rows: almost always inside one image, whose
+    // horizontal taps then sit in shared memory for the whole range
+    const int per_block = (n_items + gridDim.x - 1) / gridDim.x;
+    const int item_begin = blockIdx.x * per_block, item_end = min(n_items, item_begin + per_block);
+    if (threadIdx.x >= kLbConsumers) {
+        // ---- producer ----
+        if (threadIdx.x != kLbConsumers) return;
+        int k = 0;
+        for (int item = item_begin; item < item_end; ++item, ++k) {
+            const int stage = k % kLbStages, round = k / kLbStages;
+            if (round > 0) mbar_wait(&empty[stage], (uint32_t)(round - 1) & 1u);
+            const LbItem t = lb_item(n_imgs <= kLbSmemImgs ? simgs : imgs, item, oh);
+            sitem[stage] = t;
+            if (t.inside_y && t.tma_ok) {
+                uint8_t *r0 = lb_rows + (size_t)(stage * 2) * row_stride;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&full[stage], t.identity ? t.row_bytes : 2u * t.row_bytes);
+                bulk_g2s(r0, t.g0, t.row_bytes, &full[stage]);
+                if (!t.identity) bulk_g2s(r0 + row_stride, t.g1, t.row_bytes, &full[stage]);
+            } else {
+                mbar_arrive(&full[stage]);  // nothing to copy (padding row), or the consumers load it themselves
             }
+        }
+        return;
+    }
+    // ---- consumers ----
+    const size_t plane = (size_t)oh * ow;
+    const bool wide_rows = (ow % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    LbCoef *scoef = reinterpret_cast<LbCoef *>(lb_rows + (size_t)kLbStages * 2 * row_stride);
+    int coef_img = -1;
+    int k = 0;
+    for (int item = item_begin; item < item_end; ++item, ++k) {
+        const int stage = k % kLbStages, round = k / kLbStages;
+        const int img_now = item / oh;
+        if (img_now != coef_img) {  // block-uniform; the loads overlap the wait for the first row of the image
+            if (coef_img >= 0) consumer_sync();  // everyone is done with the previous image's taps
+            for (int x = threadIdx.x; x < ow; x += kLbConsumers) scoef[x] = coefs[(size_t)img_now * ow + x];
+            coef_img = img_now;
+            consumer_sync();
+        }
+        mbar_wait(&full[stage], (uint32_t)round & 1u);
+        const LbItem &t = sitem[stage];
+        uint8_t *w0 = lb_rows + (size_t)(stage * 2) * row_stride;
+        if (t.inside_y && !t.tma_ok) {  // unaligned source rows: ordinary loads (block-uniform branch)
+            for (uint32_t q = threadIdx.x; q < t.row_bytes; q += kLbConsumers) {
+                w0[q] = t.g0[q];
+                if (!t.identity) w0[row_stride + q] = t.g1[q];
+            }
+            consumer_sync();
         }
         const size_t obase = (size_t)t.img * 3 * plane + (size_t)t.y * ow;
-        if (t.identity) r1 = r0;  // single staged row; weights (2048, 0) make the blend an exact copy
-        const bool inside_y = t.inside_y;
-        const int cw0 = t.cy.w0, cw1 = t.cy.w1;
-        // three output pixels per thread and step, coefficient loads issued together (independent
-        // L2 round trips overlap instead of serialising over the short per-row loop)
-        for (int xb = 0; xb < ow; xb += 3 * 256) {
-            LbCoef cx[3];
-            int xs[3];
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                xs[u] = xb + u * 256 + threadIdx.x;
-                cx[u] = lb_coef(t.im, t.identity, xs[u]);
+        if (!t.inside_y) {
+            // padding row (44 % of the rows of a 16:9 camera): three constant rows, 16-byte stores
+            const float pv = norm[pad & 255];
+            if (wide_rows) {
+                if (FP16) {
+                    const uint32_t h2 = (uint32_t)__half_as_ushort(__float2half_rn(pv)) * 0x10001u;
+                    const uint4 v = make_uint4(h2, h2, h2, h2);
+                    const int per_plane = ow / 8;
+                    for (int q = threadIdx.x; q < 3 * per_plane; q += kLbConsumers) {
+                        const int c = q / per_plane, i = q - c * per_plane;
+                        st_stream(reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(out) + obase + c * plane) + i, v);
+                    }
+                } else {
+                    const uint32_t fv = __float_as_uint(pv);
+                    const uint4 v = make_uint4(fv, fv, fv, fv);
+                    const int per_plane = ow / 4;
+                    for (int q = threadIdx.x; q < 3 * per_plane; q += kLbConsumers) {
+                        const int c = q / per_plane, i = q - c * per_plane;
+                        st_stream(reinterpret_cast<uint4 *>(reinterpret_cast<float *>(out) + obase + c * plane) + i, v);
+                    }
+                }
+            } else {
+                for (int q = threadIdx.x; q < 3 * ow; q += kLbConsumers) {
+                    const int c = q / ow, x = q - c * ow;
+                    if (FP16)
+                        reinterpret_cast<__half *>(out)[obase + c * plane + x] = __float2half_rn(pv);
+                    else
+                        reinterpret_cast<float *>(out)[obase + c * plane + x] = pv;
+                }
             }
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                if (xs[u] >= ow) continue;
-                int b = pad, g = pad, r = pad;
-                if (inside_y && cx[u].o0 >= 0) {
-                    int v[3];
+        } else {
+            const uint8_t *r0 = w0;
+            const uint8_t *r1 = t.identity ? w0 : w0 + row_stride;  // single staged row; weights (2048, 0) copy it exactly
+            const int cw0 = t.cy.w0, cw1 = t.cy.w1;
+            // adjacent lanes take adjacent output pixels: their taps are ~10 bytes apart in the staged row,
+            // the mapping with the fewest shared-memory bank conflicts short of re-striding the row
+            for (int x = threadIdx.x; x < ow; x += kLbConsumers) {
+                const uint2 q = *reinterpret_cast<const uint2 *>(scoef + x);
+                const LbCoef cx = coef_from_words(q.x, q.y);
+                int v[3] = {pad, pad, pad};
+                if (cx.o0 >= 0) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const int h0 = r0[cx[u].o0 + c] * cx[u].w0 + r0[cx[u].o1 + c] * cx[u].w1;
-                        const int h1 = r1[cx[u].o0 + c] * cx[u].w0 + r1[cx[u].o1 + c] * cx[u].w1;
+                        const int h0 = r0[cx.o0 + c] * cx.w0 + r0[cx.o1 + c] * cx.w1;
+                        const int h1 = r1[cx.o0 + c] * cx.w0 + r1[cx.o1 + c] * cx.w1;
                         v[c] = linear_vblend(h0, h1, cw0, cw1);
                     }
-                    b = v[0];
-                    g = v[1];
-                    r = v[2];
                 }
-                const float fr = norm[r], fg = norm[g], fb = norm[b];
-                const int x = xs[u];
+                const float fr = norm[v[2]], fg = norm[v[1]], fb = norm[v[0]];
                 if (FP16) {
-                    __half *q = reinterpret_cast<__half *>(out);
-                    q[obase + x] = __float2half_rn(fr);
-                    q[obase + x + plane] = __float2half_rn(fg);
-                    q[obase + x + 2 * plane] = __float2half_rn(fb);
+                    __half *o = reinterpret_cast<__half *>(out) + obase + x;
+                    o[0] = __float2half_rn(fr);
+                    o[plane] = __float2half_rn(fg);
+                    o[2 * plane] = __float2half_rn(fb);
                 } else {
-                    float *q = reinterpret_cast<float *>(out);
-                    q[obase + x] = fr;
-                    q[obase + x + plane] = fg;
-                    q[obase + x + 2 * plane] = fb;
+                    float *o = reinterpret_cast<float *>(out) + obase + x;
+                    o[0] = fr;
+                    o[plane] = fg;
+                    o[2 * plane] = fb;
                 }
             }
         }
-        __syncthreads();  // everyone is done with this stage: refill it for the item after next
-        if (threadIdx.x == 0) issue(item + 2 * gridDim.x, stage);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stage]);  // this warp is done with the stage
     }
 }
 
@@ -312,7 +383,7 @@ extern "C" int bv_letterbox(bv_ctx *ctx, const uint8_t *const *srcs_host, const 
         d.scale_y = (double)h / uh;
         BV_REQUIRE(uw > 0 && uh > 0, "degenerate letterbox size");
     }
-    BV_TRY(ensure_scratch(ctx, SCR_LETTERBOX, sizeof(LetterboxImg) * 256));
+    BV_TRY(ensure_scratch(ctx, SCR_LETTERBOX, sizeof(LetterboxImg) * kLbMaxImgs + sizeof(LbCoef) * (size_t)n * out_w + 16));
     LetterboxImg *d_descs = (LetterboxImg *)ctx->scratch[SCR_LETTERBOX];
     BV_CUDA(cudaMemcpyAsync(d_descs, descs, sizeof(LetterboxImg) * n, cudaMemcpyHostToDevice, ctx->stream));
     bool fits = true;  // the staged kernel holds two source rows in shared memory
@@ -320,12 +391,28 @@ extern "C" int bv_letterbox(bv_ctx *ctx, const uint8_t *const *srcs_host, const 
     static const bool use_tma = getenv("BV_LETTERBOX_GATHER") == nullptr;
     if (fits && use_tma) {
         const int n_items = out_h * n;
-        int grid = ctx->sm_count * 4;  // persistent: 4 blocks of 45 KB per SM
+        int max_w = 0;
+        for (int i = 0; i < n; ++i) max_w = widths_host[i] > max_w ? widths_host[i] : max_w;
+        const int row_stride = (max_w * 3 + 127) & ~127;
+        const size_t smem = (size_t)kLbStages * 2 * row_stride + sizeof(LbCoef) * (size_t)out_w;
+        if (smem > (size_t)ctx->lb_smem_set) {
+            BV_CUDA(cudaFuncSetAttribute(letterbox_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            BV_CUDA(cudaFuncSetAttribute(letterbox_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->lb_smem_set = (int)smem;
+        }
+        // persistent blocks: as many as fit next to each other (dynamic rows + ~14 KB of static tables)
+        int per_sm = (int)((208 * 1024) / (smem + 6 * 1024));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+        int grid = ctx->sm_count * per_sm;
         if (grid > n_items) grid = n_items;
+        LbCoef *d_coefs = (LbCoef *)(d_descs + kLbMaxImgs);
+        BV_LAUNCH(ctx, letterbox_coef_kernel, (n * out_w + 255) / 256, 256, 0, d_descs, d_coefs, out_w, n * out_w);
         if (out_fp16)
-            BV_LAUNCH(ctx, letterbox_tma_kernel<true>, grid, 256, 0, d_descs, out_dev, out_h, out_w, pad_value, n_items);
+            BV_LAUNCH(ctx, letterbox_tma_kernel<true>, grid, kLbConsumers + 32, smem, d_descs, n, d_coefs, out_dev, out_h, out_w,
+                      pad_value, n_items, row_stride);
         else
-            BV_LAUNCH(ctx, letterbox_tma_kernel<false>, grid, 256, 0, d_descs, out_dev, out_h, out_w, pad_value, n_items);
+            BV_LAUNCH(ctx, letterbox_tma_kernel<false>, grid, kLbConsumers + 32, smem, d_descs, n, d_coefs, out_dev, out_h, out_w,
+                      pad_value, n_items, row_stride);
         return BV_OK;
     }
     dim3 grid((out_w + 255) / 256, out_h, n);
