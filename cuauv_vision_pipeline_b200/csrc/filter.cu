@@ -1,0 +1,297 @@
+// filter.cu -- the tuner-gated geometric / smoothing steps of the reference's preprocessor:
+//
+//   cv2.GaussianBlur(mat, (2k+1, 2k+1), 0)                         modules/preprocessor.py:110-114
+//   cv2.warpAffine(mat, getRotationMatrix2D(...), BORDER_REPLICATE) modules/preprocessor.py:130-135
+//   cv2.warpAffine(mat, [[1,0,tx],[0,1,ty]])  (BORDER_CONSTANT 0)   modules/preprocessor.py:144-149
+//
+// Both reproduce OpenCV 4.x's 8-bit fixed-point arithmetic bit for bit (pinned against cv2 4.13.0,
+// oracle/spec_np.py::gaussian_blur_8u / warp_affine_8u):
+//
+// GaussianBlur, uint8: the float64 kernel (tables for sizes <= 9, else exp(-x^2 / 2 sigma^2) with
+//   sigma = 0.3((n-1)/2 - 1) + 0.8, normalised) is converted to 8.8 fixed point by error diffusion
+//   from the outside in, the centre tap taking what is left of 256; the horizontal pass accumulates
+//   tap * pixel in 16 bits (8.8), the vertical pass tap * that in 32 bits (16.16), the result is
+//   (v + 2^15) >> 16; borders are BORDER_REFLECT_101.
+// warpAffine, uint8, INTER_LINEAR: the matrix is inverted in double; source coordinates are
+//   fixed point with 10 fractional bits, X = round(M0 x 1024) + round((M1 y + M2) 1024) + 16,
+//   reduced to 5 fractional bits; the four bilinear weights come from a 32x32 table of int16
+//   (float32 products scaled by 2^15, rounded, largest/smallest entry adjusted so that they sum
+//   to 2^15); result (sum + 2^14) >> 15.  Taps outside the image replicate the edge
+//   (BORDER_REPLICATE) or take the border value (BORDER_CONSTANT).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace bv {
+
+// ----------------------------------------------------------------------------------------------
+// Gaussian blur: a block stages a tile plus halo (reflected at the image border) in shared memory,
+// runs the horizontal pass into a 16-bit tile and the vertical pass out of it.
+// ----------------------------------------------------------------------------------------------
+constexpr int kBlurMaxTaps = 63;
+constexpr int kBlurTileW = 64, kBlurTileH = 32;
+struct BlurTaps {
+    int nx, ny;
+    uint16_t kx[kBlurMaxTaps], ky[kBlurMaxTaps];
+};
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+
+template <int CN>
+__global__ void __launch_bounds__(256) gaussian_blur_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int height,
+                                                            int width, BlurTaps taps) {
+    extern __shared__ __align__(16) uint8_t blur_smem[];
+    const int rx = taps.nx / 2, ry = taps.ny / 2;
+    const int raw_w = (kBlurTileW + 2 * rx) * CN;         // bytes per staged row
+    const int raw_h = kBlurTileH + 2 * ry;
+    const int hz_w = kBlurTileW * CN;                     // 16-bit values per row of the horizontal result
+    uint8_t *raw = blur_smem;
+    uint16_t *hz = reinterpret_cast<uint16_t *>(blur_smem + ((raw_w * raw_h + 15) & ~15));
+    const int x0 = blockIdx.x * kBlurTileW, y0 = blockIdx.y * kBlurTileH;
+    const size_t frame_off = (size_t)blockIdx.z * height * width * CN;
+    const uint8_t *f = src + frame_off;
+    // stage rows y0-ry .. y0+TH+ry-1, columns x0-rx .. x0+TW+rx-1, reflected
+    for (int i = threadIdx.x; i < raw_w * raw_h; i += blockDim.x) {
+        const int r = i / raw_w, b = i - r * raw_w;
+        const int px = b / CN, c = b - px * CN;
+        const int sy = reflect101(y0 - ry + r, height), sx = reflect101(x0 - rx + px, width);
+        raw[i] = f[((size_t)sy * width + sx) * CN + c];
+    }
+    __syncthreads();
+    // horizontal pass: hz[r][x*CN + c] = sum_k kx[k] * raw[r][(x + k)*CN + c]      (8.8 in 16 bits)
+    for (int i = threadIdx.x; i < hz_w * raw_h; i += blockDim.x) {
+        const int r = i / hz_w, b = i - r * hz_w;
+        const uint8_t *p = raw + r * raw_w + b;
+        uint32_t acc = 0;
+        for (int k = 0; k < taps.nx; ++k) acc += (uint32_t)taps.kx[k] * p[k * CN];
+        hz[i] = (uint16_t)(acc > 0xFFFFu ? 0xFFFFu : acc);  // ufixedpoint16 saturates (never reached: taps sum to 256)
+    }
+    __syncthreads();
+    // vertical pass
+    for (int i = threadIdx.x; i < hz_w * kBlurTileH; i += blockDim.x) {
+        const int r = i / hz_w, b = i - r * hz_w;
+        const int y = y0 + r, x = x0 + b / CN;
+        if (y >= height || x >= width) continue;
+        uint32_t acc = 0;
+        for (int k = 0; k < taps.ny; ++k) acc += (uint32_t)taps.ky[k] * hz[(r + k) * hz_w + b];
+        const uint32_t v = (acc + (1u << 15)) >> 16;
+        dst[frame_off + ((size_t)y * width + x0) * CN + b] = (uint8_t)(v > 255u ? 255u : v);
+    }
+}
+
+// OpenCV's getGaussianKernelBitExact + getGaussianKernelFixedPoint_ED for 8.8 fixed point
+static int gaussian_taps_fixed(int n, double sigma, uint16_t *out) {
+    static const double small[5][9] = {{1.},
+                                       {0.25, 0.5, 0.25},
+                                       {0.0625, 0.25, 0.375, 0.25, 0.0625},
+                                       {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125},
+                                       {4. / 256, 13. / 256, 30. / 256, 51. / 256, 60. / 256, 51. / 256, 30. / 256, 13. / 256, 4. / 256}};
+    double k[kBlurMaxTaps];
+    if (sigma <= 0 && n <= 9) {
+        for (int i = 0; i < n; ++i) k[i] = small[n / 2][i];
+    } else {
+        const double s = sigma > 0 ? sigma : ((n - 1) * 0.5 - 1) * 0.3 + 0.8;
+        const double scale2 = -0.5 / (s * s);
+        double sum = 0;
+        for (int i = 0; i < n; ++i) {
+            const double x = i - (n - 1) * 0.5;
+            k[i] = exp(scale2 * x * x);
+            sum += k[i];
+        }
+        for (int i = 0; i < n; ++i) k[i] /= sum;
+    }
+    const int h = n / 2;
+    double err = 0;
+    long acc = 0;
+    for (int i = 0; i < h; ++i) {
+        const double adj = k[i] * 256.0 + err;
+        const long v = (long)nearbyint(adj);  // cvRound: round half to even
+        err = adj - (double)v;
+        if (v < 0 || v > 256) return BV_ERR_INVALID;
+        out[i] = out[n - 1 - i] = (uint16_t)v;
+        acc += v;
+    }
+    const long centre = 256 - 2 * acc;
+    if (centre < 0) return BV_ERR_INVALID;
+    out[h] = (uint16_t)centre;
+    return BV_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// warpAffine
+// ----------------------------------------------------------------------------------------------
+struct WarpParams {
+    double m[6];  // inverted matrix (destination -> source)
+    int border_constant;
+    int border_value[4];
+};
+
+__device__ __forceinline__ int sat_round_int(double v) {
+    if (v >= 2147483647.0) return 2147483647;
+    if (v <= -2147483648.0) return (int)0x80000000;
+    return __double2int_rn(v);  // cvRound: nearest even
+}
+
+template <int CN>
+__global__ void __launch_bounds__(256) warp_affine_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int height,
+                                                          int width, int dst_h, int dst_w, WarpParams wp,
+                                                          const short *__restrict__ tab) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dst_w) return;
+    const uint8_t *f = src + (size_t)blockIdx.z * height * width * CN;
+    uint8_t *o = dst + ((size_t)blockIdx.z * dst_h * dst_w + (size_t)y * dst_w + x) * CN;
+    constexpr int AB_BITS = 10, INTER_BITS = 5, TAB = 32;
+    const double scale = (double)(1 << AB_BITS);
+    const int round_delta = (1 << AB_BITS) / TAB / 2;
+    const int adelta = sat_round_int(__dmul_rn(__dmul_rn(wp.m[0], (double)x), scale));
+    const int bdelta = sat_round_int(__dmul_rn(__dmul_rn(wp.m[3], (double)x), scale));
+    const int X0 = sat_round_int(__dmul_rn(__dadd_rn(__dmul_rn(wp.m[1], (double)y), wp.m[2]), scale)) + round_delta;
+    const int Y0 = sat_round_int(__dmul_rn(__dadd_rn(__dmul_rn(wp.m[4], (double)y), wp.m[5]), scale)) + round_delta;
+    const int X = (X0 + adelta) >> (AB_BITS - INTER_BITS), Y = (Y0 + bdelta) >> (AB_BITS - INTER_BITS);
+    int sx = X >> INTER_BITS, sy = Y >> INTER_BITS;
+    sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);  // saturate_cast<short>
+    sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);
+    const short *w = tab + ((Y & (TAB - 1)) * TAB + (X & (TAB - 1))) * 4;
+    const int w00 = w[0], w01 = w[1], w10 = w[2], w11 = w[3];
+    const int xs[2] = {sx, sx + 1}, ys[2] = {sy, sy + 1};
+    const uint8_t *p[2][2];
+    bool inside[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            inside[j][i] = xs[i] >= 0 && xs[i] < width && ys[j] >= 0 && ys[j] < height;
+            const int cx = min(max(xs[i], 0), width - 1), cy = min(max(ys[j], 0), height - 1);
+            p[j][i] = f + ((size_t)cy * width + cx) * CN;
+        }
+#pragma unroll
+    for (int c = 0; c < CN; ++c) {
+        int v[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) v[j][i] = (wp.border_constant && !inside[j][i]) ? wp.border_value[c] : (int)p[j][i][c];
+        const int s = v[0][0] * w00 + v[0][1] * w01 + v[1][0] * w10 + v[1][1] * w11;
+        o[c] = (uint8_t)sat_u8((s + (1 << 14)) >> 15);
+    }
+}
+
+// OpenCV's BilinearTab_i (initInterTab2D(INTER_LINEAR, fixpt = true)): 32 x 32 x 4 int16
+static void build_bilinear_tab(short *tab) {
+    float t1[32][2];
+    for (int i = 0; i < 32; ++i) {
+        const float x = (float)i * (1.f / 32.f);
+        t1[i][0] = 1.f - x;
+        t1[i][1] = x;
+    }
+    for (int i = 0; i < 32; ++i)
+        for (int j = 0; j < 32; ++j) {
+            short *it = tab + (i * 32 + j) * 4;
+            int isum = 0;
+            for (int k1 = 0; k1 < 2; ++k1)
+                for (int k2 = 0; k2 < 2; ++k2) {
+                    const float v = t1[i][k1] * t1[j][k2];
+                    long r = lrintf(v * 32768.f);
+                    r = r < -32768 ? -32768 : (r > 32767 ? 32767 : r);
+                    it[k1 * 2 + k2] = (short)r;
+                    isum += (int)r;
+                }
+            if (isum != 32768) {
+                // Only the entry (fy, fx) = (0, 0) gets here: 1.0 * 2^15 saturates to 32767.  OpenCV's
+                // fix-up searches the "central" 2x2 block of a ksize x ksize kernel, which for ksize = 2
+                // starts at the LAST tap (and runs past the entry into zeros), so the missing 1 lands on
+                // the bottom-right tap: {32767, 0, 0, 1}.  The pixel value is the same either way:
+                // (32767 p00 + p11 + 2^14) >> 15 == p00.
+                it[3] = (short)(it[3] - (isum - 32768));
+            }
+        }
+}
+
+}  // namespace bv
+
+using namespace bv;
+
+extern "C" int bv_gaussian_blur(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, int height, int width,
+                                int channels, int ksize_x, int ksize_y, double sigma_x, double sigma_y) {
+    BV_REQUIRE(ctx && src_dev && dst_dev, "null argument");
+    BV_REQUIRE(src_dev != dst_dev, "in-place blur is not supported");
+    BV_REQUIRE(batch > 0 && height > 0 && width > 0, "batch, height and width must be positive");
+    BV_REQUIRE(channels == 1 || channels == 3, "channels must be 1 or 3");
+    BV_REQUIRE(ksize_x >= 1 && ksize_y >= 1 && (ksize_x & 1) && (ksize_y & 1) && ksize_x <= kBlurMaxTaps && ksize_y <= kBlurMaxTaps,
+               "kernel sizes must be odd and in 1..63");
+    BV_REQUIRE(batch <= 65535, "batch too large");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    if (sigma_y <= 0) sigma_y = sigma_x;  // cv2: sigmaY = sigmaX when not given
+    BlurTaps taps;
+    memset(&taps, 0, sizeof(taps));
+    taps.nx = ksize_x;
+    taps.ny = ksize_y;
+    if (gaussian_taps_fixed(ksize_x, sigma_x, taps.kx) != BV_OK || gaussian_taps_fixed(ksize_y, sigma_y, taps.ky) != BV_OK) {
+        set_error("bv_gaussian_blur: kernel cannot be represented in 8.8 fixed point");
+        return BV_ERR_INVALID;
+    }
+    const int rx = ksize_x / 2, ry = ksize_y / 2;
+    const size_t raw = (size_t)(kBlurTileW + 2 * rx) * channels * (kBlurTileH + 2 * ry);
+    const size_t smem = ((raw + 15) & ~(size_t)15) + (size_t)kBlurTileW * channels * (kBlurTileH + 2 * ry) * 2;
+    if (smem > 200 * 1024) {
+        set_error("bv_gaussian_blur: kernel too large for the shared-memory tile");
+        return BV_ERR_UNSUPPORTED;
+    }
+    dim3 grid((width + kBlurTileW - 1) / kBlurTileW, (height + kBlurTileH - 1) / kBlurTileH, batch);
+    if (channels == 3) {
+        if (smem > 48 * 1024) BV_CUDA(cudaFuncSetAttribute(gaussian_blur_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BV_LAUNCH(ctx, gaussian_blur_kernel<3>, grid, 256, smem, src_dev, dst_dev, height, width, taps);
+    } else {
+        if (smem > 48 * 1024) BV_CUDA(cudaFuncSetAttribute(gaussian_blur_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BV_LAUNCH(ctx, gaussian_blur_kernel<1>, grid, 256, smem, src_dev, dst_dev, height, width, taps);
+    }
+    return BV_OK;
+}
+
+extern "C" int bv_warp_affine(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, int height, int width,
+                              int channels, int dst_height, int dst_width, const double *m_host, int border_mode,
+                              const uint8_t *border_value_host) {
+    BV_REQUIRE(ctx && src_dev && dst_dev && m_host, "null argument");
+    BV_REQUIRE(src_dev != dst_dev, "in-place warp is not supported");
+    BV_REQUIRE(batch > 0 && height > 0 && width > 0 && dst_height > 0 && dst_width > 0, "sizes must be positive");
+    BV_REQUIRE(channels == 1 || channels == 3, "channels must be 1 or 3");
+    BV_REQUIRE(border_mode == BV_BORDER_CONSTANT || border_mode == BV_BORDER_REPLICATE, "border mode must be constant or replicate");
+    BV_REQUIRE(height <= 32767 && width <= 32767 && batch <= 65535 && dst_height <= 65535, "image too large");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->d_bilinear_tab) {
+        static short tab[32 * 32 * 4];
+        build_bilinear_tab(tab);
+        BV_CUDA(cudaMalloc(&ctx->d_bilinear_tab, sizeof(tab)));
+        BV_CUDA(cudaMemcpyAsync(ctx->d_bilinear_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
+        BV_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    WarpParams wp;
+    memset(&wp, 0, sizeof(wp));
+    // cv::warpAffine without WARP_INVERSE_MAP: invert the 2x3 matrix in double
+    double M[6];
+    for (int i = 0; i < 6; ++i) M[i] = m_host[i];
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = M[4] * D, A22 = M[0] * D;
+    M[0] = A11;
+    M[1] *= -D;
+    M[3] *= -D;
+    M[4] = A22;
+    const double b1 = -M[0] * M[2] - M[1] * M[5];
+    const double b2 = -M[3] * M[2] - M[4] * M[5];
+    M[2] = b1;
+    M[5] = b2;
+    for (int i = 0; i < 6; ++i) wp.m[i] = M[i];
+    wp.border_constant = border_mode == BV_BORDER_CONSTANT;
+    for (int c = 0; c < channels; ++c) wp.border_value[c] = border_value_host ? border_value_host[c] : 0;
+    dim3 grid((dst_width + 255) / 256, dst_height, batch);
+    if (channels == 3)
+        BV_LAUNCH(ctx, warp_affine_kernel<3>, grid, 256, 0, src_dev, dst_dev, height, width, dst_height, dst_width, wp, ctx->d_bilinear_tab);
+    else
+        BV_LAUNCH(ctx, warp_affine_kernel<1>, grid, 256, 0, src_dev, dst_dev, height, width, dst_height, dst_width, wp, ctx->d_bilinear_tab);
+    return BV_OK;
+}

@@ -2,9 +2,10 @@
 the P0 steps: colour-space posts (51-86), colour balance (87-88), per-channel bias / contrast /
 brightness (89-109), elliptical erode / dilate (120-129), resize (136-143).
 
-The tuner-gated steps that are out of scope (Gaussian blur 110-114, Gaussian noise
-115-119, rotate 130-135, translate 144-149) raise NotImplementedError when enabled instead of
-silently doing something else.
+Gaussian blur (110-114), rotate (130-135) and translate (144-149) run on the device with OpenCV's
+8-bit fixed-point arithmetic (csrc/filter.cu).  Gaussian noise (115-119) draws from numpy's global
+random generator, which cannot be reproduced on the device: it raises NotImplementedError when
+enabled instead of silently doing something else.
 
 The frame is uploaded once and stays on the device across all enabled steps; the three point
 operations (bias, contrast, brightness) are folded on the host into one 256-entry table per
@@ -98,22 +99,26 @@ class Preprocessor:
             con, bri = self._opt("PPX_contrast"), self._opt("PPX_brightness")
             if rb != 0 or gb != 0 or bb != 0 or con != 1 or bri != 0:        # 89-109
                 cur = ctx.apply_lut(cur, point_lut(rb, gb, bb, con, bri))
-            if self._opt("PPX_gaussian_blur") or self._opt("PPX_gaussian_noise") != 0:
-                raise NotImplementedError("Gaussian blur / noise (preprocessor.py:110-119) are out of scope")
+            if self._opt("PPX_gaussian_blur"):                               # 110-114
+                k = self._opt("PPX_gaussian_blur_kernel") * 2 + 1
+                cur = ctx.gaussian_blur(cur, (k, k), 0)
+            if self._opt("PPX_gaussian_noise") != 0:                         # 115-119
+                raise NotImplementedError("Gaussian noise draws from numpy's global generator (preprocessor.py:115-119): "
+                                          "not reproducible on the device, out of scope")
             if self._opt("PPX_erode"):                                       # 120-124
                 k = self._opt("PPX_erode_kernel") * 2 + 1
                 cur = ctx.morph(cur, "erode", transform.elliptic_kernel(k, k))
             if self._opt("PPX_dilate"):                                      # 125-129
                 k = self._opt("PPX_dilate_kernel") * 2 + 1
                 cur = ctx.morph(cur, "dilate", transform.elliptic_kernel(k, k))
-            if self._opt("PPX_rotate") != 0:
-                raise NotImplementedError("rotate (preprocessor.py:130-135) is out of scope")
+            if self._opt("PPX_rotate") != 0:                                 # 130-135
+                cur = transform.rotate(cur, self._opt("PPX_rotate"))
             if self._opt("PPX_resize"):                                      # 136-139
                 cur = ctx.resize(cur, self._opt("PPX_resize_width"), self._opt("PPX_resize_height"))
             if self._opt("PPX_resize_ratio") != 1:                           # 140-143
                 r = self._opt("PPX_resize_ratio")
                 cur = ctx.resize(cur, int(cur.shape[1] * r), int(cur.shape[0] * r))
-            if self._opt("PPX_translate_x") != 0 or self._opt("PPX_translate_y") != 0:
-                raise NotImplementedError("translate (preprocessor.py:144-149) is out of scope")
+            if self._opt("PPX_translate_x") != 0 or self._opt("PPX_translate_y") != 0:     # 144-149
+                cur = transform.translate(cur, self._opt("PPX_translate_x"), self._opt("PPX_translate_y"))
             out.append(like_input(ctx, mat, cur))
         return out

@@ -299,6 +299,34 @@ class Context:
         check(lib.bv_resize_linear(self.handle, _u8ptr(src), sh, sw, _u8ptr(dst), height, width, c, b))
         return dst
 
+    @staticmethod
+    def _bhwc(src):
+        if src.dim() == 2:
+            return 1, src.shape[0], src.shape[1], 1
+        if src.dim() == 3:
+            return 1, src.shape[0], src.shape[1], src.shape[2]
+        return tuple(src.shape)
+
+    def gaussian_blur(self, src, ksize, sigma_x=0.0, sigma_y=0.0):
+        """cv2.GaussianBlur(src, ksize=(kw, kh), sigma_x, sigma_y) on uint8 (BORDER_REFLECT_101)."""
+        b, h, w, c = self._bhwc(src)
+        dst = self.empty(tuple(src.shape))
+        check(lib.bv_gaussian_blur(self.handle, _u8ptr(src), _u8ptr(dst), b, h, w, c, int(ksize[0]), int(ksize[1]),
+                                   float(sigma_x), float(sigma_y)))
+        return dst
+
+    def warp_affine(self, src, matrix, dsize=None, border="constant", border_value=(0, 0, 0)):
+        """cv2.warpAffine(src, matrix, dsize, flags=INTER_LINEAR, borderMode=..., borderValue=...) on uint8."""
+        b, h, w, c = self._bhwc(src)
+        dw, dh = (w, h) if dsize is None else (int(dsize[0]), int(dsize[1]))
+        m = np.ascontiguousarray(np.asarray(matrix, dtype=np.float64).reshape(6))
+        bv_ = np.ascontiguousarray(np.asarray(list(border_value)[:c] + [0] * max(0, c - len(border_value)), dtype=np.uint8))
+        shape = (dh, dw) if src.dim() == 2 else ((dh, dw, c) if src.dim() == 3 else (b, dh, dw, c))
+        dst = self.empty(shape)
+        check(lib.bv_warp_affine(self.handle, _u8ptr(src), _u8ptr(dst), b, h, w, c, dh, dw, ffi.from_buffer("double[]", m),
+                                 {"constant": 0, "replicate": 1}[border], ffi.from_buffer("uint8_t[]", bv_)))
+        return dst
+
     def letterbox(self, images, out_h=640, out_w=640, pad=114, half=True, out=None):
         n = len(images)
         for im in images:

@@ -246,6 +246,21 @@ int bv_letterbox(bv_ctx *ctx, const uint8_t *const *srcs_host, const int32_t *he
                  const int32_t *widths_host, int n, void *out_dev, int out_h, int out_w, int pad_value,
                  int out_fp16);
 
+/* ---- smoothing / warping steps of the preprocessor ------------------------------------------- */
+/* cv2.GaussianBlur(src, (ksize_x, ksize_y), sigma_x, sigma_y) on uint8, BORDER_REFLECT_101
+ * (modules/preprocessor.py:110-114 calls it with ksize = 2k+1 and sigma 0).  sigma <= 0: derived
+ * from the kernel size as OpenCV does.  OpenCV's 8.8 fixed-point arithmetic, bit-exact. */
+int bv_gaussian_blur(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, int height, int width,
+                     int channels, int ksize_x, int ksize_y, double sigma_x, double sigma_y);
+/* cv2.warpAffine(src, M, (dst_width, dst_height), flags=INTER_LINEAR, borderMode, borderValue) on
+ * uint8; m_host: the 2x3 forward matrix in row-major doubles, as cv2 takes it
+ * (modules/preprocessor.py:130-135 rotate with BORDER_REPLICATE, 144-149 translate with the default
+ * BORDER_CONSTANT 0).  border_value_host: `channels` bytes or NULL (0). */
+typedef enum bv_border_mode { BV_BORDER_CONSTANT = 0, BV_BORDER_REPLICATE = 1 } bv_border_mode;
+int bv_warp_affine(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, int height, int width,
+                   int channels, int dst_height, int dst_width, const double *m_host, int border_mode,
+                   const uint8_t *border_value_host);
+
 /* ---- ZED auxiliary planes (capture_sources/zed.{py,cpp}, modules/poster.py, modules/record.py) ----- */
 /* Drop the alpha byte (cv2.cvtColor(RGBA2RGB), capture_sources/zed.py:49-50; zed.cpp:54-71). */
 int bv_rgba_to_rgb(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, size_t n_pixels);

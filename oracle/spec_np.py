@@ -218,3 +218,120 @@ def resize_linear(img, dst_w, dst_h):
     out = (((b0[:, None, None] * r0) >> 16) + ((b1[:, None, None] * r1) >> 16) + 2) >> 2
     out = np.clip(out, 0, 255).astype(np.uint8)
     return out[..., 0] if squeeze else out
+
+
+# ---------------------------------------------------------------------------------------------
+# cv2.GaussianBlur on uint8 (OpenCV smooth.dispatch.cpp: getGaussianKernelBitExact +
+# getGaussianKernelFixedPoint_ED, hlineSmooth / vlineSmooth with ufixedpoint16), pinned against
+# cv2 4.13.0 in tests/test_oracle_spec.py.  Call site: modules/preprocessor.py:110-114.
+# ---------------------------------------------------------------------------------------------
+_SMALL_GAUSS = {1: [1.0], 3: [0.25, 0.5, 0.25], 5: [0.0625, 0.25, 0.375, 0.25, 0.0625],
+                7: [0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125],
+                9: [4 / 256, 13 / 256, 30 / 256, 51 / 256, 60 / 256, 51 / 256, 30 / 256, 13 / 256, 4 / 256]}
+
+
+def gaussian_kernel_f64(n, sigma=0.0):
+    if sigma <= 0 and n in _SMALL_GAUSS:
+        return np.array(_SMALL_GAUSS[n], np.float64)
+    s = sigma if sigma > 0 else ((n - 1) * 0.5 - 1) * 0.3 + 0.8
+    x = np.arange(n) - (n - 1) * 0.5
+    t = np.exp((-0.5 / (s * s)) * x * x)
+    return t / t.sum()
+
+
+def gaussian_kernel_fixed(n, sigma=0.0):
+    """8.8 fixed-point taps: error diffusion from the outside in, the centre takes the rest of 256."""
+    k = gaussian_kernel_f64(n, sigma) * 256.0
+    out = np.zeros(n, np.int64)
+    err, h = 0.0, n // 2
+    for i in range(h):
+        adj = k[i] + err
+        v = int(np.rint(adj))
+        err = adj - v
+        out[i] = out[n - 1 - i] = v
+    out[h] = 256 - 2 * out[:h].sum()
+    return out
+
+
+def gaussian_blur_8u(img, ksize, sigma_x=0.0, sigma_y=0.0):
+    kw, kh = ksize
+    fx, fy = gaussian_kernel_fixed(kw, sigma_x), gaussian_kernel_fixed(kh, sigma_y if sigma_y > 0 else sigma_x)
+    rx, ry = kw // 2, kh // 2
+    h, w = img.shape[:2]
+    iy = np.arange(-ry, h + ry)
+    ix = np.arange(-rx, w + rx)
+
+    def reflect(p, n):
+        if n == 1:
+            return np.zeros_like(p)
+        p = p.copy()
+        for _ in range(8):
+            p = np.where(p < 0, -p, p)
+            p = np.where(p >= n, 2 * n - 2 - p, p)
+        return p
+    src = img[reflect(iy, h)][:, reflect(ix, w)].astype(np.int64)
+    hz = sum(fx[k] * src[:, k:k + w] for k in range(kw))
+    hz = np.minimum(hz, 0xFFFF)
+    v = sum(fy[k] * hz[k:k + h] for k in range(kh))
+    return np.clip((v + (1 << 15)) >> 16, 0, 255).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# cv2.warpAffine on uint8, INTER_LINEAR (OpenCV imgwarp.cpp: WarpAffineInvoker + remapBilinear with
+# BilinearTab_i), pinned against cv2 4.13.0.  Call sites: modules/preprocessor.py:130-135, 144-149.
+# ---------------------------------------------------------------------------------------------
+def _bilinear_tab():
+    t = np.arange(32, dtype=np.float32) * np.float32(1 / 32)
+    t1 = np.stack([np.float32(1) - t, t], axis=1)                       # [32, 2]
+    w = (t1[:, None, :, None] * t1[None, :, None, :]).astype(np.float32)  # [fy, fx, k1, k2]
+    tab = np.rint(w * np.float32(32768)).astype(np.int64).reshape(32 * 32, 4)
+    assert (tab.sum(axis=1) == 32768).all()                              # so OpenCV's fix-up never triggers
+    return tab
+
+
+def rotation_matrix_2d(center, angle, scale):
+    a = angle * (np.pi / 180)          # cv2: angle *= CV_PI/180
+    alpha, beta = np.cos(a) * scale, np.sin(a) * scale
+    return np.array([[alpha, beta, (1 - alpha) * center[0] - beta * center[1]],
+                     [-beta, alpha, beta * center[0] + (1 - alpha) * center[1]]], np.float64)
+
+
+def warp_affine_8u(img, matrix, dsize=None, border="constant", border_value=0):
+    squeeze = img.ndim == 2
+    if squeeze:
+        img = img[..., None]
+    h, w = img.shape[:2]
+    dw, dh = (w, h) if dsize is None else dsize
+    m = np.asarray(matrix, np.float64).reshape(6).copy()
+    d = m[0] * m[4] - m[1] * m[3]
+    d = 1.0 / d if d != 0 else 0.0
+    a11, a22 = m[4] * d, m[0] * d
+    m[0], m[1], m[3], m[4] = a11, m[1] * -d, m[3] * -d, a22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    tab = _bilinear_tab()
+
+    def rnd(v):
+        return np.clip(np.rint(v), -2.0 ** 31, 2.0 ** 31 - 1).astype(np.int64)
+    xs = np.arange(dw, dtype=np.float64)
+    adelta, bdelta = rnd(m[0] * xs * 1024.0), rnd(m[3] * xs * 1024.0)
+    out = np.zeros((dh, dw, img.shape[2]), np.uint8)
+    src = img.astype(np.int64)
+    bval = np.broadcast_to(np.asarray(border_value, np.int64), (img.shape[2],))
+    for y in range(dh):
+        x0 = int(rnd(np.float64((m[1] * y + m[2]) * 1024.0))) + 16
+        y0 = int(rnd(np.float64((m[4] * y + m[5]) * 1024.0))) + 16
+        X, Y = (x0 + adelta) >> 5, (y0 + bdelta) >> 5
+        sx, sy = np.clip(X >> 5, -32768, 32767), np.clip(Y >> 5, -32768, 32767)
+        wt = tab[(Y & 31) * 32 + (X & 31)]                               # [dw, 4]
+        acc = np.zeros((dw, img.shape[2]), np.int64)
+        for q, (oy, ox) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+            yy, xx = sy + oy, sx + ox
+            px = src[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)]
+            if border == "constant":
+                outside = (yy < 0) | (yy >= h) | (xx < 0) | (xx >= w)
+                px = np.where(outside[:, None], bval[None, :], px)
+            acc += px * wt[:, q:q + 1]
+        out[y] = np.clip((acc + (1 << 14)) >> 15, 0, 255)
+    return out[..., 0] if squeeze else out

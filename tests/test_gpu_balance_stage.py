@@ -313,9 +313,20 @@ def test_preprocessor_mirror(ctx):
     ref = cv_ops.ellipse_dilate(ref, 1)
     ref = cv_ops.resize_ratio(ref, 0.37)
     assert np.array_equal(out, ref)
-    pp.options_dict["PPX_rotate"].value = 10
+    # the remaining tuner-gated steps, in the reference's order: blur (110-114) ... rotate (130-135) ... translate (144-149)
+    pp2 = Preprocessor(None)
+    for k, v in (("PPX_gaussian_blur", True), ("PPX_gaussian_blur_kernel", 2), ("PPX_rotate", 10), ("PPX_resize", True),
+                 ("PPX_resize_width", 320), ("PPX_resize_height", 200), ("PPX_translate_x", 12), ("PPX_translate_y", -7)):
+        pp2.options_dict[k].value = v
+    ref2 = cv2.GaussianBlur(img, (5, 5), 0)
+    ref2 = cv2.warpAffine(ref2, cv2.getRotationMatrix2D((ref2.shape[1] / 2, ref2.shape[0] / 2), 10, 1), (ref2.shape[1], ref2.shape[0]),
+                          borderMode=cv2.BORDER_REPLICATE)
+    ref2 = cv2.resize(ref2, (320, 200))
+    ref2 = cv2.warpAffine(ref2, np.float32([[1, 0, 12], [0, 1, -7]]), (ref2.shape[1], ref2.shape[0]))
+    assert np.array_equal(pp2.process(img)[0], ref2)
+    pp2.options_dict["PPX_gaussian_noise"].value = 3
     with pytest.raises(NotImplementedError):
-        pp.process(img)
+        pp2.process(img)
 
 
 def test_drop_in_modules(ctx):

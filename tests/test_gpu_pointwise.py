@@ -179,3 +179,54 @@ def test_thresh_color_distance_vs_oracle(ctx, shape):
         assert np.array_equal(mask, rmask) and np.array_equal(dist, rdist), kw
     with pytest.raises(NotImplementedError):
         color.thresh_color_distance(split, (1, 2, 3), 10, auto_distance_percentile=50)
+
+
+@pytest.mark.parametrize("shape", [(480, 640, 3), (479, 641, 3), (1242, 2208, 3), (97, 131), (5, 4, 3)])
+@pytest.mark.parametrize("n", [3, 5, 9, 13, 31])
+def test_gaussian_blur_vs_cv2(ctx, shape, n):
+    """modules/preprocessor.py:110-114: cv2.GaussianBlur(mat, (2k+1, 2k+1), 0), bit-exact."""
+    from cuauv_vision_pipeline_b200 import transform
+    img = synth.gen_underwater(shape[0], shape[1], n)
+    if len(shape) == 2:
+        img = np.ascontiguousarray(img[..., 1])
+    assert np.array_equal(transform.gaussian_blur(img, (n, n)), cv2.GaussianBlur(img, (n, n), 0))
+
+
+def test_gaussian_blur_rectangular_kernels_sigmas_and_batches(ctx):
+    img = synth.gen_random_bgr(200, 333, 9)
+    for (kw, kh, sx, sy) in [(7, 3, 0, 0), (1, 9, 0, 0), (5, 5, 2.5, 0), (11, 7, 1.2, 3.3), (63, 1, 0, 0)]:
+        got = ctx.download(ctx.gaussian_blur(ctx.upload(img), (kw, kh), sx, sy))
+        assert np.array_equal(got, cv2.GaussianBlur(img, (kw, kh), sx, sigmaY=sy)), (kw, kh, sx, sy)
+    batch = np.stack([synth.gen_underwater(120, 200, s) for s in range(3)])
+    got = ctx.download(ctx.gaussian_blur(ctx.upload(batch), (5, 5)))
+    for i in range(3):
+        assert np.array_equal(got[i], cv2.GaussianBlur(batch[i], (5, 5), 0))
+
+
+@pytest.mark.parametrize("shape", [(480, 640, 3), (479, 641, 3), (1242, 2208, 3), (97, 131)])
+def test_rotate_and_translate_vs_cv2(ctx, shape):
+    """modules/preprocessor.py:130-135 (rotate about the centre, BORDER_REPLICATE) and 144-149 (translate)."""
+    from cuauv_vision_pipeline_b200 import transform
+    img = synth.gen_underwater(shape[0], shape[1], 21)
+    if len(shape) == 2:
+        img = np.ascontiguousarray(img[..., 2])
+    h, w = shape[:2]
+    for ang in (10, -33.3, 90, 180, 0.5, 359):
+        m = cv2.getRotationMatrix2D((w / 2, h / 2), ang, 1)
+        assert np.array_equal(transform.rotation_matrix_2d((w / 2, h / 2), ang, 1), m)
+        assert np.array_equal(transform.rotate(img, ang), cv2.warpAffine(img, m, (w, h), borderMode=cv2.BORDER_REPLICATE)), ang
+    for tx, ty in ((25, 0), (0, -17), (-300, 40), (3.5, -2.25)):
+        m = np.float32([[1, 0, tx], [0, 1, ty]])
+        assert np.array_equal(transform.translate(img, tx, ty), cv2.warpAffine(img, m, (w, h))), (tx, ty)
+
+
+def test_warp_affine_general_matrix_dsize_and_border_value(ctx):
+    from cuauv_vision_pipeline_b200 import transform
+    img = synth.gen_underwater(300, 400, 5)
+    m = np.array([[0.8, 0.3, 10.5], [-0.2, 1.1, -4.25]])
+    assert np.array_equal(transform.warp_affine(img, m, (500, 210), "constant", (7, 99, 200)),
+                          cv2.warpAffine(img, m, (500, 210), borderValue=(7, 99, 200)))
+    assert np.array_equal(transform.warp_affine(img, m, (123, 457), "replicate"),
+                          cv2.warpAffine(img, m, (123, 457), borderMode=cv2.BORDER_REPLICATE))
+    sing = np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 5.0]])              # singular: cv2 uses D = 0
+    assert np.array_equal(transform.warp_affine(img, sing), cv2.warpAffine(img, sing, (400, 300)))

@@ -127,3 +127,35 @@ def test_hue_interval_property_of_the_hsv_round_trip():
         m = cv2.inRange(back, np.array(lo), np.array(hi)) > 0                          # [180, 65536]
         rises = (m & ~np.roll(m, 1, axis=0)).sum(axis=0)
         assert int(rises.max()) <= 1, (lo, hi)
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 7, 9, 11, 13, 17, 21, 31])
+def test_gaussian_blur_8u_model_vs_cv2(n):
+    """modules/preprocessor.py:110-114: cv2.GaussianBlur(mat, (n, n), 0) on uint8, 8.8 fixed point."""
+    rng = np.random.default_rng(n)
+    assert np.allclose(S.gaussian_kernel_f64(n), cv2.getGaussianKernel(n, 0)[:, 0], rtol=0, atol=1e-15)
+    for shape in [(37, 53, 3), (120, 160, 3), (64, 48), (5, 4, 3)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        assert np.array_equal(S.gaussian_blur_8u(img, (n, n)), cv2.GaussianBlur(img, (n, n), 0)), shape
+    img = synth.gen_underwater(96, 128, n)
+    assert np.array_equal(S.gaussian_blur_8u(img, (n, 3), 1.7, 0.9), cv2.GaussianBlur(img, (n, 3), 1.7, sigmaY=0.9))
+
+
+def test_warp_affine_8u_model_vs_cv2():
+    """modules/preprocessor.py:130-135 (rotate, BORDER_REPLICATE) and 144-149 (translate, constant 0)."""
+    rng = np.random.default_rng(3)
+    for shape in [(120, 160, 3), (97, 131, 3), (64, 80)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        h, w = shape[:2]
+        for ang in (5, 30, -47.5, 90, 180, 0.3, 359):
+            m = cv2.getRotationMatrix2D((w / 2, h / 2), ang, 1)
+            assert np.array_equal(S.rotation_matrix_2d((w / 2, h / 2), ang, 1), m)
+            assert np.array_equal(S.warp_affine_8u(img, m, (w, h), "replicate"),
+                                  cv2.warpAffine(img, m, (w, h), borderMode=cv2.BORDER_REPLICATE)), (shape, ang)
+        for tx, ty in ((5, 0), (0, 7), (-13, 4), (3.5, -2.25), (200, 0)):
+            m = np.float32([[1, 0, tx], [0, 1, ty]])
+            assert np.array_equal(S.warp_affine_8u(img, m, (w, h)), cv2.warpAffine(img, m, (w, h))), (shape, tx, ty)
+    img = synth.gen_underwater(90, 120, 4)
+    m = np.array([[0.8, 0.3, 10.5], [-0.2, 1.1, -4.25]])
+    assert np.array_equal(S.warp_affine_8u(img, m, (150, 70), "constant", (7, 99, 200)),
+                          cv2.warpAffine(img, m, (150, 70), borderValue=(7, 99, 200)))
