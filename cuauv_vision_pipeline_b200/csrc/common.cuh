@@ -60,6 +60,7 @@ enum ScratchSlot {
     SCR_CCL_PARENT2,    // union-find parents of the background regions (outer contours)
     SCR_CCL_AUX2,       // background row counts + frame-touching bitmap
     SCR_CCL_ROOTS,      // first pixel of every blob, raster order
+    SCR_HULL,           // sorted vertices + hull stack per contour (minAreaRect)
     SCR_MORPH_TMP,      // intermediate image of multi-step grey morphology
     SCR_MORPH_TMP2,
     SCR_MORPH_SE,       // structuring-element offsets

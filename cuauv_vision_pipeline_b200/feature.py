@@ -33,22 +33,32 @@ class Contour(dict):
     """One outer border (cv2.findContours RETR_EXTERNAL) reduced to its Green's-theorem sums."""
 
 
-def outer_contours(mat, max_contours=4096, points=False, max_points=None):
+def outer_contours(mat, max_contours=4096, points=False, max_points=None, rects=False):
     """utils/feature.py:5-21 on the GPU: the outermost 8-connected borders of `mat != 0`, in raster
     order of their first pixel (cv2 returns the same set, in its own order).  Each record carries
     what the reference consumes next (contour_centroid / contour_area below); with `points=True`
     also the CHAIN_APPROX_SIMPLE vertices as an int32 [n,1,2] array, exactly the array cv2 returns
-    (ready for cv2.minAreaRect as in modules/bins.py:60)."""
+    (ready for cv2.minAreaRect as in modules/bins.py:60); with `rects=True` also
+    `c["min_area_rect"] = ((cx, cy), (w, h), angle)`, cv2.minAreaRect of those vertices computed on
+    the device (min_area_rect below)."""
     from .runtime import CONTOUR_DTYPE
     ctx = ctx_for(mat)
     h, w = mat.shape[-2], mat.shape[-1]
+    points = points or rects
     if points and max_points is None:
         max_points = 4 * (h + w) + h * w // 4        # generous: borders of a very ragged mask
     table, nb, pts, npts = ctx.outer_contours(to_device(ctx, mat), max_contours=max_contours,
                                               max_points=max_points if points else 0)
     n = int(ctx.download(nb)[0])
     raw = ctx.download(table)[0, :min(n, max_contours)].copy().view(CONTOUR_DTYPE).reshape(-1)
-    out = [Contour({k: int(row[k]) for k in CONTOUR_DTYPE.names}) for row in raw if row["external"]]
+    keep = [i for i, row in enumerate(raw) if row["external"]]
+    out = [Contour({k: int(raw[i][k]) for k in CONTOUR_DTYPE.names}) for i in keep]
+    if rects:
+        rr = ctx.min_area_rects(table, nb, pts)[0]
+        for c, i in zip(out, keep):
+            q = rr[i]
+            c["min_area_rect"] = ((float(q["cx"]), float(q["cy"])), (float(q["width"]), float(q["height"])),
+                                  float(q["angle"])) if q["valid"] else None
     if points:
         needed = int(ctx.download(npts)[0])
         host = ctx.download(pts)[0, :min(needed, max_points)]
@@ -89,3 +99,17 @@ def blob_centroid(blob):
 def blob_area(blob):
     """Raster area in pixels (contour_area, utils/feature.py:255-265, is the polygon area)."""
     return float(blob["m00"])
+
+
+def min_area_rect(contour):
+    """cv2.minAreaRect(contour) (modules/bins.py:60) for a contour returned by
+    `outer_contours(..., rects=True)`: ((cx, cy), (w, h), angle), angle in [-90, 0) degrees."""
+    r = contour.get("min_area_rect")
+    if r is None:
+        raise ValueError("contour carries no rectangle: call outer_contours(..., rects=True)")
+    return r
+
+
+def min_enclosing_rect(contour):
+    """utils/feature.py:301-312."""
+    return min_area_rect(contour)

@@ -54,6 +54,7 @@ class BinDetectorGPU(ModuleBase):
         self.overlay = overlay
         self.want_contours = want_contours
         self.contours = []
+        self.valid_rects = []
         self.desc = self.ctx.make_stage(cvt="bgr2hsv", lo=self.lower_beige, hi=self.upper_beige,
                                         morph=[("open", 5, 5, 1)], label=True)
         self.blobs = []
@@ -77,7 +78,19 @@ class BinDetectorGPU(ModuleBase):
         cleaned = out["mask"]
         # the reference's own next step (bins.py:27): outer contours of the cleaned mask, as the exact
         # vertex arrays cv2.findContours returns -- ready for cv2.minAreaRect (bins.py:60) on the host
-        self.contours = feature.outer_contours(cleaned, points=True) if self.want_contours else []
+        self.contours = feature.outer_contours(cleaned, points=True, rects=True) if self.want_contours else []
+        # bins.py:58-69 verbatim on the device-computed rectangles
+        self.valid_rects = []
+        for contour in self.contours:
+            rect = contour["min_area_rect"]
+            if rect is None:
+                continue
+            (center, (w, h), angle) = rect
+            if w * h < 500:
+                continue
+            aspect_ratio = max(w, h) / min(w, h)
+            if 1.0 <= aspect_ratio <= 3.0:
+                self.valid_rects.append(rect)
         if self.overlay:
             vis = np.repeat(cleaned[..., None], 3, axis=2)
             overlayed = np.clip(np.rint(img * 0.7 + vis * 0.3), 0, 255).astype(np.uint8)   # bins.py:19-20

@@ -29,6 +29,8 @@ CONTOUR_DTYPE = np.dtype([(k, "<i8") for k in ("a00", "a10", "a01")] +
                          [(k, "<i4") for k in ("x0", "y0", "x1", "y1", "start_x", "start_y", "n_points", "n_simple",
                                                "label", "external", "point_offset", "reserved")])
 assert CONTOUR_DTYPE.itemsize == ffi.sizeof("bv_contour")
+RRECT_DTYPE = np.dtype([(k, "<f4") for k in ("cx", "cy", "width", "height", "angle")] + [("valid", "<i4")])
+assert RRECT_DTYPE.itemsize == ffi.sizeof("bv_rrect")
 
 
 def _u8ptr(t):
@@ -274,6 +276,17 @@ class Context:
                                     ffi.cast("int32_t *", points.data_ptr()) if max_points else ffi.NULL, max_points,
                                     ffi.cast("int32_t *", npts.data_ptr()) if max_points else ffi.NULL))
         return table, nb, points, npts
+
+    def min_area_rects(self, table, nb, points):
+        """cv2.minAreaRect of every external contour of `outer_contours(..., max_points > 0)`: structured numpy
+        array [B, max_contours] with fields cx, cy, width, height, angle, valid."""
+        b, max_contours = table.shape[0], table.shape[1]
+        max_points = points.shape[1]
+        rects = self.empty((b, max_contours, RRECT_DTYPE.itemsize), torch.uint8)
+        check(lib.bv_min_area_rects(self.handle, ffi.cast("bv_contour *", table.data_ptr()), ffi.cast("int32_t *", nb.data_ptr()),
+                                    ffi.cast("int32_t *", points.data_ptr()), b, max_contours, max_points,
+                                    ffi.cast("bv_rrect *", rects.data_ptr())))
+        return self.download(rects).view(RRECT_DTYPE).reshape(b, max_contours)
 
     def blobs_to_numpy(self, blobs, nb):
         """Device blob table -> list (per frame) of structured numpy arrays."""

@@ -235,6 +235,19 @@ int bv_outer_contours(bv_ctx *ctx, const uint8_t *mask_dev, int batch, int heigh
                       bv_contour *contours_dev, int max_contours, int32_t *n_contours_dev, int32_t *points_dev,
                       int max_points, int32_t *n_points_dev);
 
+/* cv2.minAreaRect of every external contour (modules/bins.py:60-69; utils/feature.py:301-312), from
+ * the vertex lists bv_outer_contours wrote (same contours_dev / n_contours_dev / points_dev /
+ * max_contours / max_points).  rects_dev: bv_rrect[batch * max_contours], entry i belongs to contour
+ * record i; valid = 0 for records that are not external or whose vertices did not fit.
+ * ((cx, cy), (width, height), angle) as cv2 4.13.0 reports them (angle in [-90, 0) degrees);
+ * float32, tolerance 1e-4 relative on the area (see csrc/rects.cu). */
+typedef struct bv_rrect {
+    float cx, cy, width, height, angle;
+    int32_t valid;
+} bv_rrect;
+int bv_min_area_rects(bv_ctx *ctx, const bv_contour *contours_dev, const int32_t *n_contours_dev,
+                      const int32_t *points_dev, int batch, int max_contours, int max_points, bv_rrect *rects_dev);
+
 /* ---- resize / YOLO input ------------------------------------------------------------------ */
 /* cv2.resize(..., INTER_LINEAR) on uint8 (utils/transform.py:179, modules/preprocessor.py:136-143). */
 int bv_resize_linear(bv_ctx *ctx, const uint8_t *src_dev, int src_h, int src_w, uint8_t *dst_dev, int dst_h,

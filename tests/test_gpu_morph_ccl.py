@@ -329,3 +329,62 @@ def test_morphology_chain_of_four_steps_with_labels(ctx, shape):
         m = cv2.erode(m, np.ones((1, 9), np.uint8))
         assert np.array_equal(mask[i], m)
         assert np.array_equal(lab[i], ccl.label_and_moments(m)[1])
+
+
+def _rect_corners(rect):
+    (cx, cy), (w, h), a = rect
+    a = np.deg2rad(a)
+    c, s = np.cos(a), np.sin(a)
+    return np.array(sorted((cx + sx * w * c - sy * h * s, cy + sx * w * s + sy * h * c)
+                           for sx, sy in ((-.5, -.5), (.5, -.5), (.5, .5), (-.5, .5))))
+
+
+@pytest.mark.parametrize("shape,seed", [((480, 640), 3), ((1080, 1920), 4), ((301, 333), 5)])
+def test_min_area_rect_of_outer_contours_vs_cv2(ctx, shape, seed):
+    """modules/bins.py:60-69: cv2.minAreaRect(contour) for every outer contour, computed on the device from the
+    device-side vertex lists.  Stated tolerance: area 1e-4 relative; centre / size / angle 1e-3 (absolute, px / degrees)
+    wherever the minimum-area rectangle is unique (two hull edges may tie to within float32 rounding)."""
+    from cuauv_vision_pipeline_b200 import feature
+    mask = synth.mask_blobs(shape[0], shape[1], seed, sigma=5.0, pct=72)
+    got = feature.outer_contours(mask, points=True, rects=True)
+    ref_contours, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    by_start = {}
+    for c in ref_contours:
+        pts = c.reshape(-1, 2)
+        i = np.lexsort((pts[:, 0], pts[:, 1]))[0]
+        by_start[(int(pts[i, 0]), int(pts[i, 1]))] = c
+    assert len(got) == len(ref_contours) and len(got) > 20
+    exact_params = 0
+    for g in got:
+        ref = cv2.minAreaRect(by_start[(g["start_x"], g["start_y"])])
+        rect = feature.min_area_rect(g)
+        assert np.array_equal(g["points"], by_start[(g["start_x"], g["start_y"])])
+        ra, ga = ref[1][0] * ref[1][1], rect[1][0] * rect[1][1]
+        assert abs(ra - ga) <= 1e-4 * max(1.0, ra), (ref, rect)
+        assert -90.0 <= rect[2] < 0.0
+        # every vertex lies inside the rectangle
+        p = g["points"].reshape(-1, 2).astype(np.float64) - np.array(rect[0])
+        a = np.deg2rad(rect[2])
+        u, v = p @ np.array([np.cos(a), np.sin(a)]), p @ np.array([-np.sin(a), np.cos(a)])
+        assert np.abs(u).max() <= rect[1][0] / 2 + 1e-2 and np.abs(v).max() <= rect[1][1] / 2 + 1e-2
+        if np.abs(_rect_corners(ref) - _rect_corners(rect)).max() <= 1e-3 * max(1.0, max(ref[1])):
+            exact_params += 1
+    assert exact_params >= 0.95 * len(got), (exact_params, len(got))
+
+
+def test_min_area_rect_degenerate_contours(ctx):
+    from cuauv_vision_pipeline_b200 import feature
+    m = np.zeros((64, 96), np.uint8)
+    m[5, 7] = 255                       # single pixel
+    m[20, 10:31] = 255                  # horizontal segment
+    m[30:50, 60] = 255                  # vertical segment
+    for k in range(12):                 # diagonal 1-px line
+        m[40 + k, 10 + k] = 255
+    m[8:16, 70:90] = 255                # axis-aligned rectangle
+    got = feature.outer_contours(m, points=True, rects=True)
+    ref_contours, _ = cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    assert len(got) == len(ref_contours) == 5
+    for g in got:
+        ref = [cv2.minAreaRect(c) for c in ref_contours if (c.reshape(-1, 2) == [g["start_x"], g["start_y"]]).all(axis=1).any()][0]
+        rect = feature.min_area_rect(g)
+        assert np.allclose([*rect[0], *rect[1], rect[2]], [*ref[0], *ref[1], ref[2]], rtol=0, atol=1e-3), (ref, rect)
