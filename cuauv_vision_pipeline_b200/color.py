@@ -40,18 +40,46 @@ def range_threshold(mat, min, max):  # noqa: A002 (reference argument names)
     return like_input(ctx, mat, ctx.in_range(to_device(ctx, mat), min, max))
 
 
+def _percentile_from_order_statistics(n, q, dtype, kth):
+    """np.percentile(a, q) (method 'linear') of a 1-d float array of n values, given a function returning its k-th
+    smallest value: numpy 2.x's own steps (lib/_function_base_impl.py: percentile -> _quantile -> _lerp), so the
+    virtual index, its dtype (that of `a` when q is a python number) and the interpolation round the same way."""
+    qq = np.true_divide(q, dtype(100))
+    virtual = np.asanyarray((n - 1) * qq)
+    prev = np.floor(virtual)
+    nxt = prev + 1
+    if virtual >= n - 1:
+        prev = nxt = -1
+    if virtual < 0:
+        prev = nxt = 0
+    prev, nxt = int(prev), int(nxt)
+    a, b = kth(prev), kth(nxt)
+    t = np.asanyarray(virtual - prev, dtype=virtual.dtype)[()]
+    diff = np.subtract(b, a)
+    out = np.add(a, diff * t)
+    if t >= 0.5:
+        out = np.subtract(b, diff * (1 - t)).astype(type(out))
+    return out
+
+
 def thresh_color_distance(split, color, distance, auto_distance_percentile=None, ignore_channels=[],  # noqa: B006
                           weights=(1, 1, 1)):
-    """utils/color.py:66-103.  Returns (mask, uint8 distance image).  The percentile option needs a
-    global float percentile and is not provided."""
-    if auto_distance_percentile:
-        raise NotImplementedError("auto_distance_percentile (utils/color.py:98-99) is not provided")
+    """utils/color.py:66-103.  Returns (mask, uint8 distance image).  With auto_distance_percentile the threshold
+    is min(np.percentile(dists, p), distance**2): the two order statistics come from the device (radix select on
+    the float32 distance image), numpy's interpolation between them is replayed on the host."""
     ctx = ctx_for(split[0])
     w = np.array([0.0 if i in ignore_channels else float(weights[i]) for i in range(3)], np.float64)
     w /= np.linalg.norm(weights)                      # norm of the UN-zeroed weights (utils/color.py:93)
     use = [0 if i in ignore_channels else 1 for i in range(3)]
     planes = [to_device(ctx, p) for p in split]
-    mask, dist = ctx.color_distance(planes, color, w, use, float(distance) ** 2)
+    if auto_distance_percentile:
+        dists = ctx.color_distance_f32(planes, color, w, use)
+        pct = _percentile_from_order_statistics(dists.numel(), auto_distance_percentile, np.float32,
+                                                lambda k: ctx.select_kth(dists, k))
+        limit = min(pct, distance ** 2)               # utils/color.py:99
+    else:
+        limit = float(distance) ** 2
+    mask, dist = ctx.color_distance(planes, color, w, use, float(limit))
     return like_input(ctx, split[0], mask), like_input(ctx, split[0], dist)
 
 

@@ -237,7 +237,8 @@ struct ColorDistParams {
 
 __global__ void __launch_bounds__(256) color_distance_kernel(const uint8_t *__restrict__ p0, const uint8_t *__restrict__ p1,
                                                              const uint8_t *__restrict__ p2, uint8_t *__restrict__ mask,
-                                                             uint8_t *__restrict__ dist, size_t n, ColorDistParams prm) {
+                                                             uint8_t *__restrict__ dist, float *__restrict__ dists_f32, size_t n,
+                                                             ColorDistParams prm) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint8_t v[3] = {p0[i], p1[i], p2[i]};
@@ -251,7 +252,32 @@ __global__ void __launch_bounds__(256) color_distance_kernel(const uint8_t *__re
         }
         if (mask) mask[i] = (d >= 0.f && d <= prm.max_dist) ? 255 : 0;
         if (dist) dist[i] = (uint8_t)(((int)__fsqrt_rn(d)) & 0xFF);  // np.uint8(np.sqrt(.)): truncate, wrap
+        if (dists_f32) dists_f32[i] = d;
     }
+}
+
+// ----------------------------------------------------------------------------------------------
+// k-th smallest of a float32 array (the order statistics np.percentile interpolates between,
+// utils/color.py:98-99): radix select over the order-preserving integer image of the floats,
+// 8 bits per pass, each pass one 256-bin histogram of the elements that match the prefix so far.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256) select_hist_kernel(const float *__restrict__ v, size_t n, uint32_t prefix, uint32_t prefix_mask,
+                                                          int shift, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = float_key(v[i]);
+        if ((k & prefix_mask) == prefix) atomicAdd(&h[(k >> shift) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -385,12 +411,12 @@ extern "C" int bv_threshold(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_de
     return BV_OK;
 }
 
-extern "C" int bv_color_distance(bv_ctx *ctx, const uint8_t *const *planes_dev, size_t n, const double *color_host,
-                                 const double *weights_host, const int32_t *use_host, double max_dist_sq,
-                                 uint8_t *mask_dev, uint8_t *dist_dev) {
+static int color_distance_launch(bv_ctx *ctx, const uint8_t *const *planes_dev, size_t n, const double *color_host,
+                                 const double *weights_host, const int32_t *use_host, double max_dist_sq, uint8_t *mask_dev,
+                                 uint8_t *dist_dev, float *dists_f32_dev) {
     BV_REQUIRE(ctx && planes_dev && planes_dev[0] && planes_dev[1] && planes_dev[2] && color_host && weights_host && use_host,
                "null argument");
-    BV_REQUIRE(mask_dev || dist_dev, "need mask_dev or dist_dev");
+    BV_REQUIRE(mask_dev || dist_dev || dists_f32_dev, "need an output");
     BV_CUDA(cudaSetDevice(ctx->device));
     if (n == 0) return BV_OK;
     ColorDistParams prm;
@@ -401,7 +427,49 @@ extern "C" int bv_color_distance(bv_ctx *ctx, const uint8_t *const *planes_dev, 
     }
     prm.max_dist = (float)max_dist_sq;
     BV_LAUNCH(ctx, color_distance_kernel, grid_for(ctx, n, 256, 8), 256, 0, planes_dev[0], planes_dev[1], planes_dev[2],
-              mask_dev, dist_dev, n, prm);
+              mask_dev, dist_dev, dists_f32_dev, n, prm);
+    return BV_OK;
+}
+
+extern "C" int bv_color_distance(bv_ctx *ctx, const uint8_t *const *planes_dev, size_t n, const double *color_host,
+                                 const double *weights_host, const int32_t *use_host, double max_dist_sq,
+                                 uint8_t *mask_dev, uint8_t *dist_dev) {
+    return color_distance_launch(ctx, planes_dev, n, color_host, weights_host, use_host, max_dist_sq, mask_dev, dist_dev, nullptr);
+}
+
+extern "C" int bv_color_distance_f32(bv_ctx *ctx, const uint8_t *const *planes_dev, size_t n, const double *color_host,
+                                     const double *weights_host, const int32_t *use_host, float *dists_dev) {
+    BV_REQUIRE(dists_dev, "null argument");
+    return color_distance_launch(ctx, planes_dev, n, color_host, weights_host, use_host, 0.0, nullptr, nullptr, dists_dev);
+}
+
+extern "C" int bv_select_kth_f32(bv_ctx *ctx, const float *values_dev, size_t n, size_t k, float *value_host) {
+    BV_REQUIRE(ctx && values_dev && value_host, "null argument");
+    BV_REQUIRE(n > 0 && k < n, "k must be below n");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    BV_TRY(ensure_scratch(ctx, SCR_MORPH_SE, 256 * sizeof(uint32_t)));
+    uint32_t *d_hist = (uint32_t *)ctx->scratch[SCR_MORPH_SE];
+    uint32_t prefix = 0, mask = 0, hist[256];
+    size_t rank = k;  // rank of the wanted element among those matching the prefix
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        BV_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(hist), ctx->stream));
+        BV_LAUNCH(ctx, select_hist_kernel, grid_for(ctx, n, 256, 8), 256, 0, values_dev, n, prefix, mask, shift, d_hist);
+        BV_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof(hist), cudaMemcpyDeviceToHost, ctx->stream));
+        BV_CUDA(cudaStreamSynchronize(ctx->stream));
+        int b = 0;
+        for (; b < 256; ++b) {
+            if (rank < hist[b]) break;
+            rank -= hist[b];
+        }
+        if (b == 256) {
+            set_error("bv_select_kth_f32: inconsistent histogram (NaN input?)");
+            return BV_ERR_INVALID;
+        }
+        prefix |= (uint32_t)b << shift;
+        mask |= 0xFFu << shift;
+    }
+    const uint32_t u = (prefix & 0x80000000u) ? (prefix & 0x7FFFFFFFu) : ~prefix;
+    memcpy(value_host, &u, sizeof(float));
     return BV_OK;
 }
 

@@ -212,6 +212,24 @@ class Context:
                                     _u8ptr(mask), _u8ptr(dist)))
         return mask, dist
 
+    def color_distance_f32(self, planes, color, weights, use):
+        """The float32 squared-distance image (utils/color.py:94-97) as a device tensor."""
+        n = planes[0].numel()
+        d = self.empty(tuple(planes[0].shape), torch.float32)
+        pp = ffi.new("uint8_t *[3]", [_u8ptr(p) for p in planes])
+        check(lib.bv_color_distance_f32(self.handle, ffi.cast("const uint8_t *const *", pp), n,
+                                        ffi.new("double[3]", [float(c) for c in color]),
+                                        ffi.new("double[3]", [float(w) for w in weights]),
+                                        ffi.new("int32_t[3]", [int(u) for u in use]), ffi.cast("float *", d.data_ptr())))
+        return d
+
+    def select_kth(self, values, k):
+        """k-th smallest (0-based) of a float32 device tensor, as np.float32."""
+        out = ffi.new("float *")
+        n = values.numel()
+        check(lib.bv_select_kth_f32(self.handle, ffi.cast("float *", values.data_ptr()), n, int(k) % n, out))
+        return np.float32(out[0])
+
     def morph(self, src, op, kernel, iterations=1):
         kernel = np.ascontiguousarray(np.asarray(kernel) != 0, dtype=np.uint8)
         kh, kw = kernel.shape

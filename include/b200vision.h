@@ -185,14 +185,21 @@ int bv_cvt_in_range(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *mask_dev, int 
 int bv_apply_lut(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, size_t n_pixels, int channels,
                  const uint8_t *lut_host);
 
-/* Weighted squared colour distance threshold (thresh_color_distance, utils/color.py:66-103, without
- * the percentile option).  planes_dev: the 3 split channels; weights_host: per-channel weights
+/* Weighted squared colour distance threshold (thresh_color_distance, utils/color.py:66-103; the percentile
+ * option is composed from the two calls below).  planes_dev: the 3 split channels; weights_host: per-channel weights
  * already normalised as the reference does (ignored channels zeroed, divided by the 2-norm of the
  * un-zeroed weights); use_host[c] = 0 skips channel c.  mask_dev: 255 where 0 <= d <= max_dist_sq;
  * dist_dev: uint8(sqrt(d)).  Either output may be NULL. */
 int bv_color_distance(bv_ctx *ctx, const uint8_t *const *planes_dev, size_t n, const double *color_host,
                       const double *weights_host, const int32_t *use_host, double max_dist_sq, uint8_t *mask_dev,
                       uint8_t *dist_dev);
+/* The float32 squared-distance image itself (the `dists` of utils/color.py:94-97), and the k-th
+ * smallest value of a float32 device array (k = 0: the minimum; NaN-free input): the two order
+ * statistics np.percentile interpolates between for auto_distance_percentile (utils/color.py:98-99);
+ * the interpolation itself is numpy's scalar arithmetic, done by the host mirror (color.py). */
+int bv_color_distance_f32(bv_ctx *ctx, const uint8_t *const *planes_dev, size_t n, const double *color_host,
+                          const double *weights_host, const int32_t *use_host, float *dists_dev);
+int bv_select_kth_f32(bv_ctx *ctx, const float *values_dev, size_t n, size_t k, float *value_host);
 
 /* ---- morphology ------------------------------------------------------------------------------ */
 /* se_host: kh*kw bytes (non-zero = member), anchor = centre; channels 1 or 3 (per channel).

@@ -26,10 +26,11 @@ def range_threshold(mat, lo, hi):
     return cv2.inRange(mat, lo, hi)
 
 
-def thresh_color_distance(split, color, distance, ignore_channels=(), weights=(1, 1, 1)):
-    """utils/color.py:66-103 without the percentile branch: weighted squared distance accumulated
-    in a float32 image (numpy evaluates weight * square in float64 and rounds on the in-place add),
-    thresholded with cv2.inRange(dists, 0, distance**2); second result np.uint8(np.sqrt(dists))."""
+def thresh_color_distance(split, color, distance, auto_distance_percentile=None, ignore_channels=(), weights=(1, 1, 1)):
+    """utils/color.py:66-103: weighted squared distance accumulated in a float32 image (numpy evaluates
+    weight * square in float64 and rounds on the in-place add), thresholded with
+    cv2.inRange(dists, 0, limit), limit = distance**2 or min(np.percentile(dists, p), distance**2) (98-101);
+    second result np.uint8(np.sqrt(dists))."""
     w = list(weights)
     for idx in ignore_channels:
         w[idx] = 0
@@ -39,8 +40,12 @@ def thresh_color_distance(split, color, distance, ignore_channels=(), weights=(1
         if i in ignore_channels:
             continue
         dists += w[i] * (np.float32(split[i]) - color[i]) ** 2
+    if auto_distance_percentile:
+        limit = min(np.percentile(dists, auto_distance_percentile), distance ** 2)
+    else:
+        limit = distance ** 2
     with np.errstate(invalid="ignore"):
-        return cv2.inRange(dists, 0, distance ** 2), (np.sqrt(dists).astype(np.int64) & 0xFF).astype(np.uint8)
+        return cv2.inRange(dists, 0, float(limit)), (np.sqrt(dists).astype(np.int64) & 0xFF).astype(np.uint8)
 
 
 def binary_threshold(mat, t):            # utils/color.py:124-137

@@ -177,8 +177,26 @@ def test_thresh_color_distance_vs_oracle(ctx, shape):
         mask, dist = color.thresh_color_distance(split, **kw)
         rmask, rdist = cv_ops.thresh_color_distance(split, **kw)
         assert np.array_equal(mask, rmask) and np.array_equal(dist, rdist), kw
-    with pytest.raises(NotImplementedError):
-        color.thresh_color_distance(split, (1, 2, 3), 10, auto_distance_percentile=50)
+    # auto_distance_percentile (utils/color.py:98-99): min(np.percentile(dists, p), distance**2)
+    for kw in (dict(color=(120, 150, 140), distance=300, auto_distance_percentile=50),
+               dict(color=(60, 128, 128), distance=45, auto_distance_percentile=1.5, weights=(0.2, 1, 1)),
+               dict(color=(200, 110, 170), distance=1000, auto_distance_percentile=99.9, ignore_channels=[0]),
+               dict(color=(100, 140, 135), distance=5, auto_distance_percentile=33.3),    # distance**2 is the smaller one
+               dict(color=(90, 120, 130), distance=1e4, auto_distance_percentile=100)):
+        mask, dist = color.thresh_color_distance(split, **kw)
+        rmask, rdist = cv_ops.thresh_color_distance(split, **kw)
+        assert np.array_equal(mask, rmask) and np.array_equal(dist, rdist), kw
+
+
+def test_select_kth_is_the_order_statistic(ctx):
+    rng = np.random.default_rng(5)
+    for vals in (rng.normal(0, 100, 100003).astype(np.float32), (rng.random(4097) ** 3 * 1e6).astype(np.float32),
+                 np.array([3.0, -0.0, 0.0, -7.5, 3.0, np.inf, -np.inf, 1e-40], np.float32), np.zeros(10, np.float32)):
+        d = ctx.upload(vals)
+        s = np.sort(vals)
+        for k in (0, 1, len(vals) // 2, len(vals) - 2, len(vals) - 1):
+            got = ctx.select_kth(d, k)
+            assert got == s[k] and np.signbit(got) == np.signbit(s[k]), (k, got, s[k])
 
 
 @pytest.mark.parametrize("shape", [(480, 640, 3), (479, 641, 3), (1242, 2208, 3), (97, 131), (5, 4, 3)])
