@@ -362,6 +362,7 @@ extern "C" int bv_letterbox(bv_ctx *ctx, const uint8_t *const *srcs_host, const 
     BV_REQUIRE(n > 0 && n <= 65535 && out_h > 0 && out_w > 0 && out_h <= 65535, "bad batch or output size");
     BV_CUDA(cudaSetDevice(ctx->device));
     static thread_local LetterboxImg descs[256];
+    memset(descs, 0, sizeof(LetterboxImg) * (size_t)(n > 0 && n <= 256 ? n : 0));  // padding bytes compare equal
     BV_REQUIRE(n <= 256, "at most 256 images per call");
     for (int i = 0; i < n; ++i) {
         const int h = heights_host[i], w = widths_host[i];
@@ -383,9 +384,18 @@ extern "C" int bv_letterbox(bv_ctx *ctx, const uint8_t *const *srcs_host, const 
         d.scale_y = (double)h / uh;
         BV_REQUIRE(uw > 0 && uh > 0, "degenerate letterbox size");
     }
-    BV_TRY(ensure_scratch(ctx, SCR_LETTERBOX, sizeof(LetterboxImg) * kLbMaxImgs + sizeof(LbCoef) * (size_t)n * out_w + 16));
+    const size_t lb_bytes = sizeof(LetterboxImg) * kLbMaxImgs + sizeof(LbCoef) * (size_t)n * out_w + 16;
+    const bool regrown = ctx->scratch_bytes[SCR_LETTERBOX] < lb_bytes;
+    BV_TRY(ensure_scratch(ctx, SCR_LETTERBOX, lb_bytes));
     LetterboxImg *d_descs = (LetterboxImg *)ctx->scratch[SCR_LETTERBOX];
-    BV_CUDA(cudaMemcpyAsync(d_descs, descs, sizeof(LetterboxImg) * n, cudaMemcpyHostToDevice, ctx->stream));
+    // the same cameras frame after frame: descriptors and tap table are already on the device
+    if (!ctx->lb_cache) ctx->lb_cache = calloc(1, sizeof(LetterboxImg) * kLbMaxImgs);
+    const bool same = !regrown && ctx->lb_cache && ctx->lb_cache_n == n && ctx->lb_cache_ow == out_w && ctx->lb_cache_oh == out_h &&
+                      memcmp(ctx->lb_cache, descs, sizeof(LetterboxImg) * n) == 0;
+    if (!same) {
+        BV_CUDA(cudaMemcpyAsync(d_descs, descs, sizeof(LetterboxImg) * n, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->lb_cache_n = 0;  // the tap table is rebuilt below (or unused by the gather kernel)
+    }
     bool fits = true;  // the staged kernel holds two source rows in shared memory
     for (int i = 0; i < n; ++i) fits = fits && (size_t)widths_host[i] * 3 <= (size_t)kLbMaxRowBytes;
     static const bool use_tma = getenv("BV_LETTERBOX_GATHER") == nullptr;
@@ -406,7 +416,15 @@ extern "C" int bv_letterbox(bv_ctx *ctx, const uint8_t *const *srcs_host, const 
         int grid = ctx->sm_count * per_sm;
         if (grid > n_items) grid = n_items;
         LbCoef *d_coefs = (LbCoef *)(d_descs + kLbMaxImgs);
-        BV_LAUNCH(ctx, letterbox_coef_kernel, (n * out_w + 255) / 256, 256, 0, d_descs, d_coefs, out_w, n * out_w);
+        if (!same) {
+            BV_LAUNCH(ctx, letterbox_coef_kernel, (n * out_w + 255) / 256, 256, 0, d_descs, d_coefs, out_w, n * out_w);
+            if (ctx->lb_cache) {
+                memcpy(ctx->lb_cache, descs, sizeof(LetterboxImg) * n);
+                ctx->lb_cache_n = n;
+                ctx->lb_cache_ow = out_w;
+                ctx->lb_cache_oh = out_h;
+            }
+        }
         if (out_fp16)
             BV_LAUNCH(ctx, letterbox_tma_kernel<true>, grid, kLbConsumers + 32, smem, d_descs, n, d_coefs, out_dev, out_h, out_w,
                       pad_value, n_items, row_stride);
