@@ -99,3 +99,26 @@ def test_two_rank_gather_on_gloo():
         assert p.exitcode == 0
     assert [m["frame"] for m in merged] == list(range(7))
     assert [m["rank"] for m in merged] == [0, 1, 0, 1, 0, 1, 0]
+
+
+def test_percentile_replay_equals_numpy():
+    """color.thresh_color_distance(auto_distance_percentile=...) takes two order statistics from the device and
+    replays numpy's interpolation on the host: same value and same dtype as np.percentile for float32 data."""
+    from cuauv_vision_pipeline_b200.color import _percentile_from_order_statistics
+    rng = np.random.default_rng(0)
+    for t in range(120):
+        n = int(rng.integers(1, 5000)) if t % 3 else int(rng.integers(100000, 3000000))
+        a = (rng.random(n) ** 2 * 1e4).astype(np.float32)
+        q = [50, 1, 99, 0, 100, 33.3, float(rng.uniform(0, 100)), np.float64(12.5), 7][t % 9]
+        s = np.sort(a)
+        got = _percentile_from_order_statistics(n, q, np.float32, lambda k: s[k])
+        ref = np.percentile(a, q)
+        assert got == ref and type(got) is type(ref), (n, q, got, ref)
+
+
+def test_rotation_matrix_equals_cv2():
+    import cv2
+    from cuauv_vision_pipeline_b200.transform import rotation_matrix_2d
+    for ang in (0, 10, -33.3, 90, 180, 359, 0.001, 720.5):
+        for c in ((320.0, 240.0), (1104.0, 621.0), (0.5, 7.25)):
+            assert np.array_equal(rotation_matrix_2d(c, ang, 1), cv2.getRotationMatrix2D(c, ang, 1))
