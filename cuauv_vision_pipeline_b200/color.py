@@ -23,8 +23,8 @@ def _convert_colorspace(code):
     return _inner
 
 
-# utils/color.py:26-32.  bgr_to_luv and lab_to_bgr have no pinned arithmetic model yet
-#  and are not provided.
+# utils/color.py:26-32.  bgr_to_luv has no pinned arithmetic model (OpenCV's 8-bit path interpolates a
+# 33^3 table built with softfloat) and is not provided.
 bgr_to_lab = _convert_colorspace("bgr2lab")
 bgr_to_hsv = _convert_colorspace("bgr2hsv")
 bgr_to_hls = _convert_colorspace("bgr2hls")
@@ -32,6 +32,7 @@ bgr_to_ycrcb = _convert_colorspace("bgr2ycrcb")
 bgr_to_gray = _convert_colorspace("bgr2gray")
 gray_to_bgr = _convert_colorspace("gray2bgr")
 hsv_to_bgr = _convert_colorspace("hsv2bgr")
+lab_to_bgr = _convert_colorspace("lab2bgr")
 
 
 def range_threshold(mat, min, max):  # noqa: A002 (reference argument names)

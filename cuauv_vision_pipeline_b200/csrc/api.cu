@@ -209,10 +209,13 @@ extern "C" int bv_create(int device, bv_ctx **out) {
     double pow_tab[256];
     for (int x = 0; x < 256; ++x) pow_tab[x] = pow((255. - x) / 255., 0.25);  // color_balance.cpp:490
     bool ok = cudaMalloc(&ctx->d_lab_gamma, sizeof(kLabGammaTab)) == cudaSuccess &&
-              cudaMalloc(&ctx->d_lab_cbrt, sizeof(kLabCbrtTab)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_lab_cbrt, sizeof(kLabCbrtTab) + sizeof(kLabToYF) + sizeof(kLabInvGammaTab)) == cudaSuccess &&
               cudaMalloc(&ctx->d_pow_quarter, sizeof(pow_tab)) == cudaSuccess &&
               cudaMemcpy(ctx->d_lab_gamma, kLabGammaTab, sizeof(kLabGammaTab), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(ctx->d_lab_cbrt, kLabCbrtTab, sizeof(kLabCbrtTab), cudaMemcpyHostToDevice) == cudaSuccess &&
+              // Lab -> BGR tables ride behind the cube-root table (convert.cuh: init_tabs<BV_LAB2BGR>)
+              cudaMemcpy(ctx->d_lab_cbrt + kLabCbrtSize, kLabToYF, sizeof(kLabToYF), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(ctx->d_lab_cbrt + kLabCbrtSize + 512, kLabInvGammaTab, sizeof(kLabInvGammaTab), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(ctx->d_pow_quarter, pow_tab, sizeof(pow_tab), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         set_error("bv_create: table upload failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -9,8 +9,12 @@ struct SmemTabs {
     int sdiv[256];
     int hdiv[256];
     uint16_t gtab[kLabGammaSize];
-    uint16_t ctab[kLabCbrtSize];
+    uint16_t ctab[kLabCbrtSize];  // BV_LAB2BGR reuses these 6 KB for its own tables (lab_yf / lab_inv_gamma below)
 };
+// Lab -> BGR tables live in the ctab area: 256 x 2 u16 (y, fy) followed by the 4096-byte inverse gamma
+__device__ __forceinline__ const uint16_t *lab_yf(const SmemTabs &t) { return t.ctab; }
+__device__ __forceinline__ const uint8_t *lab_inv_gamma(const SmemTabs &t) { return reinterpret_cast<const uint8_t *>(t.ctab + 512); }
+static_assert(512 * 2 + kLabInvGammaSize <= kLabCbrtSize * 2, "Lab->BGR tables must fit the cube-root table's shared memory");
 
 template <int CODE>
 __device__ __forceinline__ void init_tabs(SmemTabs &t, const uint16_t *__restrict__ g_gamma,
@@ -25,6 +29,8 @@ __device__ __forceinline__ void init_tabs(SmemTabs &t, const uint16_t *__restric
         for (int i = threadIdx.x; i < kLabGammaSize; i += blockDim.x) t.gtab[i] = g_gamma[i];
         for (int i = threadIdx.x; i < kLabCbrtSize; i += blockDim.x) t.ctab[i] = g_cbrt[i];
     }
+    if (CODE == BV_LAB2BGR)  // the device buffer behind g_cbrt continues with (y, fy) and the inverse gamma table
+        for (int i = threadIdx.x; i < 512 + kLabInvGammaSize / 2; i += blockDim.x) t.ctab[i] = g_cbrt[kLabCbrtSize + i];
     __syncthreads();
 }
 
@@ -45,6 +51,8 @@ __device__ __forceinline__ void convert_px(int c0, int c1, int c2, bool vec, con
         hsv2bgr(c0, c1, c2, vec, o0, o1, o2);
     } else if (CODE == BV_BGR2HLS) {
         bgr2hls(c0, c1, c2, vec, o0, o1, o2);
+    } else if (CODE == BV_LAB2BGR) {
+        lab2bgr(c0, c1, c2, lab_yf(t), lab_inv_gamma(t), o0, o1, o2);
     } else if (CODE == BV_BGR2RGB) {
         o0 = c2;
         o1 = c1;

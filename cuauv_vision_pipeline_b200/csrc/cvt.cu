@@ -335,6 +335,7 @@ int cvt_in_range_impl(bv_ctx *ctx, const uint8_t *src, uint8_t *mask, size_t npx
         case BV_HSV2BGR: return launch_cvt_inrange<BV_HSV2BGR>(ctx, src, mask, npx, width, bd);
         case BV_BGR2HLS: return launch_cvt_inrange<BV_BGR2HLS>(ctx, src, mask, npx, width, bd);
         case BV_BGR2RGB: return launch_cvt_inrange<BV_BGR2RGB>(ctx, src, mask, npx, width, bd);
+        case BV_LAB2BGR: return launch_cvt_inrange<BV_LAB2BGR>(ctx, src, mask, npx, width, bd);
         default: set_error("bv_cvt_in_range: unknown conversion code %d", code); return BV_ERR_INVALID;
     }
 }
@@ -358,6 +359,7 @@ extern "C" int bv_cvt_color(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_de
         case BV_HSV2BGR: return launch_cvt<BV_HSV2BGR>(ctx, src_dev, dst_dev, planes_dev, npx, width);
         case BV_BGR2HLS: return launch_cvt<BV_BGR2HLS>(ctx, src_dev, dst_dev, planes_dev, npx, width);
         case BV_BGR2RGB: return launch_cvt<BV_BGR2RGB>(ctx, src_dev, dst_dev, planes_dev, npx, width);
+        case BV_LAB2BGR: return launch_cvt<BV_LAB2BGR>(ctx, src_dev, dst_dev, planes_dev, npx, width);
         case BV_GRAY2BGR: {
             BV_REQUIRE(dst_dev && !planes_dev, "GRAY2BGR writes dst_dev only");
             BV_LAUNCH(ctx, gray2bgr_kernel, grid_for(ctx, npx, 256, 8), 256, 0, src_dev, dst_dev, npx);

@@ -56,7 +56,8 @@ typedef enum bv_cvt_code {
     BV_HSV2BGR = 4,   /* float32 path of OpenCV incl. its 32-px vector/tail rounding rule  */
     BV_BGR2HLS = 5,
     BV_GRAY2BGR = 6,  /* 1 -> 3 channels                                                 */
-    BV_BGR2RGB = 7
+    BV_BGR2RGB = 7,
+    BV_LAB2BGR = 8    /* OpenCV's 8-bit fixed-point Lab2RGBinteger (utils/color.py:27-29 lab_to_bgr) */
 } bv_cvt_code;
 
 /* cv2.threshold types used by utils/color.py:124-201. */

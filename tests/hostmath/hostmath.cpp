@@ -31,6 +31,7 @@ int hm_convert(const uint8_t *src, uint8_t *dst, size_t npx, int width, int code
             case 3: bv::bgr2ycrcb(c0, c1, c2, o0, o1, o2); break;
             case 4: bv::hsv2bgr(c0, c1, c2, vec, o0, o1, o2); break;
             case 5: bv::bgr2hls(c0, c1, c2, vec, o0, o1, o2); break;
+            case 8: bv::lab2bgr(c0, c1, c2, kLabToYF, kLabInvGammaTab, o0, o1, o2); break;
             default: return -1;
         }
         dst[3 * p] = (uint8_t)o0;

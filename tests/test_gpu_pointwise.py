@@ -9,7 +9,7 @@ from oracle import cv_ops, synth
 pytestmark = pytest.mark.gpu
 
 CODES = [("bgr2hsv", cv2.COLOR_BGR2HSV), ("bgr2lab", cv2.COLOR_BGR2LAB), ("bgr2ycrcb", cv2.COLOR_BGR2YCrCb),
-         ("bgr2gray", cv2.COLOR_BGR2GRAY)]
+         ("bgr2gray", cv2.COLOR_BGR2GRAY), ("lab2bgr", cv2.COLOR_LAB2BGR)]
 
 
 @pytest.fixture(scope="module")
@@ -248,3 +248,17 @@ def test_warp_affine_general_matrix_dsize_and_border_value(ctx):
                           cv2.warpAffine(img, m, (123, 457), borderMode=cv2.BORDER_REPLICATE))
     sing = np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 5.0]])              # singular: cv2 uses D = 0
     assert np.array_equal(transform.warp_affine(img, sing), cv2.warpAffine(img, sing, (400, 300)))
+
+
+def test_lab_to_bgr_mirror_odd_shape_and_round_trip(ctx):
+    """utils/color.py:27-29 lab_to_bgr (P1): OpenCV's fixed-point Lab2RGBinteger, bit-exact incl. odd widths and planes."""
+    from cuauv_vision_pipeline_b200 import color
+    img = synth.gen_underwater(479, 641, 31)
+    lab = cv2.cvtColor(img, cv2.COLOR_BGR2LAB)
+    conv, planes = color.lab_to_bgr(lab)
+    ref = cv2.cvtColor(lab, cv2.COLOR_LAB2BGR)
+    assert np.array_equal(conv, ref)
+    for k in range(3):
+        assert np.array_equal(planes[k], ref[..., k])
+    rnd = synth.gen_random_bgr(77, 129, 2)                       # arbitrary (L, a, b) triples, out-of-gamut included
+    assert np.array_equal(color.lab_to_bgr(rnd)[0], cv2.cvtColor(rnd, cv2.COLOR_LAB2BGR))

@@ -37,7 +37,8 @@ def convert(hm, img, code, one=False):
 
 
 @pytest.mark.parametrize("name,code,cvc", [("hsv", 0, cv2.COLOR_BGR2HSV), ("lab", 1, cv2.COLOR_BGR2LAB),
-                                           ("gray", 2, cv2.COLOR_BGR2GRAY), ("ycrcb", 3, cv2.COLOR_BGR2YCrCb)])
+                                           ("gray", 2, cv2.COLOR_BGR2GRAY), ("ycrcb", 3, cv2.COLOR_BGR2YCrCb),
+                                           ("lab2bgr", 8, cv2.COLOR_LAB2BGR)])
 def test_device_math_all_colors(hm, name, code, cvc):
     img = synth.all_colors_image()
     assert np.array_equal(convert(hm, img, code, one=(code == 2)), cv2.cvtColor(img, cvc))
