@@ -97,3 +97,28 @@ binary_threshold_inv = _thresh("binary_inv")    # utils/color.py:140-153
 max_threshold = _thresh("trunc", 0)             # utils/color.py:156-169
 above_threshold = _thresh("tozero", 0)          # utils/color.py:172-185
 below_threshold = _thresh("tozero_inv", 0)      # utils/color.py:188-201
+
+
+def white_balance_bgr(bgr_img):
+    """utils/color.py:370-379: BGR -> LAB, shift the a and b planes so that their means sit at 128
+    (float32, then numpy's uint8 cast), LAB -> BGR.
+
+    The per-pixel update `lab_a -= a_avg - 128; astype(uint8)` depends on the pixel value only, so it
+    is a 256-entry table per plane, built here with the very numpy expressions of the reference (same
+    float32 subtraction, same cast, wrap-around included) and applied on the device between the two
+    conversions.  Tolerance (stated): the reference takes `np.mean` of a float32 plane, a pairwise
+    float32 sum whose last bits depend on the element order; the device mean is the exact integer sum
+    / N rounded to float32, which can differ by ~1e-5.  Since every pixel's fractional part after
+    the shift is the same, the table changes only if the mean lies within that distance of an integer:
+    then single entries move by 1 LSB in a / b."""
+    ctx = ctx_for(bgr_img)
+    lab = ctx.cvt_color(to_device(ctx, bgr_img), "bgr2lab")
+    means = ctx.channel_means(lab)                                  # exact sums / N, float64
+    lut = np.empty((3, 256), np.uint8)
+    lut[0] = np.arange(256, dtype=np.uint8)
+    for k in (1, 2):
+        plane = np.arange(256, dtype=np.float32)
+        plane -= np.float32(means[k]) - 128                         # utils/color.py:375-376
+        with np.errstate(invalid="ignore"):
+            lut[k] = plane.astype(np.uint8)                         # utils/color.py:378
+    return like_input(ctx, bgr_img, ctx.cvt_color(ctx.apply_lut(lab, lut), "lab2bgr"))

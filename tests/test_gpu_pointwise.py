@@ -262,3 +262,17 @@ def test_lab_to_bgr_mirror_odd_shape_and_round_trip(ctx):
         assert np.array_equal(planes[k], ref[..., k])
     rnd = synth.gen_random_bgr(77, 129, 2)                       # arbitrary (L, a, b) triples, out-of-gamut included
     assert np.array_equal(color.lab_to_bgr(rnd)[0], cv2.cvtColor(rnd, cv2.COLOR_LAB2BGR))
+
+
+@pytest.mark.parametrize("shape,seed", [((480, 640), 1), ((1242, 2208), 2), ((479, 641), 3)])
+def test_white_balance_bgr_vs_reference_expression(ctx, shape, seed):
+    """utils/color.py:370-379 (a11, P2).  Stated tolerance: identical unless the a / b mean lies within 1e-5 of an
+    integer (the reference's float32 pairwise mean vs the exact mean here); identical on these frames."""
+    from cuauv_vision_pipeline_b200 import color
+    img = synth.gen_underwater(shape[0], shape[1], seed)
+    lab_img = cv2.cvtColor(img, cv2.COLOR_BGR2LAB).astype(np.float32)
+    lab_l, lab_a, lab_b = cv2.split(lab_img)
+    lab_a -= np.mean(lab_a) - 128
+    lab_b -= np.mean(lab_b) - 128
+    ref = cv2.cvtColor(cv2.merge((lab_l, lab_a, lab_b)).astype(np.uint8), cv2.COLOR_LAB2BGR)
+    assert np.array_equal(color.white_balance_bgr(img), ref)
