@@ -29,6 +29,8 @@
 
 namespace bv {
 
+int hsi_run(bv_ctx *ctx, uint8_t *bgr, int batch, size_t npx);  // hsi.cu
+
 constexpr int kBalThreads = 256;
 constexpr int kBalWarps = kBalThreads / 32;
 
@@ -959,8 +961,28 @@ int convert_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
 int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int width, const bv_balance_params &prm,
                 int cvt_code, const BalOutputs &out, bv_balance_stats *stats_host, const ChunkHook *after_chunk) {
     if (prm.hsi_contrast_correct) {
-        set_error("colour balance: the HSI branch (color_balance.cpp:702-774) is not implemented");
-        return BV_ERR_UNSUPPORTED;
+        // color_balance.cpp:702-774 runs after every other stage, on the balanced frame: produce that
+        // frame with the remaining flags, correct it in place (hsi.cu), then convert / threshold it.
+        const size_t npx_ = (size_t)height * width;
+        uint8_t *bgr = out.balanced;
+        if (!bgr) {
+            BV_TRY(ensure_scratch(ctx, SCR_HSI_BGR, (size_t)batch * npx_ * 3));
+            bgr = (uint8_t *)ctx->scratch[SCR_HSI_BGR];
+        }
+        bv_balance_params rest = prm;
+        rest.hsi_contrast_correct = 0;
+        BalOutputs first;
+        memset(&first, 0, sizeof(first));
+        first.balanced = bgr;
+        for (int k = 0; k < 3; ++k) first.hi[k] = 255;
+        BV_TRY(balance_run(ctx, src, batch, height, width, rest, -1, first, stats_host, nullptr));
+        BV_TRY(hsi_run(ctx, bgr, batch, npx_));
+        if (out.converted || out.mask || out.mask_bits) {
+            BalOutputs second = out;
+            second.balanced = nullptr;
+            BV_TRY(convert_run(ctx, bgr, batch, height, width, cvt_code, second));
+        }
+        return BV_OK;
     }
     const bool tiled = prm.horizontal_blocks != 1 || prm.vertical_blocks != 1;
     const size_t npx = (size_t)height * width;

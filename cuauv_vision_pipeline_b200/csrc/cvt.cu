@@ -445,10 +445,8 @@ extern "C" int bv_color_distance_f32(bv_ctx *ctx, const uint8_t *const *planes_d
     return color_distance_launch(ctx, planes_dev, n, color_host, weights_host, use_host, 0.0, nullptr, nullptr, dists_dev);
 }
 
-extern "C" int bv_select_kth_f32(bv_ctx *ctx, const float *values_dev, size_t n, size_t k, float *value_host) {
-    BV_REQUIRE(ctx && values_dev && value_host, "null argument");
-    BV_REQUIRE(n > 0 && k < n, "k must be below n");
-    BV_CUDA(cudaSetDevice(ctx->device));
+namespace bv {
+int select_kth_f32(bv_ctx *ctx, const float *values_dev, size_t n, size_t k, float *value_host) {
     BV_TRY(ensure_scratch(ctx, SCR_MORPH_SE, 256 * sizeof(uint32_t)));
     uint32_t *d_hist = (uint32_t *)ctx->scratch[SCR_MORPH_SE];
     uint32_t prefix = 0, mask = 0, hist[256];
@@ -474,6 +472,15 @@ extern "C" int bv_select_kth_f32(bv_ctx *ctx, const float *values_dev, size_t n,
     memcpy(value_host, &u, sizeof(float));
     return BV_OK;
 }
+}  // namespace bv
+
+extern "C" int bv_select_kth_f32(bv_ctx *ctx, const float *values_dev, size_t n, size_t k, float *value_host) {
+    BV_REQUIRE(ctx && values_dev && value_host, "null argument");
+    BV_REQUIRE(n > 0 && k < n, "k must be below n");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    return bv::select_kth_f32(ctx, values_dev, n, k, value_host);
+}
+
 
 extern "C" int bv_apply_lut(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, size_t n_pixels, int channels,
                             const uint8_t *lut_host) {

@@ -88,8 +88,10 @@ int stage_run(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src, int ba
         uint8_t *mask;
         int height, width;
         bool all_done;
+        int calls;
         static int run(void *self, bv_ctx *c, int f0, int nf) {
             ChainPerChunk *h = (ChainPerChunk *)self;
+            h->calls++;
             const size_t fw = bits_frame_words(h->height, h->width), fpx = (size_t)h->height * h->width;
             bool done = false;
             BV_TRY(morph_bits_chain(c, h->bits + f0 * fw, h->dst_bits ? h->dst_bits + f0 * fw : nullptr,
@@ -98,7 +100,7 @@ int stage_run(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src, int ba
             h->all_done = h->all_done && done;
             return BV_OK;
         }
-    } per_chunk{desc, bits, want_label ? tmp : nullptr, mask, height, width, true};
+    } per_chunk{desc, bits, want_label ? tmp : nullptr, mask, height, width, true, 0};
     const bool tiled_bal = desc->do_balance && (desc->balance.horizontal_blocks != 1 || desc->balance.vertical_blocks != 1);
     const bool use_hook = desc->do_balance && !tiled_bal && bits_direct && desc->n_morph > 0;
     ChunkHook hook{&ChainPerChunk::run, &per_chunk};
@@ -111,7 +113,7 @@ int stage_run(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src, int ba
     if (!need_bits) return BV_OK;
     if (!bits_direct) BV_TRY(mask_to_bits(ctx, out.mask, bits, batch, height, width));
     bool chained = false;
-    if (use_hook && per_chunk.all_done) {  // the chunks already went through the chain
+    if (use_hook && per_chunk.calls > 0 && per_chunk.all_done) {  // the chunks already went through the chain
         chained = true;
         if (want_label) bits = tmp;
     } else if (desc->n_morph > 0) {

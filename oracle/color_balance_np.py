@@ -64,6 +64,94 @@ def equalize_lut(x_gain, adaptive):
     return constrain(x * x_gain)
 
 
+
+# ---------------------------------------------------------------------------------------------
+# HSI contrast branch (P2)
+# ---------------------------------------------------------------------------------------------
+f32 = np.float32
+f64 = np.float64
+PI = np.pi
+
+
+def uchar_clip(x):
+    """(int)f then clamp to 0..255; NaN / out-of-range float->int conversion gives INT_MIN on x86."""
+    x=np.asarray(x,dtype=np.float32)
+    bad=~np.isfinite(x) | (np.abs(x)>=2147483648.0)
+    n=np.where(bad, -2147483648, np.trunc(np.where(bad,0,x))).astype(np.int64)
+    return np.clip(n,0,255).astype(np.uint8)
+def clip_f(ch, lo, hi):
+    lo=f32(lo); hi=f32(hi)
+    out=ch.copy()
+    lt=ch<lo; gt=~lt&(ch>hi); nan=~lt&~gt&np.isnan(ch)
+    out[lt]=lo; out[gt]=hi; out[nan]=lo
+    return out
+def hsi_branch(b, g, r):
+    """color_balance.cpp:702-774 on flat uint8 planes (after the other stages); returns new (b, g, r).
+    Every float / double conversion follows the compiled reference (0 differing bytes against oracle/_ref on
+    frames of >= 128 k pixels; below that the reference's second quickselect starts at index (int)min_value and its
+    result depends on std::rand()).  cos / acos are the double-precision libm functions, as in the reference."""
+    n=b.size
+    rf,gf,bf=r.astype(f32),g.astype(f32),b.astype(f32)
+    I=((rf+gf).astype(f32)+bf).astype(f32).astype(f64)/3.0
+    I=I.astype(f32)
+    mn=np.minimum(np.minimum(r,g),b).astype(f32)
+    with np.errstate(all='ignore'):
+        S=np.where(I>0, (1.0-((mn/I).astype(f32).astype(f64))), 0.0).astype(f32)
+        num=rf.astype(f64)-(0.5*g.astype(f64))-(0.5*b.astype(f64))
+        ri,gi,bi=r.astype(np.int64),g.astype(np.int64),b.astype(np.int64)
+        # (float)r*r + (float)g*g + (float)b*b - (float)(r*g) - (float)(r*b) - (float)(g*b)  : float arithmetic
+        t=(rf*rf).astype(f32); t=(t+(gf*gf).astype(f32)).astype(f32); t=(t+(bf*bf).astype(f32)).astype(f32)
+        t=(t-(ri*gi).astype(f32)).astype(f32); t=(t-(ri*bi).astype(f32)).astype(f32); t=(t-(gi*bi).astype(f32)).astype(f32)
+        den=np.sqrt(t.astype(f64))
+        H=np.arccos(num/den).astype(f32)
+        H=np.where(b>g, (PI*2-H.astype(f64)).astype(f32), H)
+    H=clip_f(H,0.,2.*PI); S=clip_f(S,0.,1.); I=clip_f(I,0.,255.)
+    def pct(ch):
+        lo=int(f32(0.002)*f32(n)); hi=int(f32(0.998)*f32(n))
+        s=np.sort(ch)
+        return s[lo], s[hi]
+    smin,smax=pct(S); S=clip_f(S,smin,smax)
+    imin,imax=pct(I); I=clip_f(I,imin,imax)
+    with np.errstate(all='ignore'):
+        s_mult=f32(1.0/f64(f32(smax-smin)))       # 750-751: float subtraction, double division
+        i_mult=f32(255.0/f64(f32(imax-imin)))
+        S=((S-smin).astype(f32)*s_mult).astype(f32); I=((I-imin).astype(f32)*i_mult).astype(f32)
+    S=clip_f(S,0.,1.); I=clip_f(I,0.,255.)
+    h,s,i=H,S,I
+    hd,sd,idd=h.astype(f64),s.astype(f64),i.astype(f64)
+    def cosh(x32):   # cos(h) with float argument
+        return np.cos(x32.astype(f64))
+    is_ = (i*s).astype(f32)           # i * s float
+    ims = (i-is_).astype(f32)         # i - i*s
+    ip2 = (i+((f32(2)*i).astype(f32)*s).astype(f32)).astype(f32)   # i + 2*i*s
+    eps=1e-6
+    feq0=np.abs(h-f32(0))<eps
+    feq1=np.abs((h-f32(2.*PI/3.)).astype(f32))<eps
+    feq2=np.abs((h-f32(4.*PI/3.)).astype(f32))<eps
+    R=np.zeros(n,np.uint8);G=np.zeros(n,np.uint8);B=np.zeros(n,np.uint8)
+    with np.errstate(all='ignore'):
+        # sector 1
+        c1=cosh(h)/np.cos(PI/3.-hd); v1=is_.astype(f64)*c1
+        r1=uchar_clip((idd+v1).astype(f32)); g1=uchar_clip((idd+is_.astype(f64)*(1-c1)).astype(f32))
+        c2=np.cos(hd-2.*PI/3.)/np.cos(PI-hd)
+        g2=uchar_clip((idd+is_.astype(f64)*c2).astype(f32)); b2=uchar_clip((idd+is_.astype(f64)*(1-c2)).astype(f32))
+        c3=np.cos(hd-4.*PI/3.)/np.cos(5.*PI/3.-hd)
+        r3=uchar_clip((idd+is_.astype(f64)*(1-c3)).astype(f32)); b3=uchar_clip((idd+is_.astype(f64)*c3).astype(f32))
+    lo=uchar_clip(ims); hi_=uchar_clip(ip2)
+    m0=feq0
+    m1=~m0&(0.<hd)&(hd<2.*PI/3.)
+    m2=~m0&~m1&feq1
+    m3=~m0&~m1&~m2&(2.*PI/3.<hd)&(hd<4.*PI/3.)
+    m4=~m0&~m1&~m2&~m3&feq2
+    m5=~(m0|m1|m2|m3|m4)
+    R[m0]=hi_[m0];G[m0]=lo[m0];B[m0]=lo[m0]
+    R[m1]=r1[m1];G[m1]=g1[m1];B[m1]=lo[m1]
+    R[m2]=lo[m2];G[m2]=hi_[m2];B[m2]=lo[m2]
+    R[m3]=lo[m3];G[m3]=g2[m3];B[m3]=b2[m3]
+    R[m4]=lo[m4];G[m4]=lo[m4];B[m4]=hi_[m4]
+    R[m5]=r3[m5];G[m5]=lo[m5];B[m5]=b3[m5]
+    return B,G,R
+
 def process_frame_np(img, equalize_rgb=True, rgb_contrast_correct=False,
                      hsv_contrast_correct=True, hsi_contrast_correct=False,
                      rgb_extrema_clipping=True, adaptive_cast_correction=False,
@@ -72,8 +160,13 @@ def process_frame_np(img, equalize_rgb=True, rgb_contrast_correct=False,
     """Returns the balanced BGR image (new array).  `sequential_mean=True` reproduces the running
     mean of 459-470 literally (python loop: small frames only); otherwise the exact mean is used,
     which the running mean equals to <=1.2e-12."""
-    if hsi_contrast_correct:
-        raise NotImplementedError("HSI branch (color_balance.cpp:702-774) is out of scope")
+    if hsi_contrast_correct:                                               # 702-774: after every other stage
+        rest = process_frame_np(img, equalize_rgb, rgb_contrast_correct, hsv_contrast_correct, False, rgb_extrema_clipping,
+                                adaptive_cast_correction, horizontal_blocks, vertical_blocks, sequential_mean, return_stats)
+        base, st = rest if return_stats else (rest, None)
+        nb, ng, nr = hsi_branch(base[..., 0].reshape(-1), base[..., 1].reshape(-1), base[..., 2].reshape(-1))
+        out = np.stack([nb, ng, nr], axis=-1).reshape(base.shape)
+        return (out, st) if return_stats else out
     img = np.ascontiguousarray(img, dtype=np.uint8)
     height, width = img.shape[:2]
     n = height * width

@@ -118,8 +118,6 @@ def test_balance_unsupported_flags_fail_loudly(ctx):
     import cuauv_vision_pipeline_b200 as bv
     d = ctx.upload(synth.gen_underwater(64, 64, 1))
     with pytest.raises(bv.BVError):
-        ctx.color_balance(d, hsi_contrast_correct=True)
-    with pytest.raises(bv.BVError):
         ctx.color_balance(d, horizontal_blocks=3)       # 64 % 3 != 0: the reference walks off the row here
 
 
@@ -416,3 +414,22 @@ def test_stage_mask_only_many_bounds_reuse_and_evict_tables(ctx):
         fast = ctx.download(ctx.stage(desc, dev, want=("mask",))["mask"])
         full = ctx.download(ctx.stage(desc, dev, want=("mask", "converted"))["mask"])
         assert np.array_equal(fast, full), (lo, hi)
+
+
+@pytest.mark.parametrize("kind,shape,seed,flags", [("underwater", (480, 640), 7, {}), ("random", (480, 640), 4, dict(hsv_contrast_correct=False)),
+                                                   ("underwater", (1242, 2208), 6, dict(equalize_rgb=False, rgb_extrema_clipping=False)),
+                                                   ("underwater", (479, 641), 9, dict(rgb_contrast_correct=True))])
+def test_balance_hsi_branch(ctx, kind, shape, seed, flags):
+    """color_balance.cpp:702-774 (P2).  Stated tolerance <= 1 LSB (CUDA's double-precision acos / cos vs glibc's);
+    frames of >= 128 k pixels, where the reference's quickselect is deterministic."""
+    img = synth.gen_underwater(shape[0], shape[1], seed) if kind == "underwater" else synth.gen_random_bgr(shape[0], shape[1], seed)
+    want = oracle_balance(img, hsi_contrast_correct=True, **flags)
+    got = ctx.download(ctx.color_balance(ctx.upload(img), hsi_contrast_correct=True, **flags))
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert int(diff.max()) <= 1
+    assert int((diff != 0).sum()) <= 8, int((diff != 0).sum())
+    # the same through the fused stage with a conversion behind it
+    desc = ctx.make_stage(balance=dict(hsi_contrast_correct=True, **flags), cvt="bgr2hsv", lo=(0, 40, 60), hi=(179, 255, 255))
+    out = ctx.stage(desc, ctx.upload(img[None]), want=("balanced", "mask"))
+    assert np.array_equal(ctx.download(out["balanced"])[0], got)
+    assert np.array_equal(ctx.download(out["mask"])[0], cv2.inRange(cv2.cvtColor(got, cv2.COLOR_BGR2HSV), np.array([0, 40, 60]), np.array([179, 255, 255])))

@@ -66,3 +66,14 @@ def test_degenerate_sv_range_is_reported():
     img = np.full((32, 32, 3), 90, np.uint8)
     with pytest.raises(ZeroDivisionError):
         cb.process_frame_np(img)
+
+
+@pytest.mark.skipif(not ref_balance.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("kind,shape,seed,flags", [("underwater", (480, 640), 7, {}), ("random", (480, 640), 4, dict(hsv_contrast_correct=False)),
+                                                   ("underwater", (1242, 2208), 6, dict(equalize_rgb=False, rgb_extrema_clipping=False))])
+def test_hsi_branch_restatement_matches_compiled_reference(kind, shape, seed, flags):
+    """color_balance.cpp:702-774 (P2): float32 HSI planes, 0.2 % / 99.8 % order statistics, sector-wise HSI -> RGB."""
+    img = synth.gen_underwater(shape[0], shape[1], seed) if kind == "underwater" else synth.gen_random_bgr(shape[0], shape[1], seed)
+    want = ref_balance.balance(img, hsi_contrast_correct=True, **flags)
+    got = cb.process_frame_np(img, hsi_contrast_correct=True, **flags)
+    assert np.array_equal(got, want)
