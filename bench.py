@@ -266,8 +266,13 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = []
     if world > 1:
         torch.cuda.set_device(local)
+        # one process per GPU: stay on the CPUs next to that GPU so the pinned buffers of the end-to-end leg
+        # are allocated on its NUMA node (at N=1 the process keeps every core for the CPU baseline leg)
+        from cuauv_vision_pipeline_b200.sharding import bind_to_gpu_numa
+        numa_cpus = bind_to_gpu_numa(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = bv.Context(local)
     peak_gbs, peak_src = read_peaks()
@@ -400,7 +405,8 @@ def run_ours(args):
                        "frames_per_step_per_gpu": BATCH, "ring_frames": RING,
                        "l2": "inputs larger than L2 (131 MB per step from a 526 MB ring; consecutive steps use "
                              "different batches)",
-                       "parallelism": "frames sharded by index over %d GPU(s), no collective" % world},
+                       "parallelism": "frames sharded by index over %d GPU(s), no collective" % world,
+                       "host_affinity": ("%d CPUs local to each GPU" % len(numa_cpus)) if numa_cpus else "default"},
             "roofline": roofline, "stage_roofline": stage_roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks, "other_workloads": others,
         }

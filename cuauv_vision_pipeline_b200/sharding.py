@@ -52,3 +52,34 @@ def gather_detections(local: Dict[int, object], dst: int = 0):
     bucket = [None] * world if rank == dst else None
     dist.gather_object(local, bucket, dst=dst)
     return merge_in_order(bucket) if rank == dst else None
+
+
+def bind_to_gpu_numa(device_index: int) -> List[int]:
+    """Pin the calling process to the CPUs local to GPU `device_index` (its PCIe root's NUMA node), so that
+    pinned frame buffers allocated afterwards are first-touched on that node and host<->device copies do
+    not cross the socket interconnect.  One module process per camera stream / GPU
+    calls this once at start-up.  Returns the CPU list, [] when the topology cannot be read (nothing is
+    changed then)."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+        with open(path) as f:
+            text = f.read().strip()
+        cpus = []
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.extend(range(int(a), int(b) + 1))
+            elif part:
+                cpus.append(int(part))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return []
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001  (no sysfs, no permission, old torch: keep the default affinity)
+        return []
