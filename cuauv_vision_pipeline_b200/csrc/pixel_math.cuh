@@ -58,16 +58,13 @@ BV_HD void bgr2hsv(int b, int g, int r, const int *sdiv, const int *hdiv, int &h
     v = imax(imax(b, g), r);
     const int vmin = imin(imin(b, g), r);
     const int diff = v - vmin;
-    int hh;
-    if (v == r)
-        hh = g - b;
-    else if (v == g)
-        hh = b - r + 2 * diff;
-    else
-        hh = r - g + 4 * diff;
+    // branch-free selection (test order r, then g, then b as OpenCV does): a warp never diverges here
+    const int hr = g - b, hg = b - r + 2 * diff, hb = r - g + 4 * diff;
+    int hh = (v == g) ? hg : hb;
+    hh = (v == r) ? hr : hh;
     s = (diff * sdiv[v] + (1 << (kHsvShift - 1))) >> kHsvShift;
     hh = (hh * hdiv[diff] + (1 << (kHsvShift - 1))) >> kHsvShift;  // arithmetic shift
-    h = hh < 0 ? hh + 180 : hh;
+    h = hh + ((hh >> 31) & 180);                                    // hh < 0: += 180
 }
 
 // ------------------------------------------------------------------------------------------
