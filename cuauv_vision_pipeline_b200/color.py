@@ -23,8 +23,8 @@ def _convert_colorspace(code):
     return _inner
 
 
-# utils/color.py:26-32.  bgr_to_luv has no pinned arithmetic model (OpenCV's 8-bit path interpolates a
-# 33^3 table built with softfloat) and is not provided.
+# utils/color.py:26-32.  bgr_to_luv: OpenCV's 33^3 trilinear table, node table rebuilt with the host libm
+# (<= 1 LSB on 0.004 % of all colours, csrc/pixel_math.cuh).
 bgr_to_lab = _convert_colorspace("bgr2lab")
 bgr_to_hsv = _convert_colorspace("bgr2hsv")
 bgr_to_hls = _convert_colorspace("bgr2hls")
@@ -33,6 +33,7 @@ bgr_to_gray = _convert_colorspace("bgr2gray")
 gray_to_bgr = _convert_colorspace("gray2bgr")
 hsv_to_bgr = _convert_colorspace("hsv2bgr")
 lab_to_bgr = _convert_colorspace("lab2bgr")
+bgr_to_luv = _convert_colorspace("bgr2luv")
 
 
 def range_threshold(mat, min, max):  # noqa: A002 (reference argument names)

@@ -249,6 +249,7 @@ extern "C" void bv_destroy(bv_ctx *ctx) {
     if (ctx->d_lab_cbrt) cudaFree(ctx->d_lab_cbrt);
     if (ctx->d_pow_quarter) cudaFree(ctx->d_pow_quarter);
     if (ctx->lb_cache) free(ctx->lb_cache);
+    if (ctx->d_luv_tab) cudaFree(ctx->d_luv_tab);
     if (ctx->d_bilinear_tab) cudaFree(ctx->d_bilinear_tab);
     if (ctx->d_ivl_flag) cudaFree(ctx->d_ivl_flag);
     for (int i = 0; i < BV_IVL_SLOTS; ++i)

@@ -94,6 +94,7 @@ struct bv_ctx {
     size_t scratch_bytes[bv::SCR_COUNT];
     uint16_t *d_lab_gamma;  // 256
     uint16_t *d_lab_cbrt;   // 3072, then the Lab->BGR tables: 512 x u16 (y, fy) and 4096 x u8 inverse gamma
+    int16_t *d_luv_tab;     // 33^3 x 4 int16 nodes of BGR2LUV (cvt.cu), built on first use
     short *d_bilinear_tab;  // 32x32x4 int16 bilinear weights of cv::warpAffine / cv::remap (filter.cu), built on first use
     double *d_pow_quarter;  // 256: pow((255-x)/255, 0.25) from the host libm (adaptive cast correction)
     // host-memory pipeline (bv_stage_host): copy streams and per-chunk events

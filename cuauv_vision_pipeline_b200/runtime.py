@@ -15,7 +15,7 @@ from ._ffi import ffi, lib, check, BVError  # noqa: F401
 CVT = {
     "bgr2hsv": lib.BV_BGR2HSV, "bgr2lab": lib.BV_BGR2LAB, "bgr2gray": lib.BV_BGR2GRAY,
     "bgr2ycrcb": lib.BV_BGR2YCRCB, "hsv2bgr": lib.BV_HSV2BGR, "bgr2hls": lib.BV_BGR2HLS,
-    "gray2bgr": lib.BV_GRAY2BGR, "bgr2rgb": lib.BV_BGR2RGB, "lab2bgr": lib.BV_LAB2BGR,
+    "gray2bgr": lib.BV_GRAY2BGR, "bgr2rgb": lib.BV_BGR2RGB, "lab2bgr": lib.BV_LAB2BGR, "bgr2luv": lib.BV_BGR2LUV,
 }
 MORPH = {"erode": lib.BV_MORPH_ERODE, "dilate": lib.BV_MORPH_DILATE, "open": lib.BV_MORPH_OPEN,
          "close": lib.BV_MORPH_CLOSE, "gradient": lib.BV_MORPH_GRADIENT}

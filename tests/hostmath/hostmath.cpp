@@ -19,6 +19,12 @@ int hm_convert(const uint8_t *src, uint8_t *dst, size_t npx, int width, int code
         sdiv[i] = bv::hsv_sdiv(i);
         hdiv[i] = bv::hsv_hdiv(i);
     }
+    static int16_t luv_tab[bv::kLuvNodes * 4];
+    static bool luv_built = false;
+    if (code == 9 && !luv_built) {
+        bv::luv_build_table(luv_tab);
+        luv_built = true;
+    }
     const int vec_end = width - (width % 32);
     for (size_t p = 0; p < npx; ++p) {
         const int c0 = src[3 * p], c1 = src[3 * p + 1], c2 = src[3 * p + 2];
@@ -32,6 +38,7 @@ int hm_convert(const uint8_t *src, uint8_t *dst, size_t npx, int width, int code
             case 4: bv::hsv2bgr(c0, c1, c2, vec, o0, o1, o2); break;
             case 5: bv::bgr2hls(c0, c1, c2, vec, o0, o1, o2); break;
             case 8: bv::lab2bgr(c0, c1, c2, kLabToYF, kLabInvGammaTab, o0, o1, o2); break;
+            case 9: bv::bgr2luv(c0, c1, c2, luv_tab, o0, o1, o2); break;
             default: return -1;
         }
         dst[3 * p] = (uint8_t)o0;
@@ -40,6 +47,8 @@ int hm_convert(const uint8_t *src, uint8_t *dst, size_t npx, int width, int code
     }
     return 0;
 }
+
+void hm_luv_table(int16_t *out) { bv::luv_build_table(out); }
 
 void hm_hsv_tables(int *sdiv, int *hdiv) {
     for (int i = 0; i < 256; ++i) {

@@ -276,3 +276,20 @@ def test_white_balance_bgr_vs_reference_expression(ctx, shape, seed):
     lab_b -= np.mean(lab_b) - 128
     ref = cv2.cvtColor(cv2.merge((lab_l, lab_a, lab_b)).astype(np.uint8), cv2.COLOR_LAB2BGR)
     assert np.array_equal(color.white_balance_bgr(img), ref)
+
+
+def test_bgr2luv_within_stated_tolerance(ctx, all_colors):
+    """utils/color.py:30 bgr_to_luv / modules/preprocessor.py:76-80 (P1).  Stated tolerance <= 1 LSB on <= 0.01 % of all
+    2^24 colours (OpenCV's node table is filled by its softfloat pow / cubeRoot, ours by the host libm)."""
+    from cuauv_vision_pipeline_b200 import color
+    got = ctx.download(ctx.cvt_color(ctx.upload(all_colors), "bgr2luv")).astype(np.int16)
+    ref = cv2.cvtColor(all_colors, cv2.COLOR_BGR2LUV).astype(np.int16)
+    d = np.abs(got - ref)
+    assert int(d.max()) <= 1
+    assert int((d != 0).any(axis=2).sum()) <= 1700
+    img = synth.gen_underwater(479, 641, 5)
+    conv, planes = color.bgr_to_luv(img)
+    r2 = cv2.cvtColor(img, cv2.COLOR_BGR2LUV).astype(np.int16)
+    assert int(np.abs(conv.astype(np.int16) - r2).max()) <= 1
+    for k in range(3):
+        assert np.array_equal(planes[k], conv[..., k])
