@@ -53,6 +53,7 @@ enum ScratchSlot {
     SCR_BAL_STATE = 0,  // per-frame histograms, LUTs, stats of the colour balance
     SCR_BAL_TILES,      // per-tile histograms and tables (tiled equalisation)
     SCR_BAL_HSV,        // H,S,V image written by pass 2 and read by pass 3 (L2 resident per chunk)
+    SCR_WARP,           // per-column / per-row fixed-point coordinate terms of warpAffine
     SCR_HSI,            // float32 H, S, I planes of one frame (HSI contrast branch)
     SCR_HSI_BGR,        // balanced BGR frames the HSI branch works on when the caller does not want them
     SCR_BITS_A,         // bit-packed masks (ping)

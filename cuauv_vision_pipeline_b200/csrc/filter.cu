@@ -41,45 +41,65 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-template <int CN>
+// Threads are laid out (byte column, row): no index division inside the passes; NT > 0 unrolls the tap loops
+// for the common small kernels (3, 5, 7 taps), NT = 0 is the generic form.
+template <int CN, int NT>
 __global__ void __launch_bounds__(256) gaussian_blur_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int height,
                                                             int width, BlurTaps taps) {
     extern __shared__ __align__(16) uint8_t blur_smem[];
-    const int rx = taps.nx / 2, ry = taps.ny / 2;
+    const int nx = NT > 0 ? NT : taps.nx, ny = NT > 0 ? NT : taps.ny;
+    const int rx = nx / 2, ry = ny / 2;
     const int raw_w = (kBlurTileW + 2 * rx) * CN;         // bytes per staged row
     const int raw_h = kBlurTileH + 2 * ry;
-    const int hz_w = kBlurTileW * CN;                     // 16-bit values per row of the horizontal result
+    constexpr int hz_w = kBlurTileW * CN;                 // 16-bit values per row of the horizontal result
     uint8_t *raw = blur_smem;
     uint16_t *hz = reinterpret_cast<uint16_t *>(blur_smem + ((raw_w * raw_h + 15) & ~15));
     const int x0 = blockIdx.x * kBlurTileW, y0 = blockIdx.y * kBlurTileH;
     const size_t frame_off = (size_t)blockIdx.z * height * width * CN;
     const uint8_t *f = src + frame_off;
-    // stage rows y0-ry .. y0+TH+ry-1, columns x0-rx .. x0+TW+rx-1, reflected
-    for (int i = threadIdx.x; i < raw_w * raw_h; i += blockDim.x) {
-        const int r = i / raw_w, b = i - r * raw_w;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 byte-columns x 4 rows per step
+    // stage rows y0-ry .. y0+TH+ry-1, columns x0-rx .. x0+TW+rx-1, reflected (BORDER_REFLECT_101)
+    for (int b = tx; b < raw_w; b += 64) {
         const int px = b / CN, c = b - px * CN;
-        const int sy = reflect101(y0 - ry + r, height), sx = reflect101(x0 - rx + px, width);
-        raw[i] = f[((size_t)sy * width + sx) * CN + c];
+        const int sx = reflect101(x0 - rx + px, width);
+        for (int r = ty; r < raw_h; r += 4) {
+            const int sy = reflect101(y0 - ry + r, height);
+            raw[r * raw_w + b] = f[((size_t)sy * width + sx) * CN + c];
+        }
     }
     __syncthreads();
-    // horizontal pass: hz[r][x*CN + c] = sum_k kx[k] * raw[r][(x + k)*CN + c]      (8.8 in 16 bits)
-    for (int i = threadIdx.x; i < hz_w * raw_h; i += blockDim.x) {
-        const int r = i / hz_w, b = i - r * hz_w;
-        const uint8_t *p = raw + r * raw_w + b;
-        uint32_t acc = 0;
-        for (int k = 0; k < taps.nx; ++k) acc += (uint32_t)taps.kx[k] * p[k * CN];
-        hz[i] = (uint16_t)(acc > 0xFFFFu ? 0xFFFFu : acc);  // ufixedpoint16 saturates (never reached: taps sum to 256)
-    }
+    // horizontal pass: hz[r][b] = sum_k kx[k] * raw[r][b + k*CN]      (8.8 in 16 bits)
+    for (int b = tx; b < hz_w; b += 64)
+        for (int r = ty; r < raw_h; r += 4) {
+            const uint8_t *p = raw + r * raw_w + b;
+            uint32_t acc = 0;
+            if (NT > 0) {
+#pragma unroll
+                for (int k = 0; k < (NT > 0 ? NT : 1); ++k) acc += (uint32_t)taps.kx[k] * p[k * CN];
+            } else {
+                for (int k = 0; k < nx; ++k) acc += (uint32_t)taps.kx[k] * p[k * CN];
+            }
+            hz[r * hz_w + b] = (uint16_t)(acc > 0xFFFFu ? 0xFFFFu : acc);  // ufixedpoint16 saturates (never reached: taps sum to 256)
+        }
     __syncthreads();
     // vertical pass
-    for (int i = threadIdx.x; i < hz_w * kBlurTileH; i += blockDim.x) {
-        const int r = i / hz_w, b = i - r * hz_w;
-        const int y = y0 + r, x = x0 + b / CN;
-        if (y >= height || x >= width) continue;
-        uint32_t acc = 0;
-        for (int k = 0; k < taps.ny; ++k) acc += (uint32_t)taps.ky[k] * hz[(r + k) * hz_w + b];
-        const uint32_t v = (acc + (1u << 15)) >> 16;
-        dst[frame_off + ((size_t)y * width + x0) * CN + b] = (uint8_t)(v > 255u ? 255u : v);
+    for (int b = tx; b < hz_w; b += 64) {
+        const int x = x0 + b / CN;
+        if (x >= width) continue;
+        for (int r = ty; r < kBlurTileH; r += 4) {
+            const int y = y0 + r;
+            if (y >= height) break;
+            const uint16_t *p = hz + r * hz_w + b;
+            uint32_t acc = 0;
+            if (NT > 0) {
+#pragma unroll
+                for (int k = 0; k < (NT > 0 ? NT : 1); ++k) acc += (uint32_t)taps.ky[k] * p[k * hz_w];
+            } else {
+                for (int k = 0; k < ny; ++k) acc += (uint32_t)taps.ky[k] * p[k * hz_w];
+            }
+            const uint32_t v = (acc + (1u << 15)) >> 16;
+            dst[frame_off + ((size_t)y * width + x0) * CN + b] = (uint8_t)(v > 255u ? 255u : v);
+        }
     }
 }
 
@@ -136,21 +156,33 @@ __device__ __forceinline__ int sat_round_int(double v) {
     return __double2int_rn(v);  // cvRound: nearest even
 }
 
+// The fixed-point coordinate terms depend on the column (adelta, bdelta) or on the row (X0, Y0) only: OpenCV
+// tabulates them per call, and so does this kernel's small prologue launch (coords = [adelta | bdelta | X0 | Y0]).
+__global__ void __launch_bounds__(256) warp_coords_kernel(int *__restrict__ coords, int dst_w, int dst_h, WarpParams wp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double scale = 1024.;  // AB_SCALE = 1 << AB_BITS, AB_BITS = 10
+    const int round_delta = 1024 / 32 / 2;
+    if (i < dst_w) {
+        coords[i] = sat_round_int(__dmul_rn(__dmul_rn(wp.m[0], (double)i), scale));
+        coords[dst_w + i] = sat_round_int(__dmul_rn(__dmul_rn(wp.m[3], (double)i), scale));
+    }
+    if (i < dst_h) {
+        coords[2 * dst_w + i] = sat_round_int(__dmul_rn(__dadd_rn(__dmul_rn(wp.m[1], (double)i), wp.m[2]), scale)) + round_delta;
+        coords[2 * dst_w + dst_h + i] = sat_round_int(__dmul_rn(__dadd_rn(__dmul_rn(wp.m[4], (double)i), wp.m[5]), scale)) + round_delta;
+    }
+}
+
 template <int CN>
 __global__ void __launch_bounds__(256) warp_affine_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int height,
                                                           int width, int dst_h, int dst_w, WarpParams wp,
-                                                          const short *__restrict__ tab) {
+                                                          const short *__restrict__ tab, const int *__restrict__ coords) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= dst_w) return;
     const uint8_t *f = src + (size_t)blockIdx.z * height * width * CN;
     uint8_t *o = dst + ((size_t)blockIdx.z * dst_h * dst_w + (size_t)y * dst_w + x) * CN;
     constexpr int AB_BITS = 10, INTER_BITS = 5, TAB = 32;
-    const double scale = (double)(1 << AB_BITS);
-    const int round_delta = (1 << AB_BITS) / TAB / 2;
-    const int adelta = sat_round_int(__dmul_rn(__dmul_rn(wp.m[0], (double)x), scale));
-    const int bdelta = sat_round_int(__dmul_rn(__dmul_rn(wp.m[3], (double)x), scale));
-    const int X0 = sat_round_int(__dmul_rn(__dadd_rn(__dmul_rn(wp.m[1], (double)y), wp.m[2]), scale)) + round_delta;
-    const int Y0 = sat_round_int(__dmul_rn(__dadd_rn(__dmul_rn(wp.m[4], (double)y), wp.m[5]), scale)) + round_delta;
+    const int adelta = __ldg(coords + x), bdelta = __ldg(coords + dst_w + x);
+    const int X0 = __ldg(coords + 2 * dst_w + y), Y0 = __ldg(coords + 2 * dst_w + dst_h + y);
     const int X = (X0 + adelta) >> (AB_BITS - INTER_BITS), Y = (Y0 + bdelta) >> (AB_BITS - INTER_BITS);
     int sx = X >> INTER_BITS, sy = Y >> INTER_BITS;
     sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);  // saturate_cast<short>
@@ -175,8 +207,8 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const uint8_t *__restr
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int i = 0; i < 2; ++i) v[j][i] = (wp.border_constant && !inside[j][i]) ? wp.border_value[c] : (int)p[j][i][c];
-        const int s = v[0][0] * w00 + v[0][1] * w01 + v[1][0] * w10 + v[1][1] * w11;
-        o[c] = (uint8_t)sat_u8((s + (1 << 14)) >> 15);
+        const int s_ = v[0][0] * w00 + v[0][1] * w01 + v[1][0] * w10 + v[1][1] * w11;
+        o[c] = (uint8_t)sat_u8((s_ + (1 << 14)) >> 15);
     }
 }
 
@@ -242,13 +274,19 @@ extern "C" int bv_gaussian_blur(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *ds
         return BV_ERR_UNSUPPORTED;
     }
     dim3 grid((width + kBlurTileW - 1) / kBlurTileW, (height + kBlurTileH - 1) / kBlurTileH, batch);
+#define BV_BLUR(CN, NT)                                                                                                          \
+    do {                                                                                                                         \
+        if (smem > 48 * 1024)                                                                                                    \
+            BV_CUDA(cudaFuncSetAttribute(gaussian_blur_kernel<CN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        BV_LAUNCH(ctx, (gaussian_blur_kernel<CN, NT>), grid, 256, smem, src_dev, dst_dev, height, width, taps);                  \
+    } while (0)
+    const int nt = (ksize_x == ksize_y && (ksize_x == 3 || ksize_x == 5 || ksize_x == 7)) ? ksize_x : 0;
     if (channels == 3) {
-        if (smem > 48 * 1024) BV_CUDA(cudaFuncSetAttribute(gaussian_blur_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        BV_LAUNCH(ctx, gaussian_blur_kernel<3>, grid, 256, smem, src_dev, dst_dev, height, width, taps);
+        if (nt == 3) BV_BLUR(3, 3); else if (nt == 5) BV_BLUR(3, 5); else if (nt == 7) BV_BLUR(3, 7); else BV_BLUR(3, 0);
     } else {
-        if (smem > 48 * 1024) BV_CUDA(cudaFuncSetAttribute(gaussian_blur_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        BV_LAUNCH(ctx, gaussian_blur_kernel<1>, grid, 256, smem, src_dev, dst_dev, height, width, taps);
+        if (nt == 3) BV_BLUR(1, 3); else if (nt == 5) BV_BLUR(1, 5); else if (nt == 7) BV_BLUR(1, 7); else BV_BLUR(1, 0);
     }
+#undef BV_BLUR
     return BV_OK;
 }
 
@@ -288,10 +326,16 @@ extern "C" int bv_warp_affine(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_
     for (int i = 0; i < 6; ++i) wp.m[i] = M[i];
     wp.border_constant = border_mode == BV_BORDER_CONSTANT;
     for (int c = 0; c < channels; ++c) wp.border_value[c] = border_value_host ? border_value_host[c] : 0;
+    BV_TRY(ensure_scratch(ctx, SCR_WARP, sizeof(int) * 2 * ((size_t)dst_width + dst_height)));
+    int *coords = (int *)ctx->scratch[SCR_WARP];
+    const int longest = dst_width > dst_height ? dst_width : dst_height;
+    BV_LAUNCH(ctx, warp_coords_kernel, (longest + 255) / 256, 256, 0, coords, dst_width, dst_height, wp);
     dim3 grid((dst_width + 255) / 256, dst_height, batch);
     if (channels == 3)
-        BV_LAUNCH(ctx, warp_affine_kernel<3>, grid, 256, 0, src_dev, dst_dev, height, width, dst_height, dst_width, wp, ctx->d_bilinear_tab);
+        BV_LAUNCH(ctx, warp_affine_kernel<3>, grid, 256, 0, src_dev, dst_dev, height, width, dst_height, dst_width, wp,
+                  ctx->d_bilinear_tab, coords);
     else
-        BV_LAUNCH(ctx, warp_affine_kernel<1>, grid, 256, 0, src_dev, dst_dev, height, width, dst_height, dst_width, wp, ctx->d_bilinear_tab);
+        BV_LAUNCH(ctx, warp_affine_kernel<1>, grid, 256, 0, src_dev, dst_dev, height, width, dst_height, dst_width, wp,
+                  ctx->d_bilinear_tab, coords);
     return BV_OK;
 }
