@@ -5,7 +5,8 @@
 //   forward   I = (r+g+b)/3, S = 1 - min/I, H = acos((r - g/2 - b/2) / sqrt(r^2+g^2+b^2-rg-rb-gb)),
 //             2 pi - H when b > g; float32 planes, clipped to [0,2pi], [0,1], [0,255] (NaN -> lower bound)
 //   bounds    the 0.2 % / 99.8 % order statistics of S and of I (the reference's quickselect; its
-//             std::rand() pivots do not change the value it returns) -- radix select on the device
+//             std::rand() pivots do not change the value it returns) -- four radix selects at once on the
+//             device, no host round trip
 //   backward  clip to the bounds, stretch to [0,1] / [0,255], HSI -> RGB by sector, (int) cast, clamp
 // The float / double mix of every expression follows the compiled reference (restated and pinned in
 // oracle/color_balance_np.py::hsi_branch: 0 differing bytes against oracle/_ref).  Tolerance (stated):
@@ -19,8 +20,6 @@
 #include "balance.cuh"
 
 namespace bv {
-
-int select_kth_f32(bv_ctx *ctx, const float *values_dev, size_t n, size_t k, float *value_host);  // cvt.cu
 
 __device__ __forceinline__ float clip_f(float v, float lo, float hi) {  // clip_channel_f_helper, 47-62
     if (v < lo) return lo;
@@ -59,6 +58,94 @@ struct HsiBounds {
     float s_min, s_max, i_min, i_max, s_mult, i_mult;
 };
 
+// ---- the four order statistics (S and I, 0.2 % and 99.8 %) without leaving the device: radix select, 8 bits
+// per round; a round is one histogram pass over both planes (four histograms: each plane against its two
+// current prefixes) and a one-block step that narrows the four prefixes ----
+struct Select4 {
+    uint32_t prefix[4];  // S low, S high, I low, I high
+    uint32_t rank[4];    // rank of the wanted element among those matching the prefix
+    uint32_t hist[4][256];
+};
+
+__device__ __forceinline__ uint32_t float_key(float f) {  // order-preserving integer image of a float
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void select4_init_kernel(Select4 *st, uint32_t lo_k, uint32_t hi_k) {
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0;
+    if (threadIdx.x < 4) {
+        st->prefix[threadIdx.x] = 0;
+        st->rank[threadIdx.x] = (threadIdx.x & 1) ? hi_k : lo_k;
+    }
+}
+
+__global__ void __launch_bounds__(256) select4_hist_kernel(const float *__restrict__ S, const float *__restrict__ I, size_t n,
+                                                           Select4 *__restrict__ st, uint32_t mask, int shift) {
+    __shared__ uint32_t h[4][256];
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t p0 = st->prefix[0], p1 = st->prefix[1], p2 = st->prefix[2], p3 = st->prefix[3];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t ks = float_key(S[i]), ki = float_key(I[i]);
+        const uint32_t bs = (ks >> shift) & 0xFFu, bi = (ki >> shift) & 0xFFu;
+        if ((ks & mask) == p0) atomicAdd(&h[0][bs], 1u);
+        if ((ks & mask) == p1) atomicAdd(&h[1][bs], 1u);
+        if ((ki & mask) == p2) atomicAdd(&h[2][bi], 1u);
+        if ((ki & mask) == p3) atomicAdd(&h[3][bi], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x)
+        if ((&h[0][0])[i]) atomicAdd(&st->hist[0][0] + i, (&h[0][0])[i]);
+}
+
+// one block of 4 warps: warp j walks histogram j to the bin that holds rank[j]
+__global__ void select4_step_kernel(Select4 *st, int shift) {
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank = st->rank[j];
+    uint32_t before = 0;
+    int found = -1;
+    for (int base = 0; base < 256 && found < 0; base += 32) {
+        const uint32_t c = st->hist[j][base + lane];
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t hit = __ballot_sync(0xFFFFFFFFu, rank < before + incl);
+        if (hit) {
+            const int l = __ffs(hit) - 1;
+            const uint32_t excl = __shfl_sync(0xFFFFFFFFu, incl - c, l);
+            found = base + l;
+            rank -= before + excl;
+        } else {
+            before += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+    }
+    __syncwarp();
+    for (int b = lane; b < 256; b += 32) st->hist[j][b] = 0;  // ready for the next round
+    if (lane == 0) {
+        st->prefix[j] |= (uint32_t)(found < 0 ? 255 : found) << shift;
+        st->rank[j] = rank;
+    }
+}
+
+__global__ void hsi_bounds_kernel(const Select4 *st, HsiBounds *bd) {
+    float v[4];
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t k = st->prefix[j];
+        v[j] = __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+    }
+    bd->s_min = v[0];
+    bd->s_max = v[1];
+    bd->i_min = v[2];
+    bd->i_max = v[3];
+    bd->s_mult = (float)(1. / (double)__fsub_rn(v[1], v[0]));      // 750-751: float subtraction, double division
+    bd->i_mult = (float)(255. / (double)__fsub_rn(v[3], v[2]));
+}
+
 // (unsigned char) of uchar_clip(f, 0, 255), 156-165: (int)f, then clamp.  x86's cvttss2si yields
 // INT_MIN for NaN and out-of-range values, which clamps to 0.
 __device__ __forceinline__ uint8_t uchar_clip(float f) {
@@ -72,7 +159,8 @@ __device__ __forceinline__ bool feq(float a, float b) { return fabs((double)__fs
 
 __global__ void __launch_bounds__(256) hsi_backward_kernel(const float *__restrict__ H, const float *__restrict__ S,
                                                            const float *__restrict__ I, uint8_t *__restrict__ bgr, size_t n,
-                                                           HsiBounds bd) {
+                                                           const HsiBounds *__restrict__ bounds) {
+    const HsiBounds bd = *bounds;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const float two_pi_3 = (float)(2. * M_PI / 3.), four_pi_3 = (float)(4. * M_PI / 3.);
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
@@ -114,22 +202,27 @@ __global__ void __launch_bounds__(256) hsi_backward_kernel(const float *__restri
     }
 }
 
-// In-place HSI contrast correction of `batch` balanced BGR frames.
+// In-place HSI contrast correction of `batch` balanced BGR frames; everything stays on the stream (no host round trip).
 int hsi_run(bv_ctx *ctx, uint8_t *bgr, int batch, size_t npx) {
-    BV_TRY(ensure_scratch(ctx, SCR_HSI, sizeof(float) * 3 * npx));
+    BV_TRY(ensure_scratch(ctx, SCR_HSI, sizeof(float) * 3 * npx + sizeof(Select4) + sizeof(HsiBounds) + 64));
     float *H = (float *)ctx->scratch[SCR_HSI], *S = H + npx, *I = S + npx;
+    Select4 *sel = (Select4 *)(I + npx);
+    HsiBounds *bd = (HsiBounds *)(sel + 1);
     const int grid = grid_for(ctx, npx, 256, 8);
-    const size_t lo_k = (size_t)(int)(0.002f * (float)npx), hi_k = (size_t)(int)(0.998f * (float)npx);  // 145-146
+    size_t lo_k = (size_t)(int)(0.002f * (float)npx), hi_k = (size_t)(int)(0.998f * (float)npx);  // 145-146
+    if (lo_k >= npx) lo_k = npx - 1;
+    if (hi_k >= npx) hi_k = npx - 1;
     for (int f = 0; f < batch; ++f) {
         uint8_t *frame = bgr + (size_t)f * npx * 3;
         BV_LAUNCH(ctx, hsi_forward_kernel, grid, 256, 0, frame, H, S, I, npx);
-        HsiBounds bd;
-        BV_TRY(select_kth_f32(ctx, S, npx, lo_k < npx ? lo_k : npx - 1, &bd.s_min));
-        BV_TRY(select_kth_f32(ctx, S, npx, hi_k < npx ? hi_k : npx - 1, &bd.s_max));
-        BV_TRY(select_kth_f32(ctx, I, npx, lo_k < npx ? lo_k : npx - 1, &bd.i_min));
-        BV_TRY(select_kth_f32(ctx, I, npx, hi_k < npx ? hi_k : npx - 1, &bd.i_max));
-        bd.s_mult = (float)(1. / (double)(bd.s_max - bd.s_min));      // 750-751: float subtraction, double division
-        bd.i_mult = (float)(255. / (double)(bd.i_max - bd.i_min));
+        BV_LAUNCH(ctx, select4_init_kernel, 1, 256, 0, sel, (uint32_t)lo_k, (uint32_t)hi_k);
+        uint32_t mask = 0;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            BV_LAUNCH(ctx, select4_hist_kernel, grid, 256, 0, S, I, npx, sel, mask, shift);
+            BV_LAUNCH(ctx, select4_step_kernel, 1, 128, 0, sel, shift);
+            mask |= 0xFFu << shift;
+        }
+        BV_LAUNCH(ctx, hsi_bounds_kernel, 1, 1, 0, sel, bd);
         BV_LAUNCH(ctx, hsi_backward_kernel, grid, 256, 0, H, S, I, frame, npx, bd);
     }
     return BV_OK;
