@@ -433,3 +433,40 @@ def test_balance_hsi_branch(ctx, kind, shape, seed, flags):
     out = ctx.stage(desc, ctx.upload(img[None]), want=("balanced", "mask"))
     assert np.array_equal(ctx.download(out["balanced"])[0], got)
     assert np.array_equal(ctx.download(out["mask"])[0], cv2.inRange(cv2.cvtColor(got, cv2.COLOR_BGR2HSV), np.array([0, 40, 60]), np.array([179, 255, 255])))
+
+
+def test_two_module_threads_with_their_own_contexts(ctx):
+    """core/base.py:701-703: every module runs process() on its own worker thread, never the main thread; two modules
+    in one process (or two processes on one GPU) each own a context.  Both threads hammer the fused stage at once
+    (different descriptions, different frame sizes) and every result must equal the single-threaded one."""
+    import threading
+    import cuauv_vision_pipeline_b200 as bv
+    jobs = [(synth.gen_underwater(480, 640, 301), dict(balance={}, cvt="bgr2hsv", lo=(0, 40, 60), hi=(179, 255, 255), morph=[("open", 5, 5, 1)], label=True)),
+            (synth.gen_underwater(360, 512, 302), dict(balance={}, cvt="bgr2lab", lo=(0, 130, 0), hi=(255, 255, 255), morph=[("close", 3, 3, 1)], label=True))]
+    want = []
+    for img, kw in jobs:
+        out = ctx.stage_host(ctx.make_stage(**kw), img[None], want=("converted", "mask", "labels"))
+        want.append({k: out[k].copy() for k in ("converted", "mask", "labels")})
+    errors = []
+
+    def worker(i):
+        try:
+            c = bv.Context(0)
+            img, kw = jobs[i]
+            desc = c.make_stage(**kw)
+            for _ in range(25):
+                out = c.stage_host(desc, img[None], want=("converted", "mask", "labels"))
+                for k in ("converted", "mask", "labels"):
+                    if not np.array_equal(out[k], want[i][k]):
+                        errors.append((i, k))
+                        return
+            c.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in (0, 1, 0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
