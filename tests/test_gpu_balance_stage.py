@@ -470,3 +470,31 @@ def test_two_module_threads_with_their_own_contexts(ctx):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("batch,chunk_mb,side", [(7, 1, 3), (9, 1, 4), (5, 2, 2)])
+def test_stage_many_chunks_on_side_streams(ctx, batch, chunk_mb, side):
+    """Batches are cut into L2-sized chunks that run on side streams, with the morphology chain launched per chunk on the
+    chunk's stream: uneven chunk counts / sizes must give exactly the per-frame results (mask-only fast path and the
+    full-output path)."""
+    frames = np.stack([synth.gen_underwater(352, 512, 700 + i) for i in range(batch)])      # 0.54 MB per frame
+    dev = ctx.upload(frames)
+    desc = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=(0, 40, 60), hi=(179, 255, 255), morph=[("open", 5, 5, 1)], label=True)
+    try:
+        ctx.set_option("l2_chunk_mb", chunk_mb)
+        ctx.set_option("side_streams", side)
+        fast = ctx.stage(desc, dev, want=("mask", "labels", "blobs"), max_blobs=2048)
+        full = ctx.stage(desc, dev, want=("balanced", "converted", "mask", "labels"), max_blobs=2048)
+        fast_mask, fast_lab = ctx.download(fast["mask"]), ctx.download(fast["labels"])
+        bal, full_mask, full_lab = ctx.download(full["balanced"]), ctx.download(full["mask"]), ctx.download(full["labels"])
+    finally:
+        ctx.set_option("l2_chunk_mb", 0)
+        ctx.set_option("side_streams", 0)
+    for i in range(batch):
+        b_ref = oracle_balance(frames[i])
+        assert np.array_equal(bal[i], b_ref), i
+        m_ref = cv2.morphologyEx(cv2.inRange(cv2.cvtColor(b_ref, cv2.COLOR_BGR2HSV), np.array([0, 40, 60]), np.array([179, 255, 255])),
+                                 cv2.MORPH_OPEN, cv_ops.rect_kernel(5))
+        assert np.array_equal(fast_mask[i], m_ref) and np.array_equal(full_mask[i], m_ref), i
+        lab_ref = ccl.label_and_moments(m_ref)[1]
+        assert np.array_equal(fast_lab[i], lab_ref) and np.array_equal(full_lab[i], lab_ref), i
