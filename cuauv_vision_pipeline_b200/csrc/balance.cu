@@ -59,42 +59,77 @@ __device__ __forceinline__ int uchar_cast(double v) {
 // channel, sum_i clamp(i, lo, hi) * cnt[i]  (the numerator of cv::mean, 426-428).
 // ----------------------------------------------------------------------------------------------
 struct StatScratch {
-    unsigned long long warp_sum[kBalWarps];
-    uint32_t warp_cnt[kBalWarps];
+    unsigned long long warp_sum[3][kBalWarps];
+    uint32_t warp_cnt[3][kBalWarps];
+    uint32_t cnt_lo[3][kBalWarps], cnt_hi[3][kBalWarps];
 };
 
-__device__ void hist_stats_block(uint32_t c, size_t npx, long long low_bound, long long high_bound, StatScratch &sc,
-                                 int &lo, int &hi, unsigned long long &clipped_sum) {
+// N histograms at once (thread t owns bin t of each): the block-wide steps -- and their barriers --
+// are shared by the channels, which keeps this tail of the histogram kernels short (one block works
+// here while the rest of the machine waits for the tables).
+template <int N>
+__device__ void hist_stats_block(const uint32_t (&c)[N], size_t npx, long long low_bound, long long high_bound, StatScratch &sc,
+                                 int (&lo)[N], int (&hi)[N], unsigned long long (&clipped_sum)[N]) {
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    uint32_t incl = c;
+    uint32_t incl[N];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl += o;
+    for (int k = 0; k < N; ++k) {
+        incl[k] = c[k];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl[k], d);
+            if (lane >= d) incl[k] += o;
+        }
     }
     __syncthreads();  // protects sc from the previous call
-    if (lane == 31) sc.warp_cnt[wid] = incl;
+    if (lane == 31)
+#pragma unroll
+        for (int k = 0; k < N; ++k) sc.warp_cnt[k][wid] = incl[k];
     __syncthreads();
-    uint32_t before = 0;
 #pragma unroll
-    for (int w = 0; w < kBalWarps; ++w)
-        if (w < wid) before += sc.warp_cnt[w];
-    const long long prefix = (long long)before + incl;          // inclusive prefix sum
-    const long long suffix = (long long)npx - prefix + c;       // inclusive suffix sum
-    lo = __syncthreads_count(prefix <= low_bound);
-    hi = __syncthreads_count(suffix > high_bound) - 1;
-    if (lo > 255) lo = 255;
-    if (hi < 0) hi = 0;
-    const int cl = t < lo ? lo : (t > hi ? hi : t);
-    unsigned long long v = (unsigned long long)cl * c;
+    for (int k = 0; k < N; ++k) {
+        uint32_t before = 0;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
-    if (lane == 0) sc.warp_sum[wid] = v;
+        for (int w = 0; w < kBalWarps; ++w)
+            if (w < wid) before += sc.warp_cnt[k][w];
+        const long long prefix = (long long)before + incl[k];          // inclusive prefix sum
+        const long long suffix = (long long)npx - prefix + c[k];        // inclusive suffix sum
+        const uint32_t wl = __popc(__ballot_sync(0xFFFFFFFFu, prefix <= low_bound));
+        const uint32_t wh = __popc(__ballot_sync(0xFFFFFFFFu, suffix > high_bound));
+        if (lane == 0) {
+            sc.cnt_lo[k][wid] = wl;
+            sc.cnt_hi[k][wid] = wh;
+        }
+    }
     __syncthreads();
-    unsigned long long tot = 0;
+    unsigned long long v[N];
 #pragma unroll
-    for (int w = 0; w < kBalWarps; ++w) tot += sc.warp_sum[w];
-    clipped_sum = tot;
+    for (int k = 0; k < N; ++k) {
+        int l = 0, h = 0;
+#pragma unroll
+        for (int w = 0; w < kBalWarps; ++w) {
+            l += (int)sc.cnt_lo[k][w];
+            h += (int)sc.cnt_hi[k][w];
+        }
+        h -= 1;
+        if (l > 255) l = 255;
+        if (h < 0) h = 0;
+        lo[k] = l;
+        hi[k] = h;
+        const int cl = t < l ? l : (t > h ? h : t);
+        v[k] = (unsigned long long)cl * c[k];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_down_sync(0xFFFFFFFFu, v[k], d);
+        if (lane == 0) sc.warp_sum[k][wid] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < kBalWarps; ++w) tot += sc.warp_sum[k][w];
+        clipped_sum[k] = tot;
+    }
 }
 
 // float32 products truncated to int, exactly as color_balance.cpp:113-114
@@ -111,11 +146,11 @@ __device__ unsigned long long block_clipped_sum(uint32_t c, int lo, int hi, Stat
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
     __syncthreads();
-    if (lane == 0) sc.warp_sum[wid] = v;
+    if (lane == 0) sc.warp_sum[0][wid] = v;
     __syncthreads();
     unsigned long long tot = 0;
 #pragma unroll
-    for (int w = 0; w < kBalWarps; ++w) tot += sc.warp_sum[w];
+    for (int w = 0; w < kBalWarps; ++w) tot += sc.warp_sum[0][w];
     return tot;
 }
 
@@ -129,16 +164,19 @@ __device__ void stats_bgr_block(BalFrame &F, size_t npx, const bv_balance_params
     const int t = threadIdx.x;
     long long lb = 0, hb = 0;
     if (prm.rgb_extrema_clipping) percentile_limits(npx, lb, hb);
-    for (int c = 0; c < 3; ++c) {
-        const uint32_t cnt = __ldcg(&F.hist_bgr[c][t]);  // written by other blocks' atomics: read at L2
-        int lo, hi;
-        unsigned long long sum;
-        hist_stats_block(cnt, npx, lb, hb, sc, lo, hi, sum);
-        if (t == 0) {
-            s_lo[c] = lo;
-            s_hi[c] = hi;
-            s_avg[c] = (double)sum / (double)npx;
-        }
+    {
+        // written by other blocks' atomics: read at L2; the three loads are in flight together
+        const uint32_t cnt[3] = {__ldcg(&F.hist_bgr[0][t]), __ldcg(&F.hist_bgr[1][t]), __ldcg(&F.hist_bgr[2][t])};
+        int lo[3], hi[3];
+        unsigned long long sum[3];
+        hist_stats_block<3>(cnt, npx, lb, hb, sc, lo, hi, sum);
+        if (t == 0)
+            for (int c = 0; c < 3; ++c) {
+                s_lo[c] = lo[c];
+                s_hi[c] = hi[c];
+                s_avg[c] = (double)sum[c] / (double)npx;
+                s_local[c] = s_avg[c];  // a single tile is the frame itself: same histogram, same clipped sum
+            }
     }
     __syncthreads();
     if (t == 0) {
@@ -171,10 +209,12 @@ __device__ void stats_bgr_block(BalFrame &F, size_t npx, const bv_balance_params
     for (int tile = 0; tile < n_tiles; ++tile) {
         const uint32_t(*hist)[256] = tiles ? tiles[tile].hist : F.hist_bgr;
         uint8_t(*lut)[256] = tiles ? tiles[tile].lut : F.lut_bgr;
-        for (int c = 0; c < 3; ++c) {
-            // local mean of the clipped tile (459-470; exact sum instead of the running mean)
-            const unsigned long long sum = block_clipped_sum(__ldcg(&hist[c][t]), s_lo[c], s_hi[c], sc);
-            if (t == 0) s_local[c] = (double)sum / (double)tile_px;
+        if (tiles) {
+            for (int c = 0; c < 3; ++c) {
+                // local mean of the clipped tile (459-470; exact sum instead of the running mean)
+                const unsigned long long sum = block_clipped_sum(__ldcg(&hist[c][t]), s_lo[c], s_hi[c], sc);
+                if (t == 0) s_local[c] = (double)sum / (double)tile_px;
+            }
         }
         __syncthreads();
         if (t == 0) {
@@ -221,15 +261,16 @@ __device__ void stats_sv_block(BalFrame &F, size_t npx, StatScratch &sc) {
     const int t = threadIdx.x;
     long long lb, hb;
     percentile_limits(npx, lb, hb);
-    for (int c = 0; c < 2; ++c) {
-        const uint32_t cnt = __ldcg(&F.hist_sv[c][t]);
-        int l, h;
-        unsigned long long sum;
-        hist_stats_block(cnt, npx, lb, hb, sc, l, h, sum);
-        if (t == 0) {
-            lo[c] = l;
-            hi[c] = h;
-        }
+    {
+        const uint32_t cnt[2] = {__ldcg(&F.hist_sv[0][t]), __ldcg(&F.hist_sv[1][t])};
+        int l[2], h[2];
+        unsigned long long sum[2];
+        hist_stats_block<2>(cnt, npx, lb, hb, sc, l, h, sum);
+        if (t == 0)
+            for (int c = 0; c < 2; ++c) {
+                lo[c] = l[c];
+                hi[c] = h[c];
+            }
     }
     __syncthreads();
     if (t == 0) {
