@@ -498,3 +498,19 @@ def test_stage_many_chunks_on_side_streams(ctx, batch, chunk_mb, side):
         assert np.array_equal(fast_mask[i], m_ref) and np.array_equal(full_mask[i], m_ref), i
         lab_ref = ccl.label_and_moments(m_ref)[1]
         assert np.array_equal(fast_lab[i], lab_ref) and np.array_equal(full_lab[i], lab_ref), i
+
+
+@pytest.mark.parametrize("shape", [(270, 496), (479, 641), (64, 32), (33, 64)])
+def test_stage_mask_only_shapes_outside_the_hue_table_path(ctx, shape):
+    """Widths that are not a multiple of 32 (cv2's scalar HSV2BGR row tail rounds differently) or odd sizes take the
+    arithmetic pass; tiny frames take the table path with a single group per row: all equal the cv2 pipeline."""
+    frames = np.stack([synth.gen_underwater(shape[0], shape[1], 40 + s) for s in range(2)])
+    lo, hi = (10, 20, 60), (30, 100, 255)
+    desc = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=lo, hi=hi, morph=[("open", 3, 3, 1)], label=True)
+    out = ctx.stage(desc, ctx.upload(frames), want=("mask", "labels", "blobs"), max_blobs=1024)
+    mask, lab = ctx.download(out["mask"]), ctx.download(out["labels"])
+    for i in range(2):
+        hsv_ref = cv2.cvtColor(oracle_balance(frames[i]), cv2.COLOR_BGR2HSV)
+        m_ref = cv2.morphologyEx(cv2.inRange(hsv_ref, np.array(lo), np.array(hi)), cv2.MORPH_OPEN, cv_ops.rect_kernel(3))
+        assert np.array_equal(mask[i], m_ref)
+        assert np.array_equal(lab[i], ccl.label_and_moments(m_ref)[1])
