@@ -103,6 +103,114 @@ __global__ void __launch_bounds__(256) gaussian_blur_kernel(const uint8_t *__res
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// The common kernels (3, 5, 7 taps; rows a multiple of 4 bytes): the image row is handled as a byte
+// stream, a thread owns 4 consecutive output bytes.  Rows are staged with aligned 32-bit loads
+// (byte-wise only where the reflected border is involved), the horizontal taps are cut out of the few
+// staged words that hold them (all offsets are compile-time), the 16-bit horizontal results move as
+// 8-byte vectors, and the result leaves as one 32-bit store.
+// ----------------------------------------------------------------------------------------------
+constexpr int kFastTileWords = 64;   // 256 bytes of a row per block
+constexpr int kFastTileH = 32;
+
+template <int CN, int NT>
+__global__ void __launch_bounds__(256) gaussian_blur_fast_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int height,
+                                                                 int width, BlurTaps taps) {
+    constexpr int R = NT / 2;                 // taps each side
+    constexpr int HB = R * CN;                // halo in bytes
+    constexpr int HBW = (HB + 3) / 4;         // ... in whole words
+    constexpr int PAD = 4 * HBW - HB;         // bytes between the staged row's start and the first tap of byte 0
+    constexpr int RAW_W = kFastTileWords + 2 * HBW;
+    constexpr int RAW_H = kFastTileH + 2 * R;
+    constexpr int SPAN = 4 + (NT - 1) * CN;   // bytes the taps of 4 adjacent outputs cover
+    constexpr int NW = (PAD + SPAN + 3) / 4;  // words that hold them
+    __shared__ uint32_t raw[RAW_H][RAW_W];
+    __shared__ __align__(8) uint16_t hz[RAW_H][kFastTileWords * 4];
+    const int row_bytes = width * CN;
+    const int x0b = blockIdx.x * kFastTileWords * 4, y0 = blockIdx.y * kFastTileH;
+    const size_t frame_off = (size_t)blockIdx.z * height * row_bytes;
+    const uint8_t *f = src + frame_off;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    // ---- stage
+    for (int w = tx; w < RAW_W; w += 64) {
+        const int gb = x0b - 4 * HBW + 4 * w;  // byte offset of this word in the image row
+        const bool inside = gb >= 0 && gb + 4 <= row_bytes;
+        int sxb[4];
+        if (!inside) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = gb + j;
+                const int px = b >= 0 ? b / CN : -((-b + CN - 1) / CN);  // floor
+                const int c = b - px * CN;
+                sxb[j] = reflect101(px, width) * CN + c;
+            }
+        }
+        for (int r = ty; r < RAW_H; r += 4) {
+            const uint8_t *row = f + (size_t)reflect101(y0 - R + r, height) * row_bytes;
+            uint32_t v;
+            if (inside)
+                v = __ldg(reinterpret_cast<const uint32_t *>(row + gb));
+            else
+                v = (uint32_t)row[sxb[0]] | ((uint32_t)row[sxb[1]] << 8) | ((uint32_t)row[sxb[2]] << 16) | ((uint32_t)row[sxb[3]] << 24);
+            raw[r][w] = v;
+        }
+    }
+    __syncthreads();
+    // ---- horizontal pass: 4 outputs per thread and row
+    uint32_t kx[NT], ky[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+        kx[k] = taps.kx[k];
+        ky[k] = taps.ky[k];
+    }
+    for (int r = ty; r < RAW_H; r += 4) {
+        uint32_t wd[NW];
+#pragma unroll
+        for (int q = 0; q < NW; ++q) wd[q] = raw[r][tx + q];
+        uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int bi = PAD + j + k * CN;  // compile-time after unrolling
+                acc[j] += kx[k] * ((wd[bi >> 2] >> (8 * (bi & 3))) & 0xFFu);
+            }
+        // 8.8 values never exceed 255 * 256: no saturation needed (taps sum to 256)
+        *reinterpret_cast<uint2 *>(&hz[r][4 * tx]) = make_uint2(acc[0] | (acc[1] << 16), acc[2] | (acc[3] << 16));
+    }
+    __syncthreads();
+    // ---- vertical pass
+    const int ob = x0b + 4 * tx;  // first output byte of this thread in the row
+    if (ob >= row_bytes) return;
+    for (int r = ty; r < kFastTileH; r += 4) {
+        const int y = y0 + r;
+        if (y >= height) break;
+        uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            const uint2 h = *reinterpret_cast<const uint2 *>(&hz[r + k][4 * tx]);
+            acc[0] += ky[k] * (h.x & 0xFFFFu);
+            acc[1] += ky[k] * (h.x >> 16);
+            acc[2] += ky[k] * (h.y & 0xFFFFu);
+            acc[3] += ky[k] * (h.y >> 16);
+        }
+        uint32_t o = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t v = (acc[j] + (1u << 15)) >> 16;
+            o |= (v > 255u ? 255u : v) << (8 * j);
+        }
+        uint8_t *out = dst + frame_off + (size_t)y * row_bytes + ob;
+        if (ob + 4 <= row_bytes) {
+            *reinterpret_cast<uint32_t *>(out) = o;
+        } else {
+            for (int j = 0; ob + j < row_bytes; ++j) out[j] = (uint8_t)(o >> (8 * j));
+        }
+    }
+}
+
 // OpenCV's getGaussianKernelBitExact + getGaussianKernelFixedPoint_ED for 8.8 fixed point
 static int gaussian_taps_fixed(int n, double sigma, uint16_t *out) {
     static const double small[5][9] = {{1.},
@@ -281,6 +389,20 @@ extern "C" int bv_gaussian_blur(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *ds
         BV_LAUNCH(ctx, (gaussian_blur_kernel<CN, NT>), grid, 256, smem, src_dev, dst_dev, height, width, taps);                  \
     } while (0)
     const int nt = (ksize_x == ksize_y && (ksize_x == 3 || ksize_x == 5 || ksize_x == 7)) ? ksize_x : 0;
+    // word-wide path: rows (and so every frame) start 4-byte aligned
+    if (nt && ((size_t)width * channels) % 4 == 0 && (reinterpret_cast<uintptr_t>(src_dev) & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(dst_dev) & 3) == 0) {
+        dim3 fgrid((unsigned)(((size_t)width * channels + kFastTileWords * 4 - 1) / (kFastTileWords * 4)),
+                   (height + kFastTileH - 1) / kFastTileH, batch);
+#define BV_BLURF(CN, NT) BV_LAUNCH(ctx, (gaussian_blur_fast_kernel<CN, NT>), fgrid, 256, 0, src_dev, dst_dev, height, width, taps)
+        if (channels == 3) {
+            if (nt == 3) BV_BLURF(3, 3); else if (nt == 5) BV_BLURF(3, 5); else BV_BLURF(3, 7);
+        } else {
+            if (nt == 3) BV_BLURF(1, 3); else if (nt == 5) BV_BLURF(1, 5); else BV_BLURF(1, 7);
+        }
+#undef BV_BLURF
+        return BV_OK;
+    }
     if (channels == 3) {
         if (nt == 3) BV_BLUR(3, 3); else if (nt == 5) BV_BLUR(3, 5); else if (nt == 7) BV_BLUR(3, 7); else BV_BLUR(3, 0);
     } else {
