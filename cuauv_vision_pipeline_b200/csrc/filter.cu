@@ -286,7 +286,9 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const uint8_t *__restr
                                                           const short *__restrict__ tab, const int *__restrict__ coords) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= dst_w) return;
-    const uint8_t *f = src + (size_t)blockIdx.z * height * width * CN;
+    const size_t frame_bytes = (size_t)height * width * CN;
+    const uint8_t *f = src + (size_t)blockIdx.z * frame_bytes;
+    const bool words_ok = (reinterpret_cast<uintptr_t>(f) & 3) == 0;  // block-uniform
     uint8_t *o = dst + ((size_t)blockIdx.z * dst_h * dst_w + (size_t)y * dst_w + x) * CN;
     constexpr int AB_BITS = 10, INTER_BITS = 5, TAB = 32;
     const int adelta = __ldg(coords + x), bdelta = __ldg(coords + dst_w + x);
@@ -297,6 +299,36 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const uint8_t *__restr
     sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);
     const short *w = tab + ((Y & (TAB - 1)) * TAB + (X & (TAB - 1))) * 4;
     const int w00 = w[0], w01 = w[1], w10 = w[2], w11 = w[3];
+    // interior pixels (all four taps inside the image): the two taps of a row are 2*CN adjacent bytes; fetch them with
+    // aligned 32-bit loads and a funnel shift instead of one load per byte
+    if (words_ok && sx >= 0 && sy >= 0 && sx + 1 < width && sy + 1 < height) {
+        const size_t off0 = ((size_t)sy * width + sx) * CN, off1 = off0 + (size_t)width * CN;
+        if (off1 + 12 <= frame_bytes) {
+            uint32_t lo[2], hi[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const size_t off = j ? off1 : off0;
+                const uint32_t *a = reinterpret_cast<const uint32_t *>(f + (off & ~(size_t)3));
+                const uint32_t w0 = __ldg(a), w1 = __ldg(a + 1), w2 = CN == 3 ? __ldg(a + 2) : 0u;
+                const uint32_t sh = 8u * (uint32_t)(off & 3);
+                lo[j] = __funnelshift_r(w0, w1, sh);   // bytes off .. off+3
+                hi[j] = __funnelshift_r(w1, w2, sh);   // bytes off+4 .. off+7
+            }
+#pragma unroll
+            for (int c = 0; c < CN; ++c) {
+                int v[2][2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    v[j][0] = (int)((lo[j] >> (8 * c)) & 0xFFu);
+                    const int b1 = CN + c;  // byte index of the right tap's channel c
+                    v[j][1] = (int)(((b1 < 4 ? lo[j] >> (8 * b1) : hi[j] >> (8 * (b1 - 4)))) & 0xFFu);
+                }
+                const int s_ = v[0][0] * w00 + v[0][1] * w01 + v[1][0] * w10 + v[1][1] * w11;
+                o[c] = (uint8_t)sat_u8((s_ + (1 << 14)) >> 15);
+            }
+            return;
+        }
+    }
     const int xs[2] = {sx, sx + 1}, ys[2] = {sy, sy + 1};
     const uint8_t *p[2][2];
     bool inside[2][2];
