@@ -202,12 +202,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
         "{\n"
         ".reg .pred p;\n"
         "LB_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"  // suspends up to the hint instead of spinning
         "@p bra LB_DONE_%=;\n"
         "bra LB_WAIT_%=;\n"
         "LB_DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(phase)
+        "r"(phase), "r"(0x989680u)
         : "memory");
 }
 

@@ -309,11 +309,32 @@ __global__ void __launch_bounds__(kLbConsumers + 32) letterbox_tma_kernel(const 
                 const LbCoef cx = coef_from_words(q.x, q.y);
                 int v[3] = {pad, pad, pad};
                 if (cx.o0 >= 0) {
+                    if ((cx.o1 == cx.o0 + 3 || cx.w1 == 0) && cx.w0 >= 0 && cx.w1 >= 0) {
+                        // the two taps are 6 adjacent bytes (or the right one has weight 0): three aligned words per
+                        // staged row, a funnel shift to the tap's byte offset, one byte-permute + one 2-way dot
+                        // product per channel (weights as int16 pairs, pixels as bytes)
+                        const uint32_t wpack = (uint32_t)(uint16_t)cx.w0 | ((uint32_t)(uint16_t)cx.w1 << 16);
+                        const int a = cx.o0 & ~3;
+                        const uint32_t sh = 8u * (uint32_t)(cx.o0 & 3);
+                        int h[2][3];  // unsigned dot product: weights are 0..2048, pixels 0..255
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int h0 = r0[cx.o0 + c] * cx.w0 + r0[cx.o1 + c] * cx.w1;
-                        const int h1 = r1[cx.o0 + c] * cx.w0 + r1[cx.o1 + c] * cx.w1;
-                        v[c] = linear_vblend(h0, h1, cw0, cw1);
+                        for (int j = 0; j < 2; ++j) {
+                            const uint32_t *q = reinterpret_cast<const uint32_t *>((j ? r1 : r0) + a);
+                            const uint32_t q0 = q[0], q1 = q[1], q2 = q[2];
+                            const uint32_t lo = __funnelshift_r(q0, q1, sh), hi = __funnelshift_r(q1, q2, sh);  // bytes o0..o0+7
+                            h[j][0] = (int)__dp2a_lo(wpack, __byte_perm(lo, hi, 0x4430), 0u);  // (byte 0, byte 3)
+                            h[j][1] = (int)__dp2a_lo(wpack, __byte_perm(lo, hi, 0x4441), 0u);  // (byte 1, byte 4)
+                            h[j][2] = (int)__dp2a_lo(wpack, __byte_perm(lo, hi, 0x4452), 0u);  // (byte 2, byte 5)
+                        }
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) v[c] = linear_vblend(h[0][c], h[1][c], cw0, cw1);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int h0 = r0[cx.o0 + c] * cx.w0 + r0[cx.o1 + c] * cx.w1;
+                            const int h1 = r1[cx.o0 + c] * cx.w0 + r1[cx.o1 + c] * cx.w1;
+                            v[c] = linear_vblend(h0, h1, cw0, cw1);
+                        }
                     }
                 }
                 const float fr = norm[v[2]], fg = norm[v[1]], fb = norm[v[0]];
