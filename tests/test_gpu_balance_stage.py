@@ -418,7 +418,8 @@ def test_stage_mask_only_many_bounds_reuse_and_evict_tables(ctx):
 
 @pytest.mark.parametrize("kind,shape,seed,flags", [("underwater", (480, 640), 7, {}), ("random", (480, 640), 4, dict(hsv_contrast_correct=False)),
                                                    ("underwater", (1242, 2208), 6, dict(equalize_rgb=False, rgb_extrema_clipping=False)),
-                                                   ("underwater", (479, 641), 9, dict(rgb_contrast_correct=True))])
+                                                   ("underwater", (479, 641), 9, dict(rgb_contrast_correct=True)),
+                                                   ("underwater", (480, 640), 11, dict(horizontal_blocks=4, vertical_blocks=2))])
 def test_balance_hsi_branch(ctx, kind, shape, seed, flags):
     """color_balance.cpp:702-774 (P2).  Stated tolerance <= 1 LSB (CUDA's double-precision acos / cos vs glibc's);
     frames of >= 128 k pixels, where the reference's quickselect is deterministic."""
