@@ -81,3 +81,40 @@ def test_product_does_not_import_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "import cv2" not in src, f
+
+
+CABI_SRC = os.path.join(ROOT, "tests", "cabi", "example.c")
+
+
+def _build_c_example(libpath, out):
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), CABI_SRC,
+                           "-L", os.path.dirname(libpath), "-lb200vision", "-Wl,-rpath," + os.path.dirname(libpath), "-o", out])
+
+
+def test_header_is_plain_c99_and_a_c_caller_links(libpath, tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and a C program that uses the legacy symbol and the fused
+    host-buffer entry point links against the library (no C++ types, no CUDA headers on the caller's side)."""
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), CABI_SRC])
+    _build_c_example(libpath, str(tmp_path / "example"))
+
+
+@pytest.mark.gpu
+def test_c_caller_gets_the_reference_results(libpath, tmp_path):
+    """tests/cabi/example.c run as a process: process_frame (modules/color_balance.py:105-107) and the bins stage
+    (modules/bins.py:13-27) called from plain C give the reference's bytes."""
+    import cv2
+    import numpy as np
+    from oracle import synth, ref_balance, color_balance_np, cv_ops
+    exe = str(tmp_path / "example")
+    _build_c_example(libpath, exe)
+    img = synth.gen_underwater(480, 640, 4242)
+    raw, bal, mask = (str(tmp_path / n) for n in ("frame.raw", "bal.raw", "mask.raw"))
+    img.tofile(raw)
+    out = subprocess.run([exe, raw, "480", "640", bal, mask], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    want = ref_balance.balance(img) if ref_balance.available() else color_balance_np.process_frame_np(img)
+    assert np.array_equal(np.fromfile(bal, np.uint8).reshape(img.shape), want)
+    _, cleaned = cv_ops.bins_mask(img)
+    assert np.array_equal(np.fromfile(mask, np.uint8).reshape(480, 640), cleaned)
+    n_ref = cv2.connectedComponents(cleaned, connectivity=8)[0] - 1
+    assert out.stdout.split()[1] == str(n_ref)
