@@ -388,11 +388,12 @@ __global__ void __launch_bounds__(kBalThreads) hist_sv_kernel(const uint8_t *__r
     __shared__ StatScratch sc;
     const int frame = blockIdx.y;
     for (int i = threadIdx.x; i < kBalWarps * 512; i += blockDim.x) (&h[0][0][0])[i] = 0;
-    for (int i = threadIdx.x; i < 768; i += blockDim.x) (&lut[0][0])[i] = (&st[frame].lut_bgr[0][0])[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         sdiv[i] = hsv_sdiv(i);
         hdiv[i] = hsv_hdiv(i);
     }
+    grid_dependency_wait();  // pass 1 (the tables of this frame) is complete from here on
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) (&lut[0][0])[i] = (&st[frame].lut_bgr[0][0])[i];
     __syncthreads();
     const uint8_t *f = src + (size_t)frame * npx * 3;
     uint32_t(*hw)[256] = h[threadIdx.x >> 5];
@@ -500,17 +501,19 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
     __shared__ FinalSmem fs;
     __shared__ SmemTabs tabs;
     const int frame = blockIdx.y;
-    if (MODE == 1 || MODE == 2)
-        for (int i = threadIdx.x; i < 768; i += blockDim.x) (&fs.lut[0][0])[i] = (&st[frame].lut_bgr[0][0])[i];
-    if (MODE >= 2)
-        for (int i = threadIdx.x; i < 512; i += blockDim.x) (&fs.lut_sv[0][0])[i] = (&st[frame].lut_sv[0][0])[i];
     if (MODE == 2) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) {
             fs.sdiv[i] = hsv_sdiv(i);
             fs.hdiv[i] = hsv_hdiv(i);
         }
     }
-    init_tabs<CODE>(tabs, g_gamma, g_cbrt);  // ends with __syncthreads()
+    init_tabs<CODE>(tabs, g_gamma, g_cbrt);  // constant tables; ends with __syncthreads()
+    grid_dependency_wait();                  // the previous pass (frame tables, H,S,V scratch) is complete from here on
+    if (MODE == 1 || MODE == 2)
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) (&fs.lut[0][0])[i] = (&st[frame].lut_bgr[0][0])[i];
+    if (MODE >= 2)
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) (&fs.lut_sv[0][0])[i] = (&st[frame].lut_sv[0][0])[i];
+    __syncthreads();
     const size_t foff = (size_t)frame * npx;
     const uint8_t *f = src + (size_t)frame * src_stride;  // BGR frame, or pass 2's H,S,V scratch (MODE 3)
     const int vec_end = width - (width % 32);
@@ -958,8 +961,8 @@ static int launch_final(bv_ctx *ctx, const uint8_t *src, size_t src_stride, cons
     dim3 grid(bpf, batch);
     const bool need_mask = out.mask || out.mask_bits;
 #define BV_FINAL(V, M)                                                                                              \
-    BV_LAUNCH(ctx, (final_kernel<MODE, CODE, V, M>), grid, kBalThreads, 0, src, src_stride, st, npx, width, out,    \
-              ctx->d_lab_gamma, ctx->d_lab_cbrt)
+    BV_LAUNCH_PDL(ctx, (final_kernel<MODE, CODE, V, M>), grid, kBalThreads, 0, src, src_stride, st, npx, width, out, \
+                  ctx->d_lab_gamma, ctx->d_lab_cbrt)
     if (vec) {
         if (need_mask) BV_FINAL(true, true); else BV_FINAL(true, false);
     } else {
@@ -1100,9 +1103,9 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
             BV_LAUNCH(ctx, hist_bgr_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx, prm, ctx->d_pow_quarter);
         if (prm.hsv_contrast_correct) {
             if (vec)
-                BV_LAUNCH(ctx, hist_sv_kernel<true>, grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
+                BV_LAUNCH_PDL(ctx, hist_sv_kernel<true>, grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
             else
-                BV_LAUNCH(ctx, hist_sv_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
+                BV_LAUNCH_PDL(ctx, hist_sv_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
         }
         BalOutputs co = out;
         if (co.balanced) co.balanced += (size_t)f0 * npx * 3;

@@ -48,6 +48,30 @@ void set_error(const char *fmt, ...);  // thread-local message, api.cu
         BV_CUDA(cudaGetLastError());                                                               \
     } while (0)
 
+// Programmatic dependent launch: the kernel may start (and run its prologue up to bv::grid_dependency_wait())
+// while the previous kernel of the stream is still draining; everything it reads that the previous kernel wrote
+// must come after that wait.  Same counting / profiling / checking as BV_LAUNCH.
+#define BV_LAUNCH_PDL(ctx, kernel, grid, block, smem, ...)                                         \
+    do {                                                                                           \
+        if ((ctx)->prof) bv::prof_begin((ctx), #kernel);                                           \
+        cudaLaunchConfig_t cfg_;                                                                   \
+        memset(&cfg_, 0, sizeof(cfg_));                                                            \
+        cfg_.gridDim = (grid);                                                                     \
+        cfg_.blockDim = (block);                                                                   \
+        cfg_.dynamicSmemBytes = (smem);                                                            \
+        cfg_.stream = (ctx)->stream;                                                               \
+        cudaLaunchAttribute attr_[1];                                                              \
+        attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                          \
+        attr_[0].val.programmaticStreamSerializationAllowed = 1;                                   \
+        cfg_.attrs = attr_;                                                                        \
+        cfg_.numAttrs = (ctx)->prof ? 0 : 1;                                                       \
+        cudaError_t le_ = cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                          \
+        (ctx)->launches++;                                                                         \
+        if ((ctx)->prof) bv::prof_end((ctx));                                                      \
+        BV_CUDA(le_);                                                                              \
+        BV_CUDA(cudaGetLastError());                                                               \
+    } while (0)
+
 // ---- scratch slots ---------------------------------------------------------------------------
 enum ScratchSlot {
     SCR_BAL_STATE = 0,  // per-frame histograms, LUTs, stats of the colour balance
@@ -131,6 +155,10 @@ void prof_end(bv_ctx *ctx);
 
 // ---- device helpers --------------------------------------------------------------------------
 #if defined(__CUDACC__)
+
+// blocks until the previous kernel of the stream has completed and its writes are visible (no-op when the kernel
+// was not launched with BV_LAUNCH_PDL)
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // streaming 128-bit load that does not pollute L1
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
