@@ -123,3 +123,14 @@ def white_balance_bgr(bgr_img):
         with np.errstate(invalid="ignore"):
             lut[k] = plane.astype(np.uint8)                         # utils/color.py:378
     return like_input(ctx, bgr_img, ctx.cvt_color(ctx.apply_lut(lab, lut), "lab2bgr"))
+
+
+def white_balance_bgr_blur(bgr_img, kernel_size):
+    """utils/color.py:381-391: as white_balance_bgr, with the a / b means taken over a kernel_size box around every
+    pixel (cv2.blur, BORDER_REPLICATE).  Bit-exact: the box sums are integers, so the double-precision mean of
+    cv2.blur, the float32 shift and numpy's uint8 cast are reproduced operation for operation on the device."""
+    kernel_size //= 2
+    kernel_size = 2 * kernel_size + 1                                   # utils/color.py:382-383
+    ctx = ctx_for(bgr_img)
+    lab = ctx.cvt_color(to_device(ctx, bgr_img), "bgr2lab")
+    return like_input(ctx, bgr_img, ctx.cvt_color(ctx.lab_shift_local_mean(lab, kernel_size), "lab2bgr"))

@@ -88,6 +88,8 @@ enum ScratchSlot {
     SCR_CCL_AUX2,       // background row counts + frame-touching bitmap
     SCR_CCL_ROOTS,      // first pixel of every blob, raster order
     SCR_HULL,           // sorted vertices + hull stack per contour (minAreaRect)
+    SCR_NOISE_RAW,      // raw MT19937 words replayed for the Gaussian-noise step
+    SCR_NOISE_AUX,      // per-block accepted counts / offsets of the polar method
     SCR_MORPH_TMP,      // intermediate image of multi-step grey morphology
     SCR_MORPH_TMP2,
     SCR_MORPH_SE,       // structuring-element offsets

@@ -383,6 +383,48 @@ static void build_bilinear_tab(short *tab) {
         }
 }
 
+// ---- white_balance_bgr_blur (utils/color.py:381-391): a / b planes shifted by their local box mean -----------------
+// cv2.blur of a float32 plane (BORDER_REPLICATE) sums in double (exact here: the values are integers 0..255) and
+// returns float(sum * (1.0 / (k*k))).  Pass 1 keeps the horizontal window sums of a and b, pass 2 adds them down the
+// column, forms `a - (mean - 128)` in float32 as numpy does and casts like numpy's astype(uint8): truncate, wrap mod 256.
+__global__ void __launch_bounds__(256) box_rows_ab_kernel(const uint8_t *__restrict__ lab, uint2 *__restrict__ sums,
+                                                         int height, int width, int radius) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= width) return;
+    const size_t row = ((size_t)blockIdx.z * height + blockIdx.y) * width;
+    const uint8_t *p = lab + row * 3;
+    unsigned sa = 0, sb = 0;
+    for (int d = -radius; d <= radius; ++d) {
+        const int xx = min(max(x + d, 0), width - 1);
+        sa += p[xx * 3 + 1];
+        sb += p[xx * 3 + 2];
+    }
+    sums[row + x] = make_uint2(sa, sb);
+}
+
+__device__ __forceinline__ uint8_t numpy_f32_to_u8(float v) { return (uint8_t)((int)v & 255); }
+
+__global__ void __launch_bounds__(256) box_cols_shift_kernel(const uint8_t *__restrict__ lab, const uint2 *__restrict__ sums,
+                                                            uint8_t *__restrict__ out, int height, int width, int radius,
+                                                            double scale) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= width) return;
+    const int y = blockIdx.y;
+    const size_t frame = (size_t)blockIdx.z * height * width;
+    unsigned sa = 0, sb = 0;
+    for (int d = -radius; d <= radius; ++d) {
+        const int yy = min(max(y + d, 0), height - 1);
+        const uint2 s = sums[frame + (size_t)yy * width + x];
+        sa += s.x;
+        sb += s.y;
+    }
+    const size_t i = (frame + (size_t)y * width + x) * 3;
+    const float ma = (float)((double)sa * scale), mb = (float)((double)sb * scale);
+    out[i] = lab[i];
+    out[i + 1] = numpy_f32_to_u8(__fsub_rn((float)lab[i + 1], __fsub_rn(ma, 128.f)));
+    out[i + 2] = numpy_f32_to_u8(__fsub_rn((float)lab[i + 2], __fsub_rn(mb, 128.f)));
+}
+
 }  // namespace bv
 
 using namespace bv;
@@ -491,5 +533,21 @@ extern "C" int bv_warp_affine(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_
     else
         BV_LAUNCH(ctx, warp_affine_kernel<1>, grid, 256, 0, src_dev, dst_dev, height, width, dst_height, dst_width, wp,
                   ctx->d_bilinear_tab, coords);
+    return BV_OK;
+}
+
+extern "C" int bv_lab_shift_local_mean(bv_ctx *ctx, const uint8_t *lab_dev, uint8_t *dst_dev, int batch, int height, int width,
+                                       int ksize) {
+    BV_REQUIRE(ctx && lab_dev && dst_dev, "null argument");
+    BV_REQUIRE(batch > 0 && height > 0 && width > 0, "batch, height and width must be positive");
+    BV_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= 4095, "ksize must be odd and in 1..4095");  // 255 k^2 < 2^32
+    BV_REQUIRE(batch <= 65535 && height <= 65535, "image too large");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    BV_TRY(ensure_scratch(ctx, SCR_WARP, sizeof(uint2) * (size_t)batch * height * width));
+    uint2 *sums = (uint2 *)ctx->scratch[SCR_WARP];
+    dim3 grid((width + 255) / 256, height, batch);
+    BV_LAUNCH(ctx, box_rows_ab_kernel, grid, 256, 0, lab_dev, sums, height, width, ksize / 2);
+    BV_LAUNCH(ctx, box_cols_shift_kernel, grid, 256, 0, lab_dev, sums, dst_dev, height, width, ksize / 2,
+              1.0 / ((double)ksize * ksize));
     return BV_OK;
 }

@@ -3,9 +3,9 @@ the P0 steps: colour-space posts (51-86), colour balance (87-88), per-channel bi
 brightness (89-109), elliptical erode / dilate (120-129), resize (136-143).
 
 Gaussian blur (110-114), rotate (130-135) and translate (144-149) run on the device with OpenCV's
-8-bit fixed-point arithmetic (csrc/filter.cu).  Gaussian noise (115-119) draws from numpy's global
-random generator, which cannot be reproduced on the device: it raises NotImplementedError when
-enabled instead of silently doing something else.
+8-bit fixed-point arithmetic (csrc/filter.cu).  Gaussian noise (115-119) replays numpy's global
+legacy generator (MT19937 + polar method) on the device from numpy.random.get_state() and hands the
+advanced state back (csrc/noise.cu), so a seeded run matches the reference frame for frame.
 
 The frame is uploaded once and stays on the device across all enabled steps; the three point
 operations (bias, contrast, brightness) are folded on the host into one 256-entry table per
@@ -105,8 +105,7 @@ class Preprocessor:
                 k = self._opt("PPX_gaussian_blur_kernel") * 2 + 1
                 cur = ctx.gaussian_blur(cur, (k, k), 0)
             if self._opt("PPX_gaussian_noise") != 0:                         # 115-119
-                raise NotImplementedError("Gaussian noise draws from numpy's global generator (preprocessor.py:115-119): "
-                                          "not reproducible on the device, out of scope")
+                cur = ctx.add_gaussian_noise(cur, self._opt("PPX_gaussian_noise"))
             if self._opt("PPX_erode"):                                       # 120-124
                 k = self._opt("PPX_erode_kernel") * 2 + 1
                 cur = ctx.morph(cur, "erode", transform.elliptic_kernel(k, k))

@@ -358,6 +358,32 @@ class Context:
                                  {"constant": 0, "replicate": 1}[border], ffi.from_buffer("uint8_t[]", bv_)))
         return dst
 
+    def lab_shift_local_mean(self, lab, ksize):
+        """a, b of a uint8 LAB image minus (their ksize x ksize box mean - 128), numpy-cast to uint8 (white_balance_bgr_blur)."""
+        b, h, w, c = self._bhwc(lab)
+        if c != 3:
+            raise BVError(-1, "lab_shift_local_mean needs a 3-channel image")
+        dst = self.empty(tuple(lab.shape))
+        check(lib.bv_lab_shift_local_mean(self.handle, _u8ptr(lab), _u8ptr(dst), b, h, w, int(ksize)))
+        return dst
+
+    def add_gaussian_noise(self, src, sigma, random_state=None):
+        """clip(src + randn(*src.shape) * sigma, 0, 255).astype(uint8) with the values numpy's legacy generator would
+        draw: numpy's global one (as modules/preprocessor.py:115-119 uses) unless a RandomState is given.  The
+        generator is advanced exactly as numpy.random.randn would advance it."""
+        rs = np.random if random_state is None else random_state
+        name, key, pos, has_gauss, cached = rs.get_state()
+        if name != "MT19937":
+            raise BVError(-1, "add_gaussian_noise needs numpy's legacy MT19937 generator")
+        st = ffi.new("bv_mt19937_state *")
+        ffi.buffer(st.key)[:] = np.ascontiguousarray(key, dtype=np.uint32).tobytes()
+        st.pos, st.has_gauss, st.gauss = int(pos), int(has_gauss), float(cached)
+        dst = self.empty(tuple(src.shape))
+        check(lib.bv_add_gaussian_noise(self.handle, _u8ptr(src), _u8ptr(dst), src.numel(), float(sigma), st))
+        rs.set_state((name, np.frombuffer(ffi.buffer(st.key), dtype=np.uint32).copy(), int(st.pos), int(st.has_gauss),
+                      float(st.gauss)))
+        return dst
+
     def letterbox(self, images, out_h=640, out_w=640, pad=114, half=True, out=None):
         n = len(images)
         for im in images:

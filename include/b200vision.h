@@ -282,6 +282,28 @@ typedef enum bv_border_mode { BV_BORDER_CONSTANT = 0, BV_BORDER_REPLICATE = 1 } 
 int bv_warp_affine(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, int height, int width,
                    int channels, int dst_height, int dst_width, const double *m_host, int border_mode,
                    const uint8_t *border_value_host);
+/* The middle step of white_balance_bgr_blur (utils/color.py:381-391) on an 8-bit LAB image: a and b are moved by
+ * their local mean, `a - (cv2.blur(a, (ksize, ksize), BORDER_REPLICATE) - 128)` in float32, then cast the way
+ * numpy's astype(uint8) casts (truncation, wrap-around); L is copied.  The BGR2LAB before and the LAB2BGR after are
+ * bv_cvt_color calls.  Bit-exact (cv2.blur of a float plane sums in double, exact for 8-bit values). */
+int bv_lab_shift_local_mean(bv_ctx *ctx, const uint8_t *lab_dev, uint8_t *dst_dev, int batch, int height, int width,
+                            int ksize);
+
+/* Gaussian-noise step of the preprocessor (modules/preprocessor.py:115-119):
+ *   dst = clip(src + numpy.random.randn(n_values) * sigma, 0, 255).astype(uint8)
+ * with the values numpy's legacy global generator (MT19937 + polar method) would draw from `state`, which is
+ * numpy.random.get_state() in C form and is advanced exactly as numpy.random.randn advances it (hand it back with
+ * numpy.random.set_state).  Synchronous.  The random values go through the device's double-precision log, which
+ * may differ from the host libm's in the last bit of ~0.1 % of the values; a pixel changes only if its sum lies
+ * within that bit of an integer (stated tolerance: <= 1 LSB, expected on < 1e-10 of the pixels). */
+typedef struct bv_mt19937_state {
+    uint32_t key[624];
+    int32_t pos;
+    int32_t has_gauss;
+    double gauss;
+} bv_mt19937_state;
+int bv_add_gaussian_noise(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, size_t n_values, double sigma,
+                          bv_mt19937_state *state);
 
 /* ---- ZED auxiliary planes (capture_sources/zed.{py,cpp}, modules/poster.py, modules/record.py) ----- */
 /* Drop the alpha byte (cv2.cvtColor(RGBA2RGB), capture_sources/zed.py:49-50; zed.cpp:54-71). */

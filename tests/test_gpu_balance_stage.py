@@ -322,9 +322,62 @@ def test_preprocessor_mirror(ctx):
     ref2 = cv2.resize(ref2, (320, 200))
     ref2 = cv2.warpAffine(ref2, np.float32([[1, 0, 12], [0, 1, -7]]), (ref2.shape[1], ref2.shape[0]))
     assert np.array_equal(pp2.process(img)[0], ref2)
+    # Gaussian noise (115-119) sits between blur and erode; numpy's global generator, seeded, is replayed on the device
     pp2.options_dict["PPX_gaussian_noise"].value = 3
-    with pytest.raises(NotImplementedError):
-        pp2.process(img)
+    np.random.seed(2024)
+    got3 = pp2.process(img)[0]
+    after_ours = np.random.get_state()
+    np.random.seed(2024)
+    ref3 = cv2.GaussianBlur(img, (5, 5), 0)
+    noise = np.random.randn(*ref3.shape) * 3
+    ref3 = np.clip(ref3 + noise, 0., 255.).astype(np.uint8)
+    after_ref = np.random.get_state()
+    ref3 = cv2.warpAffine(ref3, cv2.getRotationMatrix2D((ref3.shape[1] / 2, ref3.shape[0] / 2), 10, 1), (ref3.shape[1], ref3.shape[0]),
+                          borderMode=cv2.BORDER_REPLICATE)
+    ref3 = cv2.resize(ref3, (320, 200))
+    ref3 = cv2.warpAffine(ref3, np.float32([[1, 0, 12], [0, 1, -7]]), (ref3.shape[1], ref3.shape[0]))
+    assert np.array_equal(got3, ref3)
+    assert np.array_equal(after_ours[1], after_ref[1]) and after_ours[2:4] == after_ref[2:4]
+
+
+def _noise_reference(img, sigma):
+    """modules/preprocessor.py:115-119, verbatim."""
+    noise = np.random.randn(*img.shape) * sigma
+    return np.clip(img + noise, 0., 255.).astype(np.uint8)
+
+
+@pytest.mark.parametrize("shape,sigma,pre", [((37, 53, 3), 12.5, 0), ((37, 53, 3), 4, 1), ((480, 640, 3), 7, 311),
+                                             ((1242, 2208, 3), 20, 0), ((1, 1, 1), 50, 1), ((1, 1, 1), 50, 0),
+                                             ((5, 7), 30, 2), ((1080, 1920, 3), 1, 623)])
+def test_gaussian_noise_replays_numpy_global_generator(ctx, shape, sigma, pre):
+    """Values: stated tolerance <= 1 LSB on at most 2 pixels (device log vs libm log, include/b200vision.h); the
+    generator state after the call (key, position, cached flag) is identical, the cached value to 1 ulp, and the
+    next draws of numpy agree."""
+    img = np.random.default_rng(5).integers(0, 256, shape, dtype=np.uint8)
+    np.random.seed(99)
+    if pre:
+        np.random.randn(pre)
+    start = np.random.get_state()
+    ref = _noise_reference(img, sigma)
+    after_ref = np.random.get_state()
+    next_ref = np.random.randn(4)
+    np.random.set_state(start)
+    got = ctx.download(ctx.add_gaussian_noise(ctx.upload(img), sigma))
+    after = np.random.get_state()
+    next_got = np.random.randn(4)
+    d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    assert int(d.max()) <= 1 and int((d != 0).sum()) <= 2
+    assert np.array_equal(after[1], after_ref[1]) and after[2:4] == after_ref[2:4]
+    assert after[4] == pytest.approx(after_ref[4], rel=4e-16, abs=0)
+    assert np.allclose(next_got, next_ref, rtol=4e-16, atol=0)
+    # an own RandomState instead of the global one; two consecutive calls continue the same stream
+    rs_ref, rs = np.random.RandomState(7), np.random.RandomState(7)
+    a = np.clip(img + rs_ref.randn(*img.shape) * sigma, 0., 255.).astype(np.uint8)
+    b = np.clip(a + rs_ref.randn(*img.shape) * sigma, 0., 255.).astype(np.uint8)
+    ga = ctx.add_gaussian_noise(ctx.upload(img), sigma, random_state=rs)
+    gb = ctx.download(ctx.add_gaussian_noise(ga, sigma, random_state=rs))
+    assert int((gb != b).sum()) <= 2
+    assert rs.get_state()[2:4] == rs_ref.get_state()[2:4] and np.array_equal(rs.get_state()[1], rs_ref.get_state()[1])
 
 
 def test_drop_in_modules(ctx):

@@ -278,6 +278,25 @@ def test_white_balance_bgr_vs_reference_expression(ctx, shape, seed):
     assert np.array_equal(color.white_balance_bgr(img), ref)
 
 
+@pytest.mark.parametrize("shape,ksize,seed", [((480, 640), 15, 1), ((1242, 2208), 31, 2), ((479, 641), 4, 3),
+                                              ((37, 53), 101, 4), ((64, 64), 1, 5)])
+def test_white_balance_bgr_blur_bit_exact(ctx, shape, ksize, seed):
+    """utils/color.py:381-391 (a11, P2), the reference's own expressions; kernels larger than the image and even
+    sizes (rounded up to odd by the reference) included."""
+    from cuauv_vision_pipeline_b200 import color
+    img = synth.gen_underwater(shape[0], shape[1], seed) if seed != 4 else synth.gen_random_bgr(shape[0], shape[1], seed)
+    k = 2 * (ksize // 2) + 1
+    lab_img = cv2.cvtColor(img, cv2.COLOR_BGR2LAB).astype(np.float32)
+    lab_l, lab_a, lab_b = cv2.split(lab_img)
+    lab_a_avg = cv2.blur(lab_a, (k, k), 0, borderType=cv2.BORDER_REPLICATE)
+    lab_b_avg = cv2.blur(lab_b, (k, k), 0, borderType=cv2.BORDER_REPLICATE)
+    lab_a -= lab_a_avg - 128
+    lab_b -= lab_b_avg - 128
+    with np.errstate(invalid="ignore"):
+        ref = cv2.cvtColor(cv2.merge((lab_l, lab_a, lab_b)).astype(np.uint8), cv2.COLOR_LAB2BGR)
+    assert np.array_equal(color.white_balance_bgr_blur(img, ksize), ref)
+
+
 def test_bgr2luv_within_stated_tolerance(ctx, all_colors):
     """utils/color.py:30 bgr_to_luv / modules/preprocessor.py:76-80 (P1).  Stated tolerance <= 1 LSB on <= 0.01 % of all
     2^24 colours (OpenCV's node table is filled by its softfloat pow / cubeRoot, ours by the host libm)."""

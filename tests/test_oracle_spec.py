@@ -159,3 +159,21 @@ def test_warp_affine_8u_model_vs_cv2():
     m = np.array([[0.8, 0.3, 10.5], [-0.2, 1.1, -4.25]])
     assert np.array_equal(S.warp_affine_8u(img, m, (150, 70), "constant", (7, 99, 200)),
                           cv2.warpAffine(img, m, (150, 70), borderValue=(7, 99, 200)))
+
+
+@pytest.mark.parametrize("seed,pre,n", [(1, 0, 1000), (2, 1, 1001), (3, 3, 7), (4, 0, 1), (5, 1, 1), (6, 311, 5883),
+                                        (7, 2, 60000)])
+def test_legacy_randn_replay_matches_numpy(seed, pre, n):
+    """The restated MT19937 + polar method (oracle/mt_gauss_np.py) gives numpy.random.randn's values and leaves
+    the generator state numpy leaves (key, position, cached second value), from aligned and unaligned positions,
+    with and without a cached value at the start."""
+    from oracle import mt_gauss_np
+    np.random.seed(seed)
+    if pre:
+        np.random.randn(pre)
+    state = np.random.get_state()
+    ref = np.random.randn(n)
+    after_ref = np.random.get_state()
+    got, after = mt_gauss_np.randn_replay(state, n)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(after[1], after_ref[1]) and tuple(after[2:]) == tuple(after_ref[2:])
