@@ -446,7 +446,7 @@ struct FinalSmem {
 // returns the balanced pixel packed as b | g<<8 | r<<16
 template <int MODE>
 __device__ __forceinline__ uint32_t balance_px(uint32_t b, uint32_t g, uint32_t r, bool vec, const FinalSmem &fs) {
-    if (MODE == 3) return hsv2bgr_packed((int)b, fs.lut_sv[0][g], fs.lut_sv[1][r], vec);  // (b, g, r) hold (h, s, v)
+    if (MODE == 3) return hsv2bgr_packed<true>((int)b, fs.lut_sv[0][g], fs.lut_sv[1][r], vec);  // (b, g, r) hold (h, s, v) of pass 2
     if (MODE >= 1) {
         b = fs.lut[0][b];
         g = fs.lut[1][g];
@@ -455,7 +455,7 @@ __device__ __forceinline__ uint32_t balance_px(uint32_t b, uint32_t g, uint32_t 
     if (MODE == 2) {
         int h, s, v;
         bgr2hsv((int)b, (int)g, (int)r, fs.sdiv, fs.hdiv, h, s, v);
-        return hsv2bgr_packed(h, fs.lut_sv[0][s], fs.lut_sv[1][v], vec);
+        return hsv2bgr_packed<true>(h, fs.lut_sv[0][s], fs.lut_sv[1][v], vec);
     }
     return b | (g << 8) | (r << 16);
 }

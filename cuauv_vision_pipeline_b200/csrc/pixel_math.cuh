@@ -91,30 +91,50 @@ BV_HD uint32_t byte_perm3(uint32_t w, uint32_t sel) {
 #endif
 }
 
+// kHueBelow180: the caller guarantees H < 180 (a hue this library computed itself), so the sector is < 6.
+template <bool kHueBelow180 = false>
 BV_HD uint32_t hsv2bgr_packed(int H, int S, int V, bool vector_path) {
     const float hscale = 6.f / 180.f;
     const float inv255 = 1.f / 255.f;
+#if defined(__CUDA_ARCH__)
+    // Same float32 operations as below, with the int <-> float conversions done on the FMA / ALU pipes instead of the
+    // conversion unit (7 of them per pixel otherwise): a byte n ORed into the mantissa of 2^23 is the float 2^23 + n, and
+    // fma(2^23 + n, c, -2^23 c) rounds n*c once, exactly like fmul(float(n), c) (2^23 c is exact); adding 2^23 with
+    // round-toward-zero leaves floor(x) in the low mantissa bits for 0 <= x < 2^23.
+    const float kTwo23 = 8388608.f;
+    const float h = __fmaf_rn(__uint_as_float(0x4B000000u | (uint32_t)H), hscale, -kTwo23 * hscale);
+    const float s = __fmaf_rn(__uint_as_float(0x4B000000u | (uint32_t)S), inv255, -kTwo23 * inv255);
+    const float v = __fmaf_rn(__uint_as_float(0x4B000000u | (uint32_t)V), inv255, -kTwo23 * inv255);
+    const float hfloor = __fadd_rz(h, kTwo23);
+    int sector = (int)(__float_as_uint(hfloor) & 15u);  // h <= 255 * 6/180 = 8.5
+    const float f = BV_FSUB(h, __fsub_rn(hfloor, kTwo23));
+#else
     const float h = BV_FMUL((float)H, hscale);
     const float s = BV_FMUL((float)S, inv255);
     const float v = BV_FMUL((float)V, inv255);
     int sector = (int)h;  // h >= 0: truncation == floor
     const float f = BV_FSUB(h, (float)sector);
-    if (sector >= 6) sector -= 6;  // H >= 180 is out of contract; stay inside the table
+#endif
+    if (!kHueBelow180 && sector >= 6) sector -= 6;  // H >= 180 is out of contract; stay inside the table
     const float fm = (sector & 1) ? f : BV_FSUB(1.f, f);
     const float ymax = BV_FMUL(v, 255.f);
     const float ymin = BV_FMUL(BV_FMUL(v, BV_FSUB(1.f, s)), 255.f);
     const float ymid = BV_FMUL(BV_FMUL(v, BV_FMA(-s, fm, 1.f)), 255.f);
-    uint32_t imax, imid, imin;
+    uint32_t w;
     if (vector_path) {  // values lie in [0, 255]: no saturation needed
-        imax = (uint32_t)BV_F2I_RZ(ymax);
-        imid = (uint32_t)BV_F2I_RZ(ymid);
-        imin = (uint32_t)BV_F2I_RZ(ymin);
+#if defined(__CUDA_ARCH__)
+        // truncated values sit in byte 0 of the three sums; byte 2 of a float in [2^23, 2^23 + 256) is zero
+        const uint32_t amax = __float_as_uint(__fadd_rz(ymax, kTwo23));
+        const uint32_t amid = __float_as_uint(__fadd_rz(ymid, kTwo23));
+        const uint32_t amin = __float_as_uint(__fadd_rz(ymin, kTwo23));
+        w = __byte_perm(__byte_perm(amax, amid, 0x2240), amin, 0x3410);
+#else
+        w = (uint32_t)BV_F2I_RZ(ymax) | ((uint32_t)BV_F2I_RZ(ymid) << 8) | ((uint32_t)BV_F2I_RZ(ymin) << 16);
+#endif
     } else {
-        imax = (uint32_t)sat_u8(BV_F2I_RN(ymax));
-        imid = (uint32_t)sat_u8(BV_F2I_RN(ymid));
-        imin = (uint32_t)sat_u8(BV_F2I_RN(ymin));
+        w = (uint32_t)sat_u8(BV_F2I_RN(ymax)) | ((uint32_t)sat_u8(BV_F2I_RN(ymid)) << 8) |
+            ((uint32_t)sat_u8(BV_F2I_RN(ymin)) << 16);
     }
-    const uint32_t w = imax | (imid << 8) | (imin << 16);
     // selector nibbles (r,g,b) -> index into (max=0, mid=1, min=2), one 10-bit field per sector:
     // s0 r=max g=mid b=min | s1 g=max r=mid b=min | s2 g=max b=mid r=min
     // s3 b=max g=mid r=min | s4 b=max r=mid g=min | s5 r=max b=mid g=min
@@ -144,9 +164,11 @@ BV_HD void bgr2lab(int b, int g, int r, const uint16_t *gtab, const uint16_t *ct
     const int fX = ctab[descale(R * 1777 + G * 1541 + B * 778, 12)];
     const int fY = ctab[descale(R * 871 + G * 2929 + B * 296, 12)];
     const int fZ = ctab[descale(R * 73 + G * 448 + B * 3575, 12)];
-    L = sat_u8(descale(296 * fY - 1336934, 15));
-    a = sat_u8(descale(500 * (fX - fY) + (128 << 15), 15));
-    bb = sat_u8(descale(200 * (fY - fZ) + (128 << 15), 15));
+    // OpenCV saturates these three; over all 2^24 inputs they stay inside L 0..255, a 42..226, b 20..223 on their own
+    // (tests/test_hostmath.py compares every colour with cv2), so the clamps are left out
+    L = descale(296 * fY - 1336934, 15);
+    a = descale(500 * (fX - fY) + (128 << 15), 15);
+    bb = descale(200 * (fY - fZ) + (128 << 15), 15);
 }
 
 // ------------------------------------------------------------------------------------------
