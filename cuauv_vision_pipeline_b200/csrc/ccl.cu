@@ -606,10 +606,47 @@ __global__ void __launch_bounds__(256) bg_outer_kernel(const uint32_t *__restric
     }
 }
 
-__device__ __forceinline__ bool bit_at(const uint32_t *fb, int wpr, int width, int height, int x, int y) {
-    if ((unsigned)x >= (unsigned)width || (unsigned)y >= (unsigned)height) return false;
-    return (fb[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
+// Copy of the bit mask laid out for the border walk.  Word (w, y + 1) holds the pixels 30w-1 .. 30w+30 of row y: 30 own
+// pixels and one neighbour on either side, zero outside the frame, so the three pixels x-1, x, x+1 always sit in one
+// word (no word-edge cases in the walk); rows -1 and `height` are stored as zero rows (no row checks either); and the
+// words of one 30-pixel column are contiguous in y, so the rows y-1, y, y+1 are three adjacent words and a walk stays
+// inside one 128-byte line for 32 rows.  A lone warp issues dependent instructions every ~5 cycles, so the walk is
+// bound by the instruction count of one step, which this layout roughly halves.
+constexpr unsigned kWalkPixelsPerWord = 30;
+
+__global__ void __launch_bounds__(256) walk_bits_kernel(const uint32_t *__restrict__ bits, uint32_t *__restrict__ walk,
+                                                        int height, int width, int wpr, int wcols, uint32_t total) {
+    const uint32_t rows = (uint32_t)height + 2, per_frame = (uint32_t)wcols * rows;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t f = i / per_frame, r = i - f * per_frame;
+        const uint32_t w = r / rows;
+        const int y = (int)(r - w * rows) - 1;
+        uint32_t v = 0;
+        if (y >= 0 && y < height) {
+            const uint32_t *row = bits + ((size_t)f * height + y) * wpr;
+            const int p = (int)(kWalkPixelsPerWord * w) - 1;  // first pixel of the word
+            if (p < 0) {
+                v = row[0] << 1;
+            } else {
+                const int i0 = p >> 5;
+                v = __funnelshift_r(row[i0], i0 + 1 < wpr ? row[i0 + 1] : 0u, p & 31);
+            }
+            const int valid = width - p;  // >= 2
+            if (valid < 32) v &= (1u << valid) - 1u;
+        }
+        walk[i] = v;
+    }
 }
+
+// the 8 neighbours of (x, y) as a mask over the direction codes 0..7 = E, NE, N, NW, W, SW, S, SE
+__device__ __forceinline__ uint32_t neighbours_at(const uint32_t *__restrict__ fw, unsigned rows, int x, int y) {
+    const unsigned w = (unsigned)x / kWalkPixelsPerWord, sh = (unsigned)x - kWalkPixelsPerWord * w;
+    const uint32_t *p = fw + (w * rows + (unsigned)y);  // rows are stored shifted down by one: p[0] is row y-1
+    const uint32_t top = (p[0] >> sh) & 7u, mid = (p[1] >> sh) & 7u, bot = (p[2] >> sh) & 7u;
+    return (mid >> 2) | ((__brev(top) >> 29) << 1) | ((mid & 1u) << 4) | (bot << 5);
+}
+
+constexpr int kContourLaneStride = 4;
 
 // WRITE = false: first walk (sums, counts, externality).  WRITE = true: second walk of the external
 // borders that got a slot in the point list, emitting the CHAIN_APPROX_SIMPLE vertices.
@@ -618,12 +655,16 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
                                                       const int *__restrict__ parent_bg, const uint32_t *__restrict__ outer,
                                                       const int *__restrict__ root_px, const int *__restrict__ n_blobs,
                                                       bv_contour *__restrict__ out, int max_contours, int height, int width,
-                                                      int wpr, int *__restrict__ points, int max_points) {
+                                                      int wpr, int wcols, int *__restrict__ points, int max_points) {
     const int f = blockIdx.y;
     const int n = min(n_blobs[f], max_contours);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    // one border per thread, but only every fourth lane takes one: a warp-wide load of 32 walks touches 32 different
+    // lines and every step waits for the slowest of them
+    if (threadIdx.x & (kContourLaneStride - 1)) return;
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) / kContourLaneStride;
     if (idx >= n) return;
-    const uint32_t *fb = bits + (size_t)f * height * wpr;
+    const unsigned rows = (unsigned)height + 2;
+    const uint32_t *fw = bits + (size_t)f * wcols * rows;  // walk_bits_kernel's copy
     bv_contour c;
     int *pts = nullptr;
     int x0, y0;
@@ -660,9 +701,10 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
     int bx0 = x0, bx1 = x0, by0 = y0, by1 = y0, npts = 1, nsimple = 1;
     int s = 4;
     bool found = false;
+    const uint32_t nb0 = neighbours_at(fw, rows, x0, y0);
     for (int k = 0; k < 7; ++k) {  // clockwise from W: NW, N, NE, E, SE, S, SW
         s = (s - 1) & 7;
-        if (bit_at(fb, wpr, width, height, x0 + dx(s), y0 + dy(s))) {
+        if ((nb0 >> s) & 1u) {
             found = true;
             break;
         }
@@ -679,13 +721,14 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
         npts = 0;
         nsimple = 0;
         for (;;) {
-            int nx, ny;
-            for (;;) {  // counter-clockwise, starting just after the direction we came from
-                s = (s + 1) & 7;
-                nx = cx + dx(s);
-                ny = cy + dy(s);
-                if (bit_at(fb, wpr, width, height, nx, ny)) break;
-            }
+            // counter-clockwise, starting just after the direction we came from: the three rows around (cx, cy) are
+            // fetched at once (independent loads), the first set neighbour is a rotate + find-first-set.  The pixel we
+            // came from is always set, so the search cannot come up empty.
+            const uint32_t nb = neighbours_at(fw, rows, cx, cy);
+            const int first = (s + 1) & 7;
+            s = (first + __ffs(((nb | (nb << 8)) >> first) & 0xFFu) - 1) & 7;
+            const int ddx = dx(s), ddy = dy(s);
+            const int nx = cx + ddx, ny = cy + ddy;
             if (s != prev_s) {
                 if (WRITE) {
                     pts[2 * nsimple] = cx;
@@ -696,10 +739,11 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
             }
             if (!WRITE) {
                 // polygon edge (cx,cy) -> (nx,ny)
-                const long long dxy = (long long)cx * ny - (long long)nx * cy;
+                // cross = cx*ny - nx*cy = cx*dy - cy*dx fits 32 bits for a unit step; the products go to 64
+                const int dxy = cx * ddy - cy * ddx;
                 a00 += dxy;
-                a10 += dxy * (cx + nx);
-                a01 += dxy * (cy + ny);
+                a10 += (long long)dxy * (cx + nx);
+                a01 += (long long)dxy * (cy + ny);
                 bx0 = min(bx0, cx); bx1 = max(bx1, cx); by0 = min(by0, cy); by1 = max(by1, cy);
             }
             ++npts;
@@ -795,13 +839,20 @@ int outer_contours_bits(bv_ctx *ctx, const uint32_t *bits, int batch, int height
               outer, height, width, wpr, batch);
     // label_bits_ex wrote the blob count to n_contours (or its own scratch when NULL)
     const int *nb = n_contours ? n_contours : (int *)ctx->scratch[SCR_CCL_AUX] + 2 * total_rows;
-    dim3 grid((max_contours + 127) / 128, batch);
-    BV_LAUNCH(ctx, contour_kernel<false>, grid, 128, 0, bits, inv, parent_bg, outer, root_px, nb, contours, max_contours,
-              height, width, wpr, nullptr, 0);
+    const int wcols = (width + (int)kWalkPixelsPerWord - 1) / (int)kWalkPixelsPerWord;
+    const size_t walk_words = (size_t)batch * wcols * (height + 2);
+    BV_REQUIRE(walk_words < 0xFFFFFFFFull, "frames too large for the contour walk");
+    BV_TRY(ensure_scratch(ctx, SCR_BITS_TILED, walk_words * 4));
+    uint32_t *walk = (uint32_t *)ctx->scratch[SCR_BITS_TILED];
+    BV_LAUNCH(ctx, walk_bits_kernel, grid_for(ctx, walk_words, 256, 8), 256, 0, bits, walk, height, width, wpr, wcols,
+              (uint32_t)walk_words);
+    dim3 grid((max_contours * kContourLaneStride + 127) / 128, batch);
+    BV_LAUNCH(ctx, contour_kernel<false>, grid, 128, 0, walk, inv, parent_bg, outer, root_px, nb, contours, max_contours,
+              height, width, wpr, wcols, nullptr, 0);
     if (points && max_points > 0) {
         BV_LAUNCH(ctx, contour_offsets_kernel, batch, 1024, 0, contours, nb, max_contours, max_points, n_points);
-        BV_LAUNCH(ctx, contour_kernel<true>, grid, 128, 0, bits, inv, parent_bg, outer, root_px, nb, contours, max_contours,
-                  height, width, wpr, points, max_points);
+        BV_LAUNCH(ctx, contour_kernel<true>, grid, 128, 0, walk, inv, parent_bg, outer, root_px, nb, contours, max_contours,
+                  height, width, wpr, wcols, points, max_points);
     }
     return BV_OK;
 }

@@ -185,10 +185,38 @@ __global__ void __launch_bounds__(128) min_area_rect_kernel(const bv_contour *__
         // private scratch: [sorted points (n_in) | hull stack (n_in + 1: the chain closes on its first point)]
         P2 *sorted = scratch + (size_t)frame * (2 * (size_t)max_points + max_contours) + 2 * (size_t)c.point_offset + ci;
         P2 *hull = sorted + n_in;
-        for (int i = 0; i < n_in; ++i) sorted[i] = src[i];
-        heap_sort(sorted, n_in);
+        // Akl-Toussaint: a point inside or on the quadrilateral of the four extreme points (left, top, right, bottom)
+        // cannot be a hull vertex, so only the extremes and the points strictly outside it are sorted (exact integer
+        // cross products).  A quadrilateral without area (collinear or single points) filters nothing.
+        P2 ext[4] = {src[0], src[0], src[0], src[0]};
+        for (int i = 1; i < n_in; ++i) {
+            const P2 p = src[i];
+            if (p.x < ext[0].x) ext[0] = p;
+            if (p.y < ext[1].y) ext[1] = p;
+            if (p.x > ext[2].x) ext[2] = p;
+            if (p.y > ext[3].y) ext[3] = p;
+        }
+        long long area2 = 0;
+        for (int k = 0; k < 4; ++k)
+            area2 += (long long)ext[k].x * ext[(k + 1) & 3].y - (long long)ext[(k + 1) & 3].x * ext[k].y;
+        int n_kept = 0;
+        if (area2 == 0 || n_in <= 8) {
+            for (int i = 0; i < n_in; ++i) sorted[n_kept++] = src[i];
+        } else {
+            for (int k = 0; k < 4; ++k) sorted[n_kept++] = ext[k];
+            for (int i = 0; i < n_in; ++i) {
+                const P2 p = src[i];
+                bool outside = false;
+                for (int k = 0; k < 4; ++k) {
+                    const long long c = cross3(ext[k], ext[(k + 1) & 3], p);
+                    outside |= area2 > 0 ? c < 0 : c > 0;
+                }
+                if (outside) sorted[n_kept++] = p;
+            }
+        }
+        heap_sort(sorted, n_kept);
         int n = 0;
-        for (int i = 0; i < n_in; ++i)
+        for (int i = 0; i < n_kept; ++i)
             if (n == 0 || sorted[i].x != sorted[n - 1].x || sorted[i].y != sorted[n - 1].y) sorted[n++] = sorted[i];
         int m = 0;
         if (n <= 2) {

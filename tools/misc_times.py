@@ -55,3 +55,12 @@ timed("minAreaRect of all contours (2 masks)", lambda: bv.runtime.check(bv.runti
     bv.runtime.ffi.cast("int32_t *", pts.data_ptr()), 2, 4096, 200000,
     bv.runtime.ffi.cast("bv_rrect *", ctx.empty((2, 4096, 24), torch.uint8).data_ptr()))), per=2)
 print("contours per mask:", ctx.download(nb).tolist())
+
+# per-kernel split of the contour call (library profiler, serialised launches)
+ctx.profile(True)
+for _ in range(5):
+    contours()
+prof = ctx.profile_dump()
+ctx.profile(False)
+for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+    print("   %-28s %3d launches/call  %8.1f us/call" % (k, v["launches"] // 5, v["ms"] * 1e3 / 5))
