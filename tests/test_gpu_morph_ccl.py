@@ -282,6 +282,16 @@ def test_outer_contours_noise(ctx, density):
     check_contours(synth.mask_random(150, 211, 21, density))
 
 
+@pytest.mark.parametrize("width", [1, 2, 29, 30, 31, 59, 60, 61, 64, 90, 91])
+@pytest.mark.parametrize("height", [1, 2, 33])
+def test_outer_contours_around_the_walk_word_edges(ctx, height, width):
+    """The border walk reads its own copy of the mask in words of 30 pixels + 1 neighbour on either side
+    (csrc/ccl.cu walk_bits_kernel): widths around the multiples of 30 and 32, one- and two-row frames, dense
+    noise (borders crossing every word edge) and a full frame."""
+    check_contours(synth.mask_random(height, width, 7 * width + height, 0.55))
+    check_contours(np.full((height, width), 255, np.uint8))
+
+
 def test_outer_contours_special_shapes(ctx):
     m = np.zeros((40, 70), np.uint8)
     m[3, 5] = 255                               # single pixel
