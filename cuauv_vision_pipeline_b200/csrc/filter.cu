@@ -280,24 +280,13 @@ __global__ void __launch_bounds__(256) warp_coords_kernel(int *__restrict__ coor
     }
 }
 
+// remapBilinear of OpenCV on uint8: taps (sx, sy) .. (sx + 1, sy + 1), weights from the 32 x 32 x 4 int16 table entry `frac`
+// (= fy * 32 + fx), (sum + 2^14) >> 15; outside taps take the border value (constant) or the nearest pixel (replicate).
 template <int CN>
-__global__ void __launch_bounds__(256) warp_affine_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int height,
-                                                          int width, int dst_h, int dst_w, WarpParams wp,
-                                                          const short *__restrict__ tab, const int *__restrict__ coords) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= dst_w) return;
-    const size_t frame_bytes = (size_t)height * width * CN;
-    const uint8_t *f = src + (size_t)blockIdx.z * frame_bytes;
-    const bool words_ok = (reinterpret_cast<uintptr_t>(f) & 3) == 0;  // block-uniform
-    uint8_t *o = dst + ((size_t)blockIdx.z * dst_h * dst_w + (size_t)y * dst_w + x) * CN;
-    constexpr int AB_BITS = 10, INTER_BITS = 5, TAB = 32;
-    const int adelta = __ldg(coords + x), bdelta = __ldg(coords + dst_w + x);
-    const int X0 = __ldg(coords + 2 * dst_w + y), Y0 = __ldg(coords + 2 * dst_w + dst_h + y);
-    const int X = (X0 + adelta) >> (AB_BITS - INTER_BITS), Y = (Y0 + bdelta) >> (AB_BITS - INTER_BITS);
-    int sx = X >> INTER_BITS, sy = Y >> INTER_BITS;
-    sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);  // saturate_cast<short>
-    sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);
-    const short *w = tab + ((Y & (TAB - 1)) * TAB + (X & (TAB - 1))) * 4;
+__device__ __forceinline__ void bilinear_sample(const uint8_t *__restrict__ f, size_t frame_bytes, bool words_ok, int height, int width,
+                                                int sx, int sy, int frac, const short *__restrict__ tab, const WarpParams &wp,
+                                                uint8_t *__restrict__ o) {
+    const short *w = tab + 4 * frac;
     const int w00 = w[0], w01 = w[1], w10 = w[2], w11 = w[3];
     // interior pixels (all four taps inside the image): the two taps of a row are 2*CN adjacent bytes; fetch them with
     // aligned 32-bit loads and a funnel shift instead of one load per byte
@@ -349,6 +338,104 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const uint8_t *__restr
             for (int i = 0; i < 2; ++i) v[j][i] = (wp.border_constant && !inside[j][i]) ? wp.border_value[c] : (int)p[j][i][c];
         const int s_ = v[0][0] * w00 + v[0][1] * w01 + v[1][0] * w10 + v[1][1] * w11;
         o[c] = (uint8_t)sat_u8((s_ + (1 << 14)) >> 15);
+    }
+}
+
+template <int CN>
+__global__ void __launch_bounds__(256) warp_affine_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int height,
+                                                          int width, int dst_h, int dst_w, WarpParams wp,
+                                                          const short *__restrict__ tab, const int *__restrict__ coords) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dst_w) return;
+    const size_t frame_bytes = (size_t)height * width * CN;
+    const uint8_t *f = src + (size_t)blockIdx.z * frame_bytes;
+    const bool words_ok = (reinterpret_cast<uintptr_t>(f) & 3) == 0;  // block-uniform
+    uint8_t *o = dst + ((size_t)blockIdx.z * dst_h * dst_w + (size_t)y * dst_w + x) * CN;
+    constexpr int AB_BITS = 10, INTER_BITS = 5, TAB = 32;
+    const int adelta = __ldg(coords + x), bdelta = __ldg(coords + dst_w + x);
+    const int X0 = __ldg(coords + 2 * dst_w + y), Y0 = __ldg(coords + 2 * dst_w + dst_h + y);
+    const int X = (X0 + adelta) >> (AB_BITS - INTER_BITS), Y = (Y0 + bdelta) >> (AB_BITS - INTER_BITS);
+    int sx = X >> INTER_BITS, sy = Y >> INTER_BITS;
+    sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);  // saturate_cast<short>
+    sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);
+    bilinear_sample<CN>(f, frame_bytes, words_ok, height, width, sx, sy, (Y & (TAB - 1)) * TAB + (X & (TAB - 1)), tab, wp, o);
+}
+
+// cv2.remap(INTER_LINEAR) on uint8.  FIXED: map1 = int16 (x, y) pairs, map2 = uint16 fy * 32 + fx (CV_16SC2 + CV_16UC1).
+// Otherwise map1 / map2 are float32 x / y planes, converted the way RemapInvoker converts them block by block:
+// cvRound(x * 32) in float32, integer part saturated to short, the two 5-bit fractions.
+template <int CN, bool FIXED>
+__global__ void __launch_bounds__(256) remap_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int height, int width,
+                                                    int dst_h, int dst_w, const void *__restrict__ map1, const void *__restrict__ map2,
+                                                    WarpParams wp, const short *__restrict__ tab) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dst_w) return;
+    const size_t frame_bytes = (size_t)height * width * CN;
+    const uint8_t *f = src + (size_t)blockIdx.z * frame_bytes;
+    const bool words_ok = (reinterpret_cast<uintptr_t>(f) & 3) == 0;  // block-uniform
+    uint8_t *o = dst + ((size_t)blockIdx.z * dst_h * dst_w + (size_t)y * dst_w + x) * CN;
+    const size_t i = (size_t)y * dst_w + x;
+    int sx, sy, frac;
+    if (FIXED) {
+        const short2 xy = __ldg(static_cast<const short2 *>(map1) + i);
+        sx = xy.x;
+        sy = xy.y;
+        frac = __ldg(static_cast<const unsigned short *>(map2) + i) & 1023;
+    } else {
+        const int X = __float2int_rn(__fmul_rn(__ldg(static_cast<const float *>(map1) + i), 32.f));
+        const int Y = __float2int_rn(__fmul_rn(__ldg(static_cast<const float *>(map2) + i), 32.f));
+        sx = X >> 5;
+        sy = Y >> 5;
+        sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);  // saturate_cast<short>
+        sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);
+        frac = (Y & 31) * 32 + (X & 31);
+    }
+    bilinear_sample<CN>(f, frame_bytes, words_ok, height, width, sx, sy, frac, tab, wp, o);
+}
+
+// cv2.initUndistortRectifyMap: for every destination pixel the normalised ray through the new camera (and rotation),
+// the radial / tangential distortion polynomial, the source pixel through the original camera.  All in float64 with
+// every product and sum rounded separately, in the order of oracle/spec_np.py::init_undistort_rectify_map (which matches
+// cv2 bit for bit on the reference's camera files).  Writes float32 maps (CV_32FC1) and / or the fixed-point pair that
+// cv2.undistort builds straight from the doubles (CV_16SC2 + CV_16UC1).
+struct UndistortParams {
+    double ir[9];       // inverse of (new camera matrix x rotation)
+    double k[8];        // k1 k2 p1 p2 k3 k4 k5 k6
+    double fx, fy, cx, cy;
+};
+
+__global__ void __launch_bounds__(256) undistort_maps_kernel(UndistortParams p, int width, int height, float *__restrict__ mapx,
+                                                             float *__restrict__ mapy, short2 *__restrict__ xy,
+                                                             unsigned short *__restrict__ frac) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= width) return;
+#define MUL(a, b) __dmul_rn((a), (b))
+#define ADD(a, b) __dadd_rn((a), (b))
+    const double u = (double)j, v = (double)i;
+    const double X = ADD(MUL(p.ir[0], u), ADD(MUL(p.ir[1], v), p.ir[2]));
+    const double Y = ADD(MUL(p.ir[3], u), ADD(MUL(p.ir[4], v), p.ir[5]));
+    const double W = ADD(MUL(p.ir[6], u), ADD(MUL(p.ir[7], v), p.ir[8]));
+    const double x = __ddiv_rn(X, W), y = __ddiv_rn(Y, W);
+    const double x2 = MUL(x, x), y2 = MUL(y, y);
+    const double r2 = ADD(x2, y2), _2xy = MUL(MUL(2.0, x), y);
+    const double k1 = p.k[0], k2 = p.k[1], p1 = p.k[2], p2 = p.k[3], k3 = p.k[4], k4 = p.k[5], k5 = p.k[6], k6 = p.k[7];
+    const double num = ADD(1.0, MUL(ADD(MUL(ADD(MUL(k3, r2), k2), r2), k1), r2));
+    const double den = ADD(1.0, MUL(ADD(MUL(ADD(MUL(k6, r2), k5), r2), k4), r2));
+    const double kr = __ddiv_rn(num, den);
+    const double xd = ADD(ADD(MUL(x, kr), MUL(p1, _2xy)), MUL(p2, ADD(r2, MUL(2.0, x2))));
+    const double yd = ADD(ADD(MUL(y, kr), MUL(p1, ADD(r2, MUL(2.0, y2)))), MUL(p2, _2xy));
+    const double us = ADD(MUL(p.fx, xd), p.cx), vs = ADD(MUL(p.fy, yd), p.cy);
+#undef MUL
+#undef ADD
+    const size_t o = (size_t)i * width + j;
+    if (mapx) {
+        mapx[o] = (float)us;
+        mapy[o] = (float)vs;
+    }
+    if (xy) {
+        const int iu = sat_round_int(us * 32.0), iv = sat_round_int(vs * 32.0);  // saturate_cast<int>(u * INTER_TAB_SIZE)
+        xy[o] = make_short2((short)(iu >> 5), (short)(iv >> 5));
+        frac[o] = (unsigned short)((iv & 31) * 32 + (iu & 31));
     }
 }
 
@@ -425,6 +512,17 @@ __global__ void __launch_bounds__(256) box_cols_shift_kernel(const uint8_t *__re
     out[i + 2] = numpy_f32_to_u8(__fsub_rn((float)lab[i + 2], __fsub_rn(mb, 128.f)));
 }
 
+static int ensure_bilinear_tab(bv_ctx *ctx) {
+    if (!ctx->d_bilinear_tab) {
+        short tab[32 * 32 * 4];
+        build_bilinear_tab(tab);
+        BV_CUDA(cudaMalloc(&ctx->d_bilinear_tab, sizeof(tab)));
+        BV_CUDA(cudaMemcpyAsync(ctx->d_bilinear_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
+        BV_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return BV_OK;
+}
+
 }  // namespace bv
 
 using namespace bv;
@@ -496,13 +594,7 @@ extern "C" int bv_warp_affine(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_
     BV_REQUIRE(border_mode == BV_BORDER_CONSTANT || border_mode == BV_BORDER_REPLICATE, "border mode must be constant or replicate");
     BV_REQUIRE(height <= 32767 && width <= 32767 && batch <= 65535 && dst_height <= 65535, "image too large");
     BV_CUDA(cudaSetDevice(ctx->device));
-    if (!ctx->d_bilinear_tab) {
-        static short tab[32 * 32 * 4];
-        build_bilinear_tab(tab);
-        BV_CUDA(cudaMalloc(&ctx->d_bilinear_tab, sizeof(tab)));
-        BV_CUDA(cudaMemcpyAsync(ctx->d_bilinear_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
-        BV_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
+    BV_TRY(ensure_bilinear_tab(ctx));
     WarpParams wp;
     memset(&wp, 0, sizeof(wp));
     // cv::warpAffine without WARP_INVERSE_MAP: invert the 2x3 matrix in double
@@ -549,5 +641,59 @@ extern "C" int bv_lab_shift_local_mean(bv_ctx *ctx, const uint8_t *lab_dev, uint
     BV_LAUNCH(ctx, box_rows_ab_kernel, grid, 256, 0, lab_dev, sums, height, width, ksize / 2);
     BV_LAUNCH(ctx, box_cols_shift_kernel, grid, 256, 0, lab_dev, sums, dst_dev, height, width, ksize / 2,
               1.0 / ((double)ksize * ksize));
+    return BV_OK;
+}
+
+extern "C" int bv_remap(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, int height, int width, int channels,
+                        int dst_height, int dst_width, const void *map1_dev, const void *map2_dev, int map_format, int border_mode,
+                        const uint8_t *border_value_host) {
+    BV_REQUIRE(ctx && src_dev && dst_dev && map1_dev && map2_dev, "null argument");
+    BV_REQUIRE(src_dev != dst_dev, "in-place remap is not supported");
+    BV_REQUIRE(batch > 0 && height > 0 && width > 0 && dst_height > 0 && dst_width > 0, "sizes must be positive");
+    BV_REQUIRE(channels == 1 || channels == 3, "channels must be 1 or 3");
+    BV_REQUIRE(map_format == BV_MAP_F32 || map_format == BV_MAP_FIXED, "map format must be BV_MAP_F32 or BV_MAP_FIXED");
+    BV_REQUIRE(border_mode == BV_BORDER_CONSTANT || border_mode == BV_BORDER_REPLICATE, "border mode must be constant or replicate");
+    BV_REQUIRE(height <= 32767 && width <= 32767 && batch <= 65535 && dst_height <= 65535, "image too large");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    BV_TRY(ensure_bilinear_tab(ctx));
+    WarpParams wp;
+    memset(&wp, 0, sizeof(wp));
+    wp.border_constant = border_mode == BV_BORDER_CONSTANT;
+    for (int c = 0; c < channels; ++c) wp.border_value[c] = border_value_host ? border_value_host[c] : 0;
+    dim3 grid((dst_width + 255) / 256, dst_height, batch);
+#define BV_REMAP(CN, FX)                                                                                                    \
+    BV_LAUNCH(ctx, (remap_kernel<CN, FX>), grid, 256, 0, src_dev, dst_dev, height, width, dst_height, dst_width, map1_dev, \
+              map2_dev, wp, ctx->d_bilinear_tab)
+    if (channels == 3) {
+        if (map_format == BV_MAP_FIXED) BV_REMAP(3, true); else BV_REMAP(3, false);
+    } else {
+        if (map_format == BV_MAP_FIXED) BV_REMAP(1, true); else BV_REMAP(1, false);
+    }
+#undef BV_REMAP
+    return BV_OK;
+}
+
+extern "C" int bv_undistort_maps(bv_ctx *ctx, const double *camera_matrix_host, const double *dist_coeffs_host, int n_dist,
+                                 const double *inv_new_camera_rot_host, int width, int height, float *mapx_dev, float *mapy_dev,
+                                 int16_t *map_xy_dev, uint16_t *map_frac_dev) {
+    BV_REQUIRE(ctx && camera_matrix_host && inv_new_camera_rot_host, "null argument");
+    BV_REQUIRE(n_dist == 0 || dist_coeffs_host, "null argument");
+    BV_REQUIRE(n_dist == 0 || n_dist == 4 || n_dist == 5 || n_dist == 8, "4, 5 or 8 distortion coefficients (k1 k2 p1 p2 [k3 [k4 k5 k6]])");
+    BV_REQUIRE(width > 0 && height > 0 && height <= 65535, "sizes must be positive");
+    BV_REQUIRE((mapx_dev && mapy_dev) || (map_xy_dev && map_frac_dev), "no output map given");
+    BV_REQUIRE((mapx_dev == nullptr) == (mapy_dev == nullptr) && (map_xy_dev == nullptr) == (map_frac_dev == nullptr),
+               "maps come in pairs");
+    BV_CUDA(cudaSetDevice(ctx->device));
+    UndistortParams p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < 9; ++i) p.ir[i] = inv_new_camera_rot_host[i];
+    for (int i = 0; i < n_dist; ++i) p.k[i] = dist_coeffs_host[i];
+    p.fx = camera_matrix_host[0];
+    p.fy = camera_matrix_host[4];
+    p.cx = camera_matrix_host[2];
+    p.cy = camera_matrix_host[5];
+    dim3 grid((width + 255) / 256, height);
+    BV_LAUNCH(ctx, undistort_maps_kernel, grid, 256, 0, p, width, height, mapx_dev, mapy_dev, reinterpret_cast<short2 *>(map_xy_dev),
+              map_frac_dev);
     return BV_OK;
 }

@@ -358,6 +358,47 @@ class Context:
                                  {"constant": 0, "replicate": 1}[border], ffi.from_buffer("uint8_t[]", bv_)))
         return dst
 
+    def remap(self, src, map1, map2, border="constant", border_value=(0, 0, 0)):
+        """cv2.remap(src, map1, map2, INTER_LINEAR, borderMode, borderValue) on uint8.  Device maps: two float32 [H,W]
+        planes (x, y) or int16 [H,W,2] + uint16 [H,W] (fixed point)."""
+        b, h, w, c = self._bhwc(src)
+        fixed = map1.dtype == torch.int16
+        if fixed:
+            if map1.dim() != 3 or map1.shape[2] != 2 or map2.dtype not in (torch.uint16, torch.int16) or tuple(map2.shape) != tuple(map1.shape[:2]):
+                raise BVError(-1, "fixed-point maps are int16 [H,W,2] + uint16 [H,W]")
+        elif map1.dtype != torch.float32 or map2.dtype != torch.float32 or map1.dim() != 2 or tuple(map1.shape) != tuple(map2.shape):
+            raise BVError(-1, "float maps are two float32 [H,W] planes")
+        if not (map1.is_cuda and map2.is_cuda and map1.is_contiguous() and map2.is_contiguous()):
+            raise BVError(-1, "maps must be contiguous CUDA tensors")
+        dh, dw = int(map1.shape[0]), int(map1.shape[1])
+        bv_ = np.ascontiguousarray(np.asarray(list(border_value)[:c] + [0] * max(0, c - len(border_value)), dtype=np.uint8))
+        shape = (dh, dw) if src.dim() == 2 else ((dh, dw, c) if src.dim() == 3 else (b, dh, dw, c))
+        dst = self.empty(shape)
+        check(lib.bv_remap(self.handle, _u8ptr(src), _u8ptr(dst), b, h, w, c, dh, dw, ffi.cast("void *", map1.data_ptr()),
+                           ffi.cast("void *", map2.data_ptr()), 1 if fixed else 0, {"constant": 0, "replicate": 1}[border],
+                           ffi.from_buffer("uint8_t[]", bv_)))
+        return dst
+
+    def undistort_maps(self, camera_matrix, dist_coeffs, inv_new_camera_rot, size, fixed=False):
+        """Device maps of cv2.initUndistortRectifyMap: float32 (x, y) planes, or with fixed=True the int16 [H,W,2] +
+        uint16 [H,W] pair cv2.undistort uses.  size = (width, height)."""
+        w, h = int(size[0]), int(size[1])
+        km = np.ascontiguousarray(np.asarray(camera_matrix, np.float64).reshape(9))
+        ir = np.ascontiguousarray(np.asarray(inv_new_camera_rot, np.float64).reshape(9))
+        d = np.ascontiguousarray(np.asarray(dist_coeffs if dist_coeffs is not None else [], np.float64).ravel())
+        null = ffi.NULL
+        if fixed:
+            m1, m2 = self.empty((h, w, 2), torch.int16), self.empty((h, w), torch.uint16)
+            check(lib.bv_undistort_maps(self.handle, ffi.from_buffer("double[]", km), ffi.from_buffer("double[]", d) if d.size else null,
+                                        int(d.size), ffi.from_buffer("double[]", ir), w, h, null, null,
+                                        ffi.cast("int16_t *", m1.data_ptr()), ffi.cast("uint16_t *", m2.data_ptr())))
+        else:
+            m1, m2 = self.empty((h, w), torch.float32), self.empty((h, w), torch.float32)
+            check(lib.bv_undistort_maps(self.handle, ffi.from_buffer("double[]", km), ffi.from_buffer("double[]", d) if d.size else null,
+                                        int(d.size), ffi.from_buffer("double[]", ir), w, h, ffi.cast("float *", m1.data_ptr()),
+                                        ffi.cast("float *", m2.data_ptr()), null, null))
+        return m1, m2
+
     def lab_shift_local_mean(self, lab, ksize):
         """a, b of a uint8 LAB image minus (their ksize x ksize box mean - 128), numpy-cast to uint8 (white_balance_bgr_blur)."""
         b, h, w, c = self._bhwc(lab)

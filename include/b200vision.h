@@ -282,6 +282,25 @@ typedef enum bv_border_mode { BV_BORDER_CONSTANT = 0, BV_BORDER_REPLICATE = 1 } 
 int bv_warp_affine(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, int height, int width,
                    int channels, int dst_height, int dst_width, const double *m_host, int border_mode,
                    const uint8_t *border_value_host);
+/* Lens undistortion (include/camera_filters.hpp:6-11 declares the maps and their initialiser; the reference holds no
+ * definition or call site, so parity is pinned to the cv2 calls such a definition makes).
+ * bv_remap == cv2.remap(src, map1, map2, INTER_LINEAR, borderMode, borderValue) on uint8; the maps live on the device and
+ * serve every frame of the batch.  BV_MAP_F32: map1 / map2 are float32 x / y planes (CV_32FC1); BV_MAP_FIXED: map1 is
+ * int16 (x, y) pairs, map2 uint16 (fy * 32 + fx) (CV_16SC2 + CV_16UC1, what cv2.convertMaps and cv2.undistort use).
+ * Bit-exact in both formats. */
+typedef enum bv_map_format { BV_MAP_F32 = 0, BV_MAP_FIXED = 1 } bv_map_format;
+int bv_remap(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, int batch, int height, int width, int channels,
+             int dst_height, int dst_width, const void *map1_dev, const void *map2_dev, int map_format, int border_mode,
+             const uint8_t *border_value_host);
+/* cv2.initUndistortRectifyMap(camera_matrix, dist_coeffs, R, new_camera_matrix, (width, height), ...): float32 maps
+ * (mapx_dev / mapy_dev, CV_32FC1) and / or the fixed-point pair (map_xy_dev / map_frac_dev) that cv2.undistort derives
+ * straight from the float64 coordinates; either pair may be NULL.  camera_matrix_host: 3x3 row-major; dist_coeffs_host:
+ * n_dist = 0, 4, 5 or 8 values k1 k2 p1 p2 [k3 [k4 k5 k6]]; inv_new_camera_rot_host: inverse of
+ * (new_camera_matrix x R), 3x3 row-major.  float64 arithmetic in OpenCV's order: identical maps on the reference's
+ * camera files (lib/configs/<n>_camera_matrix_params.yaml); in general to the last float32 bit. */
+int bv_undistort_maps(bv_ctx *ctx, const double *camera_matrix_host, const double *dist_coeffs_host, int n_dist,
+                      const double *inv_new_camera_rot_host, int width, int height, float *mapx_dev, float *mapy_dev,
+                      int16_t *map_xy_dev, uint16_t *map_frac_dev);
 /* The middle step of white_balance_bgr_blur (utils/color.py:381-391) on an 8-bit LAB image: a and b are moved by
  * their local mean, `a - (cv2.blur(a, (ksize, ksize), BORDER_REPLICATE) - 128)` in float32, then cast the way
  * numpy's astype(uint8) casts (truncation, wrap-around); L is copied.  The BGR2LAB before and the LAB2BGR after are

@@ -335,3 +335,72 @@ def warp_affine_8u(img, matrix, dsize=None, border="constant", border_value=0):
             acc += px * wt[:, q:q + 1]
         out[y] = np.clip((acc + (1 << 14)) >> 15, 0, 255)
     return out[..., 0] if squeeze else out
+
+
+# ---------------------------------------------------------------------------------------------
+# cv2.remap(INTER_LINEAR) on uint8 and cv2.initUndistortRectifyMap (lens undistortion,
+# include/camera_filters.hpp:6-11).  OpenCV modules/imgproc/src/imgwarp.cpp (RemapInvoker,
+# remapBilinear) and modules/calib3d (4.x: imgproc)/src/undistort.dispatch.cpp.
+# ---------------------------------------------------------------------------------------------
+def fixed_point_maps(mapx, mapy):
+    """float32 maps -> (int16 xy [H,W,2], uint16 fractional index [H,W]) as RemapInvoker converts them per block:
+    cvRound(float32(x) * 32), integer part saturated to short, 5-bit fractions combined into fy*32 + fx."""
+    sx = np.rint(np.asarray(mapx, np.float32) * np.float32(32)).astype(np.int64)
+    sy = np.rint(np.asarray(mapy, np.float32) * np.float32(32)).astype(np.int64)
+    xy = np.stack([np.clip(sx >> 5, -32768, 32767), np.clip(sy >> 5, -32768, 32767)], axis=-1).astype(np.int16)
+    return xy, ((sy & 31) * 32 + (sx & 31)).astype(np.uint16)
+
+
+def remap_linear_8u(img, map1, map2, border="constant", border_value=0):
+    """map1/map2: float32 x / y planes, or int16 [H,W,2] + uint16 [H,W] (CV_16SC2 + CV_16UC1)."""
+    squeeze = img.ndim == 2
+    if squeeze:
+        img = img[..., None]
+    if np.asarray(map1).dtype != np.int16:
+        map1, map2 = fixed_point_maps(map1, map2)
+    h, w = img.shape[:2]
+    sx, sy = map1[..., 0].astype(np.int64), map1[..., 1].astype(np.int64)
+    wt = _bilinear_tab()[np.asarray(map2, np.int64) & 1023]                 # [H, W, 4]
+    src = img.astype(np.int64)
+    bval = np.broadcast_to(np.asarray(border_value, np.int64), (img.shape[2],))
+    acc = np.zeros(sx.shape + (img.shape[2],), np.int64)
+    for q, (oy, ox) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        yy, xx = sy + oy, sx + ox
+        px = src[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)]
+        if border == "constant":
+            outside = (yy < 0) | (yy >= h) | (xx < 0) | (xx >= w)
+            px = np.where(outside[..., None], bval, px)
+        acc += px * wt[..., q:q + 1]
+    out = np.clip((acc + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+    return out[..., 0] if squeeze else out
+
+
+def init_undistort_rectify_map(camera_matrix, dist_coeffs, new_camera_matrix, size, rotation=None, fixed=False):
+    """cv2.initUndistortRectifyMap(K, D, R, newK, (w, h), CV_32FC1) in float64 (k1 k2 p1 p2 [k3 [k4 k5 k6]]; thin-prism
+    and tilt terms not modelled): float32 x / y maps.  OpenCV evaluates the same expressions in double (with fused
+    multiply-adds in its SIMD path), so single map values can differ in the last float32 bit."""
+    w, h = size
+    k = np.zeros(8)
+    d = np.asarray(dist_coeffs, np.float64).ravel()
+    k[:min(8, d.size)] = d[:8]
+    k1, k2, p1, p2, k3, k4, k5, k6 = k
+    A = np.asarray(camera_matrix, np.float64)
+    fx, fy, cx, cy = A[0, 0], A[1, 1], A[0, 2], A[1, 2]
+    R = np.eye(3) if rotation is None else np.asarray(rotation, np.float64)
+    iR = np.linalg.inv(np.asarray(new_camera_matrix, np.float64)[:3, :3] @ R)
+    u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    X = iR[0, 0] * u + (iR[0, 1] * v + iR[0, 2])
+    Y = iR[1, 0] * u + (iR[1, 1] * v + iR[1, 2])
+    W = iR[2, 0] * u + (iR[2, 1] * v + iR[2, 2])
+    x, y = X / W, Y / W
+    x2, y2 = x * x, y * y
+    r2, _2xy = x2 + y2, 2 * x * y
+    kr = (1 + ((k3 * r2 + k2) * r2 + k1) * r2) / (1 + ((k6 * r2 + k5) * r2 + k4) * r2)
+    xd = x * kr + p1 * _2xy + p2 * (r2 + 2 * x2)
+    yd = y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy
+    us, vs = fx * xd + cx, fy * yd + cy
+    if fixed:   # the CV_16SC2 + CV_16UC1 pair, rounded straight from the doubles (what cv2.undistort builds)
+        iu = np.clip(np.rint(us * 32), -2.0 ** 31, 2.0 ** 31 - 1).astype(np.int64)
+        iv = np.clip(np.rint(vs * 32), -2.0 ** 31, 2.0 ** 31 - 1).astype(np.int64)
+        return np.stack([iu >> 5, iv >> 5], axis=-1).astype(np.int16), ((iv & 31) * 32 + (iu & 31)).astype(np.uint16)
+    return us.astype(np.float32), vs.astype(np.float32)

@@ -3,6 +3,7 @@ against the reference's own cv2 calls (oracle/cv_ops.py).  Bit-exact unless a to
 import cv2
 import numpy as np
 import pytest
+import torch
 
 from oracle import cv_ops, synth
 
@@ -312,3 +313,60 @@ def test_bgr2luv_within_stated_tolerance(ctx, all_colors):
     assert int(np.abs(conv.astype(np.int16) - r2).max()) <= 1
     for k in range(3):
         assert np.array_equal(planes[k], conv[..., k])
+
+
+_CAM_K = np.array([[904.66192735, 0.0, 481.17596262], [0.0, 902.84000422, 404.82437525], [0.0, 0.0, 1.0]])
+_CAM_D = np.array([0.48525658, 2.02550297, 0.03807578, -0.02152142, -3.30299241])   # lib/configs/1_camera_matrix_params.yaml
+
+
+@pytest.mark.parametrize("shape", [(240, 320), (479, 641), (1242, 2208)])
+def test_remap_bit_exact_vs_cv2(ctx, shape):
+    """bv_remap == cv2.remap(INTER_LINEAR) on uint8: float32 maps and the fixed-point pair, both border modes, 1 and 3
+    channels, a batch sharing one pair of maps, maps leaving the frame on every side, a destination smaller than the source."""
+    from cuauv_vision_pipeline_b200 import transform
+    h, w = shape
+    img = synth.gen_underwater(h, w, 8)
+    rng = np.random.default_rng(h)
+    mx = (np.arange(w, dtype=np.float32)[None, :] * 1.03 - 9 + rng.normal(0, 3, (h, w))).astype(np.float32)
+    my = (np.arange(h, dtype=np.float32)[:, None] * 1.02 - 7 + rng.normal(0, 3, (h, w))).astype(np.float32)
+    for border, mode in (("constant", cv2.BORDER_CONSTANT), ("replicate", cv2.BORDER_REPLICATE)):
+        assert np.array_equal(transform.remap(img, mx, my, border=border), cv2.remap(img, mx, my, cv2.INTER_LINEAR, borderMode=mode))
+    gray = np.ascontiguousarray(img[..., 2])
+    assert np.array_equal(transform.remap(gray, mx, my), cv2.remap(gray, mx, my, cv2.INTER_LINEAR))
+    assert np.array_equal(transform.remap(img, mx, my, border_value=(7, 8, 9)),
+                          cv2.remap(img, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=(7, 8, 9)))
+    m1, m2 = cv2.convertMaps(mx, my, cv2.CV_16SC2)
+    assert np.array_equal(transform.remap(img, m1, m2), cv2.remap(img, m1, m2, cv2.INTER_LINEAR))
+    small = (slice(0, h // 2), slice(0, w // 3))
+    assert np.array_equal(transform.remap(img, np.ascontiguousarray(mx[small]), np.ascontiguousarray(my[small])),
+                          cv2.remap(img, np.ascontiguousarray(mx[small]), np.ascontiguousarray(my[small]), cv2.INTER_LINEAR))
+    batch = np.stack([img, img[::-1].copy()])
+    got = ctx.download(ctx.remap(ctx.upload(batch), torch.from_numpy(mx).to(ctx.device), torch.from_numpy(my).to(ctx.device)))
+    for k in range(2):
+        assert np.array_equal(got[k], cv2.remap(batch[k], mx, my, cv2.INTER_LINEAR))
+
+
+def test_undistort_with_the_reference_camera_file(ctx):
+    """include/camera_filters.hpp:6-11 (maps built once per camera, remap per frame) with lib/configs/1_camera_matrix_params.yaml:
+    the device maps equal cv2.initUndistortRectifyMap's (float32 and fixed point), the undistorted frame equals cv2.undistort's."""
+    from cuauv_vision_pipeline_b200 import transform
+    for size in ((964, 724), (640, 480)):
+        new_k, _ = cv2.getOptimalNewCameraMatrix(_CAM_K, _CAM_D, size, 1)
+        img = synth.gen_underwater(size[1], size[0], 9)
+        for nk in (None, new_k):
+            ref_k = _CAM_K if nk is None else nk
+            mx, my = transform.init_undistort_rectify_map(_CAM_K, _CAM_D, None, nk, size)
+            rx, ry = cv2.initUndistortRectifyMap(_CAM_K, _CAM_D, None, ref_k, size, cv2.CV_32FC1)
+            assert np.array_equal(mx.cpu().numpy(), rx) and np.array_equal(my.cpu().numpy(), ry)
+            assert np.array_equal(transform.remap(img, mx, my), cv2.remap(img, rx, ry, cv2.INTER_LINEAR))
+            f1, f2 = transform.init_undistort_rectify_map(_CAM_K, _CAM_D, None, nk, size, fixed=True)
+            r1, r2 = cv2.initUndistortRectifyMap(_CAM_K, _CAM_D, None, ref_k, size, cv2.CV_16SC2)
+            assert np.array_equal(f1.cpu().numpy(), r1) and np.array_equal(f2.cpu().numpy().view(np.uint16), r2)
+            ref = cv2.undistort(img, _CAM_K, _CAM_D, None, ref_k)
+            assert np.array_equal(transform.undistort(img, _CAM_K, _CAM_D, nk), ref)
+            assert np.array_equal(transform.undistort(img, _CAM_K, _CAM_D, nk, maps=(f1, f2)), ref)     # maps reused across frames
+    rot, _ = cv2.Rodrigues(np.array([0.02, -0.03, 0.01]))
+    d8 = np.array([0.1, -0.2, 0.001, 0.002, 0.05, 0.01, -0.02, 0.003])
+    mx, my = transform.init_undistort_rectify_map(_CAM_K, d8, rot, _CAM_K, (320, 240))
+    rx, ry = cv2.initUndistortRectifyMap(_CAM_K, d8, rot, _CAM_K, (320, 240), cv2.CV_32FC1)
+    assert np.array_equal(mx.cpu().numpy(), rx) and np.array_equal(my.cpu().numpy(), ry)

@@ -122,3 +122,28 @@ def test_rotation_matrix_equals_cv2():
     for ang in (0, 10, -33.3, 90, 180, 359, 0.001, 720.5):
         for c in ((320.0, 240.0), (1104.0, 621.0), (0.5, 7.25)):
             assert np.array_equal(rotation_matrix_2d(c, ang, 1), cv2.getRotationMatrix2D(c, ang, 1))
+
+
+def test_camera_matrix_yaml_reader():
+    """The reference's camera files are OpenCV FileStorage YAML (lib/configs/1_camera_matrix_params.yaml, text copied
+    here as data): the reader needs neither OpenCV nor a YAML library."""
+    from cuauv_vision_pipeline_b200 import transform
+    text = """%YAML:1.0
+M: !!opencv-matrix
+   rows: 3
+   cols: 3
+   dt: d
+   data: [904.66192735,0.0,481.17596262,0.0,902.84000422,404.82437525,0.0,0.0,1.0]
+
+D: !!opencv-matrix
+   rows: 1
+   cols: 5
+   dt: d
+   data: [0.48525658,2.02550297,0.03807578,-0.02152142,-3.30299241]
+"""
+    m, d = transform.load_camera_matrix_params(text)
+    assert m.shape == (3, 3) and m[0, 0] == 904.66192735 and m[1, 2] == 404.82437525 and m[2, 2] == 1.0
+    assert d.tolist() == [0.48525658, 2.02550297, 0.03807578, -0.02152142, -3.30299241]
+    import pytest
+    with pytest.raises(ValueError):
+        transform.load_camera_matrix_params("%YAML:1.0\nfoo: 1\n")

@@ -177,3 +177,47 @@ def test_legacy_randn_replay_matches_numpy(seed, pre, n):
     got, after = mt_gauss_np.randn_replay(state, n)
     assert np.array_equal(got, ref)
     assert np.array_equal(after[1], after_ref[1]) and tuple(after[2:]) == tuple(after_ref[2:])
+
+
+_CAM_K = np.array([[904.66192735, 0.0, 481.17596262], [0.0, 902.84000422, 404.82437525], [0.0, 0.0, 1.0]])
+_CAM_D = np.array([0.48525658, 2.02550297, 0.03807578, -0.02152142, -3.30299241])   # lib/configs/1_camera_matrix_params.yaml
+
+
+def test_remap_linear_8u_model_vs_cv2():
+    """cv2.remap(INTER_LINEAR) on uint8 ("bilinear remap fixed-point model, not yet pinned"): float32 maps
+    are rounded to 1/32 pixel as RemapInvoker does, then the same 32 x 32 x 4 int16 weights as warpAffine."""
+    img = synth.gen_underwater(240, 320, 3)
+    rng = np.random.default_rng(1)
+    mx = (np.arange(320, dtype=np.float32)[None, :] + rng.normal(0, 4, (240, 320))).astype(np.float32)
+    my = (np.arange(240, dtype=np.float32)[:, None] + rng.normal(0, 4, (240, 320))).astype(np.float32)
+    for border, mode in (("constant", cv2.BORDER_CONSTANT), ("replicate", cv2.BORDER_REPLICATE)):
+        assert np.array_equal(S.remap_linear_8u(img, mx, my, border), cv2.remap(img, mx, my, cv2.INTER_LINEAR, borderMode=mode))
+        assert np.array_equal(S.remap_linear_8u(img[..., 1], mx, my, border),
+                              cv2.remap(np.ascontiguousarray(img[..., 1]), mx, my, cv2.INTER_LINEAR, borderMode=mode))
+    m1, m2 = cv2.convertMaps(mx, my, cv2.CV_16SC2)
+    xy, frac = S.fixed_point_maps(mx, my)
+    assert np.array_equal(xy, m1) and np.array_equal(frac, m2)
+    assert np.array_equal(S.remap_linear_8u(img, xy, frac), cv2.remap(img, m1, m2, cv2.INTER_LINEAR))
+    assert np.array_equal(S.remap_linear_8u(img, mx, my, "constant", (7, 8, 9)),
+                          cv2.remap(img, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=(7, 8, 9)))
+
+
+def test_undistort_maps_model_vs_cv2():
+    """cv2.initUndistortRectifyMap / cv2.undistort with the reference's camera file: identical maps (float32 and the fixed-point
+    pair), identical undistorted image; also with a rotation and 8 distortion coefficients."""
+    for size in ((964, 724), (640, 480)):
+        new_k, _ = cv2.getOptimalNewCameraMatrix(_CAM_K, _CAM_D, size, 1)
+        for nk in (_CAM_K, new_k):
+            rx, ry = cv2.initUndistortRectifyMap(_CAM_K, _CAM_D, None, nk, size, cv2.CV_32FC1)
+            gx, gy = S.init_undistort_rectify_map(_CAM_K, _CAM_D, nk, size)
+            assert np.array_equal(rx, gx) and np.array_equal(ry, gy)
+            r1, r2 = cv2.initUndistortRectifyMap(_CAM_K, _CAM_D, None, nk, size, cv2.CV_16SC2)
+            g1, g2 = S.init_undistort_rectify_map(_CAM_K, _CAM_D, nk, size, fixed=True)
+            assert np.array_equal(r1, g1) and np.array_equal(r2, g2)
+            img = synth.gen_underwater(size[1], size[0], 5)
+            assert np.array_equal(S.remap_linear_8u(img, g1, g2), cv2.undistort(img, _CAM_K, _CAM_D, None, nk))
+    rot, _ = cv2.Rodrigues(np.array([0.02, -0.03, 0.01]))
+    d8 = np.array([0.1, -0.2, 0.001, 0.002, 0.05, 0.01, -0.02, 0.003])
+    rx, ry = cv2.initUndistortRectifyMap(_CAM_K, d8, rot, _CAM_K, (320, 240), cv2.CV_32FC1)
+    gx, gy = S.init_undistort_rectify_map(_CAM_K, d8, _CAM_K, (320, 240), rotation=rot)
+    assert np.array_equal(rx, gx) and np.array_equal(ry, gy)

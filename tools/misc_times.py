@@ -36,6 +36,14 @@ timed("GaussianBlur 5x5", lambda: ctx.gaussian_blur(frames, (5, 5)))
 timed("GaussianBlur 31x31", lambda: ctx.gaussian_blur(frames, (31, 31)))
 m = transform.rotation_matrix_2d((W / 2, H / 2), 10, 1)
 timed("warpAffine rotate 10 deg (replicate)", lambda: ctx.warp_affine(frames, m, border="replicate"))
+_K = np.array([[904.66192735, 0.0, 481.17596262], [0.0, 902.84000422, 404.82437525], [0.0, 0.0, 1.0]]) * (W / 964.0)
+_K[2, 2] = 1.0
+_maps_f = transform.init_undistort_rectify_map(_K, [0.1, -0.2, 0.001, 0.002, 0.05], None, None, (W, H))
+_maps_q = transform.init_undistort_rectify_map(_K, [0.1, -0.2, 0.001, 0.002, 0.05], None, None, (W, H), fixed=True)
+timed("undistortion maps (float32 pair, once per camera)", lambda: transform.init_undistort_rectify_map(
+    _K, [0.1, -0.2, 0.001, 0.002, 0.05], None, None, (W, H)), per=1)
+timed("remap undistort, float32 maps", lambda: ctx.remap(frames, *_maps_f))
+timed("remap undistort, fixed-point maps", lambda: ctx.remap(frames, *_maps_q))
 timed("BGR2LAB", lambda: ctx.cvt_color(frames, "bgr2lab"))
 timed("LAB2BGR", lambda: ctx.cvt_color(frames, "lab2bgr"))
 timed("BGR2LUV", lambda: ctx.cvt_color(frames, "bgr2luv"))
