@@ -655,13 +655,13 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
                                                       const int *__restrict__ parent_bg, const uint32_t *__restrict__ outer,
                                                       const int *__restrict__ root_px, const int *__restrict__ n_blobs,
                                                       bv_contour *__restrict__ out, int max_contours, int height, int width,
-                                                      int wpr, int wcols, int *__restrict__ points, int max_points) {
+                                                      int wpr, int wcols, int *__restrict__ points, int max_points, int lane_stride) {
     const int f = blockIdx.y;
     const int n = min(n_blobs[f], max_contours);
     // one border per thread, but only every fourth lane takes one: a warp-wide load of 32 walks touches 32 different
     // lines and every step waits for the slowest of them
-    if (threadIdx.x & (kContourLaneStride - 1)) return;
-    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) / kContourLaneStride;
+    if (threadIdx.x % lane_stride) return;
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) / lane_stride;
     if (idx >= n) return;
     const unsigned rows = (unsigned)height + 2;
     const uint32_t *fw = bits + (size_t)f * wcols * rows;  // walk_bits_kernel's copy
@@ -846,13 +846,14 @@ int outer_contours_bits(bv_ctx *ctx, const uint32_t *bits, int batch, int height
     uint32_t *walk = (uint32_t *)ctx->scratch[SCR_BITS_TILED];
     BV_LAUNCH(ctx, walk_bits_kernel, grid_for(ctx, walk_words, 256, 8), 256, 0, bits, walk, height, width, wpr, wcols,
               (uint32_t)walk_words);
-    dim3 grid((max_contours * kContourLaneStride + 127) / 128, batch);
+    const int lane_stride = kContourLaneStride;
+    dim3 grid((unsigned)(((size_t)max_contours * lane_stride + 127) / 128), batch);
     BV_LAUNCH(ctx, contour_kernel<false>, grid, 128, 0, walk, inv, parent_bg, outer, root_px, nb, contours, max_contours,
-              height, width, wpr, wcols, nullptr, 0);
+              height, width, wpr, wcols, nullptr, 0, lane_stride);
     if (points && max_points > 0) {
         BV_LAUNCH(ctx, contour_offsets_kernel, batch, 1024, 0, contours, nb, max_contours, max_points, n_points);
         BV_LAUNCH(ctx, contour_kernel<true>, grid, 128, 0, walk, inv, parent_bg, outer, root_px, nb, contours, max_contours,
-                  height, width, wpr, wcols, points, max_points);
+                  height, width, wpr, wcols, points, max_points, lane_stride);
     }
     return BV_OK;
 }

@@ -60,11 +60,21 @@ __device__ __forceinline__ long long cross3(const P2 &o, const P2 &a, const P2 &
 struct HullView {
     const P2 *h;
     int n;
+    const float *ex, *ey, *el;  // edge vectors and inverse lengths computed once per edge (NULL: computed on demand)
     __device__ __forceinline__ float2 pt(int i) const {
         const P2 p = h[n - 1 - i];
         return make_float2((float)p.x, (float)p.y);
     }
     __device__ __forceinline__ void edge(int i, float &vx, float &vy, float &inv_len) const {
+        if (ex) {
+            vx = ex[i];
+            vy = ey[i];
+            inv_len = el[i];
+            return;
+        }
+        compute_edge(i, vx, vy, inv_len);
+    }
+    __device__ __forceinline__ void compute_edge(int i, float &vx, float &vy, float &inv_len) const {
         const P2 a = h[n - 1 - i], b = h[n - 1 - (i + 1 == n ? 0 : i + 1)];
         const double dx = (double)b.x - (double)a.x, dy = (double)b.y - (double)a.y;
         vx = (float)dx;
@@ -167,13 +177,123 @@ __device__ void rotating_calipers(const HullView &H, float out[6]) {
     out[5] = B2 * best_h;
 }
 
-__global__ void __launch_bounds__(128) min_area_rect_kernel(const bv_contour *__restrict__ contours,
-                                                            const int32_t *__restrict__ n_contours, const int32_t *__restrict__ points,
-                                                            int max_contours, int max_points, P2 *__restrict__ scratch,
-                                                            bv_rrect *__restrict__ rects) {
+// Akl-Toussaint prefilter + heap sort + monotone chain by ONE thread in global scratch: the fallback for contours whose
+// kept vertices do not fit the warp's shared-memory buffer (or whose coordinates do not fit 16 bits).  Returns the hull size.
+__device__ __noinline__ int hull_sequential(const P2 *__restrict__ src, int n_in, P2 *sorted, P2 *hull) {
+    P2 ext[4] = {src[0], src[0], src[0], src[0]};
+    for (int i = 1; i < n_in; ++i) {
+        const P2 p = src[i];
+        if (p.x < ext[0].x) ext[0] = p;
+        if (p.y < ext[1].y) ext[1] = p;
+        if (p.x > ext[2].x) ext[2] = p;
+        if (p.y > ext[3].y) ext[3] = p;
+    }
+    long long area2 = 0;
+    for (int k = 0; k < 4; ++k)
+        area2 += (long long)ext[k].x * ext[(k + 1) & 3].y - (long long)ext[(k + 1) & 3].x * ext[k].y;
+    int n_kept = 0;
+    if (area2 == 0 || n_in <= 8) {
+        for (int i = 0; i < n_in; ++i) sorted[n_kept++] = src[i];
+    } else {
+        for (int k = 0; k < 4; ++k) sorted[n_kept++] = ext[k];
+        for (int i = 0; i < n_in; ++i) {
+            const P2 p = src[i];
+            bool outside = false;
+            for (int k = 0; k < 4; ++k) {
+                const long long c = cross3(ext[k], ext[(k + 1) & 3], p);
+                outside |= area2 > 0 ? c < 0 : c > 0;
+            }
+            if (outside) sorted[n_kept++] = p;
+        }
+    }
+    heap_sort(sorted, n_kept);
+    int n = 0;
+    for (int i = 0; i < n_kept; ++i)
+        if (n == 0 || sorted[i].x != sorted[n - 1].x || sorted[i].y != sorted[n - 1].y) sorted[n++] = sorted[i];
+    int m = 0;
+    if (n <= 2) {
+        for (int i = 0; i < n; ++i) hull[m++] = sorted[i];
+    } else {
+        for (int i = 0; i < n; ++i) {  // lower chain
+            while (m >= 2 && cross3(hull[m - 2], hull[m - 1], sorted[i]) <= 0) --m;
+            hull[m++] = sorted[i];
+        }
+        const int lower = m + 1;
+        for (int i = n - 2; i >= 0; --i) {  // upper chain
+            while (m >= lower && cross3(hull[m - 2], hull[m - 1], sorted[i]) <= 0) --m;
+            hull[m++] = sorted[i];
+        }
+        --m;  // the first point again
+    }
+    return m;
+}
+
+// cv2.minAreaRect of a convex hull (counter-clockwise in hull[0..m), as the monotone chain leaves it)
+__device__ void rect_from_hull(const HullView &H, bv_rrect &r) {
+    const P2 *hull = H.h;
+    const int m = H.n;
+    float angle = 0.f;
+    if (m > 2) {
+        float o[6];
+        rotating_calipers(H, o);
+        r.cx = o[0] + (o[2] + o[4]) * 0.5f;
+        r.cy = o[1] + (o[3] + o[5]) * 0.5f;
+        r.width = (float)sqrt((double)o[2] * o[2] + (double)o[3] * o[3]);
+        r.height = (float)sqrt((double)o[4] * o[4] + (double)o[5] * o[5]);
+        angle = (float)atan2((double)o[3], (double)o[2]);
+    } else if (m == 2) {
+        const P2 a = hull[0], b = hull[1];  // (x, y)-sorted, the order cv::convexHull returns a segment in
+        r.cx = ((float)a.x + (float)b.x) * 0.5f;
+        r.cy = ((float)a.y + (float)b.y) * 0.5f;
+        const double dx = (double)b.x - a.x, dy = (double)b.y - a.y;
+        r.width = (float)sqrt(dx * dx + dy * dy);
+        r.height = 0.f;
+        angle = (float)atan2(dy, dx);
+    } else {
+        r.cx = (float)hull[0].x;
+        r.cy = (float)hull[0].y;
+    }
+    angle = (float)((double)angle * 180. / 3.1415926535897932384626433832795);
+    // cv2 4.13.0 reports the angle in [-90, 0): quarter turns, the sides swapping with each
+    for (int q = 0; q < 4 && !(angle < 0.f); ++q) {
+        angle -= 90.f;
+        const float t = r.width; r.width = r.height; r.height = t;
+    }
+    for (int q = 0; q < 4 && angle < -90.f; ++q) {
+        angle += 90.f;
+        const float t = r.width; r.width = r.height; r.height = t;
+    }
+    r.angle = angle;
+    r.valid = 1;
+}
+
+// One WARP per contour.  A thread per contour spends its time in a heap sort over global scratch (one dependent access
+// after the other, the frame waits for its largest contour); here the 32 lanes find the extreme points, filter and
+// compact the vertices into shared memory (ballot), sort them as packed 16+16-bit keys with a bitonic network, and
+// compute the hull's edge vectors; only the monotone chain and the calipers, both O(hull), run on lane 0, out of
+// shared memory.
+constexpr int kRectCap = 512;      // vertices a warp keeps in shared memory; more (or coordinates > 65534) -> fallback
+constexpr int kRectWarps = 2;      // warps per block
+
+struct RectWarpSmem {
+    uint32_t keys[kRectCap];
+    P2 hull[kRectCap + 1];
+    float ex[kRectCap], ey[kRectCap], el[kRectCap];
+};
+
+__device__ __forceinline__ P2 key_point(uint32_t k) { return P2{(int)(k >> 16), (int)(k & 0xFFFFu)}; }
+
+__global__ void __launch_bounds__(32 * kRectWarps) min_area_rect_kernel(const bv_contour *__restrict__ contours,
+                                                                        const int32_t *__restrict__ n_contours,
+                                                                        const int32_t *__restrict__ points, int max_contours,
+                                                                        int max_points, P2 *__restrict__ scratch,
+                                                                        bv_rrect *__restrict__ rects) {
+    __shared__ RectWarpSmem smem[kRectWarps];
     const int frame = blockIdx.y;
-    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ci >= max_contours) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int ci = blockIdx.x * kRectWarps + wib;
+    if (ci >= max_contours) return;  // warp-uniform
+    RectWarpSmem &sm = smem[wib];
     bv_rrect r;
     r.cx = r.cy = r.width = r.height = r.angle = 0.f;
     r.valid = 0;
@@ -182,93 +302,130 @@ __global__ void __launch_bounds__(128) min_area_rect_kernel(const bv_contour *__
     if (ci < total && c.external && c.point_offset >= 0 && c.n_simple > 0 && c.point_offset + c.n_simple <= max_points) {
         const int n_in = c.n_simple;
         const P2 *src = reinterpret_cast<const P2 *>(points) + (size_t)frame * max_points + c.point_offset;
-        // private scratch: [sorted points (n_in) | hull stack (n_in + 1: the chain closes on its first point)]
-        P2 *sorted = scratch + (size_t)frame * (2 * (size_t)max_points + max_contours) + 2 * (size_t)c.point_offset + ci;
-        P2 *hull = sorted + n_in;
-        // Akl-Toussaint: a point inside or on the quadrilateral of the four extreme points (left, top, right, bottom)
-        // cannot be a hull vertex, so only the extremes and the points strictly outside it are sorted (exact integer
-        // cross products).  A quadrilateral without area (collinear or single points) filters nothing.
+        // extreme points: per lane, then across the warp (ties: any of the tied points will do)
         P2 ext[4] = {src[0], src[0], src[0], src[0]};
-        for (int i = 1; i < n_in; ++i) {
+        for (int i = lane; i < n_in; i += 32) {
             const P2 p = src[i];
             if (p.x < ext[0].x) ext[0] = p;
             if (p.y < ext[1].y) ext[1] = p;
             if (p.x > ext[2].x) ext[2] = p;
             if (p.y > ext[3].y) ext[3] = p;
         }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            P2 o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                o[k].x = __shfl_down_sync(0xFFFFFFFFu, ext[k].x, off);
+                o[k].y = __shfl_down_sync(0xFFFFFFFFu, ext[k].y, off);
+            }
+            if (o[0].x < ext[0].x) ext[0] = o[0];
+            if (o[1].y < ext[1].y) ext[1] = o[1];
+            if (o[2].x > ext[2].x) ext[2] = o[2];
+            if (o[3].y > ext[3].y) ext[3] = o[3];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ext[k].x = __shfl_sync(0xFFFFFFFFu, ext[k].x, 0);
+            ext[k].y = __shfl_sync(0xFFFFFFFFu, ext[k].y, 0);
+        }
         long long area2 = 0;
+#pragma unroll
         for (int k = 0; k < 4; ++k)
             area2 += (long long)ext[k].x * ext[(k + 1) & 3].y - (long long)ext[(k + 1) & 3].x * ext[k].y;
+        // Akl-Toussaint: only the extremes and the vertices strictly outside their quadrilateral can be hull vertices
+        const bool keep_all = area2 == 0 || n_in <= 8;
         int n_kept = 0;
-        if (area2 == 0 || n_in <= 8) {
-            for (int i = 0; i < n_in; ++i) sorted[n_kept++] = src[i];
-        } else {
-            for (int k = 0; k < 4; ++k) sorted[n_kept++] = ext[k];
-            for (int i = 0; i < n_in; ++i) {
-                const P2 p = src[i];
-                bool outside = false;
-                for (int k = 0; k < 4; ++k) {
-                    const long long c = cross3(ext[k], ext[(k + 1) & 3], p);
-                    outside |= area2 > 0 ? c < 0 : c > 0;
+        if (!keep_all) {
+            if (lane < 4) sm.keys[lane] = ((uint32_t)ext[lane].x << 16) | (uint32_t)ext[lane].y;
+            n_kept = 4;
+        }
+        bool wide = false;
+        for (int base = 0; base < n_in; base += 32) {
+            const int i = base + lane;
+            bool keep = false;
+            P2 p = P2{0, 0};
+            if (i < n_in) {
+                p = src[i];
+                wide |= (unsigned)p.x > 65534u || (unsigned)p.y > 65534u;
+                keep = keep_all;
+                if (!keep_all) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const long long cr = cross3(ext[k], ext[(k + 1) & 3], p);
+                        keep |= area2 > 0 ? cr < 0 : cr > 0;
+                    }
                 }
-                if (outside) sorted[n_kept++] = p;
             }
+            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, keep);
+            const int pos = n_kept + __popc(mask & ((1u << lane) - 1u));
+            if (keep && pos < kRectCap) sm.keys[pos] = ((uint32_t)p.x << 16) | (uint32_t)p.y;
+            n_kept += __popc(mask);
         }
-        heap_sort(sorted, n_kept);
-        int n = 0;
-        for (int i = 0; i < n_kept; ++i)
-            if (n == 0 || sorted[i].x != sorted[n - 1].x || sorted[i].y != sorted[n - 1].y) sorted[n++] = sorted[i];
+        wide = __any_sync(0xFFFFFFFFu, wide);
         int m = 0;
-        if (n <= 2) {
-            for (int i = 0; i < n; ++i) hull[m++] = sorted[i];
-        } else {
-            for (int i = 0; i < n; ++i) {  // lower chain
-                while (m >= 2 && cross3(hull[m - 2], hull[m - 1], sorted[i]) <= 0) --m;
-                hull[m++] = sorted[i];
+        const P2 *hull = sm.hull;
+        const bool fallback = wide || n_kept > kRectCap;  // warp-uniform
+        if (fallback) {
+            if (lane == 0) {
+                // private scratch: [sorted points (n_in + 4) | hull stack (one more: the chain closes on its first point)]
+                P2 *sorted = scratch + (size_t)frame * (2 * (size_t)max_points + 9 * (size_t)max_contours) + 2 * (size_t)c.point_offset +
+                             9 * (size_t)ci;
+                m = hull_sequential(src, n_in, sorted, sorted + n_in + 4);
+                hull = sorted + n_in + 4;
             }
-            const int lower = m + 1;
-            for (int i = n - 2; i >= 0; --i) {  // upper chain
-                while (m >= lower && cross3(hull[m - 2], hull[m - 1], sorted[i]) <= 0) --m;
-                hull[m++] = sorted[i];
-            }
-            --m;  // the first point again
-        }
-        float angle = 0.f;
-        if (m > 2) {
-            HullView H{hull, m};
-            float o[6];
-            rotating_calipers(H, o);
-            r.cx = o[0] + (o[2] + o[4]) * 0.5f;
-            r.cy = o[1] + (o[3] + o[5]) * 0.5f;
-            r.width = (float)sqrt((double)o[2] * o[2] + (double)o[3] * o[3]);
-            r.height = (float)sqrt((double)o[4] * o[4] + (double)o[5] * o[5]);
-            angle = (float)atan2((double)o[3], (double)o[2]);
-        } else if (m == 2) {
-            const P2 a = hull[0], b = hull[1];  // (x, y)-sorted, the order cv::convexHull returns a segment in
-            r.cx = ((float)a.x + (float)b.x) * 0.5f;
-            r.cy = ((float)a.y + (float)b.y) * 0.5f;
-            const double dx = (double)b.x - a.x, dy = (double)b.y - a.y;
-            r.width = (float)sqrt(dx * dx + dy * dy);
-            r.height = 0.f;
-            angle = (float)atan2(dy, dx);
         } else {
-            r.cx = (float)hull[0].x;
-            r.cy = (float)hull[0].y;
+            int np2 = 32;
+            while (np2 < n_kept) np2 <<= 1;
+            for (int i = n_kept + lane; i < np2; i += 32) sm.keys[i] = 0xFFFFFFFFu;  // above every real key
+            __syncwarp();
+            for (int k = 2; k <= np2; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = lane; t < (np2 >> 1); t += 32) {
+                        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+                        const uint32_t a = sm.keys[lo], b = sm.keys[hi];
+                        if ((a > b) == ((lo & k) == 0)) {
+                            sm.keys[lo] = b;
+                            sm.keys[hi] = a;
+                        }
+                    }
+                    __syncwarp();
+                }
+            if (lane == 0) {
+                int n = 0;
+                for (int i = 0; i < n_kept; ++i)
+                    if (n == 0 || sm.keys[i] != sm.keys[n - 1]) sm.keys[n++] = sm.keys[i];
+                if (n <= 2) {
+                    for (int i = 0; i < n; ++i) sm.hull[m++] = key_point(sm.keys[i]);
+                } else {
+                    for (int i = 0; i < n; ++i) {  // lower chain
+                        const P2 p = key_point(sm.keys[i]);
+                        while (m >= 2 && cross3(sm.hull[m - 2], sm.hull[m - 1], p) <= 0) --m;
+                        sm.hull[m++] = p;
+                    }
+                    const int lower = m + 1;
+                    for (int i = n - 2; i >= 0; --i) {  // upper chain
+                        const P2 p = key_point(sm.keys[i]);
+                        while (m >= lower && cross3(sm.hull[m - 2], sm.hull[m - 1], p) <= 0) --m;
+                        sm.hull[m++] = p;
+                    }
+                    --m;  // the first point again
+                }
+            }
         }
-        angle = (float)((double)angle * 180. / 3.1415926535897932384626433832795);
-        // cv2 4.13.0 reports the angle in [-90, 0): quarter turns, the sides swapping with each
-        for (int q = 0; q < 4 && !(angle < 0.f); ++q) {
-            angle -= 90.f;
-            const float t = r.width; r.width = r.height; r.height = t;
+        m = __shfl_sync(0xFFFFFFFFu, m, 0);
+        __syncwarp();
+        HullView H{hull, m, nullptr, nullptr, nullptr};
+        if (!fallback && m > 2) {  // edge vectors and inverse lengths once per edge, 32 at a time
+            for (int i = lane; i < m; i += 32) H.compute_edge(i, sm.ex[i], sm.ey[i], sm.el[i]);
+            H.ex = sm.ex;
+            H.ey = sm.ey;
+            H.el = sm.el;
         }
-        for (int q = 0; q < 4 && angle < -90.f; ++q) {
-            angle += 90.f;
-            const float t = r.width; r.width = r.height; r.height = t;
-        }
-        r.angle = angle;
-        r.valid = 1;
+        __syncwarp();
+        if (lane == 0) rect_from_hull(H, r);
     }
-    rects[(size_t)frame * max_contours + ci] = r;
+    if (lane == 0) rects[(size_t)frame * max_contours + ci] = r;
 }
 
 }  // namespace bv
@@ -280,8 +437,8 @@ extern "C" int bv_min_area_rects(bv_ctx *ctx, const bv_contour *contours_dev, co
     BV_REQUIRE(ctx && contours_dev && n_contours_dev && points_dev && rects_dev, "null argument");
     BV_REQUIRE(batch > 0 && batch <= 65535 && max_contours > 0 && max_points > 0, "sizes must be positive");
     BV_CUDA(cudaSetDevice(ctx->device));
-    BV_TRY(ensure_scratch(ctx, SCR_HULL, sizeof(P2) * (size_t)batch * (2 * (size_t)max_points + max_contours)));
-    BV_LAUNCH(ctx, min_area_rect_kernel, dim3((max_contours + 127) / 128, batch), 128, 0, contours_dev, n_contours_dev, points_dev,
-              max_contours, max_points, (P2 *)ctx->scratch[SCR_HULL], rects_dev);
+    BV_TRY(ensure_scratch(ctx, SCR_HULL, sizeof(P2) * (size_t)batch * (2 * (size_t)max_points + 9 * (size_t)max_contours)));
+    BV_LAUNCH(ctx, min_area_rect_kernel, dim3((max_contours + kRectWarps - 1) / kRectWarps, batch), 32 * kRectWarps, 0, contours_dev,
+              n_contours_dev, points_dev, max_contours, max_points, (P2 *)ctx->scratch[SCR_HULL], rects_dev);
     return BV_OK;
 }

@@ -382,6 +382,34 @@ def test_min_area_rect_of_outer_contours_vs_cv2(ctx, shape, seed):
     assert exact_params >= 0.95 * len(got), (exact_params, len(got))
 
 
+def test_min_area_rect_of_contours_larger_than_the_shared_memory_buffer(ctx):
+    """A warp sorts up to 512 candidate hull vertices in shared memory (csrc/rects.cu); rough discs of radius 330 and 120 have
+    ~2000 and ~700 contour vertices outside the extreme-point quadrilateral and take the single-thread fallback, the
+    small blobs around them the warp path.  Same tolerance as above."""
+    from cuauv_vision_pipeline_b200 import feature
+    yy, xx = np.mgrid[0:800, 0:1100]
+    rng = np.random.default_rng(3)
+    m = ((xx - 400) ** 2 + (yy - 400) ** 2 <= 330 ** 2) | ((xx - 930) ** 2 + (yy - 200) ** 2 <= 120 ** 2)
+    m ^= (rng.random(m.shape) < 0.35) & ((np.abs(np.hypot(xx - 400, yy - 400) - 330) < 3) | (np.abs(np.hypot(xx - 930, yy - 200) - 120) < 3))
+    m[600:640, 850:1000] = True
+    m = m.astype(np.uint8) * 255
+    got = feature.outer_contours(m, points=True, rects=True, max_points=20000)
+    ref_contours, _ = cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    assert len(got) == len(ref_contours) and max(len(c) for c in ref_contours) > 1000
+    by_start = {}
+    for c in ref_contours:
+        pts = c.reshape(-1, 2)
+        i = np.lexsort((pts[:, 0], pts[:, 1]))[0]
+        by_start[(int(pts[i, 0]), int(pts[i, 1]))] = c
+    for g in got:
+        ref = cv2.minAreaRect(by_start[(g["start_x"], g["start_y"])])
+        rect = feature.min_area_rect(g)
+        ra, ga = ref[1][0] * ref[1][1], rect[1][0] * rect[1][1]
+        assert abs(ra - ga) <= 1e-4 * max(1.0, ra), (ref, rect)
+        if len(g["points"]) > 500:      # the discs: a unique minimum, so centre, sides and angle agree as well
+            assert np.abs(_rect_corners(ref) - _rect_corners(rect)).max() <= 2e-3 * max(ref[1]), (ref, rect)
+
+
 def test_min_area_rect_degenerate_contours(ctx):
     from cuauv_vision_pipeline_b200 import feature
     m = np.zeros((64, 96), np.uint8)
