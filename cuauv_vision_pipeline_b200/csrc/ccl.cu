@@ -647,6 +647,9 @@ __device__ __forceinline__ uint32_t neighbours_at(const uint32_t *__restrict__ f
 }
 
 constexpr int kContourLaneStride = 4;
+constexpr int kChunkPoints = 31;                  // vertices per chunk
+constexpr int kChunkInts = 2 * kChunkPoints + 2;  // + index of the next chunk + padding = 256 bytes
+constexpr int kChunksOverflowed = -2;             // the pool ran dry under this border: it is walked again
 
 // WRITE = false: first walk (sums, counts, externality).  WRITE = true: second walk of the external
 // borders that got a slot in the point list, emitting the CHAIN_APPROX_SIMPLE vertices.
@@ -655,7 +658,8 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
                                                       const int *__restrict__ parent_bg, const uint32_t *__restrict__ outer,
                                                       const int *__restrict__ root_px, const int *__restrict__ n_blobs,
                                                       bv_contour *__restrict__ out, int max_contours, int height, int width,
-                                                      int wpr, int wcols, int *__restrict__ points, int max_points, int lane_stride) {
+                                                      int wpr, int wcols, int *__restrict__ points, int max_points, int lane_stride,
+                                                      int *__restrict__ pool, int *__restrict__ pool_next, int pool_chunks) {
     const int f = blockIdx.y;
     const int n = min(n_blobs[f], max_contours);
     // one border per thread, but only every fourth lane takes one: a warp-wide load of 32 walks touches 32 different
@@ -670,7 +674,7 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
     int x0, y0;
     if (WRITE) {
         c = out[(size_t)f * max_contours + idx];
-        if (!c.external || c.point_offset < 0) return;
+        if (!c.external || c.point_offset < 0 || c.reserved != kChunksOverflowed) return;  // the gather kernel served the rest
         pts = points + ((size_t)f * max_points + c.point_offset) * 2;
         x0 = c.start_x;
         y0 = c.start_y;
@@ -699,6 +703,27 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
 #define dy(s) ((int)((0x22210001u >> (4 * (s))) & 0xFu) - 1)
     long long a00 = 0, a10 = 0, a01 = 0;
     int bx0 = x0, bx1 = x0, by0 = y0, by1 = y0, npts = 1, nsimple = 1;
+    // first walk of an external border: its vertices also go into a chain of 31-point chunks drawn from the frame's
+    // pool, so that they need not be found again by a second walk once the offsets in the point list are known
+    const bool store = !WRITE && pool != nullptr && c.external;
+    int *fpool = store ? pool + (size_t)f * pool_chunks * kChunkInts : nullptr;
+    int first_chunk = -1, chunk = -1, slot = kChunkPoints;
+    auto keep_vertex = [&](int vx, int vy) {
+        if (!store || first_chunk == kChunksOverflowed) return;
+        if (slot == kChunkPoints) {
+            const int next = atomicAdd(pool_next + f, 1);
+            if (next >= pool_chunks) {
+                first_chunk = kChunksOverflowed;
+                return;
+            }
+            if (chunk >= 0) fpool[(size_t)chunk * kChunkInts + 2 * kChunkPoints] = next; else first_chunk = next;
+            chunk = next;
+            slot = 0;
+        }
+        fpool[(size_t)chunk * kChunkInts + 2 * slot] = vx;
+        fpool[(size_t)chunk * kChunkInts + 2 * slot + 1] = vy;
+        ++slot;
+    };
     int s = 4;
     bool found = false;
     const uint32_t nb0 = neighbours_at(fw, rows, x0, y0);
@@ -714,6 +739,7 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
             pts[0] = x0;
             pts[1] = y0;
         }
+        keep_vertex(x0, y0);
     } else {
         const int x1 = x0 + dx(s), y1 = y0 + dy(s);  // i1: the first neighbour, where the walk will end
         int cx = x0, cy = y0;                        // i3
@@ -734,6 +760,7 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
                     pts[2 * nsimple] = cx;
                     pts[2 * nsimple + 1] = cy;
                 }
+                keep_vertex(cx, cy);
                 ++nsimple;
                 prev_s = s;
             }
@@ -755,7 +782,10 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
     }
 #undef dx
 #undef dy
-    if (WRITE) return;
+    if (WRITE) {
+        out[(size_t)f * max_contours + idx].reserved = 0;
+        return;
+    }
     c.a00 = a00;
     c.a10 = a10;
     c.a01 = a01;
@@ -763,7 +793,7 @@ __global__ void __launch_bounds__(128) contour_kernel(const uint32_t *__restrict
     c.n_points = npts;
     c.n_simple = nsimple;
     c.point_offset = -1;
-    c.reserved = 0;
+    c.reserved = store ? first_chunk : 0;
     out[(size_t)f * max_contours + idx] = c;
 }
 
@@ -809,6 +839,33 @@ __global__ void __launch_bounds__(1024) contour_offsets_kernel(bv_contour *__res
     if (threadIdx.x == 0 && n_points) n_points[f] = carry;
 }
 
+// One warp per external contour that got a slice of the point list: copies its chain of chunks into the slice.
+__global__ void __launch_bounds__(128) contour_gather_kernel(bv_contour *__restrict__ contours, const int *__restrict__ n_blobs,
+                                                             int max_contours, const int *__restrict__ pool, int pool_chunks,
+                                                             int *__restrict__ points, int max_points) {
+    const int f = blockIdx.y;
+    const int n = min(n_blobs[f], max_contours);
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (idx >= n) return;
+    bv_contour *c = contours + (size_t)f * max_contours + idx;
+    const int first = c->reserved, offset = c->point_offset, count = c->n_simple;
+    if (!c->external) return;
+    __syncwarp();
+    if (first == kChunksOverflowed && offset >= 0) return;    // keeps the mark: the second walk writes its vertices
+    if (lane == 0) c->reserved = 0;
+    if (offset < 0 || first < 0) return;
+    const int *fpool = pool + (size_t)f * pool_chunks * kChunkInts;
+    int *dst = points + ((size_t)f * max_points + offset) * 2;
+    int chunk = first;
+    for (int done = 0; done < count; done += kChunkPoints) {
+        const int *src = fpool + (size_t)chunk * kChunkInts;
+        const int here = min(kChunkPoints, count - done);
+        for (int k = lane; k < 2 * here; k += 32) dst[2 * done + k] = src[k];
+        chunk = src[2 * kChunkPoints];
+    }
+}
+
 int outer_contours_bits(bv_ctx *ctx, const uint32_t *bits, int batch, int height, int width, bv_contour *contours,
                         int max_contours, int32_t *n_contours, int32_t *points, int max_points, int32_t *n_points) {
     const int wpr = words_per_row(width);
@@ -848,12 +905,27 @@ int outer_contours_bits(bv_ctx *ctx, const uint32_t *bits, int batch, int height
               (uint32_t)walk_words);
     const int lane_stride = kContourLaneStride;
     dim3 grid((unsigned)(((size_t)max_contours * lane_stride + 127) / 128), batch);
+    const bool want_points = points && max_points > 0;
+    int *pool = nullptr, *pool_next = nullptr;
+    int pool_chunks = 0;
+    if (want_points) {
+        // every contour wastes less than one chunk, and the vertices that fit the list fill max_points / 31 of them
+        pool_chunks = max_points / kChunkPoints + max_contours + 1;
+        if (ctx->opt[BV_OPT_CONTOUR_POOL_CHUNKS] > 0) pool_chunks = ctx->opt[BV_OPT_CONTOUR_POOL_CHUNKS];
+        BV_TRY(ensure_scratch(ctx, SCR_CONTOUR_POOL, ((size_t)batch * pool_chunks * kChunkInts + batch) * sizeof(int)));
+        pool = (int *)ctx->scratch[SCR_CONTOUR_POOL];
+        pool_next = pool + (size_t)batch * pool_chunks * kChunkInts;
+        BV_CUDA(cudaMemsetAsync(pool_next, 0, batch * sizeof(int), ctx->stream));
+    }
     BV_LAUNCH(ctx, contour_kernel<false>, grid, 128, 0, walk, inv, parent_bg, outer, root_px, nb, contours, max_contours,
-              height, width, wpr, wcols, nullptr, 0, lane_stride);
-    if (points && max_points > 0) {
+              height, width, wpr, wcols, nullptr, 0, lane_stride, pool, pool_next, pool_chunks);
+    if (want_points) {
         BV_LAUNCH(ctx, contour_offsets_kernel, batch, 1024, 0, contours, nb, max_contours, max_points, n_points);
+        BV_LAUNCH(ctx, contour_gather_kernel, dim3((max_contours + 3) / 4, batch), 128, 0, contours, nb, max_contours, pool,
+                  pool_chunks, points, max_points);
+        // borders the pool could not hold (it is sized so that this needs more vertices than max_points): walked again
         BV_LAUNCH(ctx, contour_kernel<true>, grid, 128, 0, walk, inv, parent_bg, outer, root_px, nb, contours, max_contours,
-                  height, width, wpr, wcols, points, max_points, lane_stride);
+                  height, width, wpr, wcols, points, max_points, lane_stride, nullptr, nullptr, 0);
     }
     return BV_OK;
 }

@@ -82,6 +82,7 @@ enum ScratchSlot {
     SCR_HSI_BGR,        // balanced BGR frames the HSI branch works on when the caller does not want them
     SCR_BITS_A,         // bit-packed masks (ping)
     SCR_BITS_B,         // bit-packed masks (pong)
+    SCR_CONTOUR_POOL,   // chunked vertex storage of the contour walk (+ one allocation counter per frame)
     SCR_BITS_TILED,     // copy of the bit mask laid out for the contour walk (walk_bits_kernel)
     SCR_CCL_PARENT,     // union-find parents, int32 per pixel
     SCR_CCL_AUX,        // per-block root counts / offsets

@@ -82,7 +82,7 @@ class Context:
     def launches(self):
         return int(lib.bv_launch_count(self.handle))
 
-    OPTIONS = {"hist_bps": 0, "final_bps": 1, "side_streams": 2, "l2_chunk_mb": 3, "no_hue_table": 4}
+    OPTIONS = {"hist_bps": 0, "final_bps": 1, "side_streams": 2, "l2_chunk_mb": 3, "no_hue_table": 4, "contour_pool_chunks": 5}
 
     def set_option(self, name, value):
         """Tuning knob of the colour-balance passes (include/b200vision.h, BV_OPT_*); 0 = default."""

@@ -151,7 +151,8 @@ enum {
     BV_OPT_SIDE_STREAMS = 2, /* independent chunks of one call in flight (1..4) */
     BV_OPT_L2_CHUNK_MB = 3,  /* input bytes per chunk: the chunk and its H,S,V scratch stay in L2 across the passes */
     BV_OPT_NO_HUE_TABLE = 4, /* 1: always do the HSV round trip arithmetically (testing) */
-    BV_OPT_COUNT = 5
+    BV_OPT_CONTOUR_POOL_CHUNKS = 5, /* chunks of the contour walk's vertex pool per frame (testing the second-walk fallback) */
+    BV_OPT_COUNT = 6
 };
 int bv_set_option(bv_ctx *ctx, int option, int value);
 void bv_balance_default(bv_balance_params *p);

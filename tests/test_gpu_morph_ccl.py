@@ -292,6 +292,35 @@ def test_outer_contours_around_the_walk_word_edges(ctx, height, width):
     check_contours(np.full((height, width), 255, np.uint8))
 
 
+def test_outer_contours_when_the_vertex_pool_runs_dry(ctx):
+    """The first walk keeps the vertices in chunks drawn from a pool; borders the pool cannot hold are walked a second
+    time (csrc/ccl.cu).  A pool of 5 / 40 chunks forces that path for most / some borders; results are unchanged,
+    and the records' reserved field is back to 0 either way."""
+    from cuauv_vision_pipeline_b200 import feature
+    from cuauv_vision_pipeline_b200._host import default_context
+    mask = synth.mask_blobs(270, 480, 3, sigma=5.0)
+    want = feature.outer_contours(mask, points=True)
+    contexts = (ctx, default_context(0))
+    try:
+        for chunks in (5, 40):
+            for c in contexts:
+                c.set_option("contour_pool_chunks", chunks)
+            got = feature.outer_contours(mask, points=True)
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                assert np.array_equal(a["points"], b["points"]) and a["start_x"] == b["start_x"] and a["n_simple"] == b["n_simple"]
+            check_contours(mask)
+            t, nb, pts, npts = ctx.outer_contours(ctx.upload(mask), max_contours=1024, max_points=50000)
+            n = int(ctx.download(nb)[0])
+            recs = np.ascontiguousarray(ctx.download(t)[0, :n]).view(np.int32).reshape(n, 18)
+            assert n == len(cv_ops.outer_contours(mask)) or n > 0
+            assert not recs[:, 17].any()                                        # bv_contour.reserved
+            assert (recs[recs[:, 15] == 1][:, 16] >= 0).all()                   # every external border got its slice
+    finally:
+        for c in contexts:
+            c.set_option("contour_pool_chunks", 0)
+
+
 def test_outer_contours_special_shapes(ctx):
     m = np.zeros((40, 70), np.uint8)
     m[3, 5] = 255                               # single pixel
