@@ -382,6 +382,31 @@ def run_ours(args):
     for s in range(20):
         ctx.stage_host(desc, pin_in.array[0][s % BATCH:s % BATCH + 1], want=("converted",), out=one_out)
     single_ms = (time.perf_counter() - t0) / 20 * 1e3
+    # the box's own host<->device copy ceiling with both directions busy, measured with the same pinned buffers
+    # (it differs between boxes of the pool: 62-99 GB/s seen), so that the end-to-end number can be read against it
+    pcie = None
+    if world == 1:
+        d_in = torch.empty(pin_in.array[0].shape, dtype=torch.uint8, device="cuda")
+        d_out = torch.empty(pin_out.array.shape, dtype=torch.uint8, device="cuda")
+        t_in, t_out = torch.from_numpy(pin_in.array[0]), torch.from_numpy(pin_out.array)
+        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+        torch.cuda.synchronize()
+
+        def both_ways():
+            with torch.cuda.stream(s_up):
+                d_in.copy_(t_in, non_blocking=True)
+            with torch.cuda.stream(s_down):
+                t_out.copy_(d_out, non_blocking=True)
+        both_ways()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            both_ways()
+        torch.cuda.synchronize()
+        both_dt = (time.perf_counter() - t0) / 5
+        pcie = {"both_directions_gbs": (t_in.numel() + t_out.numel()) / both_dt / 1e9,
+                "ceiling_frames_per_s": BATCH / both_dt}
+        del d_in, d_out
     clocks = sampler.stop(mark_a, None) if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "device-resident timed region + per-kernel profile + end-to-end leg"
@@ -389,8 +414,11 @@ def run_ours(args):
            "h2d_bytes_per_step": BATCH * H * W * 3, "d2h_bytes_per_step": BATCH * H * W * 3,
            "api": "bv_stage_host (C ABI, pinned host buffers, blocking)", "steps": e2e_steps,
            "single_frame_latency_ms": single_ms,
-           "pcie_note": "8.23 MB in + 8.23 MB out per frame; this pool's boxes copy ~81 GB/s with both directions busy "
-                        "(profiles/r01_e2e_pcie.log), i.e. a ceiling of ~4.9 k frames/s per GPU"}
+           "pcie_note": "8.23 MB in + 8.23 MB out per frame, copied in both directions at once; `pcie` is this box's own "
+                        "ceiling for that (plain cudaMemcpyAsync of the same pinned buffers, no kernels)"}
+    if pcie is not None:
+        pcie["e2e_frac_of_ceiling"] = e2e["value"] / pcie["ceiling_frames_per_s"]
+        e2e["pcie"] = pcie
 
     if rank == 0:
         cores = os.cpu_count() or 1
