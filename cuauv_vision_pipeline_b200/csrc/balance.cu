@@ -766,13 +766,15 @@ static int launch_mask_from_hsv(bv_ctx *ctx, const uint8_t *hsv, size_t hsv_stri
 // Tiled equalisation (P1): horizontal_blocks x vertical_blocks > 1.  One block works inside one
 // tile (grid = blocks x tiles x frames), per pixel, with that tile's tables.  Same three passes.
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ size_t tile_pixel(const TileGeom &tg, int tile, size_t idx) {
-    const int ty = tile / tg.hb, tx = tile - ty * tg.hb;
-    const int yy = (int)(idx / tg.bw), xx = (int)(idx - (size_t)yy * tg.bw);
-    return (size_t)(ty * tg.bh + yy) * tg.width + (size_t)tx * tg.bw + xx;
+// 4 consecutive pixels = 3 aligned words (tile rows that start on a multiple of 4 pixels, 4-byte aligned frames)
+__device__ __forceinline__ void unpack_px4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t (&c)[4][3]) {
+    c[0][0] = w0 & 0xFFu; c[0][1] = (w0 >> 8) & 0xFFu; c[0][2] = (w0 >> 16) & 0xFFu;
+    c[1][0] = w0 >> 24;   c[1][1] = w1 & 0xFFu;        c[1][2] = (w1 >> 8) & 0xFFu;
+    c[2][0] = (w1 >> 16) & 0xFFu; c[2][1] = w1 >> 24;  c[2][2] = w2 & 0xFFu;
+    c[3][0] = (w2 >> 8) & 0xFFu;  c[3][1] = (w2 >> 16) & 0xFFu; c[3][2] = w2 >> 24;
 }
 
-template <int PASS>
+template <int PASS, bool VEC4>
 __global__ void __launch_bounds__(kBalThreads) hist_tiled_kernel(const uint8_t *__restrict__ src, BalFrame *__restrict__ st,
                                                                  BalTile *__restrict__ tiles, size_t npx, TileGeom tg,
                                                                  bv_balance_params prm, const double *__restrict__ pow_quarter) {
@@ -794,17 +796,47 @@ __global__ void __launch_bounds__(kBalThreads) hist_tiled_kernel(const uint8_t *
     const uint8_t *f = src + (size_t)frame * npx * 3;
     uint32_t(*hw)[256] = h[threadIdx.x >> 5];
     const size_t tile_px = (size_t)tg.bw * tg.bh;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tile_px; idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t p = tile_pixel(tg, tile, idx);
-        if (PASS == 1) {
-            atomicAdd(&hw[0][f[3 * p]], 1u);
-            atomicAdd(&hw[1][f[3 * p + 1]], 1u);
-            atomicAdd(&hw[2][f[3 * p + 2]], 1u);
-        } else {
-            int hh, ss, vv;
-            bgr2hsv(lut[0][f[3 * p]], lut[1][f[3 * p + 1]], lut[2][f[3 * p + 2]], sdiv, hdiv, hh, ss, vv);
-            atomicAdd(&hw[0][ss], 1u);
-            atomicAdd(&hw[1][vv], 1u);
+    // a warp takes whole rows of the tile, its lanes consecutive pixels of the row: no per-pixel index division
+    const int ty = tile / tg.hb, tx = tile - ty * tg.hb;
+    const int lane = threadIdx.x & 31, warps = gridDim.x * kBalWarps;
+    if (VEC4) {
+        // groups of 4 pixels, numbered row after row inside the tile, dealt out to all threads of the tile's blocks
+        const unsigned gpr = (unsigned)tg.bw >> 2, n_groups = gpr * (unsigned)tg.bh;
+        for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
+            const unsigned yy = g / gpr, gx = g - yy * gpr;
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(
+                f + ((size_t)(ty * tg.bh + (int)yy) * tg.width + (size_t)tx * tg.bw + 4 * gx) * 3);
+            uint32_t c[4][3];
+            unpack_px4(__ldg(rw), __ldg(rw + 1), __ldg(rw + 2), c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (PASS == 1) {
+                    atomicAdd(&hw[0][c[k][0]], 1u);
+                    atomicAdd(&hw[1][c[k][1]], 1u);
+                    atomicAdd(&hw[2][c[k][2]], 1u);
+                } else {
+                    int hh, ss, vv;
+                    bgr2hsv(lut[0][c[k][0]], lut[1][c[k][1]], lut[2][c[k][2]], sdiv, hdiv, hh, ss, vv);
+                    atomicAdd(&hw[0][ss], 1u);
+                    atomicAdd(&hw[1][vv], 1u);
+                }
+            }
+        }
+    }
+    for (int yy = blockIdx.x * kBalWarps + (threadIdx.x >> 5); !VEC4 && yy < tg.bh; yy += warps) {
+        const uint8_t *row = f + ((size_t)(ty * tg.bh + yy) * tg.width + (size_t)tx * tg.bw) * 3;
+        for (int xx = lane; xx < tg.bw; xx += 32) {
+            const uint8_t *px = row + 3 * xx;
+            if (PASS == 1) {
+                atomicAdd(&hw[0][px[0]], 1u);
+                atomicAdd(&hw[1][px[1]], 1u);
+                atomicAdd(&hw[2][px[2]], 1u);
+            } else {
+                int hh, ss, vv;
+                bgr2hsv(lut[0][px[0]], lut[1][px[1]], lut[2][px[2]], sdiv, hdiv, hh, ss, vv);
+                atomicAdd(&hw[0][ss], 1u);
+                atomicAdd(&hw[1][vv], 1u);
+            }
         }
     }
     __syncthreads();
@@ -829,7 +861,7 @@ __global__ void __launch_bounds__(kBalThreads) hist_tiled_kernel(const uint8_t *
     }
 }
 
-template <int MODE, int CODE>
+template <int MODE, int CODE, bool VEC4>
 __global__ void __launch_bounds__(kBalThreads) final_tiled_kernel(const uint8_t *__restrict__ src, const BalFrame *__restrict__ st,
                                                                   const BalTile *__restrict__ tiles, size_t npx, TileGeom tg,
                                                                   BalOutputs out, const uint16_t *__restrict__ g_gamma,
@@ -852,10 +884,54 @@ __global__ void __launch_bounds__(kBalThreads) final_tiled_kernel(const uint8_t 
     const int vec_end = tg.width - (tg.width % 32);
     constexpr bool kOne = CvtTraits<CODE>::kOneChannel;
     const RangeTest bd = make_range_test(out.lo, out.hi);
-    const size_t tile_px = (size_t)tg.bw * tg.bh;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tile_px; idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t p = tile_pixel(tg, tile, idx);
-        const int x = (int)(p % (size_t)tg.width);
+    __syncthreads();
+    const int ty = tile / tg.hb, tx = tile - ty * tg.hb;
+    const int lane = threadIdx.x & 31, warps = gridDim.x * kBalWarps;
+    if constexpr (VEC4) {
+        const unsigned gpr = (unsigned)tg.bw >> 2, n_groups = gpr * (unsigned)tg.bh;
+        for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
+            {
+                const unsigned yy = g / gpr, gx = g - yy * gpr;
+                const int x0 = tx * tg.bw + 4 * (int)gx;
+                const size_t p = (size_t)(ty * tg.bh + (int)yy) * tg.width + x0;
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(f + 3 * p);
+                uint32_t c[4][3];
+                unpack_px4(__ldg(rw), __ldg(rw + 1), __ldg(rw + 2), c);
+                uint32_t bal[4], cv[4];
+                uint32_t m = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool vec = x0 + k < vec_end;
+                    bal[k] = balance_px<MODE>(c[k][0], c[k][1], c[k][2], vec, fs);
+                    int o0, o1, o2;
+                    convert_px<CODE>((int)(bal[k] & 0xFF), (int)((bal[k] >> 8) & 0xFF), (int)(bal[k] >> 16), vec, tabs, o0, o1, o2);
+                    cv[k] = kOne ? (uint32_t)o0 : ((uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16));
+                    if (in_range_px<CODE>(o0, o1, o2, bd)) m |= 0xFFu << (8 * k);
+                }
+                if (out.balanced) {
+                    uint32_t *o = reinterpret_cast<uint32_t *>(out.balanced + (foff + p) * 3);
+                    o[0] = bal[0] | (bal[1] << 24);
+                    o[1] = (bal[1] >> 8) | (bal[2] << 16);
+                    o[2] = (bal[2] >> 16) | (bal[3] << 8);
+                }
+                if (out.converted) {
+                    if (kOne) {
+                        *reinterpret_cast<uint32_t *>(out.converted + foff + p) = cv[0] | (cv[1] << 8) | (cv[2] << 16) | (cv[3] << 24);
+                    } else {
+                        uint32_t *o = reinterpret_cast<uint32_t *>(out.converted + (foff + p) * 3);
+                        o[0] = cv[0] | (cv[1] << 24);
+                        o[1] = (cv[1] >> 8) | (cv[2] << 16);
+                        o[2] = (cv[2] >> 16) | (cv[3] << 8);
+                    }
+                }
+                if (out.mask) *reinterpret_cast<uint32_t *>(out.mask + foff + p) = m;
+            }
+        }
+    } else {
+    for (int yy = blockIdx.x * kBalWarps + (threadIdx.x >> 5); yy < tg.bh; yy += warps)
+    for (int xx = lane; xx < tg.bw; xx += 32) {
+        const int x = tx * tg.bw + xx;
+        const size_t p = (size_t)(ty * tg.bh + yy) * tg.width + x;
         const bool vec = x < vec_end;
         const uint32_t px = balance_px<MODE>(f[3 * p], f[3 * p + 1], f[3 * p + 2], vec, fs);
         const int b = (int)(px & 0xFF), gg = (int)((px >> 8) & 0xFF), r = (int)(px >> 16);
@@ -880,13 +956,18 @@ __global__ void __launch_bounds__(kBalThreads) final_tiled_kernel(const uint8_t 
         if (out.mask) out.mask[foff + p] = in_range_px<CODE>(o0, o1, o2, bd) ? 255 : 0;
     }
 }
+}
 
 template <int MODE>
 static int dispatch_final_tiled(bv_ctx *ctx, const uint8_t *src, const BalFrame *st, const BalTile *tiles, dim3 grid,
-                                size_t npx, const TileGeom &tg, int code, const BalOutputs &out) {
-#define BV_FT(C)                                                                                               \
-    BV_LAUNCH(ctx, (final_tiled_kernel<MODE, C>), grid, kBalThreads, 0, src, st, tiles, npx, tg, out, ctx->d_lab_gamma, \
-              ctx->d_lab_cbrt);                                                                                \
+                                size_t npx, const TileGeom &tg, int code, const BalOutputs &out, bool vec4) {
+#define BV_FT(C)                                                                                                          \
+    if (vec4)                                                                                                             \
+        BV_LAUNCH(ctx, (final_tiled_kernel<MODE, C, true>), grid, kBalThreads, 0, src, st, tiles, npx, tg, out,           \
+                  ctx->d_lab_gamma, ctx->d_lab_cbrt);                                                                     \
+    else                                                                                                                  \
+        BV_LAUNCH(ctx, (final_tiled_kernel<MODE, C, false>), grid, kBalThreads, 0, src, st, tiles, npx, tg, out,          \
+                  ctx->d_lab_gamma, ctx->d_lab_cbrt);                                                                     \
     return BV_OK
     switch (code) {
         case -1: BV_FT(-1);
@@ -924,12 +1005,24 @@ static int balance_run_tiled(bv_ctx *ctx, const uint8_t *src, int batch, int hei
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     dim3 grid(bx, n_tiles, batch);
-    BV_LAUNCH(ctx, hist_tiled_kernel<1>, grid, kBalThreads, 0, src, st, tiles, npx, tg, prm, ctx->d_pow_quarter);
+    // word-wide path: every tile row starts on a multiple of 4 pixels and all buffers are 4-byte aligned
+    auto aligned4 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 3) == 0; };
+    const bool vec4 = width % 4 == 0 && tg.bw % 4 == 0 && aligned4(src) && aligned4(out.balanced) && aligned4(out.converted) &&
+                      aligned4(out.mask);
+#define BV_HT(P)                                                                                                       \
+    do {                                                                                                               \
+        if (vec4)                                                                                                      \
+            BV_LAUNCH(ctx, (hist_tiled_kernel<P, true>), grid, kBalThreads, 0, src, st, tiles, npx, tg, prm, ctx->d_pow_quarter); \
+        else                                                                                                           \
+            BV_LAUNCH(ctx, (hist_tiled_kernel<P, false>), grid, kBalThreads, 0, src, st, tiles, npx, tg, prm, ctx->d_pow_quarter); \
+    } while (0)
+    BV_HT(1);
     if (prm.hsv_contrast_correct) {
-        BV_LAUNCH(ctx, hist_tiled_kernel<2>, grid, kBalThreads, 0, src, st, tiles, npx, tg, prm, ctx->d_pow_quarter);
-        return dispatch_final_tiled<2>(ctx, src, st, tiles, grid, npx, tg, cvt_code, out);
+        BV_HT(2);
+#undef BV_HT
+        return dispatch_final_tiled<2>(ctx, src, st, tiles, grid, npx, tg, cvt_code, out, vec4);
     }
-    return dispatch_final_tiled<1>(ctx, src, st, tiles, grid, npx, tg, cvt_code, out);
+    return dispatch_final_tiled<1>(ctx, src, st, tiles, grid, npx, tg, cvt_code, out, vec4);
 }
 
 // ----------------------------------------------------------------------------------------------
