@@ -195,17 +195,26 @@ extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8
         chunk = (batch + BV_MAX_CHUNKS - 1) / BV_MAX_CHUNKS;
         nchunks = (batch + chunk - 1) / chunk;
     }
+    // BV_HOST_TIMELINE=1 (diagnostic): device time stamps of every chunk's upload, kernels and download, to stderr
+    static const bool timeline = getenv("BV_HOST_TIMELINE") != nullptr;
+    cudaEvent_t tl[3 * BV_MAX_CHUNKS + 1];
+    if (timeline) {
+        for (int i = 0; i < 3 * nchunks + 1; ++i) BV_CUDA(cudaEventCreate(&tl[i]));
+        BV_CUDA(cudaEventRecord(tl[3 * nchunks], ctx->copy_in));
+    }
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = k * chunk, nf = (batch - f0 < chunk) ? batch - f0 : chunk;
         const size_t po = (size_t)f0 * npx;
         BV_CUDA(cudaMemcpyAsync(d_in + po * 3, src_host + po * 3, (size_t)nf * npx * 3, cudaMemcpyHostToDevice,
                                 ctx->copy_in));
+        if (timeline) BV_CUDA(cudaEventRecord(tl[3 * k], ctx->copy_in));
         BV_CUDA(cudaEventRecord(ctx->ev_in[k], ctx->copy_in));
         BV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[k], 0));
         BV_TRY(stage_run(ctx, desc, d_in + po * 3, nf, height, width, d_bal ? d_bal + po * 3 : nullptr,
                          d_cvt ? d_cvt + po * cvt_bpp : nullptr, d_mask ? d_mask + po : nullptr,
                          d_lab ? d_lab + po : nullptr, d_blobs ? d_blobs + (size_t)f0 * max_blobs : nullptr, max_blobs,
                          d_nb + f0));
+        if (timeline) BV_CUDA(cudaEventRecord(tl[3 * k + 1], ctx->stream));
         BV_CUDA(cudaEventRecord(ctx->ev_done[k], ctx->stream));
         BV_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[k], 0));
         if (balanced_host)
@@ -225,9 +234,21 @@ extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8
         if (n_blobs_host && desc->do_label)
             BV_CUDA(cudaMemcpyAsync(n_blobs_host + f0, d_nb + f0, (size_t)nf * sizeof(int32_t), cudaMemcpyDeviceToHost,
                                     ctx->copy_out));
+        if (timeline) BV_CUDA(cudaEventRecord(tl[3 * k + 2], ctx->copy_out));
     }
     BV_CUDA(cudaStreamSynchronize(ctx->copy_out));
     BV_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (timeline) {
+        for (int k = 0; k < nchunks; ++k) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, tl[3 * nchunks], tl[3 * k]);
+            cudaEventElapsedTime(&b, tl[3 * nchunks], tl[3 * k + 1]);
+            cudaEventElapsedTime(&c, tl[3 * nchunks], tl[3 * k + 2]);
+            fprintf(stderr, "bv_stage_host chunk %2d: uploaded %8.1f us, kernels done %8.1f us, downloaded %8.1f us\n", k, a * 1e3,
+                    b * 1e3, c * 1e3);
+        }
+        for (int i = 0; i < 3 * nchunks + 1; ++i) cudaEventDestroy(tl[i]);
+    }
     return BV_OK;
 }
 
