@@ -109,6 +109,60 @@ def load_camera_matrix_params(path_or_text):
     return out["M"], out["D"].ravel()
 
 
+def get_optimal_new_camera_matrix(camera_matrix, dist_coeffs, size, alpha, new_size=None):
+    """cv2.getOptimalNewCameraMatrix(camera_matrix, dist_coeffs, size, alpha, new_size)[0] without OpenCV (host-side set-up
+    arithmetic, float64, identical to cv2's result): a 9 x 9 grid over the image is undistorted into normalised coordinates
+    (five fixed-point iterations of the inverse distortion model), the inscribed and the circumscribed rectangle of the
+    grid are each mapped onto the viewport, and `alpha` blends the two projections (0: only valid pixels, 1: all
+    source pixels kept).  size / new_size = (width, height)."""
+    K = np.asarray(camera_matrix, np.float64)
+    k = np.zeros(12)
+    d = np.asarray(dist_coeffs if dist_coeffs is not None else [], np.float64).ravel()
+    k[:d.size] = d
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    ifx, ify = 1.0 / fx, 1.0 / fy
+    n = 9
+    w, h = size
+    pts = np.empty((n, n, 2))
+    for gy in range(n):
+        for gx in range(n):
+            x0 = x = (gx * (w - 1) / (n - 1) - cx) * ifx
+            y0 = y = (gy * (h - 1) / (n - 1) - cy) * ify
+            for _ in range(5):
+                r2 = x * x + y * y
+                icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2)
+                if icdist < 0:
+                    x, y = x0, y0
+                    break
+                dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2
+                dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2
+                x, y = (x0 - dx) * icdist, (y0 - dy) * icdist
+            pts[gy, gx] = (x, y)
+    inner = (pts[:, 0, 0].max(), pts[0, :, 1].max(), pts[:, n - 1, 0].min(), pts[n - 1, :, 1].min())      # x0, y0, x1, y1
+    outer = (pts[..., 0].min(), pts[..., 1].min(), pts[..., 0].max(), pts[..., 1].max())
+    nw, nh = new_size if new_size else size
+    out = K.copy()
+    proj = []
+    for x0, y0, x1, y1 in (inner, outer):
+        fxr, fyr = (nw - 1) / (x1 - x0), (nh - 1) / (y1 - y0)
+        proj.append((fxr, fyr, -fxr * x0, -fyr * y0))
+    (fx0, fy0, cx0, cy0), (fx1, fy1, cx1, cy1) = proj
+    out[0, 0] = fx0 * (1 - alpha) + fx1 * alpha
+    out[1, 1] = fy0 * (1 - alpha) + fy1 * alpha
+    out[0, 2] = cx0 * (1 - alpha) + cx1 * alpha
+    out[1, 2] = cy0 * (1 - alpha) + cy1 * alpha
+    return out
+
+
+def init_undistort_map(params, width, height, alpha=0.0, fixed=True, like=None):
+    """What include/camera_filters.hpp:11 declares (`initUndistortMap(&maps, name, width, height)`; the reference has no
+    definition): read the camera file (path, YAML text or an (M, D) pair), take the optimal new camera matrix for
+    `alpha`, build the two undistortion maps on the device.  Returns (map1, map2) for transform.remap."""
+    m, d = load_camera_matrix_params(params) if isinstance(params, str) else params
+    new_m = get_optimal_new_camera_matrix(m, d, (width, height), alpha)
+    return init_undistort_rectify_map(m, d, None, new_m, (width, height), fixed=fixed, like=like)
+
+
 def init_undistort_rectify_map(camera_matrix, dist_coeffs, rotation, new_camera_matrix, size, fixed=False, like=None):
     """cv2.initUndistortRectifyMap(camera_matrix, dist_coeffs, rotation, new_camera_matrix, size, CV_32FC1) as device maps
     (fixed=True: the CV_16SC2 + CV_16UC1 pair cv2.undistort computes).  The 3x3 inverse is taken on the host."""

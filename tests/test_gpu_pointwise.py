@@ -370,3 +370,16 @@ def test_undistort_with_the_reference_camera_file(ctx):
     mx, my = transform.init_undistort_rectify_map(_CAM_K, d8, rot, _CAM_K, (320, 240))
     rx, ry = cv2.initUndistortRectifyMap(_CAM_K, d8, rot, _CAM_K, (320, 240), cv2.CV_32FC1)
     assert np.array_equal(mx.cpu().numpy(), rx) and np.array_equal(my.cpu().numpy(), ry)
+
+
+def test_init_undistort_map_flow(ctx):
+    """The flow include/camera_filters.hpp:6-11 declares: camera file -> optimal new camera matrix -> maps (once), remap per
+    frame; equals getOptimalNewCameraMatrix + initUndistortRectifyMap(CV_16SC2) + remap of cv2."""
+    from cuauv_vision_pipeline_b200 import transform
+    w, h = 964, 724
+    img = synth.gen_underwater(h, w, 4)
+    for alpha in (0.0, 1.0):
+        maps = transform.init_undistort_map((_CAM_K, _CAM_D), w, h, alpha=alpha)
+        new_k, _ = cv2.getOptimalNewCameraMatrix(_CAM_K, _CAM_D, (w, h), alpha)
+        r1, r2 = cv2.initUndistortRectifyMap(_CAM_K, _CAM_D, None, new_k, (w, h), cv2.CV_16SC2)
+        assert np.array_equal(transform.remap(img, *maps), cv2.remap(img, r1, r2, cv2.INTER_LINEAR))

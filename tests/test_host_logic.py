@@ -147,3 +147,20 @@ D: !!opencv-matrix
     import pytest
     with pytest.raises(ValueError):
         transform.load_camera_matrix_params("%YAML:1.0\nfoo: 1\n")
+
+
+def test_optimal_new_camera_matrix_equals_cv2():
+    """transform.get_optimal_new_camera_matrix restates cv2.getOptimalNewCameraMatrix in float64 (host-side set-up of the
+    undistortion maps, include/camera_filters.hpp:6-11): identical matrices for the reference's camera file and a
+    barrel-distorted one, alpha 0 / 0.3 / 1, same and different output sizes."""
+    import cv2
+    from cuauv_vision_pipeline_b200 import transform
+    k = np.array([[904.66192735, 0.0, 481.17596262], [0.0, 902.84000422, 404.82437525], [0.0, 0.0, 1.0]])
+    for d in (np.array([0.48525658, 2.02550297, 0.03807578, -0.02152142, -3.30299241]), np.array([-0.25, 0.08, 0.001, -0.0005, 0.0]),
+              np.array([-0.3, 0.1, 0.0, 0.0])):
+        for size in ((964, 724), (640, 480)):
+            for alpha in (0.0, 0.3, 1.0):
+                ref, _ = cv2.getOptimalNewCameraMatrix(k, d, size, alpha)
+                assert np.array_equal(transform.get_optimal_new_camera_matrix(k, d, size, alpha), ref)
+        ref, _ = cv2.getOptimalNewCameraMatrix(k, d, (640, 480), 0.3, (800, 600))
+        assert np.array_equal(transform.get_optimal_new_camera_matrix(k, d, (640, 480), 0.3, (800, 600)), ref)
