@@ -153,7 +153,7 @@ def run_reference(args):
     from concurrent.futures import ThreadPoolExecutor
     from oracle import ref_balance
     cores = os.cpu_count() or 1
-    per_step = max(2, min(BATCH, cores))
+    per_step = max(2, cores)            # one frame per host thread: every core works in every step
     ring = make_ring(per_step * 2)
     cv2.setNumThreads(1)
     times = []
@@ -175,6 +175,9 @@ def run_reference(args):
                                "(BASELINE.json configs[1])",
                    "reference_sample": "each step = %d frames on the host cores (compiled reference process_frame + "
                                        "cv2.cvtColor), one frame per thread" % per_step,
+                   "reference_build": "color_balance.cpp compiled unmodified against oracle/cvshim, whose cv::cvtColor / split / merge "
+                                      "are scalar loops (real OpenCV's SIMD BGR2HSV / HSV2BGR would make this arm about 2x faster, "
+                                      "BASELINE.md section 3)",
                    "frames_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores,
                          "kind": "reference" if ref_balance.available() else "port",
@@ -183,6 +186,84 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def cpu_side_baselines(cores, budget_s=4.0):
+    """The reference's CPU OpenCV path for the other BASELINE configs, on this box's host cores (cv2's own
+    thread pool, `cores` threads), each a bounded sample (about `budget_s` seconds).  oracle/cv_ops.py holds the
+    literal calls of the reference's call sites; used here only as the timed baseline."""
+    import cv2
+    from oracle import cv_ops, synth, letterbox, ref_balance, color_balance_np
+    cv2.setNumThreads(cores)
+    res = {}
+
+    def timed(name, fn, frames, unit="frames/s", note="", per_thread=False):
+        """per_thread: one frame per host thread with cv2 single-threaded (for the chains that contain process_frame,
+        which uses two threads at most); otherwise one frame at a time with cv2's own pool over all cores."""
+        from concurrent.futures import ThreadPoolExecutor
+        fn(frames[0])
+        n, t0 = 0, time.perf_counter()
+        if per_thread:
+            cv2.setNumThreads(1)
+            with ThreadPoolExecutor(max_workers=cores) as pool:
+                while True:
+                    list(pool.map(fn, [frames[(n + i) % len(frames)] for i in range(cores)]))
+                    n += cores
+                    dt = time.perf_counter() - t0
+                    if dt > budget_s:
+                        break
+            cv2.setNumThreads(cores)
+        else:
+            while True:
+                fn(frames[n % len(frames)])
+                n += 1
+                dt = time.perf_counter() - t0
+                if dt > budget_s or n >= 400:
+                    break
+        res[name] = {"value": n / dt, "unit": unit, "cores": cores, "kind": "reference",
+                     "sample": "%d frames in %.2f s, %s%s" % (n, dt, ("one frame per thread over %d threads" % cores) if per_thread
+                                                              else ("cv2.setNumThreads(%d)" % cores), note)}
+
+    # C1: modules/red_buoy.py:21-44 at 640x480 -- CPU OpenCV is the subject of this config
+    def c1(img):
+        threshed, cleaned = cv_ops.buoy_mask(img, 150, 255)
+        cs = cv_ops.outer_contours(threshed)                  # red_buoy.py:38 uses `threshed`
+        return [(cv_ops.contour_centroid(c), cv_ops.contour_area(c)) for c in cs]
+    timed("c1_red_buoy_640x480", c1, [synth.gen_underwater(480, 640, 3400 + i) for i in range(8)])
+
+    # C3: modules/bins.py:13-27 at 1920x1080 (+ the declared labelling oracle's cv2 call)
+    def c3(img):
+        _, cleaned = cv_ops.bins_mask(img)
+        return cv2.connectedComponentsWithStats(cleaned, connectivity=8, ltype=cv2.CV_32S)
+    timed("c3_hsv_inrange_open_label_1920x1080", c3, [synth.gen_underwater(1080, 1920, 3100 + i) for i in range(4)])
+
+    # C3 as the reference literally does it: findContours + polygon moments (utils/feature.py:5-21,240-265)
+    def c3c(img):
+        _, cleaned = cv_ops.bins_mask(img)
+        return [(cv_ops.contour_centroid(c), cv2.minAreaRect(c)) for c in cv_ops.outer_contours(cleaned)]
+    timed("c3_hsv_inrange_open_contours_1920x1080", c3c, [synth.gen_underwater(1080, 1920, 3100 + i) for i in range(4)])
+
+    # C4: letterbox + normalise, per image as Ultralytics does it (modules/yolo.py:112-114 "we don't batch")
+    imgs = [synth.gen_underwater(H, W, 3300 + i) for i in range(4)]
+    timed("c4_letterbox_16x2208x1242_to_640_fp16", lambda im: letterbox.yolo_input([im], 640, 640, half=True), imgs,
+          unit="images/s", note=", oracle/letterbox.py (Ultralytics restated; parity unpinned)")
+
+    # C5: balance() + bins chain + labelling at 3840x2160, one frame per call (reference process_frame is
+    # internally 2-threaded at most, color_balance.cpp:398-418)
+    bal = ref_balance.balance if ref_balance.available() else color_balance_np.process_frame_np
+
+    def c5(img):
+        _, cleaned = cv_ops.bins_mask(bal(img))
+        return cv2.connectedComponentsWithStats(cleaned, connectivity=8, ltype=cv2.CV_32S)
+    timed("c5_balance_threshold_label_3840x2160", c5, [synth.gen_c5_frame(3200 + i) for i in range(2)],
+          note=", compiled reference process_frame (scalar cv shim) + cv2", per_thread=True)
+
+    # north-star fused stage at 2208x1242 on the CPU: balance -> HSV -> inRange -> OPEN
+    def fused(img):
+        return cv_ops.bins_mask(bal(img), (0, 40, 60), (179, 255, 255))[1]
+    timed("fused_balance_hsv_inrange_open_2208x1242", fused, imgs, per_thread=True)
+    cv2.setNumThreads(0)
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -229,12 +310,12 @@ def side_workloads(ctx, peak_gbs):
     o3 = {}
     fps("c3_hsv_inrange_open_label_1920x1080",
         lambda s: o3.update(ctx.stage(d3, ring3, want=("mask", "labels", "blobs"), max_blobs=4096, out=o3)), 16, 8 * 1080 * 1920)
-    # C5: 3840x2160 balance -> HSV -> inRange -> OPEN -> label (8 B/px), 8 streams
-    ring5 = ctx.upload(np.stack([synth.gen_underwater(2160, 3840, 3200 + i) for i in range(8)]))
-    d5 = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255), morph=[("open", 5, 5, 1)], label=True)
-    o5 = {}
-    fps("c5_balance_threshold_label_3840x2160",
-        lambda s: o5.update(ctx.stage(d5, ring5, want=("mask", "labels", "blobs"), max_blobs=8192, out=o5)), 8, 8 * 2160 * 3840)
+    # C1: 640x480 red_buoy chain (modules/red_buoy.py:21-44): LAB a-channel inRange -> OPEN -> CLOSE, mask out (4 B/px);
+    # the config's subject is the CPU path, its number sits beside this one as cpu_baseline
+    ring1 = ctx.upload(np.stack([synth.gen_underwater(480, 640, 3400 + i) for i in range(64)]))
+    d1 = ctx.make_stage(cvt="bgr2lab", lo=(0, 150, 0), hi=(255, 255, 255), morph=[("open", 5, 5, 1), ("close", 5, 5, 1)])
+    o1 = {}
+    fps("c1_red_buoy_640x480", lambda s: o1.update(ctx.stage(d1, ring1, want=("mask",), out=o1)), 64, 4 * 480 * 640)
     # C4: 16 frames -> letterbox 640x640 fp16
     imgs = [ctx.upload(synth.gen_underwater(H, W, 3300 + i)) for i in range(16)]
     bytes_batch = 16 * H * W * 3 + 16 * 3 * 640 * 640 * 2
@@ -253,9 +334,75 @@ def side_workloads(ctx, peak_gbs):
     res["stream_bgr2gray_16x2208x1242"] = {"frames_per_s": 160 / dt, "ms_per_step": 1e2 * dt,
                                            "algorithmic_gbs": 4 * H * W * 160 / dt / 1e9,
                                            "frac_of_hbm": 4 * H * W * 160 / dt / 1e9 / peak_gbs}
-    del ring, ring3, ring5, imgs, rgba
+    del ring, ring1, ring3, imgs, rgba
     torch.cuda.empty_cache()
     return res
+
+
+C5_STREAMS = 8
+C5_H, C5_W = 2160, 3840
+
+
+def c5_leg(ctx, world, rank, peak_gbs, steps=20, warmup=3):
+    """BASELINE.json configs[4]: 8 camera streams of 3840x2160 through balance -> BGR2HSV -> inRange -> OPEN 5x5 ->
+    labels + moments (modules/bins.py:13-27 behind preprocessor.py:87-88), stream s on GPU s mod N, no collective.
+    The 8 streams are fixed, so this leg scales STRONGLY with N.  One step = one new frame from every stream."""
+    import torch
+    import torch.distributed as dist
+    from oracle import synth
+    mine = [s for s in range(C5_STREAMS) if s % world == rank]
+    base = [synth.gen_c5_frame(3200 + i, C5_H, C5_W, big_target=(i == 0)) for i in range(2)]
+    # per stream a ring of two distinct frames (cyclic shifts keep the statistics, change every pixel's position)
+    rings = [ctx.upload(np.stack([np.roll(base[i], 97 * (s + 1) + 13 * i, axis=1) for s in mine])) for i in range(2)] if mine else []
+    desc = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255), morph=[("open", 5, 5, 1)], label=True)
+    out = {}
+
+    def step(s):
+        if mine:
+            out.update(ctx.stage(desc, rings[s % 2], want=("mask", "labels", "blobs"), max_blobs=8192, out=out))
+    for s in range(warmup):
+        step(s)
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ctx.torch_stream):
+        e0.record()
+    for s in range(steps):
+        step(warmup + s)
+    with torch.cuda.stream(ctx.torch_stream):
+        e1.record()
+    ctx.sync()
+    dt = e0.elapsed_time(e1) / 1e3
+    if world > 1:
+        t = torch.tensor([dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    fps = C5_STREAMS * steps / dt
+    gbs = 8 * C5_H * C5_W * fps / 1e9
+    n_blobs = int(ctx.download(out["n_blobs"])[0]) if mine else None
+    del rings
+    out.clear()
+    torch.cuda.empty_cache()
+    return {"frames_per_s": fps, "ms_per_step": 1e3 * dt / steps, "streams": C5_STREAMS, "steps": steps,
+            "streams_per_gpu": [len([s for s in range(C5_STREAMS) if s % world == r]) for r in range(world)],
+            "scaling": "strong", "shape": "%dx%d" % (C5_W, C5_H), "algorithmic_gbs": gbs,
+            "frac_of_hbm": gbs / (peak_gbs * min(world, C5_STREAMS)), "blobs_in_first_frame": n_blobs,
+            "workload": "C5: 8 streams 3840x2160, balance -> BGR2HSV -> inRange([10,20,60],[30,100,255]) -> OPEN 5x5 -> "
+                        "labels + moments, mask + labels + blob table out (8 B/px), stream s -> GPU s mod N"}
+
+
+def load_static_profile():
+    """Per-kernel numbers that only ncu can give (steady-state DRAM bytes, executed instructions), from the
+    committed capture of the same workload; bench.py measures the kernel TIME live."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f), name
+        except Exception:  # noqa: BLE001
+            continue
+    return None, None
 
 
 def run_ours(args):
@@ -277,6 +424,13 @@ def run_ours(args):
     ctx = bv.Context(local)
     peak_gbs, peak_src = read_peaks()
 
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # synthetic ring, distinct per rank (frame f of the global stream goes to rank f mod world)
     ring_np = make_ring(RING, seed0=2000 + 100 * rank)
     ring = ctx.upload(ring_np)
@@ -294,6 +448,18 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    def timed_steps(n, first):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ctx.torch_stream):
+            e0.record()
+        for s in range(n):
+            step(first + s)
+        with torch.cuda.stream(ctx.torch_stream):
+            e1.record()
+        barrier()
+        return allmax(e0.elapsed_time(e1) / 1e3)
+
     # ---- device-resident throughput ----
     for s in range(args.warmup):
         step(s)
@@ -307,22 +473,15 @@ def run_ours(args):
     barrier()
     mark_a = sampler.mark()
     launches0 = ctx.launches
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(ctx.torch_stream):
-        e0.record()
-    for s in range(args.steps):
-        step(args.warmup + s)
-    with torch.cuda.stream(ctx.torch_stream):
-        e1.record()
-    barrier()
-    elapsed = e0.elapsed_time(e1) / 1e3
+    elapsed = timed_steps(args.steps, args.warmup)
     launches = ctx.launches - launches0
-    if world > 1:
-        t = torch.tensor([elapsed], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
     value = world * BATCH * args.steps / elapsed
+    # the same step repeated for >= ~1.5 s: what a continuously running consumer sees (clocks, power cap)
+    sus_steps = int(min(20000, max(args.steps, args.sustain_s / (elapsed / args.steps))))
+    sus_elapsed = timed_steps(sus_steps, args.warmup + args.steps)
+    sustained = {"value": world * BATCH * sus_steps / sus_elapsed, "unit": "frames/s", "steps": sus_steps,
+                 "seconds": sus_elapsed}
+    mark_b = sampler.mark()
 
     # ---- per-kernel timing (library profiler: CUDA events around every launch) ----
     ctx.profile(True)
@@ -337,23 +496,37 @@ def run_ours(args):
     chunk_frames = min(chunk_frames, BATCH)
     dom_ms = prof[dom]["ms"] / prof[dom]["launches"]
     achieved = BPP_C2 * H * W * chunk_frames / (dom_ms / 1e3) / 1e9
-    traffic, traffic_src = None, None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f)
-        if dom in t["kernels"]:
-            per_frame = t["kernels"][dom]["dram_bytes_per_launch"] / t["kernels"][dom]["frames_per_launch"]
-            traffic, traffic_src = per_frame * chunk_frames, t["source"]
-    except Exception:  # noqa: BLE001
-        pass
+    static, static_name = load_static_profile()
+    traffic, traffic_src, issue = None, None, None
+    sm_clock_hz = 1.965e9
+    if static:
+        k = static.get("kernels", {}).get(dom)
+        if k:
+            if k.get("dram_bytes_per_launch") is not None:
+                traffic = k["dram_bytes_per_launch"] / k["frames_per_launch"] * chunk_frames
+                traffic_src = "profiles/%s: %s" % (static_name, static.get("source", ""))
+            if k.get("warp_instructions_per_launch"):
+                ipp = k["warp_instructions_per_launch"] * 32.0 / (k["frames_per_launch"] * H * W)
+                bound_us = ipp * H * W * chunk_frames / (148 * 4 * 32 * sm_clock_hz) * 1e6
+                issue = {"thread_instr_per_px": ipp, "issue_bound_us_per_launch": bound_us,
+                         "measured_us_per_launch": dom_ms * 1e3, "frac_of_issue_bound": bound_us / (dom_ms * 1e3),
+                         "note": "instr/px x px / (148 SM x 4 schedulers x 32 lanes x 1.965 GHz); instr from ncu "
+                                 "smsp__inst_executed.sum of profiles/%s" % static_name}
+        st = static.get("steady_state")
+    else:
+        st = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel_ms_per_launch": dom_ms, "kernel_share_of_step": prof[dom]["ms"] / total_ms,
-                "algorithmic_bytes_per_launch": BPP_C2 * H * W * chunk_frames,
+                "algorithmic_bytes_per_launch": BPP_C2 * H * W * chunk_frames, "issue": issue,
                 "note": "achieved = 6 B/px (BGR in + LAB out) x frames in one launch / that kernel's CUDA-event time"}
     stage_gbs = BPP_C2 * H * W * value / world / 1e9
     stage_roofline = {"achieved": stage_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": stage_gbs / peak_gbs,
+                      "steady_state_dram_bytes_per_frame": st,
                       "per_kernel_ms": {k: round(v["ms"] / 4, 4) for k, v in sorted(prof.items())}}
+
+    # ---- C5: 8 x 4K streams sharded by stream (strong scaling), every rank ----
+    c5 = None if args.no_side else c5_leg(ctx, world, rank, peak_gbs)
 
     # ---- end to end through the host-buffer entry point (pinned memory) ----
     pin_in = bv.PinnedArray((2, BATCH, H, W, 3))
@@ -369,11 +542,18 @@ def run_ours(args):
     for s in range(e2e_steps):
         ctx.stage_host(desc, pin_in.array[s % 2], want=("converted",), out=host_out)
     barrier()
-    e2e_dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_dt], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
+    e2e_dt = allmax(time.perf_counter() - t0)
+    # module-realistic end to end (modules/bins.py: a frame goes in, a blob table comes out): the D2H side is KBs
+    desc_bins = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255), morph=[("open", 5, 5, 1)], label=True)
+    bins_out = {}
+    for s in range(2):
+        bins_out = ctx.stage_host(desc_bins, pin_in.array[s % 2], want=("blobs",), max_blobs=1024, out=bins_out)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        ctx.stage_host(desc_bins, pin_in.array[s % 2], want=("blobs",), max_blobs=1024, out=bins_out)
+    barrier()
+    bins_dt = allmax(time.perf_counter() - t0)
     # single-frame latency of the drop-in call (what a module's process() pays per frame)
     one_out = {"converted": pin_out.array[:1]}
     for s in range(3):
@@ -382,48 +562,67 @@ def run_ours(args):
     for s in range(20):
         ctx.stage_host(desc, pin_in.array[0][s % BATCH:s % BATCH + 1], want=("converted",), out=one_out)
     single_ms = (time.perf_counter() - t0) / 20 * 1e3
-    # the box's own host<->device copy ceiling with both directions busy, measured with the same pinned buffers
-    # (it differs between boxes of the pool: 62-99 GB/s seen), so that the end-to-end number can be read against it
-    pcie = None
-    if world == 1:
-        d_in = torch.empty(pin_in.array[0].shape, dtype=torch.uint8, device="cuda")
-        d_out = torch.empty(pin_out.array.shape, dtype=torch.uint8, device="cuda")
-        t_in, t_out = torch.from_numpy(pin_in.array[0]), torch.from_numpy(pin_out.array)
-        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
-        torch.cuda.synchronize()
+    # the box's own host<->device copy ceiling, measured with the same pinned buffers and EVERY rank copying at the
+    # same time (the host memory system is shared by all GPUs of the box; it differs between boxes of the pool)
+    d_in = torch.empty(pin_in.array[0].shape, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(pin_out.array.shape, dtype=torch.uint8, device="cuda")
+    t_in, t_out = torch.from_numpy(pin_in.array[0]), torch.from_numpy(pin_out.array)
+    s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
 
-        def both_ways():
+    def copies(up, down):
+        if up:
             with torch.cuda.stream(s_up):
                 d_in.copy_(t_in, non_blocking=True)
+        if down:
             with torch.cuda.stream(s_down):
                 t_out.copy_(d_out, non_blocking=True)
-        both_ways()
-        torch.cuda.synchronize()
+
+    def copy_rate(up, down, reps=5):
+        copies(up, down)
+        barrier()
         t0 = time.perf_counter()
-        for _ in range(5):
-            both_ways()
+        for _ in range(reps):
+            copies(up, down)
         torch.cuda.synchronize()
-        both_dt = (time.perf_counter() - t0) / 5
-        pcie = {"both_directions_gbs": (t_in.numel() + t_out.numel()) / both_dt / 1e9,
-                "ceiling_frames_per_s": BATCH / both_dt}
-        del d_in, d_out
-    clocks = sampler.stop(mark_a, None) if rank == 0 else None
+        dt = time.perf_counter() - t0
+        barrier()
+        return allmax(dt) / reps
+    both_dt = copy_rate(True, True)
+    up_dt = copy_rate(True, False)
+    nbytes_in, nbytes_out = t_in.numel(), t_out.numel()
+    pcie = {"both_directions_gbs": world * (nbytes_in + nbytes_out) / both_dt / 1e9,
+            "h2d_only_gbs": world * nbytes_in / up_dt / 1e9,
+            "ceiling_frames_per_s": world * BATCH / both_dt,
+            "h2d_only_ceiling_frames_per_s": world * BATCH / up_dt,
+            "ranks_copying_concurrently": world}
+    del d_in, d_out
+    clocks = sampler.stop(mark_a, mark_b) if rank == 0 else None
     if clocks is not None:
-        clocks["window"] = "device-resident timed region + per-kernel profile + end-to-end leg"
+        clocks["window"] = "device-resident timed region + the sustained repetition (%.1f s)" % sus_elapsed
     e2e = {"value": world * BATCH * e2e_steps / e2e_dt, "unit": "frames/s",
            "h2d_bytes_per_step": BATCH * H * W * 3, "d2h_bytes_per_step": BATCH * H * W * 3,
            "api": "bv_stage_host (C ABI, pinned host buffers, blocking)", "steps": e2e_steps,
            "single_frame_latency_ms": single_ms,
            "pcie_note": "8.23 MB in + 8.23 MB out per frame, copied in both directions at once; `pcie` is this box's own "
-                        "ceiling for that (plain cudaMemcpyAsync of the same pinned buffers, no kernels)"}
-    if pcie is not None:
-        pcie["e2e_frac_of_ceiling"] = e2e["value"] / pcie["ceiling_frames_per_s"]
-        e2e["pcie"] = pcie
+                        "ceiling for that (plain cudaMemcpyAsync of the same pinned buffers on every rank at once, no kernels)",
+           "pcie": pcie,
+           "bins_module": {"value": world * BATCH * e2e_steps / bins_dt, "unit": "frames/s",
+                           "h2d_bytes_per_step": BATCH * H * W * 3, "d2h_bytes_per_step": BATCH * (1024 * 96 + 4),
+                           "frac_of_h2d_ceiling": (world * BATCH * e2e_steps / bins_dt) / pcie["h2d_only_ceiling_frames_per_s"],
+                           "workload": "frames in, blob tables out: balance -> BGR2HSV -> inRange -> OPEN 5x5 -> labels + "
+                                       "moments (modules/bins.py:13-27), bv_stage_host"}}
+    pcie["e2e_frac_of_ceiling"] = e2e["value"] / pcie["ceiling_frames_per_s"]
 
     if rank == 0:
         cores = os.cpu_count() or 1
         cpu = cpu_baseline(list(ring_np[:min(32, max(8, cores))]), cores) if (world == 1 and not args.no_cpu) else None
         others = side_workloads(ctx, peak_gbs) if (world == 1 and not args.no_side) else None
+        if others is not None and not args.no_cpu:
+            for k, v in cpu_side_baselines(cores).items():
+                if k.startswith("c5_") and c5 is not None:
+                    c5["cpu_baseline"] = v
+                else:
+                    others.setdefault(k, {})["cpu_baseline"] = v
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
@@ -435,8 +634,9 @@ def run_ours(args):
                              "different batches)",
                        "parallelism": "frames sharded by index over %d GPU(s), no collective" % world,
                        "host_affinity": ("%d CPUs local to each GPU" % len(numa_cpus)) if numa_cpus else "default"},
+            "sustained": sustained,
             "roofline": roofline, "stage_roofline": stage_roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches, "clocks": clocks, "other_workloads": others,
+            "gpu_launches": launches, "clocks": clocks, "c5": c5, "other_workloads": others,
         }
         print(json.dumps(line))
     if world > 1:
@@ -453,6 +653,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-side", action="store_true", help="skip the short measurements of the other configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (tuning sweeps only)")
+    ap.add_argument("--sustain-s", dest="sustain_s", type=float, default=1.5,
+                    help="seconds of back-to-back steps for the `sustained` value")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

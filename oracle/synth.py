@@ -98,3 +98,18 @@ def mask_diagonals(height, width):
     yy, xx = np.mgrid[0:height, 0:width]
     m[((yy + xx) % 7 == 0) | ((yy - xx) % 11 == 0)] = 255
     return m
+
+
+def gen_c5_frame(seed, height=2160, width=3840, big_target=True):
+    """C5 frame (BASELINE.json configs[4]): an underwater frame plus, optionally, one large flat bin-coloured
+    target with two holes in the right half.  After balance() -> BGR2HSV -> inRange([10,20,60],[30,100,255]) ->
+    OPEN 5x5 (modules/bins.py:13-27) seed 9100 at 3840x2160 labels it as ONE blob of ~0.94 Mpx whose third-order
+    moment m30 = 3.0e16 exceeds 2^53, so int64 accumulation is exercised."""
+    img = gen_underwater(height, width, seed)
+    if big_target:
+        y0, y1 = height * 1100 // 2160, height * 2000 // 2160
+        x0, x1 = width * 2600 // 3840, width * 3700 // 3840
+        img[y0:y1, x0:x1] = (122, 113, 53)
+        cv2.circle(img, (width * 3000 // 3840, height * 1500 // 2160), max(2, height * 120 // 2160), (30, 20, 5), -1)
+        cv2.circle(img, (width * 3400 // 3840, height * 1300 // 2160), max(2, height * 40 // 2160), (30, 20, 5), -1)
+    return img
