@@ -37,8 +37,10 @@ ffi.cdef(_cdef_text())
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    # build when the library is missing, and re-build when a source is newer than it and nvcc is here (a stale binary
+    # would silently run old kernels); on a box without nvcc the prebuilt library that travelled with the tree is used
+    from . import build as _build
+    if not os.path.exists(LIB_PATH) or (_build.needs_build() and os.path.exists(_build.NVCC)):
         _build.build()
     return ffi.dlopen(LIB_PATH)
 

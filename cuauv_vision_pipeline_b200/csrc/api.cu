@@ -223,7 +223,7 @@ extern "C" int bv_create(int device, bv_ctx **out) {
         return BV_ERR_CUDA;
     }
     static const char *const opt_env[BV_OPT_COUNT] = {"BV_HIST_BPS", "BV_FINAL_BPS", "BV_SIDE_STREAMS", "BV_L2_CHUNK_MB",
-                                                      "BV_NO_HUE_TABLE", "BV_CONTOUR_POOL_CHUNKS"};
+                                                      "BV_NO_HUE_TABLE", "BV_CONTOUR_POOL_CHUNKS", "BV_FAST_TABLES"};
     for (int i = 0; i < BV_OPT_COUNT; ++i) {
         const char *v = getenv(opt_env[i]);
         ctx->opt[i] = v ? atoi(v) : 0;
@@ -243,6 +243,10 @@ extern "C" void bv_destroy(bv_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    if (ctx->prof) {  // while the stream it synchronises on still exists
+        ctx->stream = ctx->own_stream;
+        bv_profile_enable(ctx, 0);
+    }
     for (int i = 0; i < SCR_COUNT; ++i)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->d_lab_gamma) cudaFree(ctx->d_lab_gamma);
@@ -265,10 +269,6 @@ extern "C" void bv_destroy(bv_ctx *ctx) {
     for (int i = 0; i < BV_MAX_CHUNKS; ++i) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
-    }
-    if (ctx->prof) {
-        ctx->stream = ctx->own_stream;
-        bv_profile_enable(ctx, 0);
     }
     (void)cudaGetLastError();
     free(ctx);

@@ -15,6 +15,8 @@
 namespace bv {
 
 // 16 pixels per thread: 4 x 128-bit loads (64 B), 3 x 128-bit stores (48 B)
+// SWAP: also exchange bytes 0 and 2 of every pixel (RGBA -> BGR), one byte permute per pixel
+template <bool SWAP>
 __global__ void __launch_bounds__(256) rgba_to_rgb_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                                           size_t npx, bool vec) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -26,8 +28,9 @@ __global__ void __launch_bounds__(256) rgba_to_rgb_kernel(const uint8_t *__restr
         uint32_t o[12];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // 4 RGBA words -> 3 packed words
-            const uint32_t p0 = in[4 * k] & 0xFFFFFFu, p1 = in[4 * k + 1] & 0xFFFFFFu, p2 = in[4 * k + 2] & 0xFFFFFFu,
-                           p3 = in[4 * k + 3] & 0xFFFFFFu;
+            const uint32_t sel = SWAP ? 0x4012u : 0x4210u;  // byte 3 <- 0
+            const uint32_t p0 = __byte_perm(in[4 * k], 0u, sel), p1 = __byte_perm(in[4 * k + 1], 0u, sel),
+                           p2 = __byte_perm(in[4 * k + 2], 0u, sel), p3 = __byte_perm(in[4 * k + 3], 0u, sel);
             o[3 * k] = p0 | (p1 << 24);
             o[3 * k + 1] = (p1 >> 8) | (p2 << 16);
             o[3 * k + 2] = (p2 >> 16) | (p3 << 8);
@@ -38,9 +41,9 @@ __global__ void __launch_bounds__(256) rgba_to_rgb_kernel(const uint8_t *__restr
         st_stream(w + 2, make_uint4(o[8], o[9], o[10], o[11]));
     }
     for (size_t p = ngroups * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += stride) {
-        dst[3 * p] = src[4 * p];
+        dst[3 * p] = src[4 * p + (SWAP ? 2 : 0)];
         dst[3 * p + 1] = src[4 * p + 1];
-        dst[3 * p + 2] = src[4 * p + 2];
+        dst[3 * p + 2] = src[4 * p + (SWAP ? 0 : 2)];
     }
 }
 
@@ -114,16 +117,25 @@ __global__ void __launch_bounds__(256) channel_sums_kernel(const uint8_t *__rest
 
 }  // namespace bv
 
+namespace bv {
+int rgba_to_rgb_run(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, size_t n_pixels, int swap_rb) {
+    const bool vec = host_aligned16(src_dev) && host_aligned16(dst_dev);
+    const int grid = grid_for(ctx, vec ? (n_pixels + 15) / 16 : n_pixels, 256, 8);
+    if (swap_rb)
+        BV_LAUNCH(ctx, rgba_to_rgb_kernel<true>, grid, 256, 0, src_dev, dst_dev, n_pixels, vec);
+    else
+        BV_LAUNCH(ctx, rgba_to_rgb_kernel<false>, grid, 256, 0, src_dev, dst_dev, n_pixels, vec);
+    return BV_OK;
+}
+}  // namespace bv
+
 using namespace bv;
 
 extern "C" int bv_rgba_to_rgb(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, size_t n_pixels) {
     BV_REQUIRE(ctx && src_dev && dst_dev, "null argument");
     BV_CUDA(cudaSetDevice(ctx->device));
     if (!n_pixels) return BV_OK;
-    const bool vec = host_aligned16(src_dev) && host_aligned16(dst_dev);
-    BV_LAUNCH(ctx, rgba_to_rgb_kernel, grid_for(ctx, vec ? (n_pixels + 15) / 16 : n_pixels, 256, 8), 256, 0, src_dev, dst_dev,
-              n_pixels, vec);
-    return BV_OK;
+    return rgba_to_rgb_run(ctx, src_dev, dst_dev, n_pixels, 0);
 }
 
 extern "C" int bv_normals_to_rgb01(bv_ctx *ctx, const float *src_xyzw_dev, float *dst_rgb_dev, size_t n_pixels) {

@@ -58,6 +58,10 @@ __device__ __forceinline__ int uchar_cast(double v) {
 // are the first / last non-empty bins (cv::minMaxLoc, 421-423).  Also the exact sum of the clipped
 // channel, sum_i clamp(i, lo, hi) * cnt[i]  (the numerator of cv::mean, 426-428).
 // ----------------------------------------------------------------------------------------------
+// The statistics helpers below are run by the first 256 threads (8 whole warps) of a block, thread t owning bin t; they
+// synchronise on named barrier 1 so that blocks of more than 256 threads (balance_fast.cuh) can call them too.
+__device__ __forceinline__ void stat_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 struct StatScratch {
     unsigned long long warp_sum[3][kBalWarps];
     uint32_t warp_cnt[3][kBalWarps];
@@ -81,11 +85,11 @@ __device__ void hist_stats_block(const uint32_t (&c)[N], size_t npx, long long l
             if (lane >= d) incl[k] += o;
         }
     }
-    __syncthreads();  // protects sc from the previous call
+    stat_sync();  // protects sc from the previous call
     if (lane == 31)
 #pragma unroll
         for (int k = 0; k < N; ++k) sc.warp_cnt[k][wid] = incl[k];
-    __syncthreads();
+    stat_sync();
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         uint32_t before = 0;
@@ -101,7 +105,7 @@ __device__ void hist_stats_block(const uint32_t (&c)[N], size_t npx, long long l
             sc.cnt_hi[k][wid] = wh;
         }
     }
-    __syncthreads();
+    stat_sync();
     unsigned long long v[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -122,7 +126,7 @@ __device__ void hist_stats_block(const uint32_t (&c)[N], size_t npx, long long l
         for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_down_sync(0xFFFFFFFFu, v[k], d);
         if (lane == 0) sc.warp_sum[k][wid] = v[k];
     }
-    __syncthreads();
+    stat_sync();
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         unsigned long long tot = 0;
@@ -145,9 +149,9 @@ __device__ unsigned long long block_clipped_sum(uint32_t c, int lo, int hi, Stat
     unsigned long long v = (unsigned long long)cl * c;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
-    __syncthreads();
+    stat_sync();
     if (lane == 0) sc.warp_sum[0][wid] = v;
-    __syncthreads();
+    stat_sync();
     unsigned long long tot = 0;
 #pragma unroll
     for (int w = 0; w < kBalWarps; ++w) tot += sc.warp_sum[0][w];
@@ -178,7 +182,7 @@ __device__ void stats_bgr_block(BalFrame &F, size_t npx, const bv_balance_params
                 s_local[c] = s_avg[c];  // a single tile is the frame itself: same histogram, same clipped sum
             }
     }
-    __syncthreads();
+    stat_sync();
     if (t == 0) {
         const double b = s_avg[0], g = s_avg[1], r = s_avg[2];
         for (int c = 0; c < 3; ++c) {
@@ -205,7 +209,7 @@ __device__ void stats_bgr_block(BalFrame &F, size_t npx, const bv_balance_params
             s_ratio[mx] = ((double)s_hi[mx] - 0.0) / (double)(s_hi[mx] - s_lo[mx]);
         }
     }
-    __syncthreads();
+    stat_sync();
     for (int tile = 0; tile < n_tiles; ++tile) {
         const uint32_t(*hist)[256] = tiles ? tiles[tile].hist : F.hist_bgr;
         uint8_t(*lut)[256] = tiles ? tiles[tile].lut : F.lut_bgr;
@@ -216,7 +220,7 @@ __device__ void stats_bgr_block(BalFrame &F, size_t npx, const bv_balance_params
                 if (t == 0) s_local[c] = (double)sum / (double)tile_px;
             }
         }
-        __syncthreads();
+        stat_sync();
         if (t == 0) {
             double lb_ = s_local[0], lg_ = s_local[1], lr_ = s_local[2];
             // 474: unqualified abs() == int abs(int) in the compiled reference: the difference is
@@ -237,7 +241,7 @@ __device__ void stats_bgr_block(BalFrame &F, size_t npx, const bv_balance_params
             s_dom = dom;
             if (tile == 0) F.stats.dominant = dom;
         }
-        __syncthreads();
+        stat_sync();
         // every thread builds entry t of the three composed tables
         for (int c = 0; c < 3; ++c) {
             int x = t < s_lo[c] ? s_lo[c] : (t > s_hi[c] ? s_hi[c] : t);                 // clip_channel, 25-45
@@ -251,7 +255,7 @@ __device__ void stats_bgr_block(BalFrame &F, size_t npx, const bv_balance_params
             if (prm.rgb_contrast_correct) x = uchar_cast((double)(x - s_lo[c]) * s_ratio[c]);  // 634-640
             lut[c][t] = (uint8_t)x;
         }
-        __syncthreads();
+        stat_sync();
     }
 }
 
@@ -272,7 +276,7 @@ __device__ void stats_sv_block(BalFrame &F, size_t npx, StatScratch &sc) {
                 hi[c] = h[c];
             }
     }
-    __syncthreads();
+    stat_sync();
     if (t == 0) {
         F.stats.s_min = lo[0];
         F.stats.s_max = hi[0];
@@ -373,6 +377,10 @@ __device__ __forceinline__ void store_px16_keep(uint8_t *base, size_t group, con
     q[1] = make_uint4(p.w[4], p.w[5], p.w[6], p.w[7]);
     q[2] = make_uint4(p.w[8], p.w[9], p.w[10], p.w[11]);
 }
+
+}  // namespace bv
+#include "balance_fast.cuh"
+namespace bv {
 
 // ----------------------------------------------------------------------------------------------
 // pass 2: S and V histograms of the table-corrected frame (+ statistics in the last block)
@@ -1084,6 +1092,59 @@ static bool all_vec(const uint8_t *src, const BalOutputs &out, size_t npx, int b
            vec_ok(out.mask, npx, batch, 1);
 }
 
+// ---- fast passes 2 and 3 (balance_fast.cuh): 512-thread blocks, two per SM, ~107 KB of replicated tables each ----
+static int fast_blocks_per_frame(const bv_ctx *ctx, int nf, size_t npx) {
+    int bpf = (ctx->sm_count * 2 + nf - 1) / nf;
+    const size_t need = (npx / 16 + kFastThreads - 1) / kFastThreads;
+    if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
+    return bpf;
+}
+
+template <typename K>
+static int enable_fast_smem(bv_ctx *ctx, K kernel, int bit, size_t bytes) {
+    if (!(ctx->fast_attr_set & (1u << bit))) {  // per context, hence per device
+        BV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        ctx->fast_attr_set |= 1u << bit;
+    }
+    return BV_OK;
+}
+
+static int launch_hist_sv_fast(bv_ctx *ctx, const uint8_t *src, BalFrame *st, int nf, size_t npx, uint8_t *hsv, size_t hsv_stride) {
+    BV_TRY(enable_fast_smem(ctx, hist_sv_fast_kernel, 0, sizeof(Sv2Smem)));
+    dim3 grid(fast_blocks_per_frame(ctx, nf, npx), nf);
+    BV_LAUNCH_PDL(ctx, hist_sv_fast_kernel, grid, kFastThreads, sizeof(Sv2Smem), src, st, npx, hsv, hsv_stride);
+    return BV_OK;
+}
+
+template <int CODE, int BIT>
+static int launch_final_fast(bv_ctx *ctx, const uint8_t *hsv, size_t hsv_stride, const BalFrame *st, int nf, size_t npx, int width,
+                             const BalOutputs &out) {
+    const size_t smem = CODE == BV_BGR2LAB ? sizeof(Fin2Smem) : sizeof(Fin2SmemSmall);
+    dim3 grid(fast_blocks_per_frame(ctx, nf, npx), nf);
+    if (out.mask || out.mask_bits) {
+        BV_TRY(enable_fast_smem(ctx, final_fast_kernel<CODE, true>, BIT, smem));
+        BV_LAUNCH_PDL(ctx, (final_fast_kernel<CODE, true>), grid, kFastThreads, smem, hsv, hsv_stride, st, npx, width, out,
+                      ctx->d_lab_gamma, ctx->d_lab_cbrt);
+    } else {
+        BV_TRY(enable_fast_smem(ctx, final_fast_kernel<CODE, false>, BIT + 1, smem));
+        BV_LAUNCH_PDL(ctx, (final_fast_kernel<CODE, false>), grid, kFastThreads, smem, hsv, hsv_stride, st, npx, width, out,
+                      ctx->d_lab_gamma, ctx->d_lab_cbrt);
+    }
+    return BV_OK;
+}
+
+static int dispatch_final_fast(bv_ctx *ctx, const uint8_t *hsv, size_t hsv_stride, const BalFrame *st, int nf, size_t npx, int width,
+                               int code, const BalOutputs &out) {
+    switch (code) {
+        case -1: return launch_final_fast<-1, 1>(ctx, hsv, hsv_stride, st, nf, npx, width, out);
+        case BV_BGR2HSV: return launch_final_fast<BV_BGR2HSV, 3>(ctx, hsv, hsv_stride, st, nf, npx, width, out);
+        case BV_BGR2LAB: return launch_final_fast<BV_BGR2LAB, 5>(ctx, hsv, hsv_stride, st, nf, npx, width, out);
+        case BV_BGR2GRAY: return launch_final_fast<BV_BGR2GRAY, 7>(ctx, hsv, hsv_stride, st, nf, npx, width, out);
+        case BV_BGR2YCRCB: return launch_final_fast<BV_BGR2YCRCB, 9>(ctx, hsv, hsv_stride, st, nf, npx, width, out);
+        default: return 1;  // not covered: the caller takes the generic pass
+    }
+}
+
 int convert_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int width, int cvt_code, const BalOutputs &out) {
     const size_t npx = (size_t)height * width;
     const bool vec = all_vec(src, out, npx, batch);
@@ -1158,6 +1219,9 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
             BV_TRY(ivl_table(ctx, out.lo, out.hi, &ivl));
     }
 
+    // conflict-free tables (balance_fast.cuh): whole 16-pixel groups, aligned buffers
+    const bool fast = prm.hsv_contrast_correct && vec && npx % 16 == 0 && ctx->opt[BV_OPT_FAST_TABLES] > 0;
+
     // chunk the batch so that one chunk's input stays in L2 across the three passes; chunks are
     // independent and alternate over side streams so that their passes overlap on the SMs
     int chunk = (int)(l2_chunk_bytes(ctx) / (npx * 3));
@@ -1195,7 +1259,9 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         else
             BV_LAUNCH(ctx, hist_bgr_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx, prm, ctx->d_pow_quarter);
         if (prm.hsv_contrast_correct) {
-            if (vec)
+            if (fast)
+                BV_TRY(launch_hist_sv_fast(ctx, csrc, cst, nf, npx, chsv, hsv_stride));
+            else if (vec)
                 BV_LAUNCH_PDL(ctx, hist_sv_kernel<true>, grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
             else
                 BV_LAUNCH_PDL(ctx, hist_sv_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
@@ -1205,10 +1271,16 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         if (co.converted) co.converted += (size_t)f0 * npx * (cvt_code == BV_BGR2GRAY ? 1 : 3);
         if (co.mask) co.mask += (size_t)f0 * npx;
         if (co.mask_bits) co.mask_bits += (size_t)f0 * height * (((width + 31) / 32) * 2);
-        if (ivl)
+        if (ivl) {
             BV_TRY(launch_mask_from_hsv(ctx, chsv, hsv_stride, cst, nf, npx, width, ivl, co));
-        else if (prm.hsv_contrast_correct)
-            BV_TRY(dispatch_final<3>(ctx, chsv, hsv_stride, cst, nf, npx, width, cvt_code, co, vec));
+        } else if (prm.hsv_contrast_correct) {
+            int s3 = 1;  // 1: the fast pass does not cover this case
+            if (fast && width % 32 == 0) {
+                s3 = dispatch_final_fast(ctx, chsv, hsv_stride, cst, nf, npx, width, cvt_code, co);
+                if (s3 < 0) return s3;
+            }
+            if (s3 == 1) BV_TRY(dispatch_final<3>(ctx, chsv, hsv_stride, cst, nf, npx, width, cvt_code, co, vec));
+        }
         else
             BV_TRY(dispatch_final<1>(ctx, csrc, npx * 3, cst, nf, npx, width, cvt_code, co, vec));
         if (after_chunk) BV_TRY(after_chunk->fn(after_chunk->self, ctx, f0, nf));

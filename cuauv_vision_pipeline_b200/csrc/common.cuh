@@ -104,6 +104,7 @@ enum ScratchSlot {
     SCR_HOST_LABELS,
     SCR_HOST_BLOBS,
     SCR_HOST_NBLOBS,
+    SCR_INGEST,         // landing buffer of 4-channel frames ingested from a shared-memory ring (ingest.cu)
     SCR_COUNT
 };
 
@@ -143,6 +144,7 @@ struct bv_ctx {
     } ivl[BV_IVL_SLOTS];
     int ivl_next;
     int ivl_attr_set;
+    unsigned fast_attr_set;  // bit per instantiation of the fast passes whose dynamic shared-memory size has been enabled
     int lb_smem_set;     // same for letterbox_tma_kernel
     void *lb_cache;      // host copy of the letterbox descriptors whose tap table is on the device
     int lb_cache_n, lb_cache_ow, lb_cache_oh;

@@ -82,7 +82,8 @@ class Context:
     def launches(self):
         return int(lib.bv_launch_count(self.handle))
 
-    OPTIONS = {"hist_bps": 0, "final_bps": 1, "side_streams": 2, "l2_chunk_mb": 3, "no_hue_table": 4, "contour_pool_chunks": 5}
+    OPTIONS = {"hist_bps": 0, "final_bps": 1, "side_streams": 2, "l2_chunk_mb": 3, "no_hue_table": 4, "contour_pool_chunks": 5,
+               "fast_tables": 6}
 
     def set_option(self, name, value):
         """Tuning knob of the colour-balance passes (include/b200vision.h, BV_OPT_*); 0 = default."""
@@ -183,6 +184,18 @@ class Context:
         mask = self.empty((b, h, w) if (src.dim() == 4 or (src.dim() == 3 and c == 1)) else (h, w))
         check(lib.bv_in_range(self.handle, _u8ptr(src), _u8ptr(mask), b, h, w, c,
                               ffi.from_buffer("uint8_t[]", lo8), ffi.from_buffer("uint8_t[]", hi8)))
+        return mask
+
+    def cvt_in_range(self, src, code, lo, hi):
+        """cvtColor + inRange in one pass (modules/bins.py:13-16): device BGR [H,W,3] / [B,H,W,3] -> mask."""
+        b, h, w, c = self._bhw(src)
+        if c != 3:
+            raise BVError(-1, "cvt_in_range needs a 3-channel image")
+        lo8 = np.clip(np.broadcast_to(np.asarray(lo), (3,)), 0, 255).astype(np.uint8)
+        hi8 = np.clip(np.broadcast_to(np.asarray(hi), (3,)), 0, 255).astype(np.uint8)
+        mask = self.empty(tuple(src.shape[:-1]))
+        check(lib.bv_cvt_in_range(self.handle, _u8ptr(src), _u8ptr(mask), b, h, w, CVT[code] if isinstance(code, str) else int(code),
+                                  ffi.from_buffer("uint8_t[]", lo8), ffi.from_buffer("uint8_t[]", hi8)))
         return mask
 
     def threshold(self, src, thresh, maxval, kind):

@@ -42,7 +42,8 @@ typedef enum bv_status {
     BV_ERR_CUDA = -2,        /* a CUDA runtime call failed; see bv_last_error()          */
     BV_ERR_UNSUPPORTED = -3, /* valid in the reference but not implemented here          */
     BV_ERR_NOMEM = -4,       /* device or host allocation failed                         */
-    BV_ERR_CAPACITY = -5     /* caller-provided table too small                          */
+    BV_ERR_CAPACITY = -5,    /* caller-provided table too small                          */
+    BV_ERR_NOT_READY = -6    /* bv_ingest_seqlock: nothing published yet, or torn on every try */
 } bv_status;
 
 /* Colour conversions.  Replaces cv2.cvtColor as called from utils/color.py:11-32
@@ -152,7 +153,8 @@ enum {
     BV_OPT_L2_CHUNK_MB = 3,  /* input bytes per chunk: the chunk and its H,S,V scratch stay in L2 across the passes */
     BV_OPT_NO_HUE_TABLE = 4, /* 1: always do the HSV round trip arithmetically (testing) */
     BV_OPT_CONTOUR_POOL_CHUNKS = 5, /* chunks of the contour walk's vertex pool per frame (testing the second-walk fallback) */
-    BV_OPT_COUNT = 6
+    BV_OPT_FAST_TABLES = 6, /* 1: passes 2 and 3 with per-lane replicated (bank-conflict-free) shared-memory tables; measured slower in a real step, see DESIGN.md */
+    BV_OPT_COUNT = 7
 };
 int bv_set_option(bv_ctx *ctx, int option, int value);
 void bv_balance_default(bv_balance_params *p);
@@ -324,6 +326,32 @@ typedef struct bv_mt19937_state {
 } bv_mt19937_state;
 int bv_add_gaussian_noise(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *dst_dev, size_t n_values, double sigma,
                           bv_mt19937_state *state);
+
+/* ---- shared-memory ingest (replaces Block::read_frame's memcpy, lib/camera_message_framework.cpp:423-453, and the
+ *      writable copy of core/base.py:762-768) -------------------------------------------------------------------------
+ * A ring of `slots` frame slots in host memory that a writer fills round robin and guards with a sequence lock, described
+ * by plain pointers so that the header does not depend on the transport's private struct (lib/camera_message_framework.cpp
+ * :39-54): `uid` = frames published so far, the newest one lives in slot uid % slots; slot i's sequence words are at
+ * v_begin + i * meta_stride (FrameMetadata::v_a, stamped after the payload is in place) and v_end + i * meta_stride
+ * (FrameMetadata::v_b, stamped last); its payload starts at data + i * slot_stride.  The memory should be pinned
+ * (bv_host_register on the mapping) for full-speed DMA. */
+typedef struct bv_seqlock_ring {
+    const volatile uint64_t *uid;
+    const volatile uint64_t *v_begin;
+    const volatile uint64_t *v_end;
+    size_t meta_stride;
+    const uint8_t *data;
+    size_t slot_stride;
+    int slots;
+} bv_seqlock_ring;
+/* Copies the newest frame (height x width x src_channels bytes at payload_offset inside its slot) to dst_dev as packed
+ * 3-channel pixels: one H2D DMA on the context's stream, then the slot is re-validated (v_begin == v_end as the reference
+ * reader does, and uid has not advanced far enough for the writer to be back in this slot); a torn copy is repeated up to
+ * max_retries times.  src_channels == 4 drops the fourth byte on the device (swap_rb: RGBA -> BGR).  Blocking (the
+ * validation needs the copy to be complete); the frame is ready on the context's stream when it returns.
+ * BV_ERR_NOT_READY: nothing published yet / still torn after max_retries. */
+int bv_ingest_seqlock(bv_ctx *ctx, const bv_seqlock_ring *ring, size_t payload_offset, uint8_t *dst_dev, int height,
+                      int width, int src_channels, int swap_rb, int max_retries, uint64_t *uid_out, int *retries_out);
 
 /* ---- ZED auxiliary planes (capture_sources/zed.{py,cpp}, modules/poster.py, modules/record.py) ----- */
 /* Drop the alpha byte (cv2.cvtColor(RGBA2RGB), capture_sources/zed.py:49-50; zed.cpp:54-71). */

@@ -55,6 +55,7 @@ def test_modules_fed_through_the_reference_transport(ctx):
     try:
         reader = cmf.Reader(direction)
         bins = BinDetectorGPU(video_sources=["forward"], tuners=[])
+        bins_desc = ctx.make_stage(cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255), morph=[("open", 5, 5, 1)])
         bal = ColorBalanceGPU(video_sources=["forward"])
         th = threading.Thread(target=capture_source)
         th.start()
@@ -73,11 +74,11 @@ def test_modules_fed_through_the_reference_transport(ctx):
                     check(lib.bv_host_unregister(ffi.cast("void *", pinned_ptr)))
                 pinned_ptr = reader.data_pointer()
                 check(lib.bv_host_register(ffi.cast("void *", pinned_ptr), view.nbytes))
-            direct = ctx.stage_host(bins.desc, view, want=("mask",))["mask"]
+            direct = ctx.stage_host(bins_desc, view, want=("mask",))["mask"]
             frame = np.array(view)                            # the writable copy of core/base.py:765-768
-            blobs = bins.process("forward", frame)
+            bins.process("forward", frame)
             balanced = bal.process("forward", frame)
-            seen[idx] = (direct, bins.posted["bins"].copy(), balanced.copy(), len(blobs))
+            seen[idx] = (direct, bins.posted["bins"].copy(), balanced.copy(), len(bins.blobs))
         stop.set()
         th.join()
         if pinned_ptr is not None:
@@ -85,7 +86,9 @@ def test_modules_fed_through_the_reference_transport(ctx):
         assert len(seen) >= 3, "module loop saw too few frames"
         for idx, (direct, posted, balanced, _) in seen.items():
             _, cleaned = cv_ops.bins_mask(frames[idx])
-            assert np.array_equal(direct, cleaned) and np.array_equal(posted, cleaned)
+            assert np.array_equal(direct, cleaned)
+            from test_gpu_balance_stage import reference_bins_post
+            assert np.array_equal(posted, reference_bins_post(frames[idx])[0])      # modules/bins.py:81
             want = ref_balance.balance(frames[idx]) if ref_balance.available() else color_balance_np.process_frame_np(frames[idx])
             assert np.array_equal(balanced, want)
         reader.close()

@@ -380,47 +380,69 @@ def test_gaussian_noise_replays_numpy_global_generator(ctx, shape, sigma, pre):
     assert rs.get_state()[2:4] == rs_ref.get_state()[2:4] and np.array_equal(rs.get_state()[1], rs_ref.get_state()[1])
 
 
+def reference_bins_post(img):
+    """modules/bins.py:11-81 literally (np.int0 spelled np.intp: numpy 2 removed the alias)."""
+    hsv = cv2.cvtColor(img, cv2.COLOR_BGR2HSV)
+    mask = cv2.inRange(hsv, np.array([10, 20, 60]), np.array([30, 100, 255]))
+    overlayed = cv2.addWeighted(img, 0.7, cv2.cvtColor(mask, cv2.COLOR_GRAY2BGR), 0.3, 0)
+    cleaned = cv_ops.morph_remove_noise(mask, cv_ops.rect_kernel(5))
+    valid_rects = []
+    for contour in cv_ops.outer_contours(cleaned):
+        rect = cv2.minAreaRect(contour)
+        (center, (w, h), angle) = rect
+        if w * h < 500:
+            continue
+        if 1.0 <= max(w, h) / min(w, h) <= 3.0:
+            valid_rects.append(rect)
+    for rect in valid_rects:
+        cv2.drawContours(overlayed, [cv2.boxPoints(rect).astype(np.intp)], 0, (0, 255, 0), 4)
+    return overlayed, valid_rects, cleaned
+
+
 def test_drop_in_modules(ctx):
     from cuauv_vision_pipeline_b200.modules import BinDetectorGPU, BuoyLABGPU, ColorBalanceGPU
-    img = synth.gen_underwater(480, 640, 77)
+    img = synth.gen_c5_frame(77, 480, 640)                    # contains one large bin-coloured target
+    img[60:200, 60:330] = (131, 164, 180)                    # and a beige box (HSV 20,70,180) that passes bins.py's threshold unbalanced
     mod = BinDetectorGPU(video_sources=["forward"], tuners=[])
-    blobs = mod.process("forward", img)
-    _, cleaned = cv_ops.bins_mask(img)
-    assert np.array_equal(mod.posted["bins"], cleaned)
+    rects = mod.process("forward", img.copy())
+    post_ref, rects_ref, cleaned = reference_bins_post(img)
+    assert len(rects_ref) >= 1, "the fixture must exercise the rectangle drawing of bins.py:71-74"
+    # same accepted rectangles (bins.py:58-69) to the stated minAreaRect tolerance, same posted image
+    assert len(rects) == len(rects_ref)
+    for got, want in zip(sorted(rects), sorted(rects_ref)):
+        assert got[0] == pytest.approx(want[0], abs=1e-3)
+        assert sorted(got[1]) == pytest.approx(sorted(want[1]), rel=1e-4, abs=1e-3)
+    assert np.array_equal(mod.posted["bins"], post_ref)
+    assert mod.pixels.uploads == 1 and mod.pixels.h2d_bytes == img.nbytes, "one H2D per process() call"
+    # the vertex arrays handed to minAreaRect are cv2's own (bins.py:27)
+    ref_sets = sorted(sorted(map(tuple, c.reshape(-1, 2).tolist())) for c in cv_ops.outer_contours(cleaned))
+    got_sets = sorted(sorted(map(tuple, c["points"].reshape(-1, 2).tolist())) for c in mod.contours)
+    assert got_sets == ref_sets
     n_ref, _, tab = ccl.label_and_moments(cleaned)
-    w = tab["x1"] - tab["x0"] + 1
-    h = tab["y1"] - tab["y0"] + 1
-    keep = (w * h >= 500) & (np.maximum(w, h) / np.minimum(w, h) <= 3.0)
-    assert [b["label"] for b in blobs] == (np.flatnonzero(keep) + 1).tolist()
-    # bins.py:27,60-69 literally: cv2.minAreaRect on the contour vertex arrays, same accepted rectangles
-    def valid_rects(contours):
-        keep = []
-        for c in contours:
-            (center, (w, h), angle) = cv2.minAreaRect(c)
-            if w * h < 500:
-                continue
-            if 1.0 <= max(w, h) / min(w, h) <= 3.0:
-                keep.append((center, (w, h), angle))
-        return sorted(keep)
-    assert valid_rects([c["points"] for c in mod.contours]) == valid_rects(cv_ops.outer_contours(cleaned))
+    assert len(mod.blobs) == n_ref and [b["m00"] for b in mod.blobs] == tab["m00"].tolist()
+
     buoy = BuoyLABGPU(["zed"], thresh_min=150, thresh_max=255)
-    res = buoy.process("zed", img)
-    th, cl = cv_ops.buoy_mask(img, 150, 255)
+    img2 = synth.gen_underwater(480, 640, 77)
+    res = buoy.process("zed", img2)
+    th, cl = cv_ops.buoy_mask(img2, 150, 255)
     assert np.array_equal(buoy.posted["threshed"], th) and np.array_equal(buoy.posted["threshed_cleaned"], cl)
+    assert buoy.posted_color_space["threshed"] == "GRAY"
+    assert buoy.pixels.uploads == 1, "one upload, one LAB conversion (red_buoy.py:21-34)"
     n_ref, _, tab = ccl.label_and_moments(cl)
     if n_ref:
         i = int(np.argmax(tab["m00"]))
-        assert res["pixel"] == (int(tab["m10"][i] / tab["m00"][i]), int(tab["m01"][i] / tab["m00"][i]))
-        assert res["area"] == float(tab["m00"][i])
-    else:
-        assert res is None
+        assert buoy.blob_result["pixel"] == (int(tab["m10"][i] / tab["m00"][i]), int(tab["m01"][i] / tab["m00"][i]))
+        assert buoy.blob_result["area"] == float(tab["m00"][i])
     ref_contours = cv_ops.outer_contours(th)                      # red_buoy.py:38 (un-cleaned mask)
     if ref_contours:
         best = max(ref_contours, key=cv_ops.contour_area)
-        assert buoy.contour_result["pixel"] == cv_ops.contour_centroid(best)
-        assert buoy.contour_result["area"] == cv_ops.contour_area(best)
+        assert res["pixel"] == cv_ops.contour_centroid(best)      # red_buoy.py:43-45
+        assert res["area"] == cv_ops.contour_area(best)
+    else:
+        assert res is None
     cbm = ColorBalanceGPU(["forward"])
-    assert np.array_equal(cbm.process("forward", img), oracle_balance(img))
+    assert np.array_equal(cbm.process("forward", img2), oracle_balance(img2))
+    assert np.array_equal(cbm.posted["orig"], img2) and np.array_equal(cbm.posted["balanced"], oracle_balance(img2))
 
 
 HUE_TABLE_BOUNDS = [((10, 20, 60), (30, 100, 255)),      # modules/bins.py:14-15
