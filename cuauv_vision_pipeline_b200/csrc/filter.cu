@@ -28,7 +28,7 @@ namespace bv {
 // Gaussian blur: a block stages a tile plus halo (reflected at the image border) in shared memory,
 // runs the horizontal pass into a 16-bit tile and the vertical pass out of it.
 // ----------------------------------------------------------------------------------------------
-constexpr int kBlurMaxTaps = 63;
+constexpr int kBlurMaxTaps = 201;   // the reference's tuner reaches 2 * 100 + 1 (modules/preprocessor.py:25,110-114)
 constexpr int kBlurTileW = 64, kBlurTileH = 32;
 struct BlurTaps {
     int nx, ny;
@@ -100,6 +100,57 @@ __global__ void __launch_bounds__(256) gaussian_blur_kernel(const uint8_t *__res
             const uint32_t v = (acc + (1u << 15)) >> 16;
             dst[frame_off + ((size_t)y * width + x0) * CN + b] = (uint8_t)(v > 255u ? 255u : v);
         }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Large kernels (the tile + halo no longer fits shared memory): the same two passes with the 16-bit horizontal
+// result in a global scratch image.  One thread per output byte; the taps sit in shared memory.
+// ----------------------------------------------------------------------------------------------
+template <int CN>
+__global__ void __launch_bounds__(256) blur_rows16_kernel(const uint8_t *__restrict__ src, uint16_t *__restrict__ hz, int height,
+                                                          int width, BlurTaps taps) {
+    __shared__ uint16_t k[kBlurMaxTaps];
+    for (int i = threadIdx.x; i < taps.nx; i += blockDim.x) k[i] = taps.kx[i];
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= width) return;
+    const size_t row = ((size_t)blockIdx.z * height + y) * width;
+    const int rx = taps.nx / 2;
+    uint32_t acc[CN];
+#pragma unroll
+    for (int c = 0; c < CN; ++c) acc[c] = 0;
+    for (int t = 0; t < taps.nx; ++t) {
+        const uint8_t *p = src + (row + reflect101(x - rx + t, width)) * CN;
+#pragma unroll
+        for (int c = 0; c < CN; ++c) acc[c] += (uint32_t)k[t] * p[c];
+    }
+#pragma unroll
+    for (int c = 0; c < CN; ++c) hz[(row + x) * CN + c] = (uint16_t)(acc[c] > 0xFFFFu ? 0xFFFFu : acc[c]);
+}
+
+template <int CN>
+__global__ void __launch_bounds__(256) blur_cols16_kernel(const uint16_t *__restrict__ hz, uint8_t *__restrict__ dst, int height,
+                                                          int width, BlurTaps taps) {
+    __shared__ uint16_t k[kBlurMaxTaps];
+    for (int i = threadIdx.x; i < taps.ny; i += blockDim.x) k[i] = taps.ky[i];
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= width) return;
+    const size_t frame = (size_t)blockIdx.z * height * width;
+    const int ry = taps.ny / 2;
+    uint32_t acc[CN];
+#pragma unroll
+    for (int c = 0; c < CN; ++c) acc[c] = 0;
+    for (int t = 0; t < taps.ny; ++t) {
+        const uint16_t *p = hz + (frame + (size_t)reflect101(y - ry + t, height) * width + x) * CN;
+#pragma unroll
+        for (int c = 0; c < CN; ++c) acc[c] += (uint32_t)k[t] * p[c];
+    }
+#pragma unroll
+    for (int c = 0; c < CN; ++c) {
+        const uint32_t v = (acc[c] + (1u << 15)) >> 16;
+        dst[(frame + (size_t)y * width + x) * CN + c] = (uint8_t)(v > 255u ? 255u : v);
     }
 }
 
@@ -534,7 +585,7 @@ extern "C" int bv_gaussian_blur(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *ds
     BV_REQUIRE(batch > 0 && height > 0 && width > 0, "batch, height and width must be positive");
     BV_REQUIRE(channels == 1 || channels == 3, "channels must be 1 or 3");
     BV_REQUIRE(ksize_x >= 1 && ksize_y >= 1 && (ksize_x & 1) && (ksize_y & 1) && ksize_x <= kBlurMaxTaps && ksize_y <= kBlurMaxTaps,
-               "kernel sizes must be odd and in 1..63");
+               "kernel sizes must be odd and in 1..201");
     BV_REQUIRE(batch <= 65535, "batch too large");
     BV_CUDA(cudaSetDevice(ctx->device));
     if (sigma_y <= 0) sigma_y = sigma_x;  // cv2: sigmaY = sigmaX when not given
@@ -549,9 +600,19 @@ extern "C" int bv_gaussian_blur(bv_ctx *ctx, const uint8_t *src_dev, uint8_t *ds
     const int rx = ksize_x / 2, ry = ksize_y / 2;
     const size_t raw = (size_t)(kBlurTileW + 2 * rx) * channels * (kBlurTileH + 2 * ry);
     const size_t smem = ((raw + 15) & ~(size_t)15) + (size_t)kBlurTileW * channels * (kBlurTileH + 2 * ry) * 2;
-    if (smem > 200 * 1024) {
-        set_error("bv_gaussian_blur: kernel too large for the shared-memory tile");
-        return BV_ERR_UNSUPPORTED;
+    if (smem > 200 * 1024) {  // large kernels: 16-bit horizontal result through a global scratch image
+        BV_REQUIRE(height <= 65535, "image too tall");
+        BV_TRY(ensure_scratch(ctx, SCR_MORPH_TMP, (size_t)batch * height * width * channels * sizeof(uint16_t)));
+        uint16_t *hz = (uint16_t *)ctx->scratch[SCR_MORPH_TMP];
+        dim3 g((width + 255) / 256, height, batch);
+        if (channels == 3) {
+            BV_LAUNCH(ctx, blur_rows16_kernel<3>, g, 256, 0, src_dev, hz, height, width, taps);
+            BV_LAUNCH(ctx, blur_cols16_kernel<3>, g, 256, 0, hz, dst_dev, height, width, taps);
+        } else {
+            BV_LAUNCH(ctx, blur_rows16_kernel<1>, g, 256, 0, src_dev, hz, height, width, taps);
+            BV_LAUNCH(ctx, blur_cols16_kernel<1>, g, 256, 0, hz, dst_dev, height, width, taps);
+        }
+        return BV_OK;
     }
     dim3 grid((width + kBlurTileW - 1) / kBlurTileW, (height + kBlurTileH - 1) / kBlurTileH, batch);
 #define BV_BLUR(CN, NT)                                                                                                          \

@@ -2,7 +2,7 @@
 (utils/feature.py:5-21,240-265) as connected-component labelling with exact raster moments."""
 import numpy as np
 
-from ._host import ctx_for, to_device, is_device
+from ._host import ctx_for, to_device, is_device, release_to_caller
 
 
 class Blob(dict):
@@ -24,8 +24,8 @@ def label_blobs(mat, max_blobs=4096, want_labels=True):
         b = Blob({k: int(row[k]) for k in row.dtype.names})
         b["label"] = i + 1
         out.append(b)
-    if labels is not None and not is_device(mat):
-        labels = ctx.download(labels)
+    if labels is not None:
+        labels = release_to_caller(ctx, labels) if is_device(mat) else ctx.download(labels)
     return labels, out, int(n[0])
 
 

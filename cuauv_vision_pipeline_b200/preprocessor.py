@@ -14,7 +14,7 @@ channel and applied in a single pass.
 import numpy as np
 
 from . import transform
-from ._host import ctx_for, to_device, like_input
+from ._host import ctx_for, to_device, like_input, on_ctx_stream
 
 DEFAULT_OPTIONS = {
     # name: default           (modules/preprocessor.py:10-41)
@@ -78,7 +78,9 @@ class Preprocessor:
             cur = to_device(ctx, mat)
             if self._opt("PPX_rgb_split"):                                   # 51-55
                 for k, n in ((2, "r"), (1, "g"), (0, "b")):
-                    self._post("PPX_rgb_%s_channel" % n, ctx, mat, cur[..., k].contiguous())
+                    with on_ctx_stream(ctx):                                 # the slice copy runs behind the upload
+                        plane = cur[..., k].contiguous()
+                    self._post("PPX_rgb_%s_channel" % n, ctx, mat, plane)
             for flag, code, names in (("PPX_lab_split", "bgr2lab", ("lab_l", "lab_a", "lab_b")),      # 56-60
                                       ("PPX_hsv_split", "bgr2hsv", ("hsv_h", "hsv_s", "hsv_v")),      # 61-65
                                       ("PPX_hls_split", "bgr2hls", ("hls_h", "hls_l", "hls_s")),      # 66-70

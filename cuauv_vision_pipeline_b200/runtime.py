@@ -163,17 +163,28 @@ class Context:
         check(lib.bv_cvt_color(self.handle, _u8ptr(src), _u8ptr(dst), pp, b, h, w, code_i))
         return (dst, planes) if split else dst
 
+    @staticmethod
+    def _cv_bounds(lo, hi, channels):
+        """cv2.inRange's reading of its bounds on an 8-bit image: cvRound (half to even) of each value; a bare scalar is
+        cv::Scalar(v, 0, 0, 0), i.e. on a 3-channel image it bounds channel 0 only and channels 1, 2 get [0, 0]."""
+        lo = np.rint(np.atleast_1d(np.asarray(lo, dtype=np.float64))).astype(np.int64)
+        hi = np.rint(np.atleast_1d(np.asarray(hi, dtype=np.float64))).astype(np.int64)
+        if channels == 3:
+            if lo.size == 1:
+                lo = np.array([lo[0], 0, 0], np.int64)
+            if hi.size == 1:
+                hi = np.array([hi[0], 0, 0], np.int64)
+        return lo, hi
+
     def in_range(self, src, lo, hi):
-        lo = np.atleast_1d(np.asarray(lo)).astype(np.int64)
-        hi = np.atleast_1d(np.asarray(hi)).astype(np.int64)
-        if src.dim() == 2 or (src.dim() == 3 and lo.size == 1 and src.shape[-1] != 3):
+        n_lo = np.size(lo)
+        if src.dim() == 2 or (src.dim() == 3 and n_lo == 1 and src.shape[-1] != 3):
             b, h, w, c = self._bhw(src, channels=1)
         else:
             b, h, w, c = self._bhw(src)
         if c not in (1, 3):
             raise BVError(-1, "inRange needs 1 or 3 channels")
-        if lo.size == 1 and c == 3:
-            lo, hi = np.repeat(lo, 3), np.repeat(hi, 3)
+        lo, hi = self._cv_bounds(lo, hi, c)
         # cv2.inRange compares in the scalar's domain: bounds outside [0,255] saturate harmlessly
         empty = bool(np.any(lo > 255) or np.any(hi < 0))
         lo8 = np.clip(lo, 0, 255).astype(np.uint8)
@@ -491,11 +502,12 @@ class Context:
             for k, v in balance.items():
                 setattr(d.balance, k, int(v))
         d.cvt_code = -1 if cvt is None else (CVT[cvt] if isinstance(cvt, str) else int(cvt))
-        lo = np.broadcast_to(np.asarray(lo), (3,)) if np.ndim(lo) else (int(lo), 0, 0)
-        hi = np.broadcast_to(np.asarray(hi), (3,)) if np.ndim(hi) else (int(hi), 255, 255)
+        lo, hi = Context._cv_bounds(lo, hi, 3)          # same convention as in_range / cv2.inRange
+        if np.any(lo > 255) or np.any(hi < 0) or np.any(lo > hi):
+            lo, hi = np.array([255, 255, 255]), np.array([0, 0, 0])     # empty range
         for k in range(3):
-            d.lo[k] = int(lo[k])
-            d.hi[k] = int(hi[k])
+            d.lo[k] = int(np.clip(lo[k], 0, 255))
+            d.hi[k] = int(np.clip(hi[k], 0, 255))
         if len(morph) > 4:
             raise BVError(-1, "at most 4 morphology steps")
         d.n_morph = len(morph)

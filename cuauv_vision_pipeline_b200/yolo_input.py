@@ -3,7 +3,7 @@
 over cameras in one kernel launch (the reference does not batch, modules/yolo.py:114)."""
 import numpy as np
 
-from ._host import ctx_for, to_device, is_device
+from ._host import ctx_for, to_device, like_input
 
 
 def yolo_input(images, new_shape=(640, 640), pad=114, half=True):
@@ -14,4 +14,4 @@ def yolo_input(images, new_shape=(640, 640), pad=114, half=True):
     ctx = ctx_for(images[0])
     dev = [to_device(ctx, im) for im in images]
     out = ctx.letterbox(dev, out_h=int(new_shape[0]), out_w=int(new_shape[1]), pad=int(pad), half=half)
-    return out if is_device(images[0]) else ctx.download(out)
+    return like_input(ctx, images[0], out)

@@ -4,22 +4,15 @@ of modules/poster.py:41-47, modules/record.py:106-113, modules/calibrate.py:111.
 import numpy as np
 import torch
 
-from ._host import is_device
-from .runtime import default_context
-
-
-def _ctx(x):
-    return default_context(x.device.index if is_device(x) else 0)
+from ._host import ctx_for as _ctx, like_input, to_device
 
 
 def _dev(ctx, x, dtype):
-    if is_device(x):
-        return x.contiguous()
-    return ctx.upload(np.ascontiguousarray(x, dtype=dtype))
+    return to_device(ctx, x, dtype)       # ordered behind the caller's stream when x is a CUDA tensor
 
 
 def _back(ctx, x, t):
-    return t if is_device(x) else ctx.download(t)
+    return like_input(ctx, x, t)
 
 
 def to_rgb(x):

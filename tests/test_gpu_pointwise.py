@@ -211,6 +211,19 @@ def test_gaussian_blur_vs_cv2(ctx, shape, n):
     assert np.array_equal(transform.gaussian_blur(img, (n, n)), cv2.GaussianBlur(img, (n, n), 0))
 
 
+@pytest.mark.parametrize("n", [33, 63, 101, 151, 201])
+def test_gaussian_blur_up_to_the_tuner_maximum(ctx, n):
+    """PPX_gaussian_blur_kernel spans 1..100, i.e. kernels up to 201 x 201 (modules/preprocessor.py:25,110-114); the
+    largest ones leave the shared-memory tile for the two-launch path, also on images smaller than the kernel."""
+    for shape in [(240, 320), (97, 131)]:
+        img = synth.gen_underwater(shape[0], shape[1], n)
+        assert np.array_equal(ctx.download(ctx.gaussian_blur(ctx.upload(img), (n, n))), cv2.GaussianBlur(img, (n, n), 0)), shape
+    img = synth.gen_random_bgr(150, 210, n)
+    assert np.array_equal(ctx.download(ctx.gaussian_blur(ctx.upload(img), (n, 3))), cv2.GaussianBlur(img, (n, 3), 0))
+    grey = np.ascontiguousarray(img[..., 0])
+    assert np.array_equal(ctx.download(ctx.gaussian_blur(ctx.upload(grey), (5, n))), cv2.GaussianBlur(grey, (5, n), 0))
+
+
 def test_gaussian_blur_rectangular_kernels_sigmas_and_batches(ctx):
     img = synth.gen_random_bgr(200, 333, 9)
     for (kw, kh, sx, sy) in [(7, 3, 0, 0), (1, 9, 0, 0), (5, 5, 2.5, 0), (11, 7, 1.2, 3.3), (63, 1, 0, 0)]:
@@ -383,3 +396,52 @@ def test_init_undistort_map_flow(ctx):
         new_k, _ = cv2.getOptimalNewCameraMatrix(_CAM_K, _CAM_D, (w, h), alpha)
         r1, r2 = cv2.initUndistortRectifyMap(_CAM_K, _CAM_D, None, new_k, (w, h), cv2.CV_16SC2)
         assert np.array_equal(transform.remap(img, *maps), cv2.remap(img, r1, r2, cv2.INTER_LINEAR))
+
+
+def test_mirrors_order_device_tensors_against_the_callers_stream(ctx):
+    """a CUDA tensor produced on the caller's torch stream must be complete before the context's own
+    stream reads it, and a returned tensor must be complete before the caller's stream uses it."""
+    import torch
+    from cuauv_vision_pipeline_b200 import color
+    from cuauv_vision_pipeline_b200.color_balance import balance
+    img = synth.gen_underwater(1080, 1920, 5)
+    want_lab = cv2.cvtColor(img, cv2.COLOR_BGR2LAB)
+    side = torch.cuda.Stream()
+    pinned = torch.from_numpy(img).pin_memory()
+    for rep in range(5):
+        with torch.cuda.stream(side):
+            # a long producer on the caller's stream: the frame is only correct after 40 passes of in-place arithmetic
+            d = pinned.to("cuda", non_blocking=True)
+            acc = d.to(torch.int32)
+            for _ in range(40):
+                acc = acc + 3
+            for _ in range(40):
+                acc = acc - 3
+            d = acc.to(torch.uint8)
+            lab, planes = color.bgr_to_lab(d)            # consumer: the context's stream
+            host = (lab.to(torch.int32) + 0).to(torch.uint8).cpu()   # caller's stream again
+            bal = balance(d)
+            bal_host = bal.cpu()
+        side.synchronize()
+        assert np.array_equal(host.numpy(), want_lab)
+        if rep == 0:
+            first = bal_host.numpy().copy()
+        assert np.array_equal(bal_host.numpy(), first)
+
+
+def test_in_range_reads_its_bounds_like_cv2(ctx):
+    """ADVICE r01: a bare scalar bound on a 3-channel image is cv::Scalar(v, 0, 0, 0); fractional bounds are cvRound'ed
+    (half to even); bounds outside [0, 255] saturate or empty the range."""
+    from cuauv_vision_pipeline_b200 import color
+    img = synth.all_colors_image()[:512, :512].copy()
+    grey = np.ascontiguousarray(img[..., 1])
+    cases3 = [(10, 20), ((10, 10, 10), (20, 20, 20)), ((10.5, 0.5, 1.5), (20.5, 99.5, 254.6)), ((-3.2, 0, 0), (5, 300.7, 255)),
+              ((0, 0, 0), (0, 0, 0)), ((20.6, 0, 0), (20.4, 255, 255)), (0, 255)]
+    for lo, hi in cases3:
+        want = cv2.inRange(img, np.array(lo, dtype=np.float64) if np.ndim(lo) else lo, np.array(hi, dtype=np.float64) if np.ndim(hi) else hi)
+        assert np.array_equal(color.range_threshold(img, lo, hi), want), (lo, hi)
+    for lo, hi in [(10, 20), (10.5, 20.5), (10.4, 20.6), (-3.2, 5.0), (250.1, 300.7), (19.999, 20.0001), (20.6, 20.4)]:
+        assert np.array_equal(color.range_threshold(grey, lo, hi), cv2.inRange(grey, lo, hi)), (lo, hi)
+    # make_stage uses the same convention
+    d = ctx.make_stage(cvt=None, lo=10, hi=20)
+    assert np.array_equal(ctx.download(ctx.stage(d, ctx.upload(img), want=("mask",))["mask"]), cv2.inRange(img, 10, 20))

@@ -129,7 +129,7 @@ def test_hue_interval_property_of_the_hsv_round_trip():
         assert int(rises.max()) <= 1, (lo, hi)
 
 
-@pytest.mark.parametrize("n", [1, 3, 5, 7, 9, 11, 13, 17, 21, 31])
+@pytest.mark.parametrize("n", [1, 3, 5, 7, 9, 11, 13, 17, 21, 31, 63, 101, 201])
 def test_gaussian_blur_8u_model_vs_cv2(n):
     """modules/preprocessor.py:110-114: cv2.GaussianBlur(mat, (n, n), 0) on uint8, 8.8 fixed point."""
     rng = np.random.default_rng(n)
