@@ -293,6 +293,11 @@ __device__ __forceinline__ void chain_step(uint32_t *A, uint32_t *B, int rows, i
     __syncthreads();
 }
 
+// TMA: the tile's rows are one contiguous byte range of the frame; when it starts and ends on 16 bytes one thread hands
+// it to the TMA engine as a single bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier, rows outside the
+// image are zero-filled by the block.  (Tensor-map TMA with out-of-bounds fill needs a 16-byte row pitch; a bit-packed
+// 2208-px row is 276 bytes.)
+template <bool TMA>
 __global__ void __launch_bounds__(kChainThreads) morph_chain_kernel(const uint32_t *__restrict__ src,
                                                                     uint32_t *__restrict__ dst_bits, uint8_t *__restrict__ mask,
                                                                     int height, int width, int wpr, int tiles_per_frame,
@@ -304,10 +309,37 @@ __global__ void __launch_bounds__(kChainThreads) morph_chain_kernel(const uint32
     uint32_t *A = chain_smem, *B = chain_smem + rows * wpr;
     const uint32_t *fsrc = src + (size_t)frame * height * wpr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int r = warp; r < rows; r += nwarps) {
-        const int y = ybase + r;
-        const bool inside = y >= 0 && y < height;
-        for (int wx = lane; wx < wpr; wx += 32) A[r * wpr + wx] = inside ? __ldg(fsrc + (size_t)y * wpr + wx) : 0u;
+    bool staged = false;
+    if (TMA) {
+        __shared__ uint64_t bar;
+        const int ya = max(ybase, 0), yb = min(ybase + rows, height);           // rows of the tile inside the image
+        const size_t off = (size_t)ya * wpr * 4, bytes = (size_t)(yb - ya) * wpr * 4;
+        const uint32_t *g = fsrc + (size_t)ya * wpr;
+        uint32_t *d = A + (ya - ybase) * wpr;
+        // uniform for the block: source, destination and size on 16 bytes
+        if (yb > ya && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(d) | bytes) & 15) == 0) {
+            (void)off;
+            if (threadIdx.x == 0) {
+                mbar_init(&bar, 1);
+                mbar_expect_tx(&bar, (uint32_t)bytes);
+                bulk_g2s(d, g, (uint32_t)bytes, &bar);
+            }
+            for (int r = warp; r < rows; r += nwarps) {
+                const int y = ybase + r;
+                if (y < 0 || y >= height)
+                    for (int wx = lane; wx < wpr; wx += 32) A[r * wpr + wx] = 0u;
+            }
+            __syncthreads();
+            mbar_wait(&bar, 0);
+            staged = true;
+        }
+    }
+    if (!staged) {
+        for (int r = warp; r < rows; r += nwarps) {
+            const int y = ybase + r;
+            const bool inside = y >= 0 && y < height;
+            for (int wx = lane; wx < wpr; wx += 32) A[r * wpr + wx] = inside ? __ldg(fsrc + (size_t)y * wpr + wx) : 0u;
+        }
     }
     __syncthreads();
     const int last = wpr - 1;
@@ -345,6 +377,142 @@ __global__ void __launch_bounds__(kChainThreads) morph_chain_kernel(const uint32
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// The same chain without shared memory or block barriers, for the shapes the modules use (square 3x3 / 5x5 elements,
+// 1, 2 or 4 elementary steps: ERODE / DILATE / OPEN / CLOSE / OPEN+CLOSE, rows of at most 128 words = 4096 px).
+// One WARP walks down a strip of rows; lane l keeps words l, l+32, l+64, l+96 of the current row in registers, gets
+// the neighbouring words for the horizontal taps by shuffle, and every step keeps its last 2R horizontally processed
+// rows in a register ring for the vertical taps -- a software pipeline in which step s emits row y - (s+1) R when row y
+// comes in.  A strip re-reads 2 N R rows of halo above and below; strips are cut so that every SM gets ~8 warps.
+// (The tile kernel above spends its time in 4 N block-wide barriers per 24 output rows with 1024-thread blocks, 5 active
+// lanes in the third column round of a 69-word row, and 1.4 blocks per SM: 19 us per 4-frame launch at 2208x1242; this
+// form: see profiles/r02_morph_variants.log.)
+// ----------------------------------------------------------------------------------------------
+template <int R, bool ERODE>
+__device__ __forceinline__ uint32_t hpass_sq(uint32_t l, uint32_t c, uint32_t n) {
+    uint32_t h = c;
+#pragma unroll
+    for (int d = 1; d <= R; ++d) {
+        const uint32_t a = __funnelshift_l(l, c, d), b = __funnelshift_r(c, n, d);
+        h = ERODE ? (h & a & b) : (h | a | b);
+    }
+    return h;
+}
+
+template <int R, int N, int K>
+__global__ void __launch_bounds__(256) morph_roll_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst_bits,
+                                                         uint8_t *__restrict__ mask, int batch, int height, int width, int wpr,
+                                                         int strips, int strip_rows, uint32_t erode_bits) {
+    const int lane = threadIdx.x & 31;
+    const int job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (job >= batch * strips) return;
+    const int frame = job / strips, strip = job - frame * strips;
+    const int y0 = strip * strip_rows, y1 = min(height, y0 + strip_rows);
+    const uint32_t *fsrc = src + (size_t)frame * height * wpr;
+    const int last = wpr - 1;
+    const int tail = width - last * 32;
+    const uint32_t tail_mask = tail == 32 ? 0xFFFFFFFFu : ((1u << tail) - 1u);
+    const bool wide_ok = (width % 16 == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+    uint32_t ring[N][2 * R][K];
+#pragma unroll
+    for (int s = 0; s < N; ++s)
+#pragma unroll
+        for (int j = 0; j < 2 * R; ++j)
+#pragma unroll
+            for (int k = 0; k < K; ++k) ring[s][j][k] = 0u;
+    const int prev_lane = (lane + 31) & 31, next_lane = (lane + 1) & 31;
+    // the next row's words are requested before the current row goes through the chain
+    uint32_t nxt[K];
+    const int y_begin = y0 - N * R, y_end = y1 + N * R;
+    auto load_row = [&](int y, uint32_t (&v)[K]) {
+        const bool inside = y >= 0 && y < height;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int wi = 32 * k + lane;
+            v[k] = (inside && wi < wpr) ? __ldg(fsrc + (size_t)y * wpr + wi) : 0u;
+        }
+    };
+    load_row(y_begin, nxt);
+    for (int y = y_begin; y < y_end; ++y) {
+        uint32_t cur[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) cur[k] = nxt[k];
+        if (y + 1 < y_end) load_row(y + 1, nxt);
+#pragma unroll
+        for (int s = 0; s < N; ++s) {
+            const bool erode = (erode_bits >> s) & 1u;
+            const uint32_t neutral = erode ? 0xFFFFFFFFu : 0u;
+            const int row = y - s * R;                         // index of the row `cur` holds for this step
+            const bool inside = row >= 0 && row < height;      // rows outside the image do not take part in this step
+            uint32_t v[K], rl[K], rr[K], h[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int wi = 32 * k + lane;
+                v[k] = (inside && wi < wpr) ? cur[k] : neutral;
+                if (erode && wi == last) v[k] |= ~tail_mask;   // pixels beyond the right edge count as set
+                rl[k] = __shfl_sync(0xFFFFFFFFu, v[k], prev_lane);
+                rr[k] = __shfl_sync(0xFFFFFFFFu, v[k], next_lane);
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const uint32_t l = lane == 0 ? (k > 0 ? rl[k > 0 ? k - 1 : 0] : neutral) : rl[k];
+                const uint32_t n = lane == 31 ? (k < K - 1 ? rr[k < K - 1 ? k + 1 : k] : neutral) : rr[k];
+                h[k] = erode ? hpass_sq<R, true>(l, v[k], n) : hpass_sq<R, false>(l, v[k], n);
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                uint32_t acc = h[k];
+#pragma unroll
+                for (int j = 0; j < 2 * R; ++j) acc = erode ? (acc & ring[s][j][k]) : (acc | ring[s][j][k]);
+#pragma unroll
+                for (int j = 0; j + 1 < 2 * R; ++j) ring[s][j][k] = ring[s][j + 1][k];
+                ring[s][2 * R - 1][k] = h[k];
+                cur[k] = (32 * k + lane == last) ? (acc & tail_mask) : acc;   // row `row - R` of this step's output
+            }
+        }
+        const int o = y - N * R;
+        if (o < y0 || o >= y1) continue;
+        const size_t out_row = (size_t)frame * height + o;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int wi = 32 * k + lane;
+            if (wi >= wpr) continue;
+            const uint32_t w = cur[k];
+            if (dst_bits) dst_bits[out_row * wpr + wi] = w;
+            if (mask) {
+                uint8_t *p = mask + out_row * width + (size_t)wi * 32;
+                const int n = min(32, width - wi * 32);
+                if (n == 32 && wide_ok) {
+                    uint32_t q[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) q[t] = nibble_to_bytes((w >> (4 * t)) & 0xFu);
+                    st_stream(reinterpret_cast<uint4 *>(p), make_uint4(q[0], q[1], q[2], q[3]));
+                    st_stream(reinterpret_cast<uint4 *>(p) + 1, make_uint4(q[4], q[5], q[6], q[7]));
+                } else {
+                    for (int t = 0; t < n; ++t) p[t] = ((w >> t) & 1) ? 255 : 0;
+                }
+            }
+        }
+    }
+}
+
+template <int R, int N>
+static int launch_roll(bv_ctx *ctx, const uint32_t *bits, uint32_t *dst_bits, uint8_t *mask, int batch, int height, int width,
+                       int wpr, uint32_t erode_bits) {
+    // ~8 warps per SM, at least 4 output rows per strip (the halo of 2 N R rows is re-read by every strip)
+    int strips = (ctx->sm_count * 8 + batch - 1) / batch;
+    if (strips > (height + 3) / 4) strips = (height + 3) / 4;
+    if (strips < 1) strips = 1;
+    const int strip_rows = (height + strips - 1) / strips;
+    strips = (height + strip_rows - 1) / strip_rows;
+    const int jobs = batch * strips, grid = (jobs + 7) / 8;
+    const int k = (wpr + 31) / 32;
+#define BV_ROLL(KK) BV_LAUNCH(ctx, (morph_roll_kernel<R, N, KK>), grid, 256, 0, bits, dst_bits, mask, batch, height, width, wpr, strips, strip_rows, erode_bits)
+    if (k == 1) BV_ROLL(1); else if (k == 2) BV_ROLL(2); else if (k == 3) BV_ROLL(3); else BV_ROLL(4);
+#undef BV_ROLL
+    return BV_OK;
+}
+
 // All steps as one chain, if they fit (erode / dilate / open / close with rectangles, horizontal
 // extents <= 31 per elementary step, shared memory for tile + halos).  *done = false: use the
 // step-by-step path.
@@ -372,6 +540,30 @@ int morph_bits_chain(bv_ctx *ctx, const uint32_t *bits, uint32_t *dst_bits, uint
         }
     }
     const int wpr = words_per_row(width);
+    // register-rolling form: every step a square element of the same radius 1 or 2, 1 / 2 / 4 steps, rows <= 128 words
+    if (ch.n >= 1 && wpr <= 128 && ctx->opt[BV_OPT_MORPH_VARIANT] == 0) {
+        const int r = ch.op[0].L;
+        bool square = r >= 1 && r <= 2;
+        uint32_t erode_bits = 0;
+        for (int i = 0; i < ch.n; ++i) {
+            square = square && ch.op[i].L == r && ch.op[i].R == r && ch.op[i].U == r && ch.op[i].D == r;
+            if (ch.op[i].erode) erode_bits |= 1u << i;
+        }
+        if (square && (ch.n == 1 || ch.n == 2 || ch.n == 4)) {
+            int st;
+            if (r == 1)
+                st = ch.n == 1 ? launch_roll<1, 1>(ctx, bits, dst_bits, mask, batch, height, width, wpr, erode_bits)
+                   : ch.n == 2 ? launch_roll<1, 2>(ctx, bits, dst_bits, mask, batch, height, width, wpr, erode_bits)
+                               : launch_roll<1, 4>(ctx, bits, dst_bits, mask, batch, height, width, wpr, erode_bits);
+            else
+                st = ch.n == 1 ? launch_roll<2, 1>(ctx, bits, dst_bits, mask, batch, height, width, wpr, erode_bits)
+                   : ch.n == 2 ? launch_roll<2, 2>(ctx, bits, dst_bits, mask, batch, height, width, wpr, erode_bits)
+                               : launch_roll<2, 4>(ctx, bits, dst_bits, mask, batch, height, width, wpr, erode_bits);
+            BV_TRY(st);
+            *done = true;
+            return BV_OK;
+        }
+    }
     // shared-memory rows = a multiple of the 32 warps: 32 rows while the halo leaves at least half of
     // them as output rows, more otherwise
     const int halo = ch.halo_up + ch.halo_down;
@@ -381,12 +573,17 @@ int morph_bits_chain(bv_ctx *ctx, const uint32_t *bits, uint32_t *dst_bits, uint
     const size_t smem = (size_t)2 * rows * wpr * sizeof(uint32_t);
     if (rows > 256 || smem > 200 * 1024) return BV_OK;
     if (smem > 48 * 1024 && smem > (size_t)ctx->chain_smem_set) {
-        BV_CUDA(cudaFuncSetAttribute(morph_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BV_CUDA(cudaFuncSetAttribute(morph_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BV_CUDA(cudaFuncSetAttribute(morph_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->chain_smem_set = (int)smem;
     }
     const int tiles = (height + tile_rows - 1) / tile_rows;
-    BV_LAUNCH(ctx, morph_chain_kernel, batch * tiles, kChainThreads, smem, bits, dst_bits, mask, height, width, wpr, tiles,
-              tile_rows, ch);
+    if (ctx->opt[BV_OPT_MORPH_VARIANT] == 2)
+        BV_LAUNCH(ctx, morph_chain_kernel<true>, batch * tiles, kChainThreads, smem, bits, dst_bits, mask, height, width, wpr, tiles,
+                  tile_rows, ch);
+    else
+        BV_LAUNCH(ctx, morph_chain_kernel<false>, batch * tiles, kChainThreads, smem, bits, dst_bits, mask, height, width, wpr, tiles,
+                  tile_rows, ch);
     *done = true;
     return BV_OK;
 }

@@ -154,7 +154,9 @@ enum {
     BV_OPT_NO_HUE_TABLE = 4, /* 1: always do the HSV round trip arithmetically (testing) */
     BV_OPT_CONTOUR_POOL_CHUNKS = 5, /* chunks of the contour walk's vertex pool per frame (testing the second-walk fallback) */
     BV_OPT_FAST_TABLES = 6, /* 1: passes 2 and 3 with per-lane replicated (bank-conflict-free) shared-memory tables; measured slower in a real step, see DESIGN.md */
-    BV_OPT_COUNT = 7
+    BV_OPT_MORPH_VARIANT = 7, /* binary morphology chain: 0 register-rolling warps (default), 1 shared-memory tile filled with plain loads,
+                                 2 shared-memory tile filled by one TMA bulk copy (A-B timing, profiles/r02_morph_variants.log) */
+    BV_OPT_COUNT = 8
 };
 int bv_set_option(bv_ctx *ctx, int option, int value);
 void bv_balance_default(bv_balance_params *p);
