@@ -44,10 +44,11 @@ __global__ void __launch_bounds__(1024) bench(uint32_t *out, long long *clocks, 
             if (MODE == 6) { if (((x >> 8) & 0xFFFFu) < frac) atomicAdd(&hist[r], 1u); }    // atoms, a fraction of lanes
             if (MODE == 7) acc += sm32[(r << 5) + lane];                                    // lds32 conflict-free replica (32 KB)
             // image-like data: a warp's 32 values fall into a window of `frac` bins, so several lanes share an address
-            if (MODE == 8) atomicAdd(&hist[100 + (r % frac)], 1u);                          // per-warp histogram
-            if (MODE == 9) atomicAdd(&sm32[((100 + (r % frac)) << 5) + lane], 1u);          // per-lane striped (32 KB, bank = lane)
-            if (MODE == 10) atomicAdd(&sm32[((100 + (r % frac)) << 3) + (lane & 7)], 1u);   // 8 copies (8 KB)
-            if (MODE == 11) atomicAdd(&sm32[((100 + (r % frac)) << 1) + (lane & 1)], 1u);   // 2 copies
+            // frac = window - 1 (a power of two minus one): no division in the loop
+            if (MODE == 8) atomicAdd(&hist[100 + (r & frac)], 1u);                          // per-warp histogram
+            if (MODE == 9) atomicAdd(&sm32[((100 + (r & frac)) << 5) + lane], 1u);          // per-lane striped (32 KB, bank = lane)
+            if (MODE == 10) atomicAdd(&sm32[((100 + (r & frac)) << 3) + (lane & 7)], 1u);   // 8 copies (8 KB)
+            if (MODE == 11) atomicAdd(&sm32[((100 + (r & frac)) << 1) + (lane & 1)], 1u);   // 2 copies
         }
     }
     const long long t1 = clock64();
@@ -99,12 +100,12 @@ int main() {
         run<6>("atoms1/32", threads, iters, 65536 / 32, d_out, d_clk, base);
         run<6>("atoms4/32", threads, iters, 65536 / 8, d_out, d_clk, base);
         run<6>("atoms16/32", threads, iters, 65536 / 2, d_out, d_clk, base);
-        for (uint32_t win : {4u, 16u, 64u}) {
+        for (uint32_t win : {1u, 4u, 16u, 64u, 256u}) {
             char nm[32];
-            snprintf(nm, sizeof nm, "atomsW%u", win); run<8>(nm, threads, iters, win, d_out, d_clk, base);
-            snprintf(nm, sizeof nm, "atomsW%u/s32", win); run<9>(nm, threads, iters, win, d_out, d_clk, base);
-            snprintf(nm, sizeof nm, "atomsW%u/s8", win); run<10>(nm, threads, iters, win, d_out, d_clk, base);
-            snprintf(nm, sizeof nm, "atomsW%u/s2", win); run<11>(nm, threads, iters, win, d_out, d_clk, base);
+            snprintf(nm, sizeof nm, "atomsW%u", win); run<8>(nm, threads, iters, win - 1, d_out, d_clk, base);
+            snprintf(nm, sizeof nm, "atomsW%u/s32", win); run<9>(nm, threads, iters, win - 1, d_out, d_clk, base);
+            snprintf(nm, sizeof nm, "atomsW%u/s8", win); run<10>(nm, threads, iters, win - 1, d_out, d_clk, base);
+            snprintf(nm, sizeof nm, "atomsW%u/s2", win); run<11>(nm, threads, iters, win - 1, d_out, d_clk, base);
         }
     }
     return 0;
