@@ -350,7 +350,8 @@ def c5_leg(ctx, world, rank, peak_gbs, steps=20, warmup=3):
     import torch
     import torch.distributed as dist
     from oracle import synth
-    mine = [s for s in range(C5_STREAMS) if s % world == rank]
+    from cuauv_vision_pipeline_b200.sharding import streams_for_rank   # stream s -> rank s mod N (tested with gloo, world 2)
+    mine = streams_for_rank(C5_STREAMS, rank, world)
     base = [synth.gen_c5_frame(3200 + i, C5_H, C5_W, big_target=(i == 0)) for i in range(2)]
     # per stream a ring of two distinct frames (cyclic shifts keep the statistics, change every pixel's position)
     rings = [ctx.upload(np.stack([np.roll(base[i], 97 * (s + 1) + 13 * i, axis=1) for s in mine])) for i in range(2)] if mine else []
@@ -386,7 +387,7 @@ def c5_leg(ctx, world, rank, peak_gbs, steps=20, warmup=3):
     out.clear()
     torch.cuda.empty_cache()
     return {"frames_per_s": fps, "ms_per_step": 1e3 * dt / steps, "streams": C5_STREAMS, "steps": steps,
-            "streams_per_gpu": [len([s for s in range(C5_STREAMS) if s % world == r]) for r in range(world)],
+            "streams_per_gpu": [len(streams_for_rank(C5_STREAMS, r, world)) for r in range(world)],
             "scaling": "strong", "shape": "%dx%d" % (C5_W, C5_H), "algorithmic_gbs": gbs,
             "frac_of_hbm": gbs / (peak_gbs * min(world, C5_STREAMS)), "blobs_in_first_frame": n_blobs,
             "workload": "C5: 8 streams 3840x2160, balance -> BGR2HSV -> inRange([10,20,60],[30,100,255]) -> OPEN 5x5 -> "
@@ -512,7 +513,7 @@ def run_ours(args):
                          "measured_us_per_launch": dom_ms * 1e3, "frac_of_issue_bound": bound_us / (dom_ms * 1e3),
                          "note": "instr/px x px / (148 SM x 4 schedulers x 32 lanes x 1.965 GHz); instr from ncu "
                                  "smsp__inst_executed.sum of profiles/%s" % static_name}
-        st = static.get("steady_state")
+        st = (static.get("steady_state") or {}).get("c2")
     else:
         st = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",

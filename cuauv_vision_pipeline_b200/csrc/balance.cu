@@ -370,6 +370,21 @@ __device__ __forceinline__ void hsv_group(const Px16 &in, const uint8_t (*lut)[2
     }
 }
 
+// The H,S,V scratch lives for one pass: written by pass 2, read once by pass 3.  After a warp has consumed the 32 x 48
+// bytes = 12 whole 128-byte lines of its 32 consecutive groups, lanes 0..11 tell L2 to drop those (still dirty) lines
+// instead of writing them back to HBM (discard.global.L2; the bytes are indeterminate afterwards, and the next call's
+// pass 2 rewrites them before anything reads them).  Requires the frame stride to be a multiple of 128 bytes and the
+// warp's first group to be a multiple of 32, which the callers guarantee.
+__device__ __forceinline__ void discard_scratch_lines(const uint8_t *frame_base, uint32_t first_group, uint32_t ngroups) {
+    if (first_group + 32u > ngroups) return;  // warp-uniform: a partial last round (some lanes already left the loop) keeps its lines
+    __syncwarp();                             // all 32 lanes are in this round and have stored what they computed from their loads
+    const int lane = threadIdx.x & 31;
+    if (lane < 12) {
+        const uint8_t *line = frame_base + (size_t)first_group * 48u + (size_t)lane * 128u;
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(line) : "memory");
+    }
+}
+
 // ordinary (L2 write-back) 48-byte store: the scratch image is re-read by pass 3
 __device__ __forceinline__ void store_px16_keep(uint8_t *base, size_t group, const Px16 &p) {
     uint4 *q = reinterpret_cast<uint4 *>(base) + group * 3;
@@ -570,6 +585,7 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
         }
         if (NEED_MASK && out.mask_bits)  // requires width % 16 == 0: a group never straddles rows
             out.mask_bits[((size_t)frame * height + y) * wp2 + (x0 >> 4)] = (uint16_t)bits;
+        if (MODE == 3 && (src_stride & 127) == 0) discard_scratch_lines(f, g & ~31u, ngroups);
     }
     // scalar path: trailing pixels of each frame, or everything for unaligned / odd-sized frames
     for (size_t p = (size_t)ngroups * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += stride) {
@@ -720,6 +736,7 @@ __global__ void __launch_bounds__(1024, 1) mask_from_hsv_kernel(const uint8_t *_
             const uint32_t p0 = g * 16u, y = p0 / (uint32_t)width, x0 = p0 - y * (uint32_t)width;
             out.mask_bits[((size_t)frame * height + y) * wp2 + (x0 >> 4)] = (uint16_t)bits;
         }
+        if ((hsv_stride & 127) == 0) discard_scratch_lines(f, g & ~31u, ngroups);
         in = nxt;
     }
 }
@@ -1207,7 +1224,7 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
     }
 
     // pass 2 leaves H,S,V of every pixel in a scratch image for pass 3 (frame stride padded to 16 bytes)
-    const size_t hsv_stride = (npx * 3 + 15) & ~(size_t)15;
+    const size_t hsv_stride = (npx * 3 + 127) & ~(size_t)127;   // whole 128-byte lines per frame (discard_scratch_lines)
     uint8_t *hsv = nullptr;
     const uint16_t *ivl = nullptr;
     if (prm.hsv_contrast_correct) {
