@@ -341,20 +341,24 @@ def side_workloads(ctx, peak_gbs):
 
 C5_STREAMS = 8
 C5_H, C5_W = 2160, 3840
+C5_FRAMES_PER_STREAM = 4      # consecutive frames of every stream per step (a GPU that owns one stream still gets 4 frames per call)
 
 
-def c5_leg(ctx, world, rank, peak_gbs, steps=20, warmup=3):
+def c5_leg(ctx, world, rank, peak_gbs, steps=10, warmup=3):
     """BASELINE.json configs[4]: 8 camera streams of 3840x2160 through balance -> BGR2HSV -> inRange -> OPEN 5x5 ->
     labels + moments (modules/bins.py:13-27 behind preprocessor.py:87-88), stream s on GPU s mod N, no collective.
-    The 8 streams are fixed, so this leg scales STRONGLY with N.  One step = one new frame from every stream."""
+    The 8 streams are fixed, so this leg scales STRONGLY with N.  One step = C5_FRAMES_PER_STREAM consecutive new frames
+    from every stream (32 frames in all), so that a GPU owning a single stream at N = 8 is still handed 4 frames per call."""
     import torch
     import torch.distributed as dist
     from oracle import synth
     from cuauv_vision_pipeline_b200.sharding import streams_for_rank   # stream s -> rank s mod N (tested with gloo, world 2)
     mine = streams_for_rank(C5_STREAMS, rank, world)
     base = [synth.gen_c5_frame(3200 + i, C5_H, C5_W, big_target=(i == 0)) for i in range(2)]
-    # per stream a ring of two distinct frames (cyclic shifts keep the statistics, change every pixel's position)
-    rings = [ctx.upload(np.stack([np.roll(base[i], 97 * (s + 1) + 13 * i, axis=1) for s in mine])) for i in range(2)] if mine else []
+    # two alternating step batches; frame j of stream s is a cyclic shift of a base frame (same statistics, every pixel
+    # somewhere else), laid out stream-major: [stream][frame of the step]
+    rings = [ctx.upload(np.stack([np.roll(base[(i + j) % 2], 97 * (s + 1) + 13 * (2 * i + j) + 7 * j, axis=1)
+                                  for s in mine for j in range(C5_FRAMES_PER_STREAM)])) for i in range(2)] if mine else []
     desc = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255), morph=[("open", 5, 5, 1)], label=True)
     out = {}
 
@@ -380,13 +384,14 @@ def c5_leg(ctx, world, rank, peak_gbs, steps=20, warmup=3):
         t = torch.tensor([dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    fps = C5_STREAMS * steps / dt
+    fps = C5_STREAMS * C5_FRAMES_PER_STREAM * steps / dt
     gbs = 8 * C5_H * C5_W * fps / 1e9
     n_blobs = int(ctx.download(out["n_blobs"])[0]) if mine else None
     del rings
     out.clear()
     torch.cuda.empty_cache()
     return {"frames_per_s": fps, "ms_per_step": 1e3 * dt / steps, "streams": C5_STREAMS, "steps": steps,
+            "frames_per_stream_per_step": C5_FRAMES_PER_STREAM,
             "streams_per_gpu": [len(streams_for_rank(C5_STREAMS, r, world)) for r in range(world)],
             "scaling": "strong", "shape": "%dx%d" % (C5_W, C5_H), "algorithmic_gbs": gbs,
             "frac_of_hbm": gbs / (peak_gbs * min(world, C5_STREAMS)), "blobs_in_first_frame": n_blobs,
