@@ -122,9 +122,22 @@ def cpu_reference_step(frames, pool):
     from oracle import ref_balance, color_balance_np
 
     def one(img):
-        bal = ref_balance.balance(img) if ref_balance.available() else color_balance_np.process_frame_np(img)
+        # the reference's own translation unit as fast as this host runs it: -O3 -mavx2 build when the CPU has AVX2, its
+        # cv::cvtColor calls served by real OpenCV (oracle/ref_balance.py::fastest); identical bytes to the parity oracle
+        bal = ref_balance.balance_timed(img) if ref_balance.available() else color_balance_np.process_frame_np(img)
         return cv2.cvtColor(bal, cv2.COLOR_BGR2LAB)
     return list(pool.map(one, frames))
+
+
+def reference_build_note():
+    from oracle import ref_balance
+    if not ref_balance.available():
+        return "numpy restatement of color_balance.cpp (oracle/color_balance_np.py)"
+    import numpy as np_
+    from oracle import synth
+    probe = synth.gen_underwater(120, 160, 1)
+    assert np_.array_equal(ref_balance.balance_timed(probe), ref_balance.balance(probe)), "timed reference build differs from the oracle"
+    return "color_balance.cpp compiled unmodified (" + ref_balance.fastest()[1] + "); cv::split / merge / mean of oracle/cvshim"
 
 
 def cpu_baseline(frames, cores):
@@ -141,8 +154,8 @@ def cpu_baseline(frames, cores):
     return {"value": len(frames) / dt, "unit": "frames/s", "cores": cores,
             "kind": "reference" if ref_balance.available() else "port",
             "sample": "%d frames 2208x1242: compiled reference process_frame (default flags, marshalled as "
-                      "modules/color_balance.py:93-110) + cv2.cvtColor(BGR2LAB), one frame per thread, %.2f s wall"
-                      % (len(frames), dt)}
+                      "modules/color_balance.py:93-110) + cv2.cvtColor(BGR2LAB), one frame per thread, %.2f s wall; %s"
+                      % (len(frames), dt, reference_build_note())}
 
 
 def run_reference(args):
@@ -175,9 +188,7 @@ def run_reference(args):
                                "(BASELINE.json configs[1])",
                    "reference_sample": "each step = %d frames on the host cores (compiled reference process_frame + "
                                        "cv2.cvtColor), one frame per thread" % per_step,
-                   "reference_build": "color_balance.cpp compiled unmodified against oracle/cvshim, whose cv::cvtColor / split / merge "
-                                      "are scalar loops (real OpenCV's SIMD BGR2HSV / HSV2BGR would make this arm about 2x faster, "
-                                      "BASELINE.md section 3)",
+                   "reference_build": reference_build_note(),
                    "frames_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores,
                          "kind": "reference" if ref_balance.available() else "port",
@@ -250,13 +261,13 @@ def cpu_side_baselines(cores, budget_s=4.0):
 
     # C5: balance() + bins chain + labelling at 3840x2160, one frame per call (reference process_frame is
     # internally 2-threaded at most, color_balance.cpp:398-418)
-    bal = ref_balance.balance if ref_balance.available() else color_balance_np.process_frame_np
+    bal = ref_balance.balance_timed if ref_balance.available() else color_balance_np.process_frame_np
 
     def c5(img):
         _, cleaned = cv_ops.bins_mask(bal(img))
         return cv2.connectedComponentsWithStats(cleaned, connectivity=8, ltype=cv2.CV_32S)
     timed("c5_balance_threshold_label_3840x2160", c5, [synth.gen_c5_frame(3200 + i) for i in range(2)],
-          note=", compiled reference process_frame (scalar cv shim) + cv2", per_thread=True)
+          note=", compiled reference process_frame (fastest build, real cv2 conversions) + cv2", per_thread=True)
 
     # north-star fused stage at 2208x1242 on the CPU: balance -> HSV -> inRange -> OPEN
     def fused(img):

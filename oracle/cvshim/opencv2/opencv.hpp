@@ -190,10 +190,27 @@ inline void hsv2bgr_px(const unsigned char *src, unsigned char *dst, bool vector
 
 }  // namespace shim_detail
 
+}  // namespace cv
+
+// Optional delegate for cv::cvtColor: when a host program (bench.py's reference arm) installs a function here, the two
+// conversions run in REAL OpenCV (cv2.cvtColor on views of the same buffers, SIMD and all) instead of the scalar formulas
+// below.  The parity tests never install it; the bench asserts that both ways give identical bytes before timing.
+extern "C" {
+typedef void (*bv_shim_cvtcolor_hook_t)(const unsigned char *src, unsigned char *dst, int rows, int cols, int code);
+__attribute__((visibility("default"))) bv_shim_cvtcolor_hook_t bv_shim_cvtcolor_hook = nullptr;
+}
+
+namespace cv {
+
 inline void cvtColor(const Mat &src, Mat &dst, int code) {
     // src may alias dst only when the conversion is per-pixel in place, which holds here.
     Mat out = dst;
     out.create(src.rows, src.cols, CV_8UC3);
+    if (bv_shim_cvtcolor_hook && (code == COLOR_BGR2HSV || code == COLOR_HSV2BGR)) {
+        bv_shim_cvtcolor_hook(src.data, out.data, src.rows, src.cols, code);
+        dst = out;
+        return;
+    }
     const size_t W = (size_t)src.cols;
     for (int y = 0; y < src.rows; ++y) {
         const unsigned char *s = src.data + (size_t)y * W * 3;

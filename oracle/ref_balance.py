@@ -47,3 +47,59 @@ def balance(mat, equalize_rgb=True, rgb_contrast_correct=False,
                       rgb_extrema_clipping, adaptive_cast_correction,
                       horizontal_blocks, vertical_blocks)
     return np.ctypeslib.as_array(data_p, (rows, cols, depth)).astype(np.uint8)
+
+
+# ---- timed reference arm of bench.py -------------------------------------------------------------------------------
+FAST_LIB_PATH = os.path.join(_HERE, "_ref", "libauv-color-balance-ref-avx2.so")
+_fast = None
+_hook_keepalive = None
+
+
+def _cpu_has_avx2():
+    try:
+        with open("/proc/cpuinfo") as f:
+            return " avx2 " in f.read().replace("\n", " ")
+    except OSError:
+        return False
+
+
+def fastest():
+    """(library, description): the reference's translation unit as fast as it gets on this host -- the -O3 -mavx2 build when
+    the CPU has AVX2, with cv::cvtColor delegated to REAL OpenCV (cv2.cvtColor, SIMD) through the shim's hook.  Used only as
+    the timed CPU baseline; `balance()` above (scalar shim, -O2) stays the parity oracle."""
+    global _fast, _hook_keepalive
+    if _fast is not None:
+        return _fast
+    import cv2
+    path, what = REF_LIB_PATH, "-O2"
+    if os.path.exists(FAST_LIB_PATH) and _cpu_has_avx2():
+        path, what = FAST_LIB_PATH, "-O3 -mavx2"
+    lib = ctypes.CDLL(path)
+    try:
+        hook_t = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int)
+
+        def hook(src, dst, rows, cols, code):
+            n = rows * cols * 3
+            s = np.ctypeslib.as_array(ctypes.cast(src, ctypes.POINTER(ctypes.c_uint8)), (n,)).reshape(rows, cols, 3)
+            d = np.ctypeslib.as_array(ctypes.cast(dst, ctypes.POINTER(ctypes.c_uint8)), (n,)).reshape(rows, cols, 3)
+            if src == dst:
+                d[...] = cv2.cvtColor(s, code)
+            else:
+                cv2.cvtColor(s, code, dst=d)
+        _hook_keepalive = hook_t(hook)
+        ctypes.c_void_p.in_dll(lib, "bv_shim_cvtcolor_hook").value = ctypes.cast(_hook_keepalive, ctypes.c_void_p).value
+        what += ", cv::cvtColor = real cv2.cvtColor (OpenCV %s SIMD)" % cv2.__version__
+    except (ValueError, AttributeError):
+        what += ", scalar cv shim"
+    _fast = (lib, what)
+    return _fast
+
+
+def balance_timed(mat):
+    """balance() with the default flags through `fastest()` (same marshalling)."""
+    lib, _ = fastest()
+    rows, cols = mat.shape[0], mat.shape[1]
+    data = mat.flatten()
+    data_p = data.ctypes.data_as(ctypes.POINTER(ctypes.c_int8))
+    lib.process_frame(data_p, rows, cols, 3, True, False, True, False, True, False, 1, 1)
+    return np.ctypeslib.as_array(data_p, (rows, cols, 3)).astype(np.uint8)
