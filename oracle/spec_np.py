@@ -265,7 +265,7 @@ def gaussian_blur_8u(img, ksize, sigma_x=0.0, sigma_y=0.0):
         if n == 1:
             return np.zeros_like(p)
         p = p.copy()
-        for _ in range(8):
+        while np.any((p < 0) | (p >= n)):                 # kernels larger than the image reflect more than once
             p = np.where(p < 0, -p, p)
             p = np.where(p >= n, 2 * n - 2 - p, p)
         return p
