@@ -202,6 +202,8 @@ extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8
         for (int i = 0; i < 3 * nchunks + 1; ++i) BV_CUDA(cudaEventCreate(&tl[i]));
         BV_CUDA(cudaEventRecord(tl[3 * nchunks], ctx->copy_in));
     }
+    // every upload is enqueued before the first kernel: a download into PAGEABLE host memory (small result tables in plain
+    // numpy arrays) blocks the calling thread until its chunk's kernels are done, and must not hold back the next uploads
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = k * chunk, nf = (batch - f0 < chunk) ? batch - f0 : chunk;
         const size_t po = (size_t)f0 * npx;
@@ -209,6 +211,10 @@ extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8
                                 ctx->copy_in));
         if (timeline) BV_CUDA(cudaEventRecord(tl[3 * k], ctx->copy_in));
         BV_CUDA(cudaEventRecord(ctx->ev_in[k], ctx->copy_in));
+    }
+    for (int k = 0; k < nchunks; ++k) {
+        const int f0 = k * chunk, nf = (batch - f0 < chunk) ? batch - f0 : chunk;
+        const size_t po = (size_t)f0 * npx;
         BV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[k], 0));
         BV_TRY(stage_run(ctx, desc, d_in + po * 3, nf, height, width, d_bal ? d_bal + po * 3 : nullptr,
                          d_cvt ? d_cvt + po * cvt_bpp : nullptr, d_mask ? d_mask + po : nullptr,
