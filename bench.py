@@ -352,14 +352,14 @@ def side_workloads(ctx, peak_gbs):
 
 C5_STREAMS = 8
 C5_H, C5_W = 2160, 3840
-C5_FRAMES_PER_STREAM = 4      # consecutive frames of every stream per step (a GPU that owns one stream still gets 4 frames per call)
+C5_FRAMES_PER_STREAM = 8      # consecutive frames of every stream per step (a GPU that owns one stream still gets 8 frames = two L2 chunks per call)
 
 
 def c5_leg(ctx, world, rank, peak_gbs, steps=10, warmup=3):
     """BASELINE.json configs[4]: 8 camera streams of 3840x2160 through balance -> BGR2HSV -> inRange -> OPEN 5x5 ->
     labels + moments (modules/bins.py:13-27 behind preprocessor.py:87-88), stream s on GPU s mod N, no collective.
     The 8 streams are fixed, so this leg scales STRONGLY with N.  One step = C5_FRAMES_PER_STREAM consecutive new frames
-    from every stream (32 frames in all), so that a GPU owning a single stream at N = 8 is still handed 4 frames per call."""
+    from every stream (64 frames in all), so that a GPU owning a single stream at N = 8 is still handed 8 frames per call."""
     import torch
     import torch.distributed as dist
     from oracle import synth

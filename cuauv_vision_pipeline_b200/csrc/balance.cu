@@ -683,9 +683,23 @@ __global__ void __launch_bounds__(256) ivl_build_kernel(uint16_t *__restrict__ t
 
 struct IvlSmem {
     uint16_t tab[kIvlEntries];
-    uint8_t lsv[2][256];
     uint64_t bar;
 };
+
+// Per-frame composition of the S / V stretch tables into the interval table: entry (S, V) of frame f =
+// table[(S'[S] << 8) | V'[V]], so that pass 3 indexes with the scratch image's own S and V bytes and needs ONE shared-memory
+// look-up per pixel instead of three (the stretch tables are frame statistics, the interval table is not).  256 KB per
+// 4-frame chunk, built in ~2 us behind pass 2 (programmatic dependent launch), read back by the TMA copy below.
+__global__ void __launch_bounds__(1024) ivl_compose_kernel(const uint16_t *__restrict__ table, const BalFrame *__restrict__ st,
+                                                           uint16_t *__restrict__ composed) {
+    __shared__ uint8_t lsv[2][256];
+    const int frame = blockIdx.y;
+    grid_dependency_wait();  // pass 2 (the S / V tables of this frame) is complete from here on
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&lsv[0][0])[i] = (&st[frame].lut_sv[0][0])[i];
+    __syncthreads();
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kIvlEntries; idx += gridDim.x * blockDim.x)
+        composed[(size_t)frame * kIvlEntries + idx] = __ldg(table + (((uint32_t)lsv[0][idx >> 8] << 8) | lsv[1][idx & 255]));
+}
 
 // pass 3 of the fast path: H,S,V scratch -> S/V stretch tables -> hue interval -> mask
 __global__ void __launch_bounds__(1024, 1) mask_from_hsv_kernel(const uint8_t *__restrict__ hsv, size_t hsv_stride,
@@ -698,10 +712,10 @@ __global__ void __launch_bounds__(1024, 1) mask_from_hsv_kernel(const uint8_t *_
     if (threadIdx.x == 0) {
         mbar_init(&sm.bar, 1);
         mbar_expect_tx(&sm.bar, kIvlBytes);
+        const unsigned char *mine = reinterpret_cast<const unsigned char *>(table + (size_t)frame * kIvlEntries);  // this frame's composed table
         for (uint32_t o = 0; o < kIvlBytes; o += 32768u)
-            bulk_g2s(reinterpret_cast<unsigned char *>(sm.tab) + o, reinterpret_cast<const unsigned char *>(table) + o, 32768u, &sm.bar);
+            bulk_g2s(reinterpret_cast<unsigned char *>(sm.tab) + o, mine + o, 32768u, &sm.bar);
     }
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sm.lsv[0][0])[i] = (&st[frame].lut_sv[0][0])[i];
     __syncthreads();
     mbar_wait(&sm.bar, 0);
     const uint8_t *f = hsv + (size_t)frame * hsv_stride;
@@ -718,8 +732,7 @@ __global__ void __launch_bounds__(1024, 1) mask_from_hsv_kernel(const uint8_t *_
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const uint32_t h = BV_GETB(in.w, 3 * j);
-            const uint32_t s = sm.lsv[0][BV_GETB(in.w, 3 * j + 1)], v = sm.lsv[1][BV_GETB(in.w, 3 * j + 2)];
-            const uint32_t e = sm.tab[(s << 8) | v];
+            const uint32_t e = sm.tab[(BV_GETB(in.w, 3 * j + 1) << 8) | BV_GETB(in.w, 3 * j + 2)];   // composed: indexed by the raw S, V
             if (((h - (e & 0xFFu)) & 0xFFu) <= (e >> 8)) bits |= 1u << j;
         }
         if (out.mask) {
@@ -775,7 +788,7 @@ static int ivl_table(bv_ctx *ctx, const uint8_t lo[3], const uint8_t hi[3], cons
 }
 
 static int launch_mask_from_hsv(bv_ctx *ctx, const uint8_t *hsv, size_t hsv_stride, const BalFrame *st, int batch, size_t npx,
-                                int width, const uint16_t *table, const BalOutputs &out) {
+                                int width, const uint16_t *table, uint16_t *composed, const BalOutputs &out) {
     if (!ctx->ivl_attr_set) {  // per device
         BV_CUDA(cudaFuncSetAttribute(mask_from_hsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IvlSmem)));
         ctx->ivl_attr_set = 1;
@@ -783,7 +796,8 @@ static int launch_mask_from_hsv(bv_ctx *ctx, const uint8_t *hsv, size_t hsv_stri
     int bpf = (ctx->sm_count + batch - 1) / batch;  // one 1024-thread block per SM
     const size_t need = (npx / 16 + 1023) / 1024;
     if ((size_t)bpf > need) bpf = (int)(need ? need : 1);
-    BV_LAUNCH(ctx, mask_from_hsv_kernel, dim3(bpf, batch), 1024, sizeof(IvlSmem), hsv, hsv_stride, st, table, npx, width, out);
+    BV_LAUNCH_PDL(ctx, ivl_compose_kernel, dim3(8, batch), 1024, 0, table, st, composed);
+    BV_LAUNCH(ctx, mask_from_hsv_kernel, dim3(bpf, batch), 1024, sizeof(IvlSmem), hsv, hsv_stride, st, composed, npx, width, out);
     return BV_OK;
 }
 
@@ -1227,6 +1241,7 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
     const size_t hsv_stride = (npx * 3 + 127) & ~(size_t)127;   // whole 128-byte lines per frame (discard_scratch_lines)
     uint8_t *hsv = nullptr;
     const uint16_t *ivl = nullptr;
+    uint16_t *ivl_frames = nullptr;
     if (prm.hsv_contrast_correct) {
         BV_TRY(ensure_scratch(ctx, SCR_BAL_HSV, hsv_stride * (size_t)batch));
         hsv = (uint8_t *)ctx->scratch[SCR_BAL_HSV];
@@ -1234,6 +1249,10 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         if (cvt_code == BV_BGR2HSV && !out.balanced && !out.converted && (out.mask || out.mask_bits) && vec && npx % 16 == 0 &&
             width % 32 == 0)
             BV_TRY(ivl_table(ctx, out.lo, out.hi, &ivl));
+        if (ivl) {  // one composed copy per frame of the batch
+            BV_TRY(ensure_scratch(ctx, SCR_IVL_FRAMES, (size_t)batch * kIvlBytes));
+            ivl_frames = (uint16_t *)ctx->scratch[SCR_IVL_FRAMES];
+        }
     }
 
     // conflict-free tables (balance_fast.cuh): whole 16-pixel groups, aligned buffers
@@ -1289,7 +1308,7 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         if (co.mask) co.mask += (size_t)f0 * npx;
         if (co.mask_bits) co.mask_bits += (size_t)f0 * height * (((width + 31) / 32) * 2);
         if (ivl) {
-            BV_TRY(launch_mask_from_hsv(ctx, chsv, hsv_stride, cst, nf, npx, width, ivl, co));
+            BV_TRY(launch_mask_from_hsv(ctx, chsv, hsv_stride, cst, nf, npx, width, ivl, ivl_frames + (size_t)f0 * kIvlEntries, co));
         } else if (prm.hsv_contrast_correct) {
             int s3 = 1;  // 1: the fast pass does not cover this case
             if (fast && width % 32 == 0) {

@@ -104,6 +104,7 @@ enum ScratchSlot {
     SCR_HOST_LABELS,
     SCR_HOST_BLOBS,
     SCR_HOST_NBLOBS,
+    SCR_IVL_FRAMES,     // hue-interval table composed with every frame's S / V stretch tables (balance.cu)
     SCR_INGEST,         // landing buffer of 4-channel frames ingested from a shared-memory ring (ingest.cu)
     SCR_COUNT
 };
