@@ -13,6 +13,8 @@
 
 namespace bv {
 
+int rcp_tables_check(bv_ctx *ctx);  // balance.cu
+
 static thread_local char g_error[512] = "";
 
 void set_error(const char *fmt, ...) {
@@ -222,8 +224,12 @@ extern "C" int bv_create(int device, bv_ctx **out) {
         bv_destroy(ctx);
         return BV_ERR_CUDA;
     }
+    if (bv::rcp_tables_check(ctx) != BV_OK) {
+        bv_destroy(ctx);
+        return BV_ERR_UNSUPPORTED;
+    }
     static const char *const opt_env[BV_OPT_COUNT] = {"BV_HIST_BPS", "BV_FINAL_BPS", "BV_SIDE_STREAMS", "BV_L2_CHUNK_MB",
-                                                      "BV_NO_HUE_TABLE", "BV_CONTOUR_POOL_CHUNKS", "BV_FAST_TABLES", "BV_MORPH_VARIANT"};
+                                                      "BV_NO_HUE_TABLE", "BV_CONTOUR_POOL_CHUNKS", "BV_FAST_TABLES", "BV_MORPH_VARIANT", "BV_NO_RCP_TABLES"};
     for (int i = 0; i < BV_OPT_COUNT; ++i) {
         const char *v = getenv(opt_env[i]);
         ctx->opt[i] = v ? atoi(v) : 0;

@@ -356,17 +356,20 @@ __device__ __forceinline__ void put_px(uint32_t (&w)[12], uint32_t p) {
 }
 
 // pixels J..15 of a 16-pixel group of pass 2: tables -> BGR2HSV -> S and V counted, H,S,V packed
-template <int J>
+template <int J, bool RCP>
 __device__ __forceinline__ void hsv_group(const Px16 &in, const uint8_t (*lut)[256], const int *sdiv, const int *hdiv,
                                           uint32_t (*hw)[256], Px16 &o) {
     if constexpr (J < 16) {
         int hh, ss, vv;
-        bgr2hsv(lut[0][BV_GETB(in.w, 3 * J)], lut[1][BV_GETB(in.w, 3 * J + 1)], lut[2][BV_GETB(in.w, 3 * J + 2)], sdiv, hdiv, hh,
-                ss, vv);
+        if (RCP)
+            bgr2hsv_rcp(lut[0][BV_GETB(in.w, 3 * J)], lut[1][BV_GETB(in.w, 3 * J + 1)], lut[2][BV_GETB(in.w, 3 * J + 2)], hh, ss, vv);
+        else
+            bgr2hsv(lut[0][BV_GETB(in.w, 3 * J)], lut[1][BV_GETB(in.w, 3 * J + 1)], lut[2][BV_GETB(in.w, 3 * J + 2)], sdiv, hdiv, hh,
+                    ss, vv);
         atomicAdd(&hw[0][ss], 1u);
         atomicAdd(&hw[1][vv], 1u);
         put_px<J>(o.w, (uint32_t)hh | ((uint32_t)ss << 8) | ((uint32_t)vv << 16));
-        hsv_group<J + 1>(in, lut, sdiv, hdiv, hw, o);
+        hsv_group<J + 1, RCP>(in, lut, sdiv, hdiv, hw, o);
     }
 }
 
@@ -402,7 +405,8 @@ namespace bv {
 // ----------------------------------------------------------------------------------------------
 // The full H,S,V of every pixel is kept in `hsv` (frame stride hsv_stride bytes, 16-byte aligned):
 // pass 3 starts from it instead of repeating the three table look-ups and the conversion.
-template <bool VEC>
+// RCP: sdiv / hdiv from the reciprocal unit instead of shared memory (pixel_math.cuh: rint_quotient_rcp)
+template <bool VEC, bool RCP>
 __global__ void __launch_bounds__(kBalThreads) hist_sv_kernel(const uint8_t *__restrict__ src, BalFrame *__restrict__ st,
                                                               size_t npx, uint8_t *__restrict__ hsv, size_t hsv_stride) {
     __shared__ uint32_t h[kBalWarps][2][256];
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(kBalThreads) hist_sv_kernel(const uint8_t *__r
         Px16 o;
 #pragma unroll
         for (int k = 0; k < 12; ++k) o.w[k] = 0;
-        hsv_group<0>(in, lut, sdiv, hdiv, hw, o);
+        hsv_group<0, RCP>(in, lut, sdiv, hdiv, hw, o);
         store_px16_keep(hf, g, o);
         in = nxt;
     }
@@ -1123,6 +1127,40 @@ static bool all_vec(const uint8_t *src, const BalOutputs &out, size_t npx, int b
            vec_ok(out.mask, npx, batch, 1);
 }
 
+static int rcp_tables_usable(bv_ctx *ctx, bool *ok);
+
+// sdiv / hdiv through the reciprocal unit: compared once per context with the integer formulas, all 2 x 256 values
+__global__ void rcp_tables_check_kernel(int *bad) {
+    const int d = threadIdx.x;
+    if (rint_quotient_rcp((float)(255 << kHsvShift), d) != hsv_sdiv(d) ||
+        rint_quotient_rcp((float)((180 << kHsvShift) / 6), d) != hsv_hdiv(d))
+        atomicOr(bad, 1);
+}
+
+int rcp_tables_check(bv_ctx *ctx) {   // called by bv_create: every BGR2HSV of the library relies on it
+    bool ok = false;
+    BV_TRY(rcp_tables_usable(ctx, &ok));
+    if (ctx->rcp_state != 1) {
+        set_error("bv_create: rcp.approx.f32 of this device does not reproduce OpenCV's sdiv / hdiv tables (library is built for sm_100a)");
+        return BV_ERR_UNSUPPORTED;
+    }
+    return BV_OK;
+}
+
+static int rcp_tables_usable(bv_ctx *ctx, bool *ok) {
+    if (ctx->rcp_state == 0) {
+        if (!ctx->d_ivl_flag) BV_CUDA(cudaMalloc(&ctx->d_ivl_flag, sizeof(int)));
+        BV_CUDA(cudaMemsetAsync(ctx->d_ivl_flag, 0, sizeof(int), ctx->stream));
+        BV_LAUNCH(ctx, rcp_tables_check_kernel, 1, 256, 0, ctx->d_ivl_flag);
+        int bad = 1;
+        BV_CUDA(cudaMemcpyAsync(&bad, ctx->d_ivl_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        BV_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->rcp_state = bad ? 2 : 1;
+    }
+    *ok = ctx->rcp_state == 1 && ctx->opt[BV_OPT_NO_RCP_TABLES] <= 0;
+    return BV_OK;
+}
+
 // ---- fast passes 2 and 3 (balance_fast.cuh): 512-thread blocks, two per SM, ~107 KB of replicated tables each ----
 static int fast_blocks_per_frame(const bv_ctx *ctx, int nf, size_t npx) {
     int bpf = (ctx->sm_count * 2 + nf - 1) / nf;
@@ -1255,6 +1293,8 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         }
     }
 
+    bool rcp = false;
+    if (prm.hsv_contrast_correct) BV_TRY(rcp_tables_usable(ctx, &rcp));
     // conflict-free tables (balance_fast.cuh): whole 16-pixel groups, aligned buffers
     const bool fast = prm.hsv_contrast_correct && vec && npx % 16 == 0 && ctx->opt[BV_OPT_FAST_TABLES] > 0;
 
@@ -1297,10 +1337,12 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
         if (prm.hsv_contrast_correct) {
             if (fast)
                 BV_TRY(launch_hist_sv_fast(ctx, csrc, cst, nf, npx, chsv, hsv_stride));
+            else if (vec && rcp)
+                BV_LAUNCH_PDL(ctx, (hist_sv_kernel<true, true>), grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
             else if (vec)
-                BV_LAUNCH_PDL(ctx, hist_sv_kernel<true>, grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
+                BV_LAUNCH_PDL(ctx, (hist_sv_kernel<true, false>), grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
             else
-                BV_LAUNCH_PDL(ctx, hist_sv_kernel<false>, grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
+                BV_LAUNCH_PDL(ctx, (hist_sv_kernel<false, false>), grid, kBalThreads, 0, csrc, cst, npx, chsv, hsv_stride);
         }
         BalOutputs co = out;
         if (co.balanced) co.balanced += (size_t)f0 * npx * 3;

@@ -19,12 +19,6 @@ static_assert(512 * 2 + kLabInvGammaSize <= kLabCbrtSize * 2, "Lab->BGR tables m
 template <int CODE>
 __device__ __forceinline__ void init_tabs(SmemTabs &t, const uint16_t *__restrict__ g_gamma,
                                           const uint16_t *__restrict__ g_cbrt) {
-    if (CODE == BV_BGR2HSV) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-            t.sdiv[i] = hsv_sdiv(i);
-            t.hdiv[i] = hsv_hdiv(i);
-        }
-    }
     if (CODE == BV_BGR2LAB) {
         for (int i = threadIdx.x; i < kLabGammaSize; i += blockDim.x) t.gtab[i] = g_gamma[i];
         for (int i = threadIdx.x; i < kLabCbrtSize; i += blockDim.x) t.ctab[i] = g_cbrt[i];
@@ -39,7 +33,11 @@ template <int CODE>
 __device__ __forceinline__ void convert_px(int c0, int c1, int c2, bool vec, const SmemTabs &t, int &o0, int &o1,
                                            int &o2) {
     if (CODE == BV_BGR2HSV) {
+#if defined(__CUDA_ARCH__)
+        bgr2hsv_rcp(c0, c1, c2, o0, o1, o2);   // sdiv / hdiv from the reciprocal unit: identical values (checked per device at bv_create)
+#else
         bgr2hsv(c0, c1, c2, t.sdiv, t.hdiv, o0, o1, o2);
+#endif
     } else if (CODE == BV_BGR2LAB) {
         bgr2lab(c0, c1, c2, t.gtab, t.ctab, o0, o1, o2);
     } else if (CODE == BV_BGR2GRAY) {

@@ -67,6 +67,38 @@ BV_HD void bgr2hsv(int b, int g, int r, const int *sdiv, const int *hdiv, int &h
     h = hh + ((hh >> 31) & 180);                                    // hh < 0: += 180
 }
 
+#if defined(__CUDACC__)
+// The two table entries computed instead of looked up: rint(num / d) for d in 0..255 with num = 255 << 12 (sdiv) or
+// (180 << 12) / 6 (hdiv), through the reciprocal unit (MUFU.RCP, a pipe this path does not otherwise use) so that the
+// shared-memory instruction path, which bounds the histogram passes, loses two look-ups per pixel.
+// Exact: num / d = k + r / d with an integer remainder r, never a tie (pixel_math.cuh above), so the quotient is at least
+// 1 / (2d) away from the nearest rounding boundary, while the computed value is off by at most
+// num / d * (2^-23 [rcp.approx, 1 ulp] + 2^-24 [the multiply]) <= 0.19 / d.  d = 0 gives 1 / 0 = +inf, whose sum with the
+// magic constant keeps an all-zero low mantissa: 0, as the tables define.  rcp_tables_check_kernel (balance.cu) compares
+// all 2 x 256 values with the integer formulas on the device once per context; a mismatch switches the tables back on.
+__device__ __forceinline__ int rint_quotient_rcp(float num, int d) {
+    const float df = __fsub_rn(__uint_as_float(0x4B000000u | (uint32_t)d), 8388608.f);   // float(d) without the conversion unit
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(df));
+    const float q = __fmul_rn(num, r);
+    return (int)(__float_as_uint(__fadd_rn(q, 12582912.f)) & 0x3FFFFFu);                 // 2^23 + 2^22: rint in the low mantissa bits
+}
+
+__device__ __forceinline__ void bgr2hsv_rcp(int b, int g, int r, int &h, int &s, int &v) {
+    v = imax(imax(b, g), r);
+    const int vmin = imin(imin(b, g), r);
+    const int diff = v - vmin;
+    const int hr = g - b, hg = b - r + 2 * diff, hb = r - g + 4 * diff;
+    int hh = (v == g) ? hg : hb;
+    hh = (v == r) ? hr : hh;
+    const int sd = rint_quotient_rcp((float)(255 << kHsvShift), v);
+    const int hd = rint_quotient_rcp((float)((180 << kHsvShift) / 6), diff);
+    s = (diff * sd + (1 << (kHsvShift - 1))) >> kHsvShift;
+    hh = (hh * hd + (1 << (kHsvShift - 1))) >> kHsvShift;
+    h = hh + ((hh >> 31) & 180);
+}
+#endif
+
 // ------------------------------------------------------------------------------------------
 // HSV -> BGR, 8-bit, float32.  As cv2 4.13.0 computes it (measured over every H<180,S,V): the
 // bracket is a single-rounding multiply-add; whole 32-pixel groups of a row ("vector path")

@@ -156,7 +156,8 @@ enum {
     BV_OPT_FAST_TABLES = 6, /* 1: passes 2 and 3 with per-lane replicated (bank-conflict-free) shared-memory tables; measured slower in a real step, see DESIGN.md */
     BV_OPT_MORPH_VARIANT = 7, /* binary morphology chain: 0 register-rolling warps (default), 1 shared-memory tile filled with plain loads,
                                  2 shared-memory tile filled by one TMA bulk copy (A-B timing, profiles/r02_morph_variants.log) */
-    BV_OPT_COUNT = 8
+    BV_OPT_NO_RCP_TABLES = 8, /* 1: pass 2 looks sdiv / hdiv up in shared memory instead of computing them with the reciprocal unit (A-B timing) */
+    BV_OPT_COUNT = 9
 };
 int bv_set_option(bv_ctx *ctx, int option, int value);
 void bv_balance_default(bv_balance_params *p);
