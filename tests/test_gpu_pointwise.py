@@ -311,19 +311,19 @@ def test_white_balance_bgr_blur_bit_exact(ctx, shape, ksize, seed):
     assert np.array_equal(color.white_balance_bgr_blur(img, ksize), ref)
 
 
-def test_bgr2luv_within_stated_tolerance(ctx, all_colors):
-    """utils/color.py:30 bgr_to_luv / modules/preprocessor.py:76-80 (P1).  Stated tolerance <= 1 LSB on <= 0.01 % of all
-    2^24 colours (OpenCV's node table is filled by its softfloat pow / cubeRoot, ours by the host libm)."""
+def test_bgr2luv_all_colors(ctx, all_colors):
+    """utils/color.py:30 bgr_to_luv / modules/preprocessor.py:76-80 (P1).  Bit-exact over all 2^24 colours since round 2: the
+    node table is the host libm's plus 97 fitted entries (csrc/luv_fix.inc) that make it OpenCV's own.  (The table is built
+    with powf / cbrtf of the host at run time: with a libm that rounds other nodes differently the stated bound is <= 1 LSB.)"""
     from cuauv_vision_pipeline_b200 import color
-    got = ctx.download(ctx.cvt_color(ctx.upload(all_colors), "bgr2luv")).astype(np.int16)
-    ref = cv2.cvtColor(all_colors, cv2.COLOR_BGR2LUV).astype(np.int16)
-    d = np.abs(got - ref)
-    assert int(d.max()) <= 1
-    assert int((d != 0).any(axis=2).sum()) <= 1700
+    got = ctx.download(ctx.cvt_color(ctx.upload(all_colors), "bgr2luv"))
+    ref = cv2.cvtColor(all_colors, cv2.COLOR_BGR2LUV)
+    d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    assert int(d.max()) <= 1, "stated bound"
+    assert int((d != 0).any(axis=2).sum()) == 0, "expected: identical bytes"
     img = synth.gen_underwater(479, 641, 5)
     conv, planes = color.bgr_to_luv(img)
-    r2 = cv2.cvtColor(img, cv2.COLOR_BGR2LUV).astype(np.int16)
-    assert int(np.abs(conv.astype(np.int16) - r2).max()) <= 1
+    assert np.array_equal(conv, cv2.cvtColor(img, cv2.COLOR_BGR2LUV))
     for k in range(3):
         assert np.array_equal(planes[k], conv[..., k])
 
