@@ -350,13 +350,21 @@ BV_HD void bgr2hls(int bi, int gi, int ri, bool fused, int &H, int &L, int &S) {
     if (diff > 1.1920928955078125e-07f) {  // FLT_EPSILON
         s = l < 0.5f ? BV_FDIV(diff, sm) : BV_FDIV(diff, BV_FSUB(2.f, sm));
         const float k = BV_FDIV(60.f, diff);
-        if (vmax == r)
+        bool wrapped = false;
+        if (vmax == r) {
             h = BV_FMUL(BV_FSUB(g, b), k);
-        else if (vmax == g)
+            // cv2's vector path wraps a negative hue with the product still unrounded: fma(g - b, k, 360) (measured: the three
+            // colours of all 2^24 where (g - b) k + 360 is a rounding tie, e.g. BGR (244, 211, 255), need the single rounding)
+            if (fused && h < 0.f) {
+                h = BV_FMA(BV_FSUB(g, b), k, 360.f);
+                wrapped = true;
+            }
+        } else if (vmax == g) {
             h = fused ? BV_FMA(BV_FSUB(b, r), k, 120.f) : BV_FADD(BV_FMUL(BV_FSUB(b, r), k), 120.f);
-        else
+        } else {
             h = fused ? BV_FMA(BV_FSUB(r, g), k, 240.f) : BV_FADD(BV_FMUL(BV_FSUB(r, g), k), 240.f);
-        if (h < 0.f) h = BV_FADD(h, 360.f);
+        }
+        if (!wrapped && h < 0.f) h = BV_FADD(h, 360.f);
     }
     H = sat_u8(BV_F2I_RN(BV_FMUL(h, 0.5f)));
     L = sat_u8(BV_F2I_RN(BV_FMUL(l, 255.f)));

@@ -171,7 +171,12 @@ def bgr2hls(img, fused=True):
         else:
             hg = (((b - r).astype(f32) * k).astype(f32) + f32(120.0)).astype(f32)
             hb = (((r - g).astype(f32) * k).astype(f32) + f32(240.0)).astype(f32)
-        h = np.where(vmax == r, ((g - b).astype(f32) * k).astype(f32), np.where(vmax == g, hg, hb)).astype(f32)
+        hr = ((g - b).astype(f32) * k).astype(f32)
+        if fused:   # cv2's vector path wraps a negative hue with the product still unrounded: fma(g - b, k, 360)
+            hr = np.where(hr < 0, _fmaf((g - b).astype(f32), k, np.full_like(k, 360.0)), hr)
+        else:
+            hr = np.where(hr < 0, (hr + f32(360.0)).astype(f32), hr)
+        h = np.where(vmax == r, hr, np.where(vmax == g, hg, hb)).astype(f32)
     h = np.where(h < 0, (h + f32(360.0)).astype(f32), h)
     chroma = diff > np.finfo(np.float32).eps
     h = np.where(chroma, h, f32(0))

@@ -45,13 +45,13 @@ def test_hsv2bgr_every_hsv_and_tail_rule(ctx, width):
     assert np.array_equal(got, cv2.cvtColor(im, cv2.COLOR_HSV2BGR))
 
 
-def test_hls_within_stated_tolerance(ctx, all_colors):
-    """P1 conversion.  Tolerance: L and S exact, |dH| <= 1 on at most 8 of 2^24 colours."""
-    got = ctx.download(ctx.cvt_color(ctx.upload(all_colors), "bgr2hls")).astype(np.int16)
-    ref = cv2.cvtColor(all_colors, cv2.COLOR_BGR2HLS).astype(np.int16)
-    d = np.abs(got - ref)
-    assert d[..., 1].max() == 0 and d[..., 2].max() == 0
-    assert d[..., 0].max() <= 1 and int((d[..., 0] > 0).sum()) <= 8
+def test_hls_all_colors(ctx, all_colors):
+    """P1 conversion, bit-exact over all 2^24 colours since round 2 (cv2's vector path wraps a negative hue inside the
+    multiply-add, which decides three rounding ties); the row-tail path on an odd width."""
+    got = ctx.download(ctx.cvt_color(ctx.upload(all_colors), "bgr2hls"))
+    assert np.array_equal(got, cv2.cvtColor(all_colors, cv2.COLOR_BGR2HLS))
+    tail = np.ascontiguousarray(all_colors[:64, :4000].reshape(-1, 25, 3))
+    assert np.array_equal(ctx.download(ctx.cvt_color(ctx.upload(tail), "bgr2hls")), cv2.cvtColor(tail, cv2.COLOR_BGR2HLS))
 
 
 @pytest.mark.parametrize("shape", [(479, 641), (1, 1), (3, 5), (17, 16), (1243, 2209)])

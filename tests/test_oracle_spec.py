@@ -17,7 +17,8 @@ def all_colors():
 
 @pytest.mark.parametrize("name,fn,code", [("hsv", S.bgr2hsv, cv2.COLOR_BGR2HSV), ("lab", S.bgr2lab, cv2.COLOR_BGR2LAB),
                                           ("gray", S.bgr2gray, cv2.COLOR_BGR2GRAY),
-                                          ("ycrcb", S.bgr2ycrcb, cv2.COLOR_BGR2YCrCb)])
+                                          ("ycrcb", S.bgr2ycrcb, cv2.COLOR_BGR2YCrCb),
+                                          ("hls", S.bgr2hls, cv2.COLOR_BGR2HLS)])
 def test_conversion_all_colors(all_colors, name, fn, code):
     ref = cv2.cvtColor(all_colors, code)
     for y0 in range(0, 4096, 512):
