@@ -720,8 +720,6 @@ __global__ void __launch_bounds__(1024, 1) mask_from_hsv_kernel(const uint8_t *_
         for (uint32_t o = 0; o < kIvlBytes; o += 32768u)
             bulk_g2s(reinterpret_cast<unsigned char *>(sm.tab) + o, mine + o, 32768u, &sm.bar);
     }
-    __syncthreads();
-    mbar_wait(&sm.bar, 0);
     const uint8_t *f = hsv + (size_t)frame * hsv_stride;
     const size_t foff = (size_t)frame * npx;
     const uint32_t stride = gridDim.x * blockDim.x, ngroups = (uint32_t)(npx / 16);
@@ -729,7 +727,9 @@ __global__ void __launch_bounds__(1024, 1) mask_from_hsv_kernel(const uint8_t *_
     const int wp2 = ((width + 31) / 32) * 2;
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     Px16 in, nxt;
-    if (g < ngroups) load_px16<false>(f, g, in);
+    if (g < ngroups) load_px16<false>(f, g, in);   // the first group travels while the table is still on its way
+    __syncthreads();
+    mbar_wait(&sm.bar, 0);
     for (; g < ngroups; g += stride) {
         if (g + stride < ngroups) load_px16<false>(f, g + stride, nxt);  // prefetch the next group
         uint32_t bits = 0;

@@ -74,13 +74,12 @@ class GpuPixels:
         return a
 
     def _contours(self, mask_dev, rects):
-        before = 0
+        """Outer contours of a DEVICE mask (no re-upload): vertex lists, polygon centroid / area, optionally minAreaRect."""
         cs = feature.outer_contours(mask_dev, points=True, rects=rects)
         for c in cs:
             c["centroid"] = feature.contour_centroid(c)
             c["area"] = feature.contour_area(c)
-            before += 0 if c.get("points") is None else c["points"].nbytes
-        self.d2h_bytes += before + 72 * len(cs)
+            self.d2h_bytes += 72 + (0 if c.get("points") is None else c["points"].nbytes)
         return cs
 
     def bins(self, img, lo, hi):
