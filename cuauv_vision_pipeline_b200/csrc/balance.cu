@@ -489,7 +489,7 @@ __device__ __forceinline__ uint32_t balance_px(uint32_t b, uint32_t g, uint32_t 
 
 // one group of 16 pixels.  TRACK_X: the group touches the row tail (width % 32 columns), where
 // cv2's scalar HSV2BGR / HLS rounding applies, or wraps to the next row.
-template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, int J>
+template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, bool BAL, int J>
 struct GroupBody {
     static __device__ __forceinline__ void run(const Px16 &in, int x, int width, int vec_end, const FinalSmem &fs,
                                                const SmemTabs &tabs, const RangeTest &bd, Px16 &ob, Px16 &oc, uint32_t (&q)[4],
@@ -497,7 +497,7 @@ struct GroupBody {
         constexpr bool kOne = CvtTraits<CODE>::kOneChannel;
         const bool vec = TRACK_X ? (x < vec_end) : true;
         const uint32_t p = balance_px<MODE>(BV_GETB(in.w, 3 * J), BV_GETB(in.w, 3 * J + 1), BV_GETB(in.w, 3 * J + 2), vec, fs);
-        put_px<J>(ob.w, p);
+        if (BAL) put_px<J>(ob.w, p);   // packing the balanced pixel costs ~2.5 instructions: only when that output exists
         int o0, o1, o2;
         convert_px<CODE>((int)(p & 0xFF), (int)((p >> 8) & 0xFF), (int)(p >> 16), vec, tabs, o0, o1, o2);
         if (kOne) {
@@ -511,16 +511,17 @@ struct GroupBody {
         if (TRACK_X) {
             if (++x == width) x = 0;
         }
-        GroupBody<MODE, CODE, TRACK_X, NEED_MASK, J + 1>::run(in, x, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
+        GroupBody<MODE, CODE, TRACK_X, NEED_MASK, BAL, J + 1>::run(in, x, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
     }
 };
-template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK>
-struct GroupBody<MODE, CODE, TRACK_X, NEED_MASK, 16> {
+template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, bool BAL>
+struct GroupBody<MODE, CODE, TRACK_X, NEED_MASK, BAL, 16> {
     static __device__ __forceinline__ void run(const Px16 &, int, int, int, const FinalSmem &, const SmemTabs &,
                                                const RangeTest &, Px16 &, Px16 &, uint32_t (&)[4], uint32_t &) {}
 };
 
-template <int MODE, int CODE, bool VEC, bool NEED_MASK>
+// BAL: the balanced image is an output (always when CODE == -1); without it the vector path skips packing it
+template <int MODE, int CODE, bool VEC, bool NEED_MASK, bool BAL = true>
 __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__restrict__ src, size_t src_stride,
                                                             const BalFrame *__restrict__ st, size_t npx, int width,
                                                             BalOutputs out, const uint16_t *__restrict__ g_gamma,
@@ -566,10 +567,10 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
 #pragma unroll
         for (int k = 0; k < 12; ++k) ob.w[k] = oc.w[k] = 0;
         if (kNeedX && (int)x0 + 16 > vec_end)
-            GroupBody<MODE, CODE, true, NEED_MASK, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
+            GroupBody<MODE, CODE, true, NEED_MASK, BAL, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
         else
-            GroupBody<MODE, CODE, false, NEED_MASK, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
-        if (out.balanced) store_px16(out.balanced + foff * 3, g, ob);
+            GroupBody<MODE, CODE, false, NEED_MASK, BAL, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
+        if (BAL && out.balanced) store_px16(out.balanced + foff * 3, g, ob);
         if (out.converted) {
             if (kOne)
                 st_stream(reinterpret_cast<uint4 *>(out.converted + foff) + g, make_uint4(q[0], q[1], q[2], q[3]));
@@ -1099,12 +1100,18 @@ static int launch_final(bv_ctx *ctx, const uint8_t *src, size_t src_stride, cons
 #define BV_FINAL(V, M)                                                                                              \
     BV_LAUNCH_PDL(ctx, (final_kernel<MODE, CODE, V, M>), grid, kBalThreads, 0, src, src_stride, st, npx, width, out, \
                   ctx->d_lab_gamma, ctx->d_lab_cbrt)
-    if (vec) {
+#define BV_FINAL_NOBAL(M)                                                                                                     \
+    BV_LAUNCH_PDL(ctx, (final_kernel<MODE, CODE, true, M, false>), grid, kBalThreads, 0, src, src_stride, st, npx, width, out, \
+                  ctx->d_lab_gamma, ctx->d_lab_cbrt)
+    if (vec && CODE != -1 && !out.balanced) {   // the common module case: only the converted image / the mask leave the pass
+        if (need_mask) BV_FINAL_NOBAL(true); else BV_FINAL_NOBAL(false);
+    } else if (vec) {
         if (need_mask) BV_FINAL(true, true); else BV_FINAL(true, false);
     } else {
         if (need_mask) BV_FINAL(false, true); else BV_FINAL(false, false);
     }
 #undef BV_FINAL
+#undef BV_FINAL_NOBAL
     return BV_OK;
 }
 
