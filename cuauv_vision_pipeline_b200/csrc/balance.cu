@@ -470,6 +470,72 @@ struct FinalSmem {
     int sdiv[256], hdiv[256];
 };
 
+// SVT > 0 (MODE 3, whole 32-pixel groups only): the S / V stretch tables hold what HSV -> BGR starts from instead of the
+// stretched byte.  1: s = S'/255 and v = V'/255 as float32 (the per-pixel int -> float step is gone); 2: 8-byte entries
+// {s, 1 - s} and {v, 2^23 + trunc(v * 255)} (also the max channel and one subtraction).  Same float32 operations in the same
+// order, computed once per table entry instead of once per pixel: results are identical by construction.
+template <int SVT>
+struct SvTabs {
+    float f1[2][256];
+};
+template <>
+struct SvTabs<2> {
+    float2 f2[2][256];
+};
+template <>
+struct SvTabs<0> {};
+
+template <int SVT>
+__device__ __forceinline__ void fill_sv_tabs(SvTabs<SVT> &t, const uint8_t (*lut_sv)[256]) {
+    const float kTwo23 = 8388608.f, inv255 = 1.f / 255.f;
+    if constexpr (SVT > 0) {
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+            const uint32_t n = (&lut_sv[0][0])[i];
+            const float x = __fmaf_rn(__uint_as_float(0x4B000000u | n), inv255, -kTwo23 * inv255);
+            if constexpr (SVT == 1) {
+                (&t.f1[0][0])[i] = x;
+            } else {
+                const float y = i < 256 ? BV_FSUB(1.f, x) : __fadd_rz(BV_FMUL(x, 255.f), kTwo23);
+                (&t.f2[0][0])[i] = make_float2(x, y);
+            }
+        }
+    }
+}
+
+// hsv2bgr_packed<true>(H, S', V', vector path) with S' / V' taken through the tables above (raw S, V index them)
+template <int SVT>
+__device__ __forceinline__ uint32_t hsv2bgr_tab(uint32_t H, uint32_t S, uint32_t V, const SvTabs<SVT> &t) {
+    const float kTwo23 = 8388608.f, hscale = 6.f / 180.f;
+    const float h = __fmaf_rn(__uint_as_float(0x4B000000u | H), hscale, -kTwo23 * hscale);
+    float s, oms, v;
+    uint32_t amax;
+    if constexpr (SVT == 2) {
+        const float2 es = t.f2[0][S], ev = t.f2[1][V];
+        s = es.x;
+        oms = es.y;
+        v = ev.x;
+        amax = __float_as_uint(ev.y);
+    } else {
+        s = t.f1[0][S];
+        v = t.f1[1][V];
+        oms = BV_FSUB(1.f, s);
+        amax = __float_as_uint(__fadd_rz(BV_FMUL(v, 255.f), kTwo23));
+    }
+    const float hfloor = __fadd_rz(h, kTwo23);
+    const int sector = (int)(__float_as_uint(hfloor) & 15u);
+    const float f = BV_FSUB(h, __fsub_rn(hfloor, kTwo23));
+    const float fm = (sector & 1) ? f : BV_FSUB(1.f, f);
+    const float ymin = BV_FMUL(BV_FMUL(v, oms), 255.f);
+    const float ymid = BV_FMUL(BV_FMUL(v, BV_FMA(-s, fm, 1.f)), 255.f);
+    const uint32_t amid = __float_as_uint(__fadd_rz(ymid, kTwo23));
+    const uint32_t amin = __float_as_uint(__fadd_rz(ymin, kTwo23));
+    const uint32_t w = __byte_perm(__byte_perm(amax, amid, 0x2240), amin, 0x3410);
+    const unsigned long long kSel = 0x012ull | (0x102ull << 10) | (0x201ull << 20) | (0x210ull << 30) | (0x120ull << 40) |
+                                    (0x021ull << 50);   // as hsv2bgr_packed (pixel_math.cuh)
+    const uint32_t sel = (uint32_t)(kSel >> (10 * sector)) & 0x3FFu;
+    return __byte_perm(w, 0u, sel | 0x4000u);
+}
+
 // returns the balanced pixel packed as b | g<<8 | r<<16
 template <int MODE>
 __device__ __forceinline__ uint32_t balance_px(uint32_t b, uint32_t g, uint32_t r, bool vec, const FinalSmem &fs) {
@@ -489,14 +555,18 @@ __device__ __forceinline__ uint32_t balance_px(uint32_t b, uint32_t g, uint32_t 
 
 // one group of 16 pixels.  TRACK_X: the group touches the row tail (width % 32 columns), where
 // cv2's scalar HSV2BGR / HLS rounding applies, or wraps to the next row.
-template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, bool BAL, int J>
+template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, bool BAL, int SVT, int J>
 struct GroupBody {
     static __device__ __forceinline__ void run(const Px16 &in, int x, int width, int vec_end, const FinalSmem &fs,
-                                               const SmemTabs &tabs, const RangeTest &bd, Px16 &ob, Px16 &oc, uint32_t (&q)[4],
-                                               uint32_t &bits) {
+                                               const SvTabs<SVT> &svt, const SmemTabs &tabs, const RangeTest &bd, Px16 &ob,
+                                               Px16 &oc, uint32_t (&q)[4], uint32_t &bits) {
         constexpr bool kOne = CvtTraits<CODE>::kOneChannel;
         const bool vec = TRACK_X ? (x < vec_end) : true;
-        const uint32_t p = balance_px<MODE>(BV_GETB(in.w, 3 * J), BV_GETB(in.w, 3 * J + 1), BV_GETB(in.w, 3 * J + 2), vec, fs);
+        uint32_t p;
+        if constexpr (SVT > 0 && MODE == 3 && !TRACK_X)
+            p = hsv2bgr_tab<SVT>(BV_GETB(in.w, 3 * J), BV_GETB(in.w, 3 * J + 1), BV_GETB(in.w, 3 * J + 2), svt);
+        else
+            p = balance_px<MODE>(BV_GETB(in.w, 3 * J), BV_GETB(in.w, 3 * J + 1), BV_GETB(in.w, 3 * J + 2), vec, fs);
         if (BAL) put_px<J>(ob.w, p);   // packing the balanced pixel costs ~2.5 instructions: only when that output exists
         int o0, o1, o2;
         convert_px<CODE>((int)(p & 0xFF), (int)((p >> 8) & 0xFF), (int)(p >> 16), vec, tabs, o0, o1, o2);
@@ -511,23 +581,24 @@ struct GroupBody {
         if (TRACK_X) {
             if (++x == width) x = 0;
         }
-        GroupBody<MODE, CODE, TRACK_X, NEED_MASK, BAL, J + 1>::run(in, x, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
+        GroupBody<MODE, CODE, TRACK_X, NEED_MASK, BAL, SVT, J + 1>::run(in, x, width, vec_end, fs, svt, tabs, bd, ob, oc, q, bits);
     }
 };
-template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, bool BAL>
-struct GroupBody<MODE, CODE, TRACK_X, NEED_MASK, BAL, 16> {
-    static __device__ __forceinline__ void run(const Px16 &, int, int, int, const FinalSmem &, const SmemTabs &,
-                                               const RangeTest &, Px16 &, Px16 &, uint32_t (&)[4], uint32_t &) {}
+template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, bool BAL, int SVT>
+struct GroupBody<MODE, CODE, TRACK_X, NEED_MASK, BAL, SVT, 16> {
+    static __device__ __forceinline__ void run(const Px16 &, int, int, int, const FinalSmem &, const SvTabs<SVT> &,
+                                               const SmemTabs &, const RangeTest &, Px16 &, Px16 &, uint32_t (&)[4], uint32_t &) {}
 };
 
 // BAL: the balanced image is an output (always when CODE == -1); without it the vector path skips packing it
-template <int MODE, int CODE, bool VEC, bool NEED_MASK, bool BAL = true>
+template <int MODE, int CODE, bool VEC, bool NEED_MASK, bool BAL = true, int SVT = 0>
 __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__restrict__ src, size_t src_stride,
                                                             const BalFrame *__restrict__ st, size_t npx, int width,
                                                             BalOutputs out, const uint16_t *__restrict__ g_gamma,
                                                             const uint16_t *__restrict__ g_cbrt) {
     __shared__ FinalSmem fs;
     __shared__ SmemTabs tabs;
+    __shared__ SvTabs<SVT> svt;
     const int frame = blockIdx.y;
     if (MODE == 2) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -541,6 +612,7 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
         for (int i = threadIdx.x; i < 768; i += blockDim.x) (&fs.lut[0][0])[i] = (&st[frame].lut_bgr[0][0])[i];
     if (MODE >= 2)
         for (int i = threadIdx.x; i < 512; i += blockDim.x) (&fs.lut_sv[0][0])[i] = (&st[frame].lut_sv[0][0])[i];
+    fill_sv_tabs<SVT>(svt, st[frame].lut_sv);
     __syncthreads();
     const size_t foff = (size_t)frame * npx;
     const uint8_t *f = src + (size_t)frame * src_stride;  // BGR frame, or pass 2's H,S,V scratch (MODE 3)
@@ -567,9 +639,9 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
 #pragma unroll
         for (int k = 0; k < 12; ++k) ob.w[k] = oc.w[k] = 0;
         if (kNeedX && (int)x0 + 16 > vec_end)
-            GroupBody<MODE, CODE, true, NEED_MASK, BAL, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
+            GroupBody<MODE, CODE, true, NEED_MASK, BAL, SVT, 0>::run(in, (int)x0, width, vec_end, fs, svt, tabs, bd, ob, oc, q, bits);
         else
-            GroupBody<MODE, CODE, false, NEED_MASK, BAL, 0>::run(in, (int)x0, width, vec_end, fs, tabs, bd, ob, oc, q, bits);
+            GroupBody<MODE, CODE, false, NEED_MASK, BAL, SVT, 0>::run(in, (int)x0, width, vec_end, fs, svt, tabs, bd, ob, oc, q, bits);
         if (BAL && out.balanced) store_px16(out.balanced + foff * 3, g, ob);
         if (out.converted) {
             if (kOne)
@@ -1103,7 +1175,15 @@ static int launch_final(bv_ctx *ctx, const uint8_t *src, size_t src_stride, cons
 #define BV_FINAL_NOBAL(M)                                                                                                     \
     BV_LAUNCH_PDL(ctx, (final_kernel<MODE, CODE, true, M, false>), grid, kBalThreads, 0, src, src_stride, st, npx, width, out, \
                   ctx->d_lab_gamma, ctx->d_lab_cbrt)
-    if (vec && CODE != -1 && !out.balanced) {   // the common module case: only the converted image / the mask leave the pass
+    const int svt = ctx->opt[BV_OPT_FINAL_SV_TABLES];
+    if (MODE == 3 && CODE == BV_BGR2LAB && vec && !out.balanced && !need_mask && svt > 0) {   // experiment: DESIGN.md 4b
+        if (svt == 1)
+            BV_LAUNCH_PDL(ctx, (final_kernel<MODE, CODE, true, false, false, (MODE == 3 && CODE == BV_BGR2LAB) ? 1 : 0>), grid,
+                          kBalThreads, 0, src, src_stride, st, npx, width, out, ctx->d_lab_gamma, ctx->d_lab_cbrt);
+        else
+            BV_LAUNCH_PDL(ctx, (final_kernel<MODE, CODE, true, false, false, (MODE == 3 && CODE == BV_BGR2LAB) ? 2 : 0>), grid,
+                          kBalThreads, 0, src, src_stride, st, npx, width, out, ctx->d_lab_gamma, ctx->d_lab_cbrt);
+    } else if (vec && CODE != -1 && !out.balanced) {   // the common module case: only the converted image / the mask leave the pass
         if (need_mask) BV_FINAL_NOBAL(true); else BV_FINAL_NOBAL(false);
     } else if (vec) {
         if (need_mask) BV_FINAL(true, true); else BV_FINAL(true, false);
