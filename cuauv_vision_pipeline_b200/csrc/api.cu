@@ -203,6 +203,8 @@ extern "C" int bv_create(int device, bv_ctx **out) {
         ok_aux = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
     ok_aux = ok_aux && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok_aux && i < BV_HOST_SLOTS; ++i)
+        ok_aux = cudaEventCreateWithFlags(&ctx->ev_slot[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok_aux) {
         set_error("bv_create: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         bv_destroy(ctx);
@@ -272,6 +274,8 @@ extern "C" void bv_destroy(bv_ctx *ctx) {
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int i = 0; i < BV_HOST_SLOTS; ++i)
+        if (ctx->ev_slot[i]) cudaEventDestroy(ctx->ev_slot[i]);
     for (int i = 0; i < BV_MAX_CHUNKS; ++i) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);

@@ -308,17 +308,22 @@ __device__ __forceinline__ bool last_block_of_frame(uint32_t *ticket, unsigned b
 // the frame's histogram in HBM with one atomic per non-empty bin per block; the last block of a
 // frame then computes the statistics and tables (no separate launch).
 // ----------------------------------------------------------------------------------------------
+// Shared-memory layout: 4 KB per warp (three 1 KB histograms + 1 KB unused), so that a counter's byte offset is
+// (warp << 12) | (channel << 10) | (value << 2): the warp part is ORed into the mask that isolates the value (one LOP3) and the
+// channel part is an immediate of the ATOMS, i.e. shift + and-or + ATOMS per sample instead of shift + and + add + ATOMS.
+constexpr int kHistWarpWords = 1024;
 template <bool VEC>
 __global__ void __launch_bounds__(kBalThreads) hist_bgr_kernel(const uint8_t *__restrict__ src, BalFrame *__restrict__ st,
                                                                size_t npx, bv_balance_params prm,
                                                                const double *__restrict__ pow_quarter) {
-    __shared__ uint32_t h[kBalWarps][3][256];
+    __shared__ uint32_t h[kBalWarps][kHistWarpWords];
     __shared__ StatScratch sc;
-    for (int i = threadIdx.x; i < kBalWarps * 768; i += blockDim.x) (&h[0][0][0])[i] = 0;
+    for (int i = threadIdx.x; i < kBalWarps * kHistWarpWords; i += blockDim.x) (&h[0][0])[i] = 0;
     __syncthreads();
     const int frame = blockIdx.y;
     const uint8_t *f = src + (size_t)frame * npx * 3;
-    uint32_t(*hw)[256] = h[threadIdx.x >> 5];
+    unsigned char *hbytes = reinterpret_cast<unsigned char *>(&h[0][0]);
+    const uint32_t woff = (threadIdx.x >> 5) << 12;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t ngroups = VEC ? npx / 16 : 0;
     // the next group's 48 bytes are requested before the current group's 48 atomics are issued, so
@@ -329,19 +334,25 @@ __global__ void __launch_bounds__(kBalThreads) hist_bgr_kernel(const uint8_t *__
     for (; g < ngroups; g += stride) {
         if (g + stride < ngroups) load_px16<true>(f, g + stride, nxt);
 #pragma unroll
-        for (int k = 0; k < 48; ++k) atomicAdd(&hw[k % 3][BV_GETB(in.w, k)], 1u);
+        for (int k = 0; k < 48; ++k) {
+            const uint32_t w = in.w[k >> 2];
+            const int sh = 8 * (k & 3) - 2;   // value << 2, straight from its place in the word
+            const uint32_t off = ((sh < 0 ? w << 2 : w >> sh) & 0x3FCu) | woff;
+            atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off + (k % 3) * 1024), 1u);
+        }
         in = nxt;
     }
+    uint32_t *hw = h[threadIdx.x >> 5];
     for (size_t p = ngroups * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += stride) {
-        atomicAdd(&hw[0][f[3 * p]], 1u);
-        atomicAdd(&hw[1][f[3 * p + 1]], 1u);
-        atomicAdd(&hw[2][f[3 * p + 2]], 1u);
+        atomicAdd(&hw[f[3 * p]], 1u);
+        atomicAdd(&hw[256 + f[3 * p + 1]], 1u);
+        atomicAdd(&hw[512 + f[3 * p + 2]], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 768; i += blockDim.x) {
         uint32_t s = 0;
 #pragma unroll
-        for (int w = 0; w < kBalWarps; ++w) s += (&h[w][0][0])[i];
+        for (int w = 0; w < kBalWarps; ++w) s += h[w][i];
         if (s) atomicAdd(&st[frame].hist_bgr[0][0] + i, s);
     }
     if (last_block_of_frame(&st[frame].ticket[0], gridDim.x)) stats_bgr_block(st[frame], npx, prm, pow_quarter, sc, nullptr, 1, npx);

@@ -104,6 +104,13 @@ enum ScratchSlot {
     SCR_HOST_LABELS,
     SCR_HOST_BLOBS,
     SCR_HOST_NBLOBS,
+    SCR_HOST1_IN,       // second staging set (slot 1 of bv_stage_host_submit), same order as the first
+    SCR_HOST1_BAL,
+    SCR_HOST1_CVT,
+    SCR_HOST1_MASK,
+    SCR_HOST1_LABELS,
+    SCR_HOST1_BLOBS,
+    SCR_HOST1_NBLOBS,
     SCR_IVL_FRAMES,     // hue-interval table composed with every frame's S / V stretch tables (balance.cu)
     SCR_INGEST,         // landing buffer of 4-channel frames ingested from a shared-memory ring (ingest.cu)
     SCR_COUNT
@@ -113,6 +120,7 @@ enum ScratchSlot {
 
 #define BV_MAX_CHUNKS 64
 #define BV_MAX_SIDE 4
+#define BV_HOST_SLOTS 2
 #define BV_IVL_SLOTS 4
 
 struct bv_ctx {
@@ -131,6 +139,8 @@ struct bv_ctx {
     // host-memory pipeline (bv_stage_host): copy streams and per-chunk events
     cudaStream_t copy_in, copy_out;
     cudaEvent_t ev_in[BV_MAX_CHUNKS], ev_done[BV_MAX_CHUNKS];
+    cudaEvent_t ev_slot[BV_HOST_SLOTS];  // end of the last download of the call in flight on each staging set
+    int slot_busy[BV_HOST_SLOTS];
     int overlapped;  // the current call spreads its chunks over side streams (small grids per kernel)
     void *prof;  // per-kernel CUDA-event timing, only while bv_profile_enable(ctx, 1)
     // side streams: independent chunks of one call run concurrently so that the issue-bound final

@@ -152,10 +152,12 @@ extern "C" int bv_stage(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *s
                      blobs_dev, blobs_dev ? max_blobs : 0, n_blobs_dev);
 }
 
-extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src_host, int batch, int height,
-                             int width, uint8_t *balanced_host, uint8_t *converted_host, uint8_t *mask_host,
-                             int32_t *labels_host, bv_blob *blobs_host, int max_blobs, int32_t *n_blobs_host) {
+// Enqueues one host-buffer call on staging set `slot`: uploads, kernels, downloads; no synchronisation.
+static int stage_host_enqueue(bv_ctx *ctx, int slot, const bv_stage_desc *desc, const uint8_t *src_host, int batch, int height,
+                              int width, uint8_t *balanced_host, uint8_t *converted_host, uint8_t *mask_host,
+                              int32_t *labels_host, bv_blob *blobs_host, int max_blobs, int32_t *n_blobs_host) {
     BV_REQUIRE(ctx && src_host, "null context or source");
+    BV_REQUIRE(slot >= 0 && slot < BV_HOST_SLOTS, "slot must be 0 or 1");
     BV_REQUIRE(batch > 0 && height > 0 && width > 0, "batch, height and width must be positive");
     BV_REQUIRE(max_blobs >= 0, "max_blobs must be >= 0");
     BV_TRY(validate_desc(desc));
@@ -163,22 +165,26 @@ extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8
     const size_t npx = (size_t)height * width;
     const size_t cvt_bpp = desc->cvt_code == BV_BGR2GRAY ? 1 : 3;
     if (!blobs_host) max_blobs = 0;
-    // device staging for the whole batch: no buffer is reused inside one call, so the three
+    // device staging for the whole batch, one set per slot: no buffer is reused inside one call, so the three
     // streams below need no back-pressure
-    BV_TRY(ensure_scratch(ctx, SCR_HOST_IN, (size_t)batch * npx * 3));
-    if (balanced_host) BV_TRY(ensure_scratch(ctx, SCR_HOST_BAL, (size_t)batch * npx * 3));
-    if (converted_host) BV_TRY(ensure_scratch(ctx, SCR_HOST_CVT, (size_t)batch * npx * cvt_bpp));
-    if (mask_host) BV_TRY(ensure_scratch(ctx, SCR_HOST_MASK, (size_t)batch * npx));
-    if (labels_host) BV_TRY(ensure_scratch(ctx, SCR_HOST_LABELS, (size_t)batch * npx * 4));
-    if (max_blobs) BV_TRY(ensure_scratch(ctx, SCR_HOST_BLOBS, (size_t)batch * max_blobs * sizeof(bv_blob)));
-    BV_TRY(ensure_scratch(ctx, SCR_HOST_NBLOBS, (size_t)batch * sizeof(int32_t)));
-    uint8_t *d_in = (uint8_t *)ctx->scratch[SCR_HOST_IN];
-    uint8_t *d_bal = balanced_host ? (uint8_t *)ctx->scratch[SCR_HOST_BAL] : nullptr;
-    uint8_t *d_cvt = converted_host ? (uint8_t *)ctx->scratch[SCR_HOST_CVT] : nullptr;
-    uint8_t *d_mask = mask_host ? (uint8_t *)ctx->scratch[SCR_HOST_MASK] : nullptr;
-    int32_t *d_lab = labels_host ? (int32_t *)ctx->scratch[SCR_HOST_LABELS] : nullptr;
-    bv_blob *d_blobs = max_blobs ? (bv_blob *)ctx->scratch[SCR_HOST_BLOBS] : nullptr;
-    int32_t *d_nb = (int32_t *)ctx->scratch[SCR_HOST_NBLOBS];
+    const int base = SCR_HOST_IN + slot * (SCR_HOST_NBLOBS - SCR_HOST_IN + 1);
+    const int s_in = base, s_bal = base + (SCR_HOST_BAL - SCR_HOST_IN), s_cvt = base + (SCR_HOST_CVT - SCR_HOST_IN),
+              s_mask = base + (SCR_HOST_MASK - SCR_HOST_IN), s_lab = base + (SCR_HOST_LABELS - SCR_HOST_IN),
+              s_blobs = base + (SCR_HOST_BLOBS - SCR_HOST_IN), s_nb = base + (SCR_HOST_NBLOBS - SCR_HOST_IN);
+    BV_TRY(ensure_scratch(ctx, s_in, (size_t)batch * npx * 3));
+    if (balanced_host) BV_TRY(ensure_scratch(ctx, s_bal, (size_t)batch * npx * 3));
+    if (converted_host) BV_TRY(ensure_scratch(ctx, s_cvt, (size_t)batch * npx * cvt_bpp));
+    if (mask_host) BV_TRY(ensure_scratch(ctx, s_mask, (size_t)batch * npx));
+    if (labels_host) BV_TRY(ensure_scratch(ctx, s_lab, (size_t)batch * npx * 4));
+    if (max_blobs) BV_TRY(ensure_scratch(ctx, s_blobs, (size_t)batch * max_blobs * sizeof(bv_blob)));
+    BV_TRY(ensure_scratch(ctx, s_nb, (size_t)batch * sizeof(int32_t)));
+    uint8_t *d_in = (uint8_t *)ctx->scratch[s_in];
+    uint8_t *d_bal = balanced_host ? (uint8_t *)ctx->scratch[s_bal] : nullptr;
+    uint8_t *d_cvt = converted_host ? (uint8_t *)ctx->scratch[s_cvt] : nullptr;
+    uint8_t *d_mask = mask_host ? (uint8_t *)ctx->scratch[s_mask] : nullptr;
+    int32_t *d_lab = labels_host ? (int32_t *)ctx->scratch[s_lab] : nullptr;
+    bv_blob *d_blobs = max_blobs ? (bv_blob *)ctx->scratch[s_blobs] : nullptr;
+    int32_t *d_nb = (int32_t *)ctx->scratch[s_nb];
 
     // chunked three-stage pipeline: H2D (copy-in stream) -> kernels (context stream) -> D2H
     // (copy-out stream); PCIe is full duplex, so uploads of chunk k+1 overlap downloads of k-1.
@@ -203,7 +209,8 @@ extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8
         BV_CUDA(cudaEventRecord(tl[3 * nchunks], ctx->copy_in));
     }
     // every upload is enqueued before the first kernel: a download into PAGEABLE host memory (small result tables in plain
-    // numpy arrays) blocks the calling thread until its chunk's kernels are done, and must not hold back the next uploads
+    // numpy arrays) blocks the calling thread until its chunk's kernels are done, and must not hold back the next uploads.
+    // The per-chunk events are shared by both slots: a stream wait refers to the record that precedes it in program order.
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = k * chunk, nf = (batch - f0 < chunk) ? batch - f0 : chunk;
         const size_t po = (size_t)f0 * npx;
@@ -242,9 +249,10 @@ extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8
                                     ctx->copy_out));
         if (timeline) BV_CUDA(cudaEventRecord(tl[3 * k + 2], ctx->copy_out));
     }
-    BV_CUDA(cudaStreamSynchronize(ctx->copy_out));
-    BV_CUDA(cudaStreamSynchronize(ctx->stream));
+    BV_CUDA(cudaEventRecord(ctx->ev_slot[slot], ctx->copy_out));   // everything of this call precedes it on copy_out
+    ctx->slot_busy[slot] = 1;
     if (timeline) {
+        BV_CUDA(cudaEventSynchronize(ctx->ev_slot[slot]));
         for (int k = 0; k < nchunks; ++k) {
             float a = 0, b = 0, c = 0;
             cudaEventElapsedTime(&a, tl[3 * nchunks], tl[3 * k]);
@@ -255,6 +263,38 @@ extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8
         }
         for (int i = 0; i < 3 * nchunks + 1; ++i) cudaEventDestroy(tl[i]);
     }
+    return BV_OK;
+}
+
+extern "C" int bv_stage_host_wait(bv_ctx *ctx, int slot) {
+    BV_REQUIRE(ctx, "null context");
+    BV_REQUIRE(slot >= 0 && slot < BV_HOST_SLOTS, "slot must be 0 or 1");
+    if (!ctx->slot_busy[slot]) return BV_OK;
+    BV_CUDA(cudaSetDevice(ctx->device));
+    BV_CUDA(cudaEventSynchronize(ctx->ev_slot[slot]));
+    ctx->slot_busy[slot] = 0;
+    return BV_OK;
+}
+
+extern "C" int bv_stage_host_submit(bv_ctx *ctx, int slot, const bv_stage_desc *desc, const uint8_t *src_host, int batch,
+                                    int height, int width, uint8_t *balanced_host, uint8_t *converted_host, uint8_t *mask_host,
+                                    int32_t *labels_host, bv_blob *blobs_host, int max_blobs, int32_t *n_blobs_host) {
+    BV_REQUIRE(ctx, "null context");
+    BV_REQUIRE(slot >= 0 && slot < BV_HOST_SLOTS, "slot must be 0 or 1");
+    BV_TRY(bv_stage_host_wait(ctx, slot));   // the slot's device staging is free again once its previous call has completed
+    return stage_host_enqueue(ctx, slot, desc, src_host, batch, height, width, balanced_host, converted_host, mask_host,
+                              labels_host, blobs_host, max_blobs, n_blobs_host);
+}
+
+extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src_host, int batch, int height,
+                             int width, uint8_t *balanced_host, uint8_t *converted_host, uint8_t *mask_host,
+                             int32_t *labels_host, bv_blob *blobs_host, int max_blobs, int32_t *n_blobs_host) {
+    BV_REQUIRE(ctx, "null context");
+    BV_TRY(bv_stage_host_wait(ctx, 0));
+    BV_TRY(stage_host_enqueue(ctx, 0, desc, src_host, batch, height, width, balanced_host, converted_host, mask_host, labels_host,
+                              blobs_host, max_blobs, n_blobs_host));
+    BV_TRY(bv_stage_host_wait(ctx, 0));
+    BV_CUDA(cudaStreamSynchronize(ctx->stream));
     return BV_OK;
 }
 

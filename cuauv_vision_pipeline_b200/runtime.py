@@ -50,10 +50,14 @@ class Context:
         # ordered with the kernels without any extra synchronisation
         self.torch_stream = torch.cuda.ExternalStream(int(ffi.cast("uintptr_t", lib.bv_stream(self._ctx))),
                                                       device=self.device)
+        self._inflight = {}   # slot -> host arrays of an asynchronous stage_host call
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
         if self._ctx is not None:
+            for slot in list(self._inflight):
+                lib.bv_stage_host_wait(self._ctx, slot)
+            self._inflight.clear()
             lib.bv_destroy(self._ctx)
             self._ctx = None
 
@@ -547,9 +551,12 @@ class Context:
                            ffi.cast("int32_t *", nb.data_ptr()) if nb is not None else ffi.NULL))
         return out
 
-    def stage_host(self, desc, src, want=("mask",), max_blobs=1024, out=None):
+    def stage_host(self, desc, src, want=("mask",), max_blobs=1024, out=None, slot=None):
         """Same stage on HOST arrays (numpy, ideally pinned): upload, run, download, blocking.
-        Returns a dict of numpy arrays; `out` may carry preallocated (pinned) arrays."""
+        Returns a dict of numpy arrays; `out` may carry preallocated (pinned) arrays.
+        slot = 0 or 1: asynchronous form (bv_stage_host_submit): returns at once, the arrays of the returned dict are
+        complete after `stage_host_wait(slot)`; two calls (one per slot) may be in flight.  The caller keeps `src` and
+        the returned arrays alive (and unmodified) until then."""
         src = np.ascontiguousarray(src, dtype=np.uint8)
         if src.ndim == 3:
             b, (h, w, c) = 1, src.shape
@@ -576,35 +583,55 @@ class Context:
 
         def p(a, ctype):
             return ffi.cast(ctype, a.ctypes.data) if a is not None else ffi.NULL
-        check(lib.bv_stage_host(self.handle, desc, p(src, "uint8_t *"), b, h, w, p(balanced, "uint8_t *"),
-                                p(converted, "uint8_t *"), p(mask, "uint8_t *"), p(labels, "int32_t *"),
-                                p(blobs, "bv_blob *"), max_blobs if blobs is not None else 0, p(nb, "int32_t *")))
+        if slot is None:
+            check(lib.bv_stage_host(self.handle, desc, p(src, "uint8_t *"), b, h, w, p(balanced, "uint8_t *"),
+                                    p(converted, "uint8_t *"), p(mask, "uint8_t *"), p(labels, "int32_t *"),
+                                    p(blobs, "bv_blob *"), max_blobs if blobs is not None else 0, p(nb, "int32_t *")))
+        else:
+            check(lib.bv_stage_host_submit(self.handle, int(slot), desc, p(src, "uint8_t *"), b, h, w, p(balanced, "uint8_t *"),
+                                           p(converted, "uint8_t *"), p(mask, "uint8_t *"), p(labels, "int32_t *"),
+                                           p(blobs, "bv_blob *"), max_blobs if blobs is not None else 0, p(nb, "int32_t *")))
+            self._inflight[int(slot)] = (src, out)   # keeps the buffers alive until the wait
         return out
+
+    def stage_host_wait(self, slot):
+        """Blocks until the call submitted on `slot` has delivered its results to the host arrays."""
+        check(lib.bv_stage_host_wait(self.handle, int(slot)))
+        self._inflight.pop(int(slot), None)
 
 
 # ---- pinned numpy buffers --------------------------------------------------------------------
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc'ed block; numpy views made from it keep it (and so the memory) alive."""
+
+    def __init__(self, nbytes):
+        self._ptr = lib.bv_host_alloc(max(nbytes, 1))
+        if self._ptr == ffi.NULL:
+            raise BVError(-4, ffi.string(lib.bv_last_error()).decode())
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "version": 3,
+                                    "data": (int(ffi.cast("uintptr_t", self._ptr)), False)}
+
+    def __del__(self):
+        try:
+            if self._ptr is not None and self._ptr != ffi.NULL:
+                lib.bv_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
 class PinnedArray:
-    """numpy array over cudaHostAlloc'ed memory (full-speed PCIe for the *_host entry points)."""
+    """numpy array over cudaHostAlloc'ed memory (full-speed PCIe for the *_host entry points).  `.array` (and any view
+    of it) owns a reference to the block: the memory is released when the last of them is gone."""
 
     def __init__(self, shape, dtype=np.uint8):
         dtype = np.dtype(dtype)
         nbytes = int(np.prod(shape)) * dtype.itemsize
-        self._ptr = lib.bv_host_alloc(max(nbytes, 1))
-        if self._ptr == ffi.NULL:
-            raise BVError(-4, ffi.string(lib.bv_last_error()).decode())
-        self.array = np.frombuffer(ffi.buffer(self._ptr, nbytes), dtype=dtype).reshape(shape)
+        block = _PinnedBlock(nbytes)
+        self.array = np.asarray(block)[:nbytes].view(dtype).reshape(shape)
 
     def free(self):
-        if self._ptr is not None and self._ptr != ffi.NULL:
-            self.array = None
-            lib.bv_host_free(self._ptr)
-            self._ptr = None
-
-    def __del__(self):
-        try:
-            self.free()
-        except Exception:
-            pass
+        self.array = None
 
 
 # ---- default contexts (one per device, created on first use) ----------------------------------

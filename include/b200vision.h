@@ -384,6 +384,18 @@ int bv_stage(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src_dev, int
 int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src_host, int batch, int height,
                   int width, uint8_t *balanced_host, uint8_t *converted_host, uint8_t *mask_host,
                   int32_t *labels_host, bv_blob *blobs_host, int max_blobs, int32_t *n_blobs_host);
+/* The same call split in two, for a caller that has the next batch ready while the previous one is still being returned
+ * (the vision daemon runs one module process per camera, core/base.py:669-844; a process that serves several cameras, or
+ * works on frame k's results while frame k+1 is on its way, uses this).  bv_stage_host_submit enqueues the uploads, the
+ * kernels and the downloads and returns; the host output buffers are complete after bv_stage_host_wait(ctx, slot).
+ * slot is 0 or 1: each has its own device staging, so two calls can be in flight and the uploads of one overlap the
+ * downloads of the other (PCIe is full duplex).  Calls execute in submission order.  Submitting on a slot first waits
+ * for that slot's previous call.  Host buffers must stay valid until the wait returns and should be pinned
+ * (bv_host_alloc / bv_host_register): a copy from or to pageable memory makes the submit block. */
+int bv_stage_host_submit(bv_ctx *ctx, int slot, const bv_stage_desc *desc, const uint8_t *src_host, int batch, int height,
+                         int width, uint8_t *balanced_host, uint8_t *converted_host, uint8_t *mask_host,
+                         int32_t *labels_host, bv_blob *blobs_host, int max_blobs, int32_t *n_blobs_host);
+int bv_stage_host_wait(bv_ctx *ctx, int slot);
 
 /* ---- pinned host memory (so the *_host entry points run at full PCIe speed) ---------------- */
 void *bv_host_alloc(size_t bytes);               /* cudaHostAlloc; NULL on failure            */

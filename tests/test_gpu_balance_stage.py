@@ -224,6 +224,49 @@ def test_stage_host_equals_device_stage(ctx):
     assert np.array_equal(res["converted"], host["converted"])
 
 
+def test_stage_host_submit_wait_two_batches_in_flight(ctx):
+    """bv_stage_host_submit / _wait: two calls in flight on the two staging slots deliver what the blocking call delivers,
+    for different batch sizes and stages per slot, over several rounds (a slot is re-used while the other is in flight)."""
+    import cuauv_vision_pipeline_b200 as bv
+    shapes = [(9, 360, 640), (5, 480, 656)]
+    descs = [ctx.make_stage(balance={}, cvt="bgr2lab"),
+             ctx.make_stage(balance={}, cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255), morph=[("open", 5, 5, 1)], label=True)]
+    wants = [("converted",), ("mask", "blobs")]
+    rounds = 4
+    src = [[bv.PinnedArray(shapes[k] + (3,)) for _ in range(rounds)] for k in range(2)]
+    expect = [[None] * rounds for _ in range(2)]
+    for k in range(2):
+        for r in range(rounds):
+            b, h, w = shapes[k]
+            src[k][r].array[...] = np.stack([synth.gen_underwater(h, w, 1000 * k + 10 * r + i) for i in range(b)])
+            expect[k][r] = {n: np.array(v, copy=True)
+                            for n, v in ctx.stage_host(descs[k], src[k][r].array, want=wants[k], max_blobs=256).items()}
+    pins = [bv.PinnedArray(shapes[0] + (3,)), bv.PinnedArray(shapes[1]), bv.PinnedArray((shapes[1][0], 256), bv.BLOB_DTYPE),
+            bv.PinnedArray((shapes[1][0],), np.int32)]   # the PinnedArray objects own the memory: keep them
+    outs = [{"converted": pins[0].array}, {"mask": pins[1].array, "blobs": pins[2].array, "n_blobs": pins[3].array}]
+    for r in range(rounds):
+        for k in range(2):     # both slots in flight before either is waited for
+            ctx.stage_host(descs[k], src[k][r].array, want=wants[k], max_blobs=256, out=outs[k], slot=k)
+        for k in (1, 0):
+            ctx.stage_host_wait(k)
+            for n in wants[k]:
+                if n == "blobs":
+                    for i in range(shapes[k][0]):
+                        nb = int(expect[k][r]["n_blobs"][i])
+                        assert int(outs[k]["n_blobs"][i]) == nb
+                        assert np.array_equal(outs[k]["blobs"][i][:nb], expect[k][r]["blobs"][i][:nb]), (r, k, i)
+                else:
+                    assert np.array_equal(outs[k][n], expect[k][r][n]), (r, k, n)
+    # back-to-back submits on ONE slot: the second waits for the first by itself
+    ctx.stage_host(descs[0], src[0][0].array, want=wants[0], out=outs[0], slot=0)
+    ctx.stage_host(descs[0], src[0][1].array, want=wants[0], out=outs[0], slot=0)
+    ctx.stage_host_wait(0)
+    assert np.array_equal(outs[0]["converted"], expect[0][1]["converted"])
+    ctx.stage_host_wait(1)   # nothing in flight: returns at once
+    with pytest.raises(Exception):
+        ctx.stage_host(descs[0], src[0][0].array, want=wants[0], out=outs[0], slot=2)
+
+
 def test_stage_gradient_and_threshold_on_bgr(ctx):
     img = synth.gen_underwater(200, 320, 33)
     desc = ctx.make_stage(cvt=None, lo=(60, 40, 0), hi=(255, 200, 120), morph=[("gradient", 3, 3, 1)])
