@@ -1400,8 +1400,11 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
     // independent and alternate over side streams so that their passes overlap on the SMs
     int chunk = (int)(l2_chunk_bytes(ctx) / (npx * 3));
     // large frames (4K: 25 MB each): a launch over a single frame is mostly ramp-up and tail, which costs more
-    // than the L2 misses of a bigger chunk (tools/tune_c5.py: 16.9 k vs 15.8 k frames/s at 3840x2160)
-    if (chunk < 4 && ctx->opt[BV_OPT_L2_CHUNK_MB] <= 0) chunk = 4;
+    // than the L2 misses of a bigger chunk (tools/tune_c5.py: 16.9 k vs 15.8 k frames/s at 3840x2160 with 4 frames);
+    // when the stage hangs morphology + labelling behind every chunk (after_chunk), two frames per chunk keep all four
+    // side streams busy on an 8-frame call (tools/c3_overlap.py: 19.8 k vs 18.5 k frames/s)
+    const int min_chunk = after_chunk ? 2 : 4;
+    if (chunk < min_chunk && ctx->opt[BV_OPT_L2_CHUNK_MB] <= 0) chunk = min_chunk;
     if (chunk < 1) chunk = 1;
     const int nchunks = (batch + chunk - 1) / chunk;
     int nside = side_streams(ctx);

@@ -193,9 +193,11 @@ __global__ void __launch_bounds__(256) ccl_count_kernel(const uint32_t *__restri
     }
 }
 
-// one block per frame: exclusive scan of the row counts
+// one block per frame: exclusive scan of the row counts; then the frame's blob table entries are cleared (the block knows
+// the count it has just produced: no separate launch)
 __global__ void __launch_bounds__(1024) ccl_scan_kernel(const int *__restrict__ row_count, int *__restrict__ row_off,
-                                                        int *__restrict__ n_blobs, int height) {
+                                                        int *__restrict__ n_blobs, int height, bv_blob *__restrict__ blobs,
+                                                        int max_blobs, int width) {
     __shared__ int warp_sums[32];
     __shared__ int carry;
     const int f = blockIdx.x;
@@ -230,6 +232,18 @@ __global__ void __launch_bounds__(1024) ccl_scan_kernel(const int *__restrict__ 
         __syncthreads();
     }
     if (threadIdx.x == 0) n_blobs[f] = carry;
+    if (blobs) {
+        const int n = min(carry, max_blobs);   // carry is final: the loop ended with a barrier
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            bv_blob b;
+            b.m00 = b.m10 = b.m01 = b.m20 = b.m11 = b.m02 = b.m30 = b.m21 = b.m12 = b.m03 = 0;
+            b.x0 = width;
+            b.y0 = height;
+            b.x1 = -1;
+            b.y1 = -1;
+            blobs[(size_t)f * max_blobs + i] = b;
+        }
+    }
 }
 
 // one warp per row: number the roots of the row in raster order, store -(label) in parent[root]
@@ -275,113 +289,110 @@ __global__ void __launch_bounds__(256) ccl_rank_kernel(const uint32_t *__restric
     }
 }
 
-__global__ void __launch_bounds__(256) ccl_blob_init_kernel(bv_blob *__restrict__ blobs, const int *__restrict__ n_blobs,
-                                                            int max_blobs, int height, int width) {
-    const int f = blockIdx.y;
-    const int n = min(n_blobs[f], max_blobs);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        bv_blob b;
-        b.m00 = b.m10 = b.m01 = b.m20 = b.m11 = b.m02 = b.m30 = b.m21 = b.m12 = b.m03 = 0;
-        b.x0 = width;
-        b.y0 = height;
-        b.x1 = -1;
-        b.y1 = -1;
-        blobs[(size_t)f * max_blobs + i] = b;
-    }
+// sum_{x=a}^{b} x^k, k = 0..3, in closed form (exact in 64-bit for any image size that fits 32-bit pixel indices)
+__device__ __forceinline__ void run_power_sums(int a, int b, int &n, int &s1, long long &s2, long long &s3) {
+    const long long A = a, B = b, Am = A - 1;
+    n = b - a + 1;
+    s1 = (int)((A + B) * (long long)n / 2);            // <= 32 * 65535 per run
+    // S2(k) = k(k+1)(2k+1)/6, S3(k) = (k(k+1)/2)^2
+    s2 = B * (B + 1) * (2 * B + 1) / 6 - Am * (Am + 1) * (2 * Am + 1) / 6;
+    const long long tb = B * (B + 1) / 2, ta = Am * (Am + 1) / 2;
+    s3 = tb * tb - ta * ta;
 }
 
-struct RunSums {
-    long long m00, m10, m01, m20, m11, m02, m30, m21, m12, m03;
-    int x0, y0, x1, y1;
+// the ten raster moments of a set of pixels of ONE row y from the power sums of their x
+__device__ __forceinline__ void row_moments(int n, int s1, long long s2, long long s3, int y, unsigned long long (&m)[10]) {
+    const long long Y = y, N = n, S1 = s1;
+    m[0] = (unsigned long long)N;                // m00
+    m[1] = (unsigned long long)S1;               // m10
+    m[2] = (unsigned long long)(Y * N);          // m01
+    m[3] = (unsigned long long)s2;               // m20
+    m[4] = (unsigned long long)(Y * S1);         // m11
+    m[5] = (unsigned long long)(Y * Y * N);      // m02
+    m[6] = (unsigned long long)s3;               // m30
+    m[7] = (unsigned long long)(Y * s2);         // m21
+    m[8] = (unsigned long long)(Y * Y * S1);     // m12
+    m[9] = (unsigned long long)(Y * Y * Y * N);  // m03
+}
+
+// per-warp accumulator of the blob the warp currently "carries" (shared memory: no registers, no shuffles)
+struct WarpAcc {
+    unsigned long long m[10];
+    int box[4];   // x0, y0, x1, y1
 };
 
-// sum_{x=a}^{b} x^k in closed form (exact in 64-bit for any image size that fits 32-bit pixels indices)
-__device__ __forceinline__ void run_sums(int a, int b, int y, RunSums &r) {
-    const long long n = b - a + 1;
-    const long long A = a, B = b;
-    const long long s1 = (A + B) * n / 2;
-    // S2(k) = k(k+1)(2k+1)/6, S3(k) = (k(k+1)/2)^2
-    const long long Am = A - 1;
-    const long long s2 = B * (B + 1) * (2 * B + 1) / 6 - Am * (Am + 1) * (2 * Am + 1) / 6;
-    const long long tb = B * (B + 1) / 2, ta = Am * (Am + 1) / 2;
-    const long long s3 = tb * tb - ta * ta;
-    const long long Y = y;
-    r.m00 = n;
-    r.m10 = s1;
-    r.m01 = Y * n;
-    r.m20 = s2;
-    r.m11 = Y * s1;
-    r.m02 = Y * Y * n;
-    r.m30 = s3;
-    r.m21 = Y * s2;
-    r.m12 = Y * Y * s1;
-    r.m03 = Y * Y * Y * n;
-    r.x0 = a;
-    r.x1 = b;
-    r.y0 = r.y1 = y;
+__device__ __forceinline__ void acc_reset(WarpAcc &a, int lane) {
+    if (lane < 10) a.m[lane] = 0;
+    else if (lane < 14) a.box[lane - 10] = (lane < 12) ? 0x7FFFFFFF : -1;
 }
 
-__device__ __forceinline__ void blob_atomic_add(bv_blob *b, const RunSums &r) {
-    atomicAdd((unsigned long long *)&b->m00, (unsigned long long)r.m00);
-    atomicAdd((unsigned long long *)&b->m10, (unsigned long long)r.m10);
-    atomicAdd((unsigned long long *)&b->m01, (unsigned long long)r.m01);
-    atomicAdd((unsigned long long *)&b->m20, (unsigned long long)r.m20);
-    atomicAdd((unsigned long long *)&b->m11, (unsigned long long)r.m11);
-    atomicAdd((unsigned long long *)&b->m02, (unsigned long long)r.m02);
-    atomicAdd((unsigned long long *)&b->m30, (unsigned long long)r.m30);
-    atomicAdd((unsigned long long *)&b->m21, (unsigned long long)r.m21);
-    atomicAdd((unsigned long long *)&b->m12, (unsigned long long)r.m12);
-    atomicAdd((unsigned long long *)&b->m03, (unsigned long long)r.m03);
-    atomicMin(&b->x0, r.x0);
-    atomicMin(&b->y0, r.y0);
-    atomicMax(&b->x1, r.x1);
-    atomicMax(&b->y1, r.y1);
+// all lanes of the warp: add the accumulator to its blob (one atomic per non-zero field) and clear it
+__device__ __forceinline__ void acc_flush(WarpAcc &a, bv_blob *blobs, int max_blobs, long long key, int lane) {
+    __syncwarp();
+    if (key != 0) {
+        bv_blob *b = &blobs[(size_t)(key >> 32) * max_blobs + ((int)(key & 0xFFFFFFFFll) - 1)];
+        if (lane < 10) {
+            const unsigned long long v = a.m[lane];
+            if (v) atomicAdd(reinterpret_cast<unsigned long long *>(&b->m00) + lane, v);
+        } else if (lane < 12) {
+            atomicMin(&b->x0 + (lane - 10), a.box[lane - 10]);
+        } else if (lane < 14) {
+            atomicMax(&b->x0 + (lane - 10), a.box[lane - 10]);
+        }
+    }
+    acc_reset(a, lane);
+    __syncwarp();
 }
 
-// final: labels + moments.  All 32 lanes of a warp stay in the loop together (the segmented
-// reduction uses full-warp shuffles).  A lane owns one 32-px word; its 32 labels are staged in a
-// padded shared-memory tile (row = lane, bank-conflict-free) and the warp then writes the 32 words
-// out row by row, so every store instruction covers 128 contiguous bytes of the label image.
-__global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ parent,
-                                                        int *__restrict__ labels, bv_blob *__restrict__ blobs,
-                                                        int max_blobs, int height, int width, int wpr,
-                                                        uint32_t total_words) {
+// final: labels + moments.  All 32 lanes of a warp stay in the loop together (the segmented reduction uses full-warp
+// shuffles).  A lane owns one 32-px word; its 32 labels are staged in a padded shared-memory tile (row = lane,
+// bank-conflict-free) and the warp then writes the 32 words out row by row, so every store instruction covers 128
+// contiguous bytes of the label image.
+// Moments: the pixels a warp sees of one blob in one step lie on one row (the segment key contains the row), so only the
+// four power sums of x (n, sum x, sum x^2, sum x^3) go through the segmented reduction -- 6 registers per shuffle level
+// instead of the 20 of ten 64-bit moments -- and the segment head multiplies by the powers of y.  The blob with the most
+// pixels in the step is "carried": its segments are added (shared-memory atomics) into the warp's accumulator and reach
+// the table with one set of global atomics when another blob takes over or the kernel ends, so a blob that covers much
+// of the frame costs a handful of atomic sets per WARP instead of one per 1024-pixel segment (they all hit the same
+// addresses and serialise in L2).  Everything else goes to the table directly.
+__global__ void __launch_bounds__(256, 4) ccl_final_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ parent,
+                                                           int *__restrict__ labels, bv_blob *__restrict__ blobs,
+                                                           int max_blobs, int height, int width, int wpr,
+                                                           uint32_t total_words) {
     __shared__ int tile[8][32][33];
+    __shared__ WarpAcc accs[8];
     const int lane = threadIdx.x & 31;
     const bool full_words = (width & 31) == 0;
     int(*my_tile)[33] = tile[threadIdx.x >> 5];
+    WarpAcc &acc = accs[threadIdx.x >> 5];
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounded = (total_words + 31u) / 32u * 32u;
-    long long carry_key = 0;  // (frame << 32) | label of the blob this warp accumulates in registers
-    RunSums carry;
-    carry.m00 = carry.m10 = carry.m01 = carry.m20 = carry.m11 = carry.m02 = carry.m30 = carry.m21 = carry.m12 = carry.m03 = 0;
-    carry.x0 = carry.y0 = 0x7FFFFFFF;
-    carry.x1 = carry.y1 = -1;
+    long long carry_key = 0;  // (frame << 32) | label of the blob this warp accumulates; warp-uniform
+    acc_reset(acc, lane);
+    __syncwarp();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
         const bool valid = i < total_words;
         const uint32_t w = valid ? bits[i] : 0u;
-        const WordPos wp = word_pos(valid ? i : 0, wpr, height);
-        const size_t frame = (wp.row - wp.y) / (uint32_t)height;
-        const int *fp = parent + (size_t)(wp.row - wp.y) * width;
-        const int xbase = wp.wx * 32;
-        if (labels && full_words && !__any_sync(0xFFFFFFFFu, w != 0)) {
+        const uint32_t warp_first = i - lane;  // word index owned by lane 0
+        if (!__any_sync(0xFFFFFFFFu, w != 0)) {
             // empty warp (the common case on sparse masks): 4 KB of zeros, 128-bit coalesced stores
-            const uint32_t warp_first = i - lane;
-            if (warp_first + 32 <= total_words) {
+            if (!labels) continue;
+            if (full_words && warp_first + 32 <= total_words) {
                 int4 *base = reinterpret_cast<int4 *>(labels + (size_t)warp_first * 32);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) base[k * 32 + lane] = make_int4(0, 0, 0, 0);
                 continue;
             }
         }
+        const WordPos wp = word_pos(valid ? i : 0, wpr, height);
+        const uint32_t frame = (wp.row - wp.y) / (uint32_t)height;
+        const int *fp = parent + (size_t)(wp.row - wp.y) * width;
+        const int xbase = wp.wx * 32;
         uint32_t rest = w;
         int written = 0;  // pixels of this word already staged
         while (__any_sync(0xFFFFFFFFu, rest != 0)) {
-            int lab = 0;
-            RunSums rs;
-            rs.m00 = rs.m10 = rs.m01 = rs.m20 = rs.m11 = rs.m02 = rs.m30 = rs.m21 = rs.m12 = rs.m03 = 0;
-            rs.x0 = rs.y0 = 0x7FFFFFFF;
-            rs.x1 = rs.y1 = -1;
+            int lab = 0, n = 0, s1 = 0, xa = 0, xb = 0;
+            long long s2 = 0, s3 = 0;
             if (rest) {
                 const int s = __ffs(rest) - 1;
                 const uint32_t from_s = rest >> s;
@@ -396,11 +407,13 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restri
                     for (int x = s; x <= e; ++x) my_tile[lane][x] = lab;
                     written = e + 1;
                 }
-                if (blobs) run_sums(xbase + s, xbase + e, wp.y, rs);
+                xa = xbase + s;
+                xb = xbase + e;
+                if (blobs) run_power_sums(xa, xb, n, s1, s2, s3);
             }
             if (blobs) {
-                // segmented reduction over consecutive lanes with the same (frame, label)
-                const long long key = lab ? ((long long)frame << 32) | (unsigned)lab : -(long long)lane - 1;
+                // segmented reduction over consecutive lanes with the same (row, label)
+                const long long key = lab ? ((long long)wp.row << 32) | (unsigned)lab : -(long long)lane - 1;
                 const long long prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
                 const bool head = lane == 0 || prev != key;
                 const unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
@@ -409,81 +422,62 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restri
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const bool take = lane + d <= seg_end;
-#define BV_SEG_ADD(field)                                                         \
-    {                                                                             \
-        const long long o = __shfl_down_sync(0xFFFFFFFFu, rs.field, d);           \
-        if (take) rs.field += o;                                                  \
-    }
-                    BV_SEG_ADD(m00) BV_SEG_ADD(m10) BV_SEG_ADD(m01) BV_SEG_ADD(m20) BV_SEG_ADD(m11)
-                    BV_SEG_ADD(m02) BV_SEG_ADD(m30) BV_SEG_ADD(m21) BV_SEG_ADD(m12) BV_SEG_ADD(m03)
-#undef BV_SEG_ADD
-                    const int ox0 = __shfl_down_sync(0xFFFFFFFFu, rs.x0, d), oy0 = __shfl_down_sync(0xFFFFFFFFu, rs.y0, d);
-                    const int ox1 = __shfl_down_sync(0xFFFFFFFFu, rs.x1, d), oy1 = __shfl_down_sync(0xFFFFFFFFu, rs.y1, d);
+                    const int on = __shfl_down_sync(0xFFFFFFFFu, n, d), o1 = __shfl_down_sync(0xFFFFFFFFu, s1, d);
+                    const long long o2 = __shfl_down_sync(0xFFFFFFFFu, s2, d), o3 = __shfl_down_sync(0xFFFFFFFFu, s3, d);
                     if (take) {
-                        rs.x0 = min(rs.x0, ox0);
-                        rs.y0 = min(rs.y0, oy0);
-                        rs.x1 = max(rs.x1, ox1);
-                        rs.y1 = max(rs.y1, oy1);
+                        n += on;
+                        s1 += o1;
+                        s2 += o2;
+                        s3 += o3;
                     }
                 }
-                // Warp-level carry: the segment with the most pixels in this step designates the
-                // "carried" blob; all segments of that blob are summed across the warp into registers
-                // and only flushed (one set of global atomics) when another blob takes over or the
-                // kernel ends.  A blob that covers much of the frame therefore costs a handful of
-                // atomic sets per WARP instead of one per 1024-pixel segment (they all hit the same
-                // addresses and serialise in L2).  Everything else goes to the table directly.
+                const int x_last = __shfl_sync(0xFFFFFFFFu, xb, seg_end);   // lanes ascend in x inside a row
                 const bool counted = head && lab && lab <= max_blobs;
-                long long best = counted ? rs.m00 : 0;
-                long long best_key = counted ? key : 0;
+                const long long fkey = ((long long)frame << 32) | (unsigned)lab;
+                // the segment with the most pixels in this step designates the carried blob
+                int best = counted ? n : 0;
+                long long best_key = counted ? fkey : 0;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) {
-                    const long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
+                    const int ob = __shfl_xor_sync(0xFFFFFFFFu, best, d);
                     const long long ok = __shfl_xor_sync(0xFFFFFFFFu, best_key, d);
                     if (ob > best || (ob == best && ok > best_key)) {
                         best = ob;
                         best_key = ok;
                     }
                 }
-                if (best_key != 0) {
+                if (best_key != 0) {   // warp-uniform
                     if (best_key != carry_key) {
-                        if (carry_key != 0 && lane == 0)
-                            blob_atomic_add(&blobs[(size_t)(carry_key >> 32) * max_blobs + ((int)(carry_key & 0xFFFFFFFFll) - 1)], carry);
+                        acc_flush(acc, blobs, max_blobs, carry_key, lane);
                         carry_key = best_key;
-                        carry.m00 = carry.m10 = carry.m01 = carry.m20 = carry.m11 = carry.m02 = 0;
-                        carry.m30 = carry.m21 = carry.m12 = carry.m03 = 0;
-                        carry.x0 = carry.y0 = 0x7FFFFFFF;
-                        carry.x1 = carry.y1 = -1;
                     }
-                    const bool mine = counted && key == carry_key;
-                    RunSums t = rs;
-                    if (!mine) {
-                        t.m00 = t.m10 = t.m01 = t.m20 = t.m11 = t.m02 = t.m30 = t.m21 = t.m12 = t.m03 = 0;
-                        t.x0 = t.y0 = 0x7FFFFFFF;
-                        t.x1 = t.y1 = -1;
-                    }
+                    if (counted) {
+                        unsigned long long m[10];
+                        row_moments(n, s1, s2, s3, wp.y, m);
+                        if (fkey == carry_key) {
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) {
-#define BV_ALL_ADD(field) t.field += __shfl_xor_sync(0xFFFFFFFFu, t.field, d);
-                        BV_ALL_ADD(m00) BV_ALL_ADD(m10) BV_ALL_ADD(m01) BV_ALL_ADD(m20) BV_ALL_ADD(m11)
-                        BV_ALL_ADD(m02) BV_ALL_ADD(m30) BV_ALL_ADD(m21) BV_ALL_ADD(m12) BV_ALL_ADD(m03)
-#undef BV_ALL_ADD
-                        t.x0 = min(t.x0, __shfl_xor_sync(0xFFFFFFFFu, t.x0, d));
-                        t.y0 = min(t.y0, __shfl_xor_sync(0xFFFFFFFFu, t.y0, d));
-                        t.x1 = max(t.x1, __shfl_xor_sync(0xFFFFFFFFu, t.x1, d));
-                        t.y1 = max(t.y1, __shfl_xor_sync(0xFFFFFFFFu, t.y1, d));
+                            for (int k = 0; k < 10; ++k) atomicAdd(&acc.m[k], m[k]);
+                            atomicMin(&acc.box[0], xa);
+                            atomicMin(&acc.box[1], wp.y);
+                            atomicMax(&acc.box[2], x_last);
+                            atomicMax(&acc.box[3], wp.y);
+                        } else {
+                            bv_blob *b = &blobs[frame * (size_t)max_blobs + (lab - 1)];
+                            unsigned long long *bm = reinterpret_cast<unsigned long long *>(&b->m00);
+#pragma unroll
+                            for (int k = 0; k < 10; ++k) atomicAdd(bm + k, m[k]);
+                            atomicMin(&b->x0, xa);
+                            atomicMin(&b->y0, wp.y);
+                            atomicMax(&b->x1, x_last);
+                            atomicMax(&b->y1, wp.y);
+                        }
                     }
-                    carry.m00 += t.m00; carry.m10 += t.m10; carry.m01 += t.m01; carry.m20 += t.m20; carry.m11 += t.m11;
-                    carry.m02 += t.m02; carry.m30 += t.m30; carry.m21 += t.m21; carry.m12 += t.m12; carry.m03 += t.m03;
-                    carry.x0 = min(carry.x0, t.x0); carry.y0 = min(carry.y0, t.y0);
-                    carry.x1 = max(carry.x1, t.x1); carry.y1 = max(carry.y1, t.y1);
-                    if (counted && !mine) blob_atomic_add(&blobs[frame * (size_t)max_blobs + (lab - 1)], rs);
                 }
             }
         }
         if (labels) {
             for (int x = written; x < 32; ++x) my_tile[lane][x] = 0;
             __syncwarp();
-            const uint32_t warp_first = i - lane;  // word index owned by lane 0
             if (full_words) {  // width % 32 == 0: the label image is linear in the word index
                 int *base = labels + (size_t)warp_first * 32;
                 const int nk = min(32u, total_words - warp_first);
@@ -503,20 +497,50 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(const uint32_t *__restri
             __syncwarp();
         }
     }
-    if (blobs && carry_key != 0 && lane == 0)
-        blob_atomic_add(&blobs[(size_t)(carry_key >> 32) * max_blobs + ((int)(carry_key & 0xFFFFFFFFll) - 1)], carry);
+    if (blobs) acc_flush(acc, blobs, max_blobs, carry_key, lane);
+}
+
+// Scratch of the labelling for a batch of `batch` frames; frames f0.. of the batch use the slices at f0 (label_scratch_slice),
+// so that independent chunks of one batch can be labelled concurrently on different streams.
+int label_scratch(bv_ctx *ctx, int batch, int height, int width, LabelScratch *ls) {
+    const size_t total_rows = (size_t)batch * height;
+    BV_TRY(ensure_scratch(ctx, SCR_CCL_PARENT, total_rows * width * sizeof(int)));
+    BV_TRY(ensure_scratch(ctx, SCR_CCL_AUX, (total_rows * 2 + batch) * sizeof(int)));
+    ls->parent = (int *)ctx->scratch[SCR_CCL_PARENT];
+    ls->row_count = (int *)ctx->scratch[SCR_CCL_AUX];
+    ls->row_off = ls->row_count + total_rows;
+    ls->n_fallback = ls->row_off + total_rows;
+    return BV_OK;
+}
+
+static LabelScratch label_scratch_slice(const LabelScratch &ls, int f0, int height, int width) {
+    LabelScratch s;
+    s.parent = ls.parent + (size_t)f0 * height * width;
+    s.row_count = ls.row_count + (size_t)f0 * height;
+    s.row_off = ls.row_off + (size_t)f0 * height;
+    s.n_fallback = ls.n_fallback + f0;
+    return s;
 }
 
 static int label_bits_ex(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, int height, int width,
-                         bv_blob *blobs, int max_blobs, int32_t *n_blobs, int *root_px, int max_roots);
+                         bv_blob *blobs, int max_blobs, int32_t *n_blobs, int *root_px, int max_roots, const LabelScratch &sc);
 
 int label_bits(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, int height, int width, bv_blob *blobs,
                int max_blobs, int32_t *n_blobs) {
-    return label_bits_ex(ctx, bits, labels, batch, height, width, blobs, max_blobs, n_blobs, nullptr, 0);
+    LabelScratch ls;
+    BV_TRY(label_scratch(ctx, batch, height, width, &ls));
+    return label_bits_ex(ctx, bits, labels, batch, height, width, blobs, max_blobs, n_blobs, nullptr, 0, ls);
+}
+
+// frames f0 .. f0 + nf - 1 of a batch whose scratch is `ls`; every pointer argument already points at frame f0
+int label_bits_slice(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int f0, int nf, int height, int width, bv_blob *blobs,
+                     int max_blobs, int32_t *n_blobs, const LabelScratch &ls) {
+    return label_bits_ex(ctx, bits, labels, nf, height, width, blobs, max_blobs, n_blobs, nullptr, 0,
+                         label_scratch_slice(ls, f0, height, width));
 }
 
 static int label_bits_ex(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, int height, int width,
-                         bv_blob *blobs, int max_blobs, int32_t *n_blobs, int *root_px, int max_roots) {
+                         bv_blob *blobs, int max_blobs, int32_t *n_blobs, int *root_px, int max_roots, const LabelScratch &sc) {
     const int wpr = words_per_row(width);
     const size_t total_words = (size_t)batch * height * wpr;
     const size_t total_rows = (size_t)batch * height;
@@ -524,29 +548,22 @@ static int label_bits_ex(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int
         set_error("bv_label: frame or batch too large for 32-bit indices");
         return BV_ERR_INVALID;
     }
-    BV_TRY(ensure_scratch(ctx, SCR_CCL_PARENT, total_rows * width * sizeof(int)));
-    BV_TRY(ensure_scratch(ctx, SCR_CCL_AUX, (total_rows * 2 + batch) * sizeof(int)));
-    int *parent = (int *)ctx->scratch[SCR_CCL_PARENT];
-    int *row_count = (int *)ctx->scratch[SCR_CCL_AUX];
-    int *row_off = row_count + total_rows;
-    int *nb = n_blobs ? n_blobs : row_off + total_rows;
+    int *parent = sc.parent;
+    int *row_count = sc.row_count;
+    int *row_off = sc.row_off;
+    int *nb = n_blobs ? n_blobs : sc.n_fallback;
     const int gw = grid_for(ctx, total_words, 256, 8);
     const int gr = grid_for(ctx, total_rows * 32, 256, 8);
     BV_LAUNCH(ctx, ccl_init_kernel, gw, 256, 0, bits, parent, height, width, wpr, (uint32_t)total_words);
     BV_LAUNCH(ctx, ccl_merge_kernel<true>, gw, 256, 0, bits, parent, height, width, wpr, (uint32_t)total_words);
     BV_LAUNCH(ctx, ccl_count_kernel, gr, 256, 0, bits, parent, row_count, height, width, wpr, total_rows);
-    BV_LAUNCH(ctx, ccl_scan_kernel, batch, 1024, 0, row_count, row_off, nb, height);
+    BV_LAUNCH(ctx, ccl_scan_kernel, batch, 1024, 0, row_count, row_off, nb, height, (max_blobs > 0 ? blobs : nullptr), max_blobs, width);
     BV_LAUNCH(ctx, ccl_rank_kernel, gr, 256, 0, bits, parent, row_off, height, width, wpr, total_rows, root_px, max_roots);
-    if (blobs && max_blobs > 0) {
-        dim3 g((unsigned)min(64, (max_blobs + 255) / 256), batch);
-        BV_LAUNCH(ctx, ccl_blob_init_kernel, g, 256, 0, blobs, nb, max_blobs, height, width);
-    }
     if (labels || (blobs && max_blobs > 0))
         BV_LAUNCH(ctx, ccl_final_kernel, gw, 256, 0, bits, parent, labels, (max_blobs > 0 ? blobs : nullptr), max_blobs,
                   height, width, wpr, (uint32_t)total_words);
     return BV_OK;
 }
-
 
 // ----------------------------------------------------------------------------------------------
 // Outer borders as cv2.findContours(RETR_EXTERNAL) follows them, with the Green's-theorem sums of
@@ -883,7 +900,9 @@ int outer_contours_bits(bv_ctx *ctx, const uint32_t *bits, int batch, int height
     int *row_count_bg = (int *)ctx->scratch[SCR_CCL_AUX2];
     uint32_t *outer = (uint32_t *)(row_count_bg + total_rows);
     // foreground: labels are not needed, only the roots in raster order
-    BV_TRY(label_bits_ex(ctx, bits, nullptr, batch, height, width, nullptr, 0, n_contours, root_px, max_contours));
+    LabelScratch ls;
+    BV_TRY(label_scratch(ctx, batch, height, width, &ls));
+    BV_TRY(label_bits_ex(ctx, bits, nullptr, batch, height, width, nullptr, 0, n_contours, root_px, max_contours, ls));
     // background, 4-connected
     const int gw = grid_for(ctx, total_words, 256, 8);
     const int gr = grid_for(ctx, total_rows * 32, 256, 8);

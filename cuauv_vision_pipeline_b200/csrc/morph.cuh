@@ -24,4 +24,17 @@ int morph_bits_rect(bv_ctx *ctx, uint32_t *bits, uint32_t *tmp, uint32_t *tmp2, 
 int morph_bits_chain(bv_ctx *ctx, const uint32_t *bits, uint32_t *dst_bits, uint8_t *mask, int batch, int height, int width,
                      int n_steps, const int *ops, const int *kws, const int *khs, const int *iters, bool *done);
 
+// ---- labelling (ccl.cu) ----
+struct LabelScratch {
+    int *parent;      // union-find parents, one int per pixel of the batch
+    int *row_count;   // roots per row
+    int *row_off;     // exclusive scan of row_count per frame
+    int *n_fallback;  // blob counts when the caller does not want them
+};
+int label_scratch(bv_ctx *ctx, int batch, int height, int width, LabelScratch *ls);
+int label_bits(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, int height, int width, bv_blob *blobs,
+               int max_blobs, int32_t *n_blobs);
+int label_bits_slice(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int f0, int nf, int height, int width, bv_blob *blobs,
+                     int max_blobs, int32_t *n_blobs, const LabelScratch &ls);
+
 }  // namespace bv

@@ -20,9 +20,6 @@
 #include "morph.cuh"
 
 namespace bv {
-int label_bits(bv_ctx *ctx, const uint32_t *bits, int32_t *labels, int batch, int height, int width, bv_blob *blobs,
-               int max_blobs, int32_t *n_blobs);  // ccl.cu
-
 static int validate_desc(const bv_stage_desc *d) {
     BV_REQUIRE(d, "null stage description");
     BV_REQUIRE(d->n_morph >= 0 && d->n_morph <= 4, "n_morph must be 0..4");
@@ -35,6 +32,86 @@ static int validate_desc(const bv_stage_desc *d) {
     BV_REQUIRE(d->cvt_code == -1 || d->cvt_code == BV_BGR2HSV || d->cvt_code == BV_BGR2LAB ||
                    d->cvt_code == BV_BGR2GRAY || d->cvt_code == BV_BGR2YCRCB || d->cvt_code == BV_BGR2HLS,
                "cvt_code must be -1, BGR2HSV, BGR2LAB, BGR2GRAY, BGR2YCRCB or BGR2HLS");
+    return BV_OK;
+}
+
+// Everything behind the threshold for frames f0 .. f0 + nf - 1, on the context's CURRENT stream: uint8 mask -> bits (odd
+// widths), the morphology steps, bits -> uint8 mask, labels + moments.  All buffers are whole-batch buffers; the chunk works
+// on its own slices, so the chunks of one call run concurrently on the side streams: the latency-bound union-find kernels
+// of one chunk fill the SMs together with the issue-bound pixel passes of the next.
+struct StageTail {
+    const bv_stage_desc *desc;
+    int height, width;
+    bool bits_direct, want_label;
+    uint32_t *bits, *tmp, *tmp2;   // whole batch
+    const uint8_t *thr_mask;       // thresholded uint8 mask when the bits do not come straight from the pixel pass
+    uint8_t *mask;                 // caller's mask (may be null)
+    int32_t *labels;
+    bv_blob *blobs;
+    int max_blobs;
+    int32_t *n_blobs;
+    LabelScratch ls;
+    int calls;
+
+    int run(bv_ctx *c, int f0, int nf) {
+        ++calls;
+        const size_t fw = bits_frame_words(height, width), fpx = (size_t)height * width;
+        uint32_t *b = bits + f0 * fw, *t = tmp + f0 * fw, *t2 = tmp2 + f0 * fw;
+        uint8_t *m = mask ? mask + f0 * fpx : nullptr;
+        if (!bits_direct) BV_TRY(mask_to_bits(c, thr_mask + f0 * fpx, b, nf, height, width));
+        const uint32_t *res = b;
+        if (desc->n_morph > 0) {
+            bool chained = false;   // one launch for the whole chain; it also expands the final bits into the uint8 mask
+            BV_TRY(morph_bits_chain(c, b, want_label ? t : nullptr, m, nf, height, width, desc->n_morph, desc->morph_op,
+                                    desc->morph_kw, desc->morph_kh, desc->morph_iters, &chained));
+            if (chained) {
+                if (want_label) res = t;
+            } else {
+                for (int i = 0; i < desc->n_morph; ++i)
+                    BV_TRY(morph_bits_rect(c, b, t, t2, nf, height, width, desc->morph_op[i], desc->morph_kw[i], desc->morph_kh[i],
+                                           desc->morph_iters[i]));
+                if (m) BV_TRY(bits_to_mask(c, b, m, nf, height, width));
+            }
+        }
+        if (want_label)
+            BV_TRY(label_bits_slice(c, res, labels ? labels + f0 * fpx : nullptr, f0, nf, height, width,
+                                    blobs ? blobs + (size_t)f0 * max_blobs : nullptr, max_blobs, n_blobs ? n_blobs + f0 : nullptr, ls));
+        return BV_OK;
+    }
+    static int hook(void *self, bv_ctx *c, int f0, int nf) { return ((StageTail *)self)->run(c, f0, nf); }
+};
+
+// Runs fn(f0, nf) for consecutive chunks of the batch, alternating over the side streams (fork from / join into the
+// context's stream), like balance_run does for its own chunks.
+template <class Fn>
+static int for_chunks_on_side_streams(bv_ctx *ctx, int batch, int chunk, Fn fn) {
+    if (chunk < 1) chunk = 1;
+    const int nchunks = (batch + chunk - 1) / chunk;
+    int nside = ctx->opt[BV_OPT_SIDE_STREAMS] > 0 ? ctx->opt[BV_OPT_SIDE_STREAMS] : 4;
+    if (nside > BV_MAX_SIDE) nside = BV_MAX_SIDE;
+    if (nside > nchunks) nside = nchunks;
+    if (ctx->prof) nside = 1;  // per-kernel timing wants serialised launches
+    cudaStream_t main_stream = ctx->stream;
+    if (nside > 1) {
+        BV_CUDA(cudaEventRecord(ctx->ev_fork, main_stream));
+        for (int i = 0; i < nside; ++i) BV_CUDA(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+    }
+    struct Restore {  // every exit path puts the context's stream back
+        bv_ctx *c;
+        cudaStream_t s;
+        ~Restore() { c->stream = s; }
+    } restore{ctx, main_stream};
+    for (int k = 0; k < nchunks; ++k) {
+        const int f0 = k * chunk, nf = (batch - f0 < chunk) ? batch - f0 : chunk;
+        if (nside > 1) ctx->stream = ctx->side[k % nside];
+        BV_TRY(fn(f0, nf));
+    }
+    ctx->stream = main_stream;
+    if (nside > 1)
+        for (int i = 0; i < nside; ++i) {
+            BV_CUDA(cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
+            BV_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join[i], 0));
+        }
     return BV_OK;
 }
 
@@ -52,22 +129,31 @@ int stage_run(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src, int ba
         out.lo[k] = desc->lo[k];
         out.hi[k] = desc->hi[k];
     }
-    uint32_t *bits = nullptr, *tmp = nullptr, *tmp2 = nullptr;
-    const size_t words = (size_t)batch * bits_frame_words(height, width);
-    bool bits_direct = false;
+    const bool tiled = desc->do_balance && (desc->balance.horizontal_blocks != 1 || desc->balance.vertical_blocks != 1);
+    StageTail tail;
+    memset(&tail, 0, sizeof(tail));
+    tail.desc = desc;
+    tail.height = height;
+    tail.width = width;
+    tail.want_label = want_label;
+    tail.mask = mask;
+    tail.labels = labels;
+    tail.blobs = blobs;
+    tail.max_blobs = max_blobs;
+    tail.n_blobs = n_blobs;
     if (need_bits) {
+        const size_t words = (size_t)batch * bits_frame_words(height, width);
         BV_TRY(ensure_scratch(ctx, SCR_BITS_A, words * 4));
         BV_TRY(ensure_scratch(ctx, SCR_BITS_B, words * 8));
-        bits = (uint32_t *)ctx->scratch[SCR_BITS_A];
-        tmp = (uint32_t *)ctx->scratch[SCR_BITS_B];
-        tmp2 = tmp + words;
+        tail.bits = (uint32_t *)ctx->scratch[SCR_BITS_A];
+        tail.tmp = (uint32_t *)ctx->scratch[SCR_BITS_B];
+        tail.tmp2 = tail.tmp + words;
         const bool aligned = host_aligned16(src) && (!balanced || host_aligned16(balanced)) &&
                              (!converted || host_aligned16(converted)) && (!mask || host_aligned16(mask));
-        const bool tiled = desc->do_balance && (desc->balance.horizontal_blocks != 1 || desc->balance.vertical_blocks != 1);
-        bits_direct = aligned && (width % 16 == 0) && !tiled;
-        if (bits_direct) {
-            if (width % 32 != 0) BV_CUDA(cudaMemsetAsync(bits, 0, words * 4, ctx->stream));
-            out.mask_bits = (uint16_t *)bits;
+        tail.bits_direct = aligned && (width % 16 == 0) && !tiled;
+        if (tail.bits_direct) {
+            if (width % 32 != 0) BV_CUDA(cudaMemsetAsync(tail.bits, 0, words * 4, ctx->stream));
+            out.mask_bits = (uint16_t *)tail.bits;
             if (desc->n_morph == 0) out.mask = mask;  // the thresholded mask is already final
         } else {
             // odd widths: go through a uint8 mask (the caller's buffer doubles as the intermediate)
@@ -77,59 +163,49 @@ int stage_run(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src, int ba
                 BV_TRY(ensure_scratch(ctx, SCR_STAGE_IMG, (size_t)batch * npx));
                 out.mask = (uint8_t *)ctx->scratch[SCR_STAGE_IMG];
             }
+            tail.thr_mask = out.mask;
         }
+        if (want_label) BV_TRY(label_scratch(ctx, batch, height, width, &tail.ls));   // before any stream forks
     } else {
         out.mask = mask;
     }
-    // Morphology of a chunk right behind its threshold pass, on the chunk's own stream
-    struct ChainPerChunk {
-        const bv_stage_desc *desc;
-        uint32_t *bits, *dst_bits;
-        uint8_t *mask;
-        int height, width;
-        bool all_done;
-        int calls;
-        static int run(void *self, bv_ctx *c, int f0, int nf) {
-            ChainPerChunk *h = (ChainPerChunk *)self;
-            h->calls++;
-            const size_t fw = bits_frame_words(h->height, h->width), fpx = (size_t)h->height * h->width;
-            bool done = false;
-            BV_TRY(morph_bits_chain(c, h->bits + f0 * fw, h->dst_bits ? h->dst_bits + f0 * fw : nullptr,
-                                    h->mask ? h->mask + f0 * fpx : nullptr, nf, h->height, h->width, h->desc->n_morph,
-                                    h->desc->morph_op, h->desc->morph_kw, h->desc->morph_kh, h->desc->morph_iters, &done));
-            h->all_done = h->all_done && done;
-            return BV_OK;
-        }
-    } per_chunk{desc, bits, want_label ? tmp : nullptr, mask, height, width, true, 0};
-    const bool tiled_bal = desc->do_balance && (desc->balance.horizontal_blocks != 1 || desc->balance.vertical_blocks != 1);
-    const bool use_hook = desc->do_balance && !tiled_bal && bits_direct && desc->n_morph > 0;
-    ChunkHook hook{&ChainPerChunk::run, &per_chunk};
-    if (out.balanced || out.converted || out.mask || out.mask_bits) {
-        if (desc->do_balance)
+    const bool pixel_pass = out.balanced || out.converted || out.mask || out.mask_bits;
+    if (desc->do_balance) {
+        // balance_run spreads its chunks over the side streams and calls the hook behind every chunk's last pass
+        ChunkHook hook{&StageTail::hook, &tail};
+        const bool use_hook = need_bits && !tiled;
+        if (pixel_pass)
             BV_TRY(balance_run(ctx, src, batch, height, width, desc->balance, desc->cvt_code, out, nullptr, use_hook ? &hook : nullptr));
-        else
-            BV_TRY(convert_run(ctx, src, batch, height, width, desc->cvt_code, out));
+        if (need_bits && tail.calls == 0) BV_TRY(tail.run(ctx, 0, batch));   // tiled / HSI paths do not chunk
+        return BV_OK;
     }
-    if (!need_bits) return BV_OK;
-    if (!bits_direct) BV_TRY(mask_to_bits(ctx, out.mask, bits, batch, height, width));
-    bool chained = false;
-    if (use_hook && per_chunk.calls > 0 && per_chunk.all_done) {  // the chunks already went through the chain
-        chained = true;
-        if (want_label) bits = tmp;
-    } else if (desc->n_morph > 0) {
-        // one launch for the whole chain; it also expands the final bits into the uint8 mask
-        BV_TRY(morph_bits_chain(ctx, bits, want_label ? tmp : nullptr, mask, batch, height, width, desc->n_morph, desc->morph_op,
-                                desc->morph_kw, desc->morph_kh, desc->morph_iters, &chained));
-        if (chained && want_label) bits = tmp;
+    // no balance: chunks of whole frames (input + outputs of a chunk stay in L2 between its kernels), on the side streams
+    // when the work is worth splitting
+    int chunk = batch;
+    if (need_bits && batch > 1) {
+        const size_t l2_chunk = (size_t)(ctx->opt[BV_OPT_L2_CHUNK_MB] > 0 ? ctx->opt[BV_OPT_L2_CHUNK_MB] : 33) << 20;
+        chunk = (int)(l2_chunk / (npx * 3));
+        const int quarter = (batch + 3) / 4;
+        if (chunk > quarter) chunk = quarter;
+        const size_t min_px = (size_t)1 << 20;   // below ~1 Mpx per chunk the launches cost more than the overlap returns
+        if ((size_t)chunk * npx < min_px) chunk = (int)((min_px + npx - 1) / npx);
+        if (chunk < 1) chunk = 1;
+        if (chunk > batch) chunk = batch;
     }
-    if (!chained) {
-        for (int i = 0; i < desc->n_morph; ++i)
-            BV_TRY(morph_bits_rect(ctx, bits, tmp, tmp2, batch, height, width, desc->morph_op[i], desc->morph_kw[i],
-                                   desc->morph_kh[i], desc->morph_iters[i]));
-        if (mask && (desc->n_morph > 0)) BV_TRY(bits_to_mask(ctx, bits, mask, batch, height, width));
-    }
-    if (want_label) BV_TRY(label_bits(ctx, bits, labels, batch, height, width, blobs, max_blobs, n_blobs));
-    return BV_OK;
+    const size_t cvt_bpp = desc->cvt_code == BV_BGR2GRAY ? 1 : 3;
+    return for_chunks_on_side_streams(ctx, batch, chunk, [&](int f0, int nf) -> int {
+        if (pixel_pass) {
+            BalOutputs co = out;
+            const size_t po = (size_t)f0 * npx;
+            if (co.balanced) co.balanced += po * 3;
+            if (co.converted) co.converted += po * cvt_bpp;
+            if (co.mask) co.mask += po;
+            if (co.mask_bits) co.mask_bits += (size_t)f0 * height * (((width + 31) / 32) * 2);
+            BV_TRY(convert_run(ctx, src + po * 3, nf, height, width, desc->cvt_code, co));
+        }
+        if (need_bits) BV_TRY(tail.run(ctx, f0, nf));
+        return BV_OK;
+    });
 }
 
 // process-wide context behind the legacy symbol

@@ -72,3 +72,34 @@ def test_c5_host_entry_sharded_streams_equal_device_stage(ctx):
         assert np.array_equal(ctx.download(one["labels"])[0], lab_all[s])
         m_ref, n_ref, lab_ref, _ = oracle_chain(frames[s])
         assert np.array_equal(mask_all[s], m_ref) and np.array_equal(lab_all[s], lab_ref)
+
+
+@pytest.mark.parametrize("shape,batch", [((1080, 1920), 12), ((1000, 1050), 8)])
+def test_unbalanced_stage_chunks_on_side_streams_equal_cv2_and_single_frames(ctx, shape, batch):
+    """BASELINE.json configs[2] ("C3": HSV inRange -> OPEN -> labels) as a batch: without colour balance the stage splits
+    the batch into chunks of whole frames on the side streams (pixel pass, morphology and labelling of one chunk overlap
+    the other chunks').  1920 wide: bits straight from the pixel pass; 1050 wide (width % 16 != 0): through the uint8 mask.
+    Every frame against cv2 + oracle/ccl.py, and the same frames one call each."""
+    h, w = shape
+    frames = np.stack([synth.gen_underwater(h, w, 300 + i) for i in range(batch)])
+    desc = ctx.make_stage(cvt="bgr2hsv", lo=LO, hi=HI, morph=[("open", 5, 5, 1)], label=True)
+    want = ("converted", "mask", "labels", "blobs")
+    out = ctx.stage(desc, ctx.upload(frames), want=want, max_blobs=4096)
+    got = {k: ctx.download(out[k]) for k in ("converted", "mask", "labels")}
+    n, tables = ctx.blobs_to_numpy(out["blobs"], out["n_blobs"])
+    for i in range(batch):
+        hsv = cv2.cvtColor(frames[i], cv2.COLOR_BGR2HSV)
+        m_ref = cv2.morphologyEx(cv2.inRange(hsv, np.array(LO), np.array(HI)), cv2.MORPH_OPEN, cv_ops.rect_kernel(5))
+        n_ref, lab_ref, tab = ccl.label_and_moments(m_ref)
+        assert np.array_equal(got["converted"][i], hsv), i
+        assert np.array_equal(got["mask"][i], m_ref), i
+        assert int(n[i]) == n_ref and np.array_equal(got["labels"][i], lab_ref), i
+        for key in ccl.MOMENT_KEYS + ("x0", "y0", "x1", "y1"):
+            assert np.array_equal(tables[i][key].astype(np.int64), tab[key]), (i, key)
+    for i in (0, batch - 1):     # one frame per call: no chunking at all
+        one = ctx.stage(desc, ctx.upload(frames[i]), want=("mask", "labels"), max_blobs=4096)
+        assert np.array_equal(ctx.download(one["mask"]), got["mask"][i])
+        assert np.array_equal(ctx.download(one["labels"]), got["labels"][i])
+    # the host entry point (uploads chunked, too) delivers the same
+    host = ctx.stage_host(desc, frames, want=("mask", "labels"), max_blobs=4096)
+    assert np.array_equal(host["mask"], got["mask"]) and np.array_equal(host["labels"], got["labels"])
