@@ -1401,9 +1401,13 @@ int balance_run(bv_ctx *ctx, const uint8_t *src, int batch, int height, int widt
     int chunk = (int)(l2_chunk_bytes(ctx) / (npx * 3));
     // large frames (4K: 25 MB each): a launch over a single frame is mostly ramp-up and tail, which costs more
     // than the L2 misses of a bigger chunk (tools/tune_c5.py: 16.9 k vs 15.8 k frames/s at 3840x2160 with 4 frames);
-    // when the stage hangs morphology + labelling behind every chunk (after_chunk), two frames per chunk keep all four
-    // side streams busy on an 8-frame call (tools/c3_overlap.py: 19.8 k vs 18.5 k frames/s)
-    const int min_chunk = after_chunk ? 2 : 4;
+    // when the stage hangs morphology + labelling behind every chunk (after_chunk), a short call is better off with two
+    // or three frames per chunk so that all side streams have one (tools/c3_overlap.py: 8 frames, 19.8 k vs 18.5 k frames/s)
+    int min_chunk = 4;
+    if (after_chunk) {
+        const int per_stream = (batch + side_streams(ctx) - 1) / side_streams(ctx);
+        min_chunk = per_stream < 2 ? 2 : (per_stream > 4 ? 4 : per_stream);
+    }
     if (chunk < min_chunk && ctx->opt[BV_OPT_L2_CHUNK_MB] <= 0) chunk = min_chunk;
     if (chunk < 1) chunk = 1;
     const int nchunks = (batch + chunk - 1) / chunk;
