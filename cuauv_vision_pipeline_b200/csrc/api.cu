@@ -231,7 +231,7 @@ extern "C" int bv_create(int device, bv_ctx **out) {
         return BV_ERR_UNSUPPORTED;
     }
     static const char *const opt_env[BV_OPT_COUNT] = {"BV_HIST_BPS", "BV_FINAL_BPS", "BV_SIDE_STREAMS", "BV_L2_CHUNK_MB",
-                                                      "BV_NO_HUE_TABLE", "BV_CONTOUR_POOL_CHUNKS", "BV_FAST_TABLES", "BV_MORPH_VARIANT", "BV_NO_RCP_TABLES", "BV_FINAL_SV_TABLES"};
+                                                      "BV_NO_HUE_TABLE", "BV_CONTOUR_POOL_CHUNKS", "BV_FAST_TABLES", "BV_MORPH_VARIANT", "BV_NO_RCP_TABLES", "BV_FINAL_SV_TABLES", "BV_MORPH_WARPS"};
     for (int i = 0; i < BV_OPT_COUNT; ++i) {
         const char *v = getenv(opt_env[i]);
         ctx->opt[i] = v ? atoi(v) : 0;

@@ -499,8 +499,10 @@ __global__ void __launch_bounds__(256) morph_roll_kernel(const uint32_t *__restr
 template <int R, int N>
 static int launch_roll(bv_ctx *ctx, const uint32_t *bits, uint32_t *dst_bits, uint8_t *mask, int batch, int height, int width,
                        int wpr, uint32_t erode_bits) {
-    // ~8 warps per SM, at least 4 output rows per strip (the halo of 2 N R rows is re-read by every strip)
-    int strips = (ctx->sm_count * 8 + batch - 1) / batch;
+    // warps per SM (BV_OPT_MORPH_WARPS, default 8), at least 4 output rows per strip (the halo of 2 N R rows is re-read
+    // and re-computed by every strip: fewer, taller strips do less work but offer less parallelism)
+    const int wps = ctx->opt[BV_OPT_MORPH_WARPS] > 0 ? ctx->opt[BV_OPT_MORPH_WARPS] : 8;
+    int strips = (ctx->sm_count * wps + batch - 1) / batch;
     if (strips > (height + 3) / 4) strips = (height + 3) / 4;
     if (strips < 1) strips = 1;
     const int strip_rows = (height + strips - 1) / strips;

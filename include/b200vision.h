@@ -158,7 +158,8 @@ enum {
                                  2 shared-memory tile filled by one TMA bulk copy (A-B timing, profiles/r02_morph_variants.log) */
     BV_OPT_NO_RCP_TABLES = 8, /* 1: pass 2 looks sdiv / hdiv up in shared memory instead of computing them with the reciprocal unit (A-B timing) */
     BV_OPT_FINAL_SV_TABLES = 9, /* pass 3 of balance -> BGR2LAB: 0 byte S'/V' tables (default); 1 float32 s, v tables; 2 8-byte {s, 1-s} / {v, trunc(255 v)} tables (A-B timing) */
-    BV_OPT_COUNT = 10
+    BV_OPT_MORPH_WARPS = 10, /* register-rolling morphology: row strips (= warps) per SM over the whole launch; taller strips re-compute less halo */
+    BV_OPT_COUNT = 11
 };
 int bv_set_option(bv_ctx *ctx, int option, int value);
 void bv_balance_default(bv_balance_params *p);
