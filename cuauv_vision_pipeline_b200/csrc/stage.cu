@@ -264,11 +264,15 @@ static int stage_host_enqueue(bv_ctx *ctx, int slot, const bv_stage_desc *desc, 
 
     // chunked three-stage pipeline: H2D (copy-in stream) -> kernels (context stream) -> D2H
     // (copy-out stream); PCIe is full duplex, so uploads of chunk k+1 overlap downloads of k-1.
-    static const size_t chunk_bytes = []() {
+    // A lone call wants small pieces (16 MB: its first upload and last download overlap nothing); when the other slot
+    // is in flight the overlap comes from that call, and whole batches keep the kernels efficient and the copies long
+    // (tools/e2e_pipe_sweep.py: two batches in flight 5 056 frames/s with 16 MB pieces, 5 613 with one piece per batch).
+    static const long env_chunk_mb = []() {
         const char *e = getenv("BV_HOST_CHUNK_MB");
-        long mb = e ? atol(e) : 16;
-        return (size_t)(mb < 1 ? 1 : mb) << 20;
+        return e ? atol(e) : 0L;
     }();
+    const bool pipelined = ctx->slot_busy[1 - slot] != 0;
+    const size_t chunk_bytes = (size_t)(env_chunk_mb > 0 ? env_chunk_mb : (pipelined ? 256 : 16)) << 20;
     int chunk = (int)(chunk_bytes / (npx * 3));
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;
