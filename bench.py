@@ -6,12 +6,12 @@
 
 Workload (BASELINE.json configs[1], "C2"): ZED 2208x1242 stereo frames through balance() (default
 flags, modules/color_balance.py:93-96) and BGR2LAB (utils/color.py:26).  One step = one batch of
-16 frames (8 stereo pairs) per GPU taken from a ring of 64 distinct synthetic frames (526 MB, > L2;
+32 frames (16 stereo pairs, 263 MB > L2) per GPU taken from a ring of 64 distinct synthetic frames (526 MB;
 consecutive steps use different batches).  Frames shard by index across GPUs with no collective
-("weak" scaling: 16 frames per GPU per step).
+("weak" scaling: 32 frames per GPU per step).
 
 One JSON line on stdout (rank 0).  `value`: device-resident frames/s, CUDA events on the library's
-stream.  `e2e`: same stage through bv_stage_host with pinned HOST buffers, H2D + D2H inside the
+stream.  `e2e`: same stage through bv_stage_host_submit / _wait (and, beside it, the blocking bv_stage_host) with pinned HOST buffers, H2D + D2H inside the
 timed region.  `roofline`: dominant kernel, per-launch CUDA-event time from the library's own
 profiler; `stage_roofline`: the whole step against the algorithmic 6 B/px.  `cpu_baseline`: the
 reference's compiled process_frame + cv2.cvtColor on the host cores (reported, not a target).
@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 H, W = 1242, 2208
-BATCH = 16
+BATCH = 32   # frames per call: the join at the end of a call drains the side streams, 32 frames amortise it (tools/batch_sweep.py: 16 -> 32 frames +5 %)
 RING = 64
 BPP_C2 = 6          # BGR in (3) + LAB image out (3)
 METRIC = "frames/sec at 2208x1242"
@@ -310,11 +310,14 @@ def side_workloads(ctx, peak_gbs):
         res[name] = {"frames_per_s": v, "ms_per_step": 1e3 * dt / steps,
                      "algorithmic_gbs": bpp_px * v / 1e9, "frac_of_hbm": bpp_px * v / 1e9 / peak_gbs}
     # north-star stage at 2208x1242: balance -> HSV -> inRange -> OPEN 5x5, mask out (4 B/px)
-    ring = ctx.upload(np.stack([synth.gen_underwater(H, W, 3000 + i) for i in range(16)]))
+    base = [synth.gen_underwater(H, W, 3000 + i) for i in range(16)]
+    ring = ctx.upload(np.stack(base + [np.roll(b, 131, axis=1) for b in base]))     # 32 frames per call, 263 MB > L2
     desc = ctx.make_stage(balance={}, cvt="bgr2hsv", lo=(0, 40, 60), hi=(179, 255, 255), morph=[("open", 5, 5, 1)])
     out = {}
     fps("fused_balance_hsv_inrange_open_2208x1242", lambda s: out.update(ctx.stage(desc, ring, want=("mask",), out=out)),
-        16, 4 * H * W)
+        32, 4 * H * W)
+    res["fused_balance_hsv_inrange_open_2208x1242"]["frames_per_call"] = 32
+    ring = ring[:16]
     # C3: 1920x1080 HSV inRange -> OPEN -> CCL + moments (8 B/px)
     ring3 = ctx.upload(np.stack([synth.gen_underwater(1080, 1920, 3100 + i) for i in range(16)]))
     d3 = ctx.make_stage(cvt="bgr2hsv", lo=(10, 20, 60), hi=(30, 100, 255), morph=[("open", 5, 5, 1)], label=True)
@@ -658,11 +661,11 @@ def run_ours(args):
         clocks["window"] = "device-resident timed region + the sustained repetition (%.1f s)" % sus_elapsed
     e2e = {"value": world * BATCH * e2e_steps / e2e_pipe_dt, "unit": "frames/s",
            "h2d_bytes_per_step": BATCH * H * W * 3, "d2h_bytes_per_step": BATCH * H * W * 3,
-           "api": "bv_stage_host_submit / bv_stage_host_wait (C ABI, pinned host buffers, two 16-frame batches in flight: "
-                  "every step uploads its 16 frames and returns its 16 LAB images inside the timed region)",
+           "api": "bv_stage_host_submit / bv_stage_host_wait (C ABI, pinned host buffers, two %d-frame batches in flight: "
+                  "every step uploads its frames and returns their LAB images inside the timed region)" % BATCH,
            "steps": e2e_steps,
            "blocking_call": {"value": world * BATCH * e2e_steps / e2e_dt, "unit": "frames/s",
-                             "api": "bv_stage_host (one blocking call per 16-frame batch)"},
+                             "api": "bv_stage_host (one blocking call per %d-frame batch)" % BATCH},
            "single_frame_latency_ms": single_ms,
            "pcie_note": "8.23 MB in + 8.23 MB out per frame, copied in both directions at once; `pcie` is this box's own "
                         "ceiling for that (plain cudaMemcpyAsync of the same pinned buffers on every rank at once, no kernels)",
@@ -692,8 +695,8 @@ def run_ours(args):
             "config": {"workload": "C2: ZED 2208x1242 stereo frames, balance() default flags -> BGR2LAB image "
                                    "(BASELINE.json configs[1])",
                        "frames_per_step_per_gpu": BATCH, "ring_frames": RING,
-                       "l2": "inputs larger than L2 (131 MB per step from a 526 MB ring; consecutive steps use "
-                             "different batches)",
+                       "l2": ("inputs larger than L2 (%d MB per step from a 526 MB ring; consecutive steps use "
+                              "different batches)") % (BATCH * H * W * 3 // 1000000),
                        "parallelism": "frames sharded by index over %d GPU(s), no collective" % world,
                        "host_affinity": ("%d CPUs local to each GPU" % len(numa_cpus)) if numa_cpus else "default"},
             "sustained": sustained,
