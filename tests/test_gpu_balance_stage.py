@@ -633,3 +633,33 @@ def test_stage_mask_only_shapes_outside_the_hue_table_path(ctx, shape):
         m_ref = cv2.morphologyEx(cv2.inRange(hsv_ref, np.array(lo), np.array(hi)), cv2.MORPH_OPEN, cv_ops.rect_kernel(3))
         assert np.array_equal(mask[i], m_ref)
         assert np.array_equal(lab[i], ccl.label_and_moments(m_ref)[1])
+
+
+@pytest.mark.parametrize("option,values", [("final_sv_tables", (1, 2)), ("morph_warps", (1, 3)), ("no_rcp_tables", (1,)),
+                                           ("fast_tables", (1,)), ("morph_variant", (1, 2)), ("no_hue_table", (1,))])
+def test_tuning_options_do_not_change_results(ctx, option, values):
+    """Every A-B knob of the library (bv_set_option / BV_* environment variables) selects another implementation of the
+    same arithmetic: outputs are identical to the default's, on the stages the knobs act on."""
+    frames = np.stack([synth.gen_underwater(416, 672, 900 + i) for i in range(6)])
+    dev = ctx.upload(frames)
+    stages = [(ctx.make_stage(balance={}, cvt="bgr2lab"), ("converted",)),
+              (ctx.make_stage(balance={}, cvt="bgr2hsv", lo=(0, 40, 60), hi=(179, 255, 255), morph=[("open", 5, 5, 1)], label=True),
+               ("mask", "labels")),
+              (ctx.make_stage(cvt="bgr2lab", lo=(0, 120, 0), hi=(255, 255, 255), morph=[("open", 3, 3, 1), ("close", 5, 5, 1)]),
+               ("mask",))]
+
+    def run():
+        res = []
+        for desc, want in stages:
+            out = ctx.stage(desc, dev, want=want, max_blobs=2048)
+            res.extend(ctx.download(out[k]).copy() for k in want)
+        return res
+    ref = run()
+    try:
+        for v in values:
+            ctx.set_option(option, v)
+            got = run()
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b), (option, v)
+    finally:
+        ctx.set_option(option, 0)
