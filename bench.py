@@ -6,9 +6,9 @@
 
 Workload (BASELINE.json configs[1], "C2"): ZED 2208x1242 stereo frames through balance() (default
 flags, modules/color_balance.py:93-96) and BGR2LAB (utils/color.py:26).  One step = one batch of
-32 frames (16 stereo pairs, 263 MB > L2) per GPU taken from a ring of 64 distinct synthetic frames (526 MB;
+64 frames (32 stereo pairs, 526 MB > L2) per GPU taken from a ring of 128 synthetic frames (1.05 GB;
 consecutive steps use different batches).  Frames shard by index across GPUs with no collective
-("weak" scaling: 32 frames per GPU per step).
+("weak" scaling: 64 frames per GPU per step).  The host-buffer legs move 32 frames per call.
 
 One JSON line on stdout (rank 0).  `value`: device-resident frames/s, CUDA events on the library's
 stream.  `e2e`: same stage through bv_stage_host_submit / _wait (and, beside it, the blocking bv_stage_host) with pinned HOST buffers, H2D + D2H inside the
@@ -31,8 +31,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 H, W = 1242, 2208
-BATCH = 32   # frames per call: the join at the end of a call drains the side streams, 32 frames amortise it (tools/batch_sweep.py: 16 -> 32 frames +5 %)
-RING = 64
+BATCH = 64       # frames per device-resident call: the join at the end of a call drains the side streams; long calls amortise it
+                 # and take 8-frame chunks (tools/batch_sweep.py: 16 / 32 / 64 frames per call = 64.7 / 68.9 / 71.8 k frames/s)
+E2E_BATCH = 32   # frames per host-buffer call (pinned buffers: 4 x 263 MB)
+RING = 128       # 64 generated frames + 64 cyclic shifts of them (same statistics, every pixel somewhere else)
 BPP_C2 = 6          # BGR in (3) + LAB image out (3)
 METRIC = "frames/sec at 2208x1242"
 
@@ -452,8 +454,8 @@ def run_ours(args):
         return float(t.item())
 
     # synthetic ring, distinct per rank (frame f of the global stream goes to rank f mod world)
-    ring_np = make_ring(RING, seed0=2000 + 100 * rank)
-    ring = ctx.upload(ring_np)
+    ring_np = make_ring(RING // 2, seed0=2000 + 100 * rank)
+    ring = torch.cat([ctx.upload(ring_np), ctx.upload(np.roll(ring_np, 211, axis=2))])
     n_batches = RING // BATCH
     desc = ctx.make_stage(balance={}, cvt="bgr2lab")
     out = {}
@@ -511,9 +513,9 @@ def run_ours(args):
     ctx.profile(False)
     total_ms = sum(v["ms"] for v in prof.values()) or 1.0
     dom = max(prof, key=lambda k: prof[k]["ms"])
-    # one launch of any pass covers one L2-sized chunk of frames
-    chunk_frames = max(1, int(os.environ.get("BV_L2_CHUNK_MB", "33")) * (1 << 20) // (H * W * 3))
-    chunk_frames = min(chunk_frames, BATCH)
+    # one launch of any pass covers one chunk of frames (the library sizes it: L2, call length): 4 profiled steps of BATCH
+    # frames went through `launches` launches of the dominant kernel
+    chunk_frames = max(1, (4 * BATCH) // max(1, prof[dom]["launches"]))
     dom_ms = prof[dom]["ms"] / prof[dom]["launches"]
     achieved = BPP_C2 * H * W * chunk_frames / (dom_ms / 1e3) / 1e9
     static, static_name = load_static_profile()
@@ -552,16 +554,17 @@ def run_ours(args):
     stage_gbs = BPP_C2 * H * W * value / world / 1e9
     stage_roofline = {"achieved": stage_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": stage_gbs / peak_gbs,
                       "steady_state_dram_bytes_per_frame": st,
-                      "per_kernel_ms": {k: round(v["ms"] / 4, 4) for k, v in sorted(prof.items())}}
+                      "per_kernel_ms": {k: round(v["ms"] / 4, 4) for k, v in sorted(prof.items())},
+                      "frames_per_launch": chunk_frames}
 
     # ---- C5: 8 x 4K streams sharded by stream (strong scaling), every rank ----
     c5 = None if args.no_side else c5_leg(ctx, world, rank, peak_gbs)
 
     # ---- end to end through the host-buffer entry point (pinned memory) ----
-    pin_in = bv.PinnedArray((2, BATCH, H, W, 3))
-    pin_in.array[0] = ring_np[:BATCH]
-    pin_in.array[1] = ring_np[BATCH:2 * BATCH]
-    pin_out = bv.PinnedArray((BATCH, H, W, 3))
+    pin_in = bv.PinnedArray((2, E2E_BATCH, H, W, 3))
+    pin_in.array[0] = ring_np[:E2E_BATCH]
+    pin_in.array[1] = ring_np[E2E_BATCH:2 * E2E_BATCH]
+    pin_out = bv.PinnedArray((E2E_BATCH, H, W, 3))
     host_out = {"converted": pin_out.array}
     e2e_steps = max(3, min(args.steps, 30))   # a step moves 263 MB over PCIe (~3 ms): 30 steps amortise the first upload / last download
     for s in range(2):
@@ -574,7 +577,7 @@ def run_ours(args):
     e2e_dt = allmax(time.perf_counter() - t0)
     # the same work through the asynchronous pair (bv_stage_host_submit / _wait): two batches in flight, one per staging
     # slot, so that the uploads of batch k+1 run while batch k is still being returned (PCIe is full duplex)
-    pin_out2 = bv.PinnedArray((BATCH, H, W, 3))
+    pin_out2 = bv.PinnedArray((E2E_BATCH, H, W, 3))
     host_outs = [host_out, {"converted": pin_out2.array}]
 
     def pipelined(steps):
@@ -599,8 +602,8 @@ def run_ours(args):
         ctx.stage_host(desc_bins, pin_in.array[s % 2], want=("blobs",), max_blobs=1024, out=bins_out)
     barrier()
     bins_dt = allmax(time.perf_counter() - t0)
-    pin_blobs = [bv.PinnedArray((BATCH, 1024), bv.BLOB_DTYPE) for _ in range(2)]
-    pin_nb = [bv.PinnedArray((BATCH,), np.int32) for _ in range(2)]
+    pin_blobs = [bv.PinnedArray((E2E_BATCH, 1024), bv.BLOB_DTYPE) for _ in range(2)]
+    pin_nb = [bv.PinnedArray((E2E_BATCH,), np.int32) for _ in range(2)]
     bins_outs = [{"blobs": pin_blobs[i].array, "n_blobs": pin_nb[i].array} for i in range(2)]
 
     def bins_pipelined(steps):
@@ -620,7 +623,7 @@ def run_ours(args):
         ctx.stage_host(desc, pin_in.array[0][:1], want=("converted",), out=one_out)
     t0 = time.perf_counter()
     for s in range(20):
-        ctx.stage_host(desc, pin_in.array[0][s % BATCH:s % BATCH + 1], want=("converted",), out=one_out)
+        ctx.stage_host(desc, pin_in.array[0][s % E2E_BATCH:s % E2E_BATCH + 1], want=("converted",), out=one_out)
     single_ms = (time.perf_counter() - t0) / 20 * 1e3
     # the box's own host<->device copy ceiling, measured with the same pinned buffers and EVERY rank copying at the
     # same time (the host memory system is shared by all GPUs of the box; it differs between boxes of the pool)
@@ -652,28 +655,28 @@ def run_ours(args):
     nbytes_in, nbytes_out = t_in.numel(), t_out.numel()
     pcie = {"both_directions_gbs": world * (nbytes_in + nbytes_out) / both_dt / 1e9,
             "h2d_only_gbs": world * nbytes_in / up_dt / 1e9,
-            "ceiling_frames_per_s": world * BATCH / both_dt,
-            "h2d_only_ceiling_frames_per_s": world * BATCH / up_dt,
+            "ceiling_frames_per_s": world * E2E_BATCH / both_dt,
+            "h2d_only_ceiling_frames_per_s": world * E2E_BATCH / up_dt,
             "ranks_copying_concurrently": world}
     del d_in, d_out
     clocks = sampler.stop(mark_a, mark_b) if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "device-resident timed region + the sustained repetition (%.1f s)" % sus_elapsed
-    e2e = {"value": world * BATCH * e2e_steps / e2e_pipe_dt, "unit": "frames/s",
-           "h2d_bytes_per_step": BATCH * H * W * 3, "d2h_bytes_per_step": BATCH * H * W * 3,
+    e2e = {"value": world * E2E_BATCH * e2e_steps / e2e_pipe_dt, "unit": "frames/s",
+           "h2d_bytes_per_step": E2E_BATCH * H * W * 3, "d2h_bytes_per_step": E2E_BATCH * H * W * 3,
            "api": "bv_stage_host_submit / bv_stage_host_wait (C ABI, pinned host buffers, two %d-frame batches in flight: "
-                  "every step uploads its frames and returns their LAB images inside the timed region)" % BATCH,
+                  "every step uploads its frames and returns their LAB images inside the timed region)" % E2E_BATCH,
            "steps": e2e_steps,
-           "blocking_call": {"value": world * BATCH * e2e_steps / e2e_dt, "unit": "frames/s",
-                             "api": "bv_stage_host (one blocking call per %d-frame batch)" % BATCH},
+           "blocking_call": {"value": world * E2E_BATCH * e2e_steps / e2e_dt, "unit": "frames/s",
+                             "api": "bv_stage_host (one blocking call per %d-frame batch)" % E2E_BATCH},
            "single_frame_latency_ms": single_ms,
            "pcie_note": "8.23 MB in + 8.23 MB out per frame, copied in both directions at once; `pcie` is this box's own "
                         "ceiling for that (plain cudaMemcpyAsync of the same pinned buffers on every rank at once, no kernels)",
            "pcie": pcie,
-           "bins_module": {"value": world * BATCH * e2e_steps / bins_pipe_dt, "unit": "frames/s",
-                           "blocking_call": world * BATCH * e2e_steps / bins_dt,
-                           "h2d_bytes_per_step": BATCH * H * W * 3, "d2h_bytes_per_step": BATCH * (1024 * 96 + 4),
-                           "frac_of_h2d_ceiling": (world * BATCH * e2e_steps / bins_pipe_dt) / pcie["h2d_only_ceiling_frames_per_s"],
+           "bins_module": {"value": world * E2E_BATCH * e2e_steps / bins_pipe_dt, "unit": "frames/s",
+                           "blocking_call": world * E2E_BATCH * e2e_steps / bins_dt,
+                           "h2d_bytes_per_step": E2E_BATCH * H * W * 3, "d2h_bytes_per_step": E2E_BATCH * (1024 * 96 + 4),
+                           "frac_of_h2d_ceiling": (world * E2E_BATCH * e2e_steps / bins_pipe_dt) / pcie["h2d_only_ceiling_frames_per_s"],
                            "workload": "frames in, blob tables out: balance -> BGR2HSV -> inRange -> OPEN 5x5 -> labels + "
                                        "moments (modules/bins.py:13-27), bv_stage_host_submit / _wait (blocking_call: bv_stage_host)"}}
     pcie["e2e_frac_of_ceiling"] = e2e["value"] / pcie["ceiling_frames_per_s"]
@@ -695,7 +698,7 @@ def run_ours(args):
             "config": {"workload": "C2: ZED 2208x1242 stereo frames, balance() default flags -> BGR2LAB image "
                                    "(BASELINE.json configs[1])",
                        "frames_per_step_per_gpu": BATCH, "ring_frames": RING,
-                       "l2": ("inputs larger than L2 (%d MB per step from a 526 MB ring; consecutive steps use "
+                       "l2": ("inputs larger than L2 (%d MB per step from a 1.05 GB ring; consecutive steps use "
                               "different batches)") % (BATCH * H * W * 3 // 1000000),
                        "parallelism": "frames sharded by index over %d GPU(s), no collective" % world,
                        "host_affinity": ("%d CPUs local to each GPU" % len(numa_cpus)) if numa_cpus else "default"},
