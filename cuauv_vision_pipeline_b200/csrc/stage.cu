@@ -346,6 +346,15 @@ static int stage_host_enqueue(bv_ctx *ctx, int slot, const bv_stage_desc *desc, 
     return BV_OK;
 }
 
+// An enqueue that failed half-way (bad description, out of memory) may have copies and kernels of the call in flight with no
+// completion event recorded: wait for them, so that the caller's buffers and the slot's staging are quiescent on return.
+static void drain_after_failed_enqueue(bv_ctx *ctx) {
+    cudaStreamSynchronize(ctx->copy_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_out);
+    (void)cudaGetLastError();
+}
+
 extern "C" int bv_stage_host_wait(bv_ctx *ctx, int slot) {
     BV_REQUIRE(ctx, "null context");
     BV_REQUIRE(slot >= 0 && slot < BV_HOST_SLOTS, "slot must be 0 or 1");
@@ -362,8 +371,10 @@ extern "C" int bv_stage_host_submit(bv_ctx *ctx, int slot, const bv_stage_desc *
     BV_REQUIRE(ctx, "null context");
     BV_REQUIRE(slot >= 0 && slot < BV_HOST_SLOTS, "slot must be 0 or 1");
     BV_TRY(bv_stage_host_wait(ctx, slot));   // the slot's device staging is free again once its previous call has completed
-    return stage_host_enqueue(ctx, slot, desc, src_host, batch, height, width, balanced_host, converted_host, mask_host,
-                              labels_host, blobs_host, max_blobs, n_blobs_host);
+    const int st = stage_host_enqueue(ctx, slot, desc, src_host, batch, height, width, balanced_host, converted_host, mask_host,
+                                      labels_host, blobs_host, max_blobs, n_blobs_host);
+    if (st != BV_OK) drain_after_failed_enqueue(ctx);
+    return st;
 }
 
 extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8_t *src_host, int batch, int height,
@@ -371,8 +382,12 @@ extern "C" int bv_stage_host(bv_ctx *ctx, const bv_stage_desc *desc, const uint8
                              int32_t *labels_host, bv_blob *blobs_host, int max_blobs, int32_t *n_blobs_host) {
     BV_REQUIRE(ctx, "null context");
     BV_TRY(bv_stage_host_wait(ctx, 0));
-    BV_TRY(stage_host_enqueue(ctx, 0, desc, src_host, batch, height, width, balanced_host, converted_host, mask_host, labels_host,
-                              blobs_host, max_blobs, n_blobs_host));
+    const int st = stage_host_enqueue(ctx, 0, desc, src_host, batch, height, width, balanced_host, converted_host, mask_host,
+                                      labels_host, blobs_host, max_blobs, n_blobs_host);
+    if (st != BV_OK) {
+        drain_after_failed_enqueue(ctx);
+        return st;
+    }
     BV_TRY(bv_stage_host_wait(ctx, 0));
     BV_CUDA(cudaStreamSynchronize(ctx->stream));
     return BV_OK;

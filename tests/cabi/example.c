@@ -46,6 +46,28 @@ int main(int argc, char **argv) {
         fprintf(stderr, "bv_stage_host: %s\n", bv_last_error());
         return 6;
     }
+    /* the same call split in two (bv_stage_host_submit / bv_stage_host_wait): both slots in flight, same results */
+    {
+        uint8_t *mask2[2];
+        bv_blob blobs2[2][256];
+        int32_t n2[2] = {0, 0};
+        int k;
+        for (k = 0; k < 2; ++k) {
+            mask2[k] = (uint8_t *)malloc(n);
+            if (bv_stage_host_submit(ctx, k, &d, frame, 1, h, w, NULL, NULL, mask2[k], NULL, blobs2[k], 256, &n2[k]) != BV_OK) {
+                fprintf(stderr, "bv_stage_host_submit: %s\n", bv_last_error());
+                return 7;
+            }
+        }
+        for (k = 1; k >= 0; --k) {
+            if (bv_stage_host_wait(ctx, k) != BV_OK || n2[k] != n_blobs || memcmp(mask2[k], mask, n) != 0 ||
+                memcmp(blobs2[k], blobs, sizeof(bv_blob) * (size_t)n_blobs) != 0) {
+                fprintf(stderr, "submit / wait differs from the blocking call (slot %d)\n", k);
+                return 8;
+            }
+            free(mask2[k]);
+        }
+    }
     bv_destroy(ctx);
 
     f = fopen(argv[4], "wb"); fwrite(bal, 1, n * 3, f); fclose(f);
