@@ -85,8 +85,8 @@ __device__ __forceinline__ int rint_quotient_rcp(float num, int d) {
 }
 
 __device__ __forceinline__ void bgr2hsv_rcp(int b, int g, int r, int &h, int &s, int &v) {
-    v = imax(imax(b, g), r);
-    const int vmin = imin(imin(b, g), r);
+    v = __vimax3_s32(b, g, r);               // one VIMNMX3 each (the nested two-input form compiles to two for the minimum)
+    const int vmin = __vimin3_s32(b, g, r);
     const int diff = v - vmin;
     const int hr = g - b, hg = b - r + 2 * diff, hb = r - g + 4 * diff;
     int hh = (v == g) ? hg : hb;
@@ -95,7 +95,9 @@ __device__ __forceinline__ void bgr2hsv_rcp(int b, int g, int r, int &h, int &s,
     const int hd = rint_quotient_rcp((float)((180 << kHsvShift) / 6), diff);
     s = (diff * sd + (1 << (kHsvShift - 1))) >> kHsvShift;
     hh = (hh * hd + (1 << (kHsvShift - 1))) >> kHsvShift;
-    h = hh + ((hh >> 31) & 180);
+    // hh < 0: += 180.  hh lies in [-180, 180], so as unsigned numbers the smaller of hh and hh + 180 is the answer
+    // (a negative hh is huge): one add + one unsigned min instead of shift + and + add
+    h = (int)umin((unsigned)hh, (unsigned)(hh + 180));
 }
 #endif
 
