@@ -225,7 +225,11 @@ __device__ __forceinline__ void store_px16(uint8_t *base, size_t group, const Px
 }
 
 // byte k (compile-time constant after unrolling) of a packed word array
-#define BV_GETB(W, k) (((W)[(k) >> 2] >> (8 * ((k)&3))) & 0xFFu)
+// (bytes 1 and 2 of a word through one byte-permute instead of shift + mask)
+__device__ __forceinline__ uint32_t bv_word_byte(uint32_t w, int b) {
+    return b == 0 ? (w & 0xFFu) : b == 3 ? (w >> 24) : __byte_perm(w, 0u, 0x4440u | (uint32_t)b);
+}
+#define BV_GETB(W, k) bv::bv_word_byte((W)[(k) >> 2], (k)&3)
 #define BV_PUTB(W, k, v) ((W)[(k) >> 2] |= ((uint32_t)(v)) << (8 * ((k)&3)))
 
 // ---- TMA bulk copy (cp.async.bulk, SASS: UBLKCP) completing on an mbarrier ----
