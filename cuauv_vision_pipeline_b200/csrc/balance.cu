@@ -785,8 +785,10 @@ __global__ void __launch_bounds__(1024) ivl_compose_kernel(const uint16_t *__res
     grid_dependency_wait();  // pass 2 (the S / V tables of this frame) is complete from here on
     for (int i = threadIdx.x; i < 512; i += blockDim.x) (&lsv[0][0])[i] = (&st[frame].lut_sv[0][0])[i];
     __syncthreads();
+    // entry index = (V << 8) | S: S and V are neighbouring bytes of the scratch image, so pass 3 takes the index out of the
+    // packed words with one byte-permute
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kIvlEntries; idx += gridDim.x * blockDim.x)
-        composed[(size_t)frame * kIvlEntries + idx] = __ldg(table + (((uint32_t)lsv[0][idx >> 8] << 8) | lsv[1][idx & 255]));
+        composed[(size_t)frame * kIvlEntries + idx] = __ldg(table + (((uint32_t)lsv[0][idx & 255] << 8) | lsv[1][idx >> 8]));
 }
 
 // pass 3 of the fast path: H,S,V scratch -> S/V stretch tables -> hue interval -> mask
@@ -820,7 +822,14 @@ __global__ void __launch_bounds__(1024, 1) mask_from_hsv_kernel(const uint8_t *_
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const uint32_t h = BV_GETB(in.w, 3 * j);
-            const uint32_t e = sm.tab[(BV_GETB(in.w, 3 * j + 1) << 8) | BV_GETB(in.w, 3 * j + 2)];   // composed: indexed by the raw S, V
+            // bytes 3j+1 (S) and 3j+2 (V) as one little-endian 16-bit field = (V << 8) | S, possibly across two words
+            const int o = 3 * j + 1, wi = o >> 2, bi = o & 3;
+            uint32_t sv;
+            if (bi < 3)   // both bytes in one word: one byte-permute (second operand = 0 supplies the zero bytes)
+                sv = __byte_perm(in.w[wi], 0u, 0x4400u | (uint32_t)((bi + 1) << 4) | (uint32_t)bi);
+            else          // S is the last byte of a word, V the first of the next (4 of the 16 pixels)
+                sv = __funnelshift_r(in.w[wi], in.w[wi + 1 < 12 ? wi + 1 : wi], 24) & 0xFFFFu;
+            const uint32_t e = sm.tab[sv];   // composed per frame: indexed by the raw S, V
             if (((h - (e & 0xFFu)) & 0xFFu) <= (e >> 8)) bits |= 1u << j;
         }
         if (out.mask) {
