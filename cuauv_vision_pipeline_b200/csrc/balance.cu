@@ -581,7 +581,7 @@ __device__ __forceinline__ uint32_t balance_px(uint32_t b, uint32_t g, uint32_t 
 
 // one group of 16 pixels.  TRACK_X: the group touches the row tail (width % 32 columns), where
 // cv2's scalar HSV2BGR / HLS rounding applies, or wraps to the next row.
-template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, bool BAL, int SVT, int J>
+template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, bool BAL, int SVT, bool CVT, int J>
 struct GroupBody {
     static __device__ __forceinline__ void run(const Px16 &in, int x, int width, int vec_end, const FinalSmem &fs,
                                                const SvTabs<SVT> &svt, const SmemTabs &tabs, const RangeTest &bd, Px16 &ob,
@@ -596,28 +596,30 @@ struct GroupBody {
         if (BAL) put_px<J>(ob.w, p);   // packing the balanced pixel costs ~2.5 instructions: only when that output exists
         int o0, o1, o2;
         convert_px<CODE>((int)(p & 0xFF), (int)((p >> 8) & 0xFF), (int)(p >> 16), vec, tabs, o0, o1, o2);
-        if (kOne) {
-            BV_PUTB(q, J, o0);
-        } else {
-            put_px3<J>(oc.w, stg, (uint32_t)o0, (uint32_t)o1, (uint32_t)o2);
+        if (CVT) {   // the converted image is an output (a mask-only call skips assembling it)
+            if (kOne) {
+                BV_PUTB(q, J, o0);
+            } else {
+                put_px3<J>(oc.w, stg, (uint32_t)o0, (uint32_t)o1, (uint32_t)o2);
+            }
         }
         if (NEED_MASK)
             if (in_range_px<CODE>(o0, o1, o2, bd)) bits |= 1u << J;
         if (TRACK_X) {
             if (++x == width) x = 0;
         }
-        GroupBody<MODE, CODE, TRACK_X, NEED_MASK, BAL, SVT, J + 1>::run(in, x, width, vec_end, fs, svt, tabs, bd, ob, oc, q, bits, stg);
+        GroupBody<MODE, CODE, TRACK_X, NEED_MASK, BAL, SVT, CVT, J + 1>::run(in, x, width, vec_end, fs, svt, tabs, bd, ob, oc, q, bits, stg);
     }
 };
-template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, bool BAL, int SVT>
-struct GroupBody<MODE, CODE, TRACK_X, NEED_MASK, BAL, SVT, 16> {
+template <int MODE, int CODE, bool TRACK_X, bool NEED_MASK, bool BAL, int SVT, bool CVT>
+struct GroupBody<MODE, CODE, TRACK_X, NEED_MASK, BAL, SVT, CVT, 16> {
     static __device__ __forceinline__ void run(const Px16 &, int, int, int, const FinalSmem &, const SvTabs<SVT> &,
                                                const SmemTabs &, const RangeTest &, Px16 &, Px16 &, uint32_t (&)[4], uint32_t &,
                                                uint32_t (&)[4]) {}
 };
 
 // BAL: the balanced image is an output (always when CODE == -1); without it the vector path skips packing it
-template <int MODE, int CODE, bool VEC, bool NEED_MASK, bool BAL = true, int SVT = 0>
+template <int MODE, int CODE, bool VEC, bool NEED_MASK, bool BAL = true, int SVT = 0, bool CVT = true>
 __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__restrict__ src, size_t src_stride,
                                                             const BalFrame *__restrict__ st, size_t npx, int width,
                                                             BalOutputs out, const uint16_t *__restrict__ g_gamma,
@@ -666,11 +668,11 @@ __global__ void __launch_bounds__(kBalThreads) final_kernel(const uint8_t *__res
 #pragma unroll
         for (int k = 0; k < 12; ++k) ob.w[k] = oc.w[k] = 0;
         if (kNeedX && (int)x0 + 16 > vec_end)
-            GroupBody<MODE, CODE, true, NEED_MASK, BAL, SVT, 0>::run(in, (int)x0, width, vec_end, fs, svt, tabs, bd, ob, oc, q, bits, stg);
+            GroupBody<MODE, CODE, true, NEED_MASK, BAL, SVT, CVT, 0>::run(in, (int)x0, width, vec_end, fs, svt, tabs, bd, ob, oc, q, bits, stg);
         else
-            GroupBody<MODE, CODE, false, NEED_MASK, BAL, SVT, 0>::run(in, (int)x0, width, vec_end, fs, svt, tabs, bd, ob, oc, q, bits, stg);
+            GroupBody<MODE, CODE, false, NEED_MASK, BAL, SVT, CVT, 0>::run(in, (int)x0, width, vec_end, fs, svt, tabs, bd, ob, oc, q, bits, stg);
         if (BAL && out.balanced) store_px16(out.balanced + foff * 3, g, ob);
-        if (out.converted) {
+        if (CVT && out.converted) {
             if (kOne)
                 st_stream(reinterpret_cast<uint4 *>(out.converted + foff) + g, make_uint4(q[0], q[1], q[2], q[3]));
             else
@@ -1219,6 +1221,9 @@ static int launch_final(bv_ctx *ctx, const uint8_t *src, size_t src_stride, cons
         else
             BV_LAUNCH_PDL(ctx, (final_kernel<MODE, CODE, true, false, false, (MODE == 3 && CODE == BV_BGR2LAB) ? 2 : 0>), grid,
                           kBalThreads, 0, src, src_stride, st, npx, width, out, ctx->d_lab_gamma, ctx->d_lab_cbrt);
+    } else if (vec && CODE != -1 && !out.balanced && !out.converted && need_mask) {   // mask only (modules/bins.py, red_buoy.py)
+        BV_LAUNCH_PDL(ctx, (final_kernel<MODE, CODE, true, true, false, 0, false>), grid, kBalThreads, 0, src, src_stride, st, npx,
+                      width, out, ctx->d_lab_gamma, ctx->d_lab_cbrt);
     } else if (vec && CODE != -1 && !out.balanced) {   // the common module case: only the converted image / the mask leave the pass
         if (need_mask) BV_FINAL_NOBAL(true); else BV_FINAL_NOBAL(false);
     } else if (vec) {
