@@ -40,6 +40,18 @@ def balance(mat, equalize_rgb=True, rgb_contrast_correct=False,
     cols = mat.shape[1]
     depth = 3
     c_int8_p = ctypes.POINTER(ctypes.c_int8)
+    if hsi_contrast_correct:
+        # The reference's HSI branch is not repeatable on a cold start: its eight conversion threads share an unsynchronised
+        # memo table (rgb_to_hsi_cache, color_balance.cpp:180-185 read, 208-212 write), so a thread can see entry [0] of a
+        # colour as valid while [1] / [2] are still being written by another one -- one pixel of the frame then carries a
+        # stale S or I (seen on ~4 % of first calls in a process; tests/test_gpu_balance_stage.py reports which side moved).
+        # A first pass over a throw-away copy fills the table for every colour of this frame; the second pass only reads
+        # complete entries and is what the oracle returns.
+        warm = mat.flatten()
+        lib.process_frame(warm.ctypes.data_as(c_int8_p), rows, cols, depth, equalize_rgb,
+                          rgb_contrast_correct, hsv_contrast_correct, hsi_contrast_correct,
+                          rgb_extrema_clipping, adaptive_cast_correction,
+                          horizontal_blocks, vertical_blocks)
     data = mat.flatten()
     data_p = data.ctypes.data_as(c_int8_p)
     lib.process_frame(data_p, rows, cols, depth, equalize_rgb,
